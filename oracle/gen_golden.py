@@ -1,0 +1,234 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference; see oracle/ref_shim):
+    python -m oracle.gen_golden
+The vectors are committed; the GPU box (which has no reference tree) replays them.  Every file stores the
+constructor kwargs as a JSON string under `config`, the injected inputs (actions, and for GridWorld the uniform
+`u` that Generator.choice consumed on that step, read from a clone of the env's PCG64 state) and the reference's
+outputs.  numpy version used is recorded in `numpy_version` (matters for PendulumDisk, see oracle/pendulums.py).
+"""
+import json
+import os
+
+import numpy as np
+
+from oracle.ref_shim import load_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CONFIG2_LAYOUT = dict(  # SURVEY.md 8(d) config 2 -- canonical 8x8 layout
+    rows=8, cols=8, start_state=(0, 0),
+    walls={(1, 1), (1, 2), (2, 5), (3, 5), (4, 5), (6, 2), (6, 3), (5, 6)},
+    terminal_states={(7, 7): 1.0, (0, 7): -1.0},
+    special_transitions={((3, 3), 0): ((6, 6), 0.5)},
+    episode_length_limit=200,
+)
+
+
+def _jsonable_grid_cfg(cfg):
+    c = dict(cfg)
+    if c.get("walls") is not None:
+        c["walls"] = sorted(list(w) for w in c["walls"])
+    if c.get("terminal_states") is not None:
+        c["terminal_states"] = [[list(k), v] for k, v in c["terminal_states"].items()]
+    if c.get("special_transitions") is not None:
+        c["special_transitions"] = [[list(k[0]), int(k[1]), list(v[0]), v[1]]
+                                    for k, v in c["special_transitions"].items()]
+    if "start_state" in c:
+        c["start_state"] = list(c["start_state"])
+    return json.dumps(c)
+
+
+def _peek_uniform(gen):
+    clone = np.random.Generator(np.random.PCG64())
+    clone.bit_generator.state = gen.bit_generator.state
+    return clone.random()
+
+
+def _dump_mdp(env):
+    S = env.rows * env.cols
+    count = np.zeros(S * 4, np.int32)
+    nxt = np.full((S * 4, 4, 2), -1, np.int32)
+    rew = np.zeros((S * 4, 4), np.float64)
+    done = np.zeros((S * 4, 4), bool)
+    prob = np.zeros((S * 4, 4), np.float64)
+    for (s, a), outs in env.mdp.items():
+        if not (0 <= s[0] < env.rows and 0 <= s[1] < env.cols):
+            continue
+        row = (s[0] * env.cols + s[1]) * 4 + int(a)
+        count[row] = len(outs)
+        for k, (to, r, d, p) in enumerate(outs):
+            nxt[row, k] = to
+            rew[row, k] = r
+            done[row, k] = d
+            prob[row, k] = p
+    return dict(mdp_count=count, mdp_next=nxt, mdp_reward=rew, mdp_done=done, mdp_prob=prob, P=env.P)
+
+
+def gridworld_case(R, name, cfg, n_steps, seed, action_seed, runtime_specials=()):
+    kw = dict(cfg)
+    if kw.get("special_transitions"):
+        kw["special_transitions"] = {(k[0], R.Action(k[1])): v for k, v in kw["special_transitions"].items()}
+    env = R.GridWorld(seed=seed, **kw)
+    for (fs, a, ts, rw) in runtime_specials:
+        env.add_special_transition(fs, R.Action(a), ts, rw)
+    arng = np.random.default_rng(action_seed)
+    actions = arng.integers(0, 4, n_steps)
+    rec = dict(action=[], u=[], pre=[], post=[], reward=[], done=[], trunc=[], raised=[], ep_len=[])
+    env.reset()
+    for a in actions:
+        pre = env.state
+        u = _peek_uniform(env.np_random)
+        try:
+            s, r, d, t, _ = env.step(int(a))
+            raised = 0
+        except ValueError as e:
+            # reference raises before mutating state; numpy's choice() raises before drawing
+            s, r, d, t = env.state, 0.0, False, False
+            raised = 1 if "sum to 1" in str(e) else 2
+        rec["action"].append(a); rec["u"].append(u); rec["pre"].append(pre); rec["post"].append(s)
+        rec["reward"].append(r); rec["done"].append(d); rec["trunc"].append(t); rec["raised"].append(raised)
+        rec["ep_len"].append(env.episode_length_counter)
+        if d or t:
+            env.reset()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(_dump_mdp(env))
+    out["config"] = _jsonable_grid_cfg(cfg)
+    out["runtime_specials"] = json.dumps([[list(fs), int(a), None if ts is None else list(ts), rw]
+                                          for fs, a, ts, rw in runtime_specials])
+    out["seed"] = seed
+    out["numpy_version"] = np.__version__
+    np.savez_compressed(os.path.join(OUT, f"gridworld_{name}.npz"), **out)
+    print(name, "steps", n_steps, "raised", int((out["raised"] > 0).sum()), "episodes", int((out["done"] | out["trunc"]).sum()))
+
+
+def random_grid_cfg(rng):
+    rows, cols = int(rng.integers(2, 10)), int(rng.integers(2, 10))
+    cells = [(r, c) for r in range(rows) for c in range(cols)]
+    rng.shuffle(cells)
+    n_w = int(rng.integers(0, max(1, len(cells) // 4)))
+    n_t = int(rng.integers(1, 3))
+    walls = set(map(tuple, cells[:n_w]))
+    terms = {tuple(c): float(np.round(rng.uniform(-2, 2), 3)) for c in cells[n_w:n_w + n_t]}
+    free = [tuple(c) for c in cells[n_w + n_t:]]
+    start = free[0] if free else tuple(cells[-1])
+    specials = {}
+    for _ in range(int(rng.integers(0, 4))):
+        if not free:
+            break
+        fs = free[int(rng.integers(len(free)))]
+        to = tuple(cells[int(rng.integers(len(cells)))])
+        specials[(fs, int(rng.integers(4)))] = (to, float(np.round(rng.uniform(-1, 1), 3)))
+    p = float(rng.choice([1.0, 1.0, 0.9, 0.7, 0.5, 0.25, 0.0]))
+    rewards = None if rng.random() < 0.5 else {"valid_move": float(np.round(rng.uniform(-0.5, 0), 3)),
+                                                 "out_of_bounds": float(np.round(rng.uniform(-2, 0), 3)),
+                                                 "wall_collision": -3.0, "default": 0.25}
+    lim = None if rng.random() < 0.3 else int(rng.integers(3, 60))
+    return dict(rows=rows, cols=cols, start_state=tuple(int(x) for x in start), walls=walls,
+                terminal_states=terms, special_transitions=specials, rewards=rewards, p_success=p,
+                episode_length_limit=lim)
+
+
+BANDIT_ARMS = {  # SURVEY.md 8(d) config 3 (families/params of tests/envs/k_armed_bandit/test_k_armed_bandit.py:65-72)
+    0: dict(distribution="normal", mean=5, std=1),
+    1: dict(distribution="uniform", low=4, high=6),
+    2: dict(distribution="exponential", scale=0.2),
+    3: dict(distribution="gamma", shape=9, scale=0.55),
+    4: dict(distribution="logistic", loc=5, scale=0.3),
+    5: dict(distribution="lognormal", mean=1.6, sigma=0.3),
+    6: dict(distribution="weibull", a=2),
+    7: dict(distribution="beta", a=2, b=5),
+}
+
+
+def bandit_shift_functions():
+    return [{"function": lambda t: 0.1 * t, "target_param": "mean"},
+            {"function": lambda t: -0.01 * t, "target_param": "std"}]
+
+
+def bandit_case(R, name, k, arm_params, seed, n_steps, action_seed, reset_at=()):
+    env = R.KArmedBandit(k=k, arm_params=arm_params, seed=seed)
+    actions = np.random.default_rng(action_seed).integers(0, k, n_steps)
+    rewards, timesteps, means0 = [], [], []
+    for i, a in enumerate(actions):
+        if i in reset_at:
+            env.reset()
+        _, r, d, t, _ = env.step(int(a))
+        assert d is True and t is False
+        rewards.append(r)
+        timesteps.append(env.timestep)
+        means0.append(env.arms[0].current_params.get("mean", np.nan))
+    np.savez_compressed(os.path.join(OUT, f"bandit_{name}.npz"), action=actions, reward=np.array(rewards),
+                        timestep=np.array(timesteps), arm0_mean=np.array(means0, np.float64),
+                        reset_at=np.array(sorted(reset_at), np.int64), k=k, seed=seed,
+                        numpy_version=np.__version__)
+    print("bandit", name, "mean reward", float(np.mean(rewards)))
+
+
+def pendulum_case(R, cls_name, name, kw, n_steps, action_seed, init_seed):
+    cls = getattr(R, cls_name)
+    dim = 4 if cls_name == "CartPole" else 2
+    env = cls(**kw)
+    rng = np.random.default_rng(action_seed)
+    irng = np.random.default_rng(init_seed)
+    wide = kw.pop("_wide_init", False) if "_wide_init" in kw else False
+    rec = dict(pre=[], action=[], post=[], reward=[], done=[], trunc=[], acc=[], step=[])
+
+    def new_init():
+        if cls_name == "CartPole":
+            return irng.uniform(-0.05, 0.05, dim)
+        return irng.uniform([-np.pi, -20.0], [np.pi, 20.0]) if irng.random() < 0.5 else irng.uniform(-0.01, 0.01, dim)
+
+    env.reset(initial_state=new_init())
+    for _ in range(n_steps):
+        a = rng.uniform(-3, 3, (1,)).astype(np.float32)
+        pre = np.array(env.state, np.float64)
+        obs, r, d, t, info = env.step(a)
+        rec["pre"].append(pre); rec["action"].append(a[0]); rec["post"].append(obs); rec["reward"].append(r)
+        rec["done"].append(d); rec["trunc"].append(t); rec["step"].append(info["steps"])
+        rec["acc"].append([info["x_acc"], info["theta_acc"]] if cls_name == "CartPole" else [info["alpha_dot_dot"]])
+        if d or t:
+            env.reset(initial_state=new_init())
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["config"] = json.dumps(kw)
+    out["numpy_version"] = np.__version__
+    np.savez_compressed(os.path.join(OUT, f"{cls_name.lower()}_{name}.npz"), **out)
+    print(cls_name, name, "episodes", int((out["done"] | out["trunc"]).sum()), "done", int(out["done"].sum()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = load_reference()
+    # -- GridWorld ---------------------------------------------------------------------------------------
+    gridworld_case(R, "default", dict(), 3000, seed=0, action_seed=0)                        # BASELINE config 1
+    gridworld_case(R, "slip_seed42", dict(p_success=0.5), 3000, seed=42, action_seed=1)       # test_grid_world.py:20-22
+    gridworld_case(R, "config2_p1", dict(CONFIG2_LAYOUT, p_success=1.0), 6000, seed=3, action_seed=2)
+    gridworld_case(R, "config2_p08", dict(CONFIG2_LAYOUT, p_success=0.8), 6000, seed=4, action_seed=3)
+    gridworld_case(R, "limit10", dict(episode_length_limit=10), 200, seed=5, action_seed=4)  # test_grid_world.py:154-166
+    gridworld_case(R, "runtime_special", dict(), 1500, seed=6, action_seed=5,
+                   runtime_specials=[((0, 0), 2, (4, 4), 0.5), ((2, 2), 1, None, None)])      # test_grid_world.py:50-67
+    gridworld_case(R, "p0", dict(rows=4, cols=6, terminal_states={(3, 5): 2.0}, p_success=0.0), 1500, seed=7, action_seed=6)
+    crng = np.random.default_rng(2024)
+    for i in range(12):
+        gridworld_case(R, f"random{i:02d}", random_grid_cfg(crng), 800, seed=100 + i, action_seed=200 + i)
+    # -- KArmedBandit ------------------------------------------------------------------------------------
+    bandit_case(R, "default_seed0", 10, None, 0, 500, action_seed=0)                          # README known answer
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items()}
+    arms[0]["param_functions"] = bandit_shift_functions()
+    bandit_case(R, "config3", 10, arms, 11, 90, action_seed=1, reset_at=(40,))
+    arms_lo = {0: dict(distribution="gamma", shape=0.4, scale=2.0), 1: dict(distribution="beta", a=0.5, b=0.7),
+               2: dict(distribution="gamma", shape=1.0, scale=3.0), 3: dict(distribution="weibull", a=0.7)}
+    bandit_case(R, "small_shapes", 4, arms_lo, 5, 1500, action_seed=2)
+    # -- pendulums ---------------------------------------------------------------------------------------
+    pendulum_case(R, "CartPole", "default", dict(), 3000, 0, 1)
+    pendulum_case(R, "CartPole", "continuous", dict(continuous_reward=True, tau=0.01, episode_length_limit=50), 1500, 2, 3)
+    pendulum_case(R, "CartPole", "nonlinear_angle", dict(continuous_reward=True, nonlinear_reward=True,
+                                                          reward_decay_rate=30.0, angle_termination=0.1), 1500, 4, 5)
+    pendulum_case(R, "PendulumDisk", "default", dict(), 3000, 6, 7)
+    pendulum_case(R, "PendulumDisk", "continuous", dict(continuous_reward=True, tau=0.01, episode_length_limit=50), 1500, 8, 9)
+    pendulum_case(R, "PendulumDisk", "nonlinear_angle", dict(continuous_reward=True, nonlinear_reward=True,
+                                                              reward_decay_rate=30.0, angle_termination=2.0), 1500, 10, 11)
+
+
+if __name__ == "__main__":
+    main()

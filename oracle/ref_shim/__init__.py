@@ -1,0 +1,49 @@
+"""TEST INFRASTRUCTURE ONLY.
+
+Import shim that makes the *unmodified* reference (mariusdgm/rl-envs-forge, mounted read-only at
+/root/reference) importable in the build container, where gymnasium / matplotlib / pygame / seaborn
+are not installed and the package itself is not pip-installed (rl_envs_forge/__init__.py:1-3 calls
+importlib.metadata.version and would raise PackageNotFoundError).
+
+Used only by oracle/gen_golden.py and the `needs_reference` tests.  /root/reference does not exist
+on the GPU box; nothing that runs there may call `load_reference()`.
+"""
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("ENVFORGE_REFERENCE_ROOT", "/root/reference")
+_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "rl_envs_forge", "envs"))
+
+
+def load_reference():
+    """Return a namespace with the four reference env classes, imported from REFERENCE_ROOT."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    for name in ("gymnasium", "matplotlib", "pygame", "seaborn"):
+        try:
+            importlib.import_module(name)
+        except ImportError:
+            if _STUBS not in sys.path:
+                sys.path.insert(0, _STUBS)
+            importlib.import_module(name)
+    if "rl_envs_forge" not in sys.modules:
+        pkg = types.ModuleType("rl_envs_forge")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "rl_envs_forge")]
+        pkg.__version__ = "5.22.0"
+        sys.modules["rl_envs_forge"] = pkg
+    ns = types.SimpleNamespace()
+    gw = importlib.import_module("rl_envs_forge.envs.grid_world.grid_world")
+    kb = importlib.import_module("rl_envs_forge.envs.k_armed_bandit.k_armed_bandit")
+    cp = importlib.import_module("rl_envs_forge.envs.inverted_pendulum.cart_pole.cart_pole")
+    pd = importlib.import_module("rl_envs_forge.envs.inverted_pendulum.pendulum_disk.pendulum_disk")
+    ns.GridWorld, ns.Action = gw.GridWorld, gw.Action
+    ns.KArmedBandit, ns.Arm = kb.KArmedBandit, kb.Arm
+    ns.CartPole = cp.CartPole
+    ns.PendulumDisk = pd.PendulumDisk
+    return ns
