@@ -1,0 +1,217 @@
+/*
+ * envforge_b200 -- C ABI of the B200-native batched-stepping engine for the data-parallel hot path of
+ * mariusdgm/rl-envs-forge (GridWorld, KArmedBandit, CartPole, PendulumDisk).
+ *
+ * The reference has no FFI layer: its boundary for this path is the gymnasium Env protocol implemented by four
+ * Python classes.  Each entry point below replaces the per-instance Python method cited next to it with one call
+ * that advances N independent instances held as structure-of-arrays device buffers.
+ *
+ * Conventions
+ *   - Plain C types only.  Every buffer is DEVICE memory owned by the caller (PyTorch in the shipped host code);
+ *     the library never allocates, frees or retains device memory and keeps no global state.  Descriptor structs
+ *     (ef_grid_desc, ef_pendulum_params, ef_bandit_desc) are small HOST structs passed by pointer and copied into
+ *     kernel parameters; pointers inside them are device pointers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous and
+ *     stream-ordered; buffers must stay alive until the stream has passed the launch.  Re-entrant; one device per
+ *     call (the caller's current device).
+ *   - Return value: EF_OK (0) or an ef_status code; never throws, never exits.  `ef_status_string` names a code.
+ *   - Global env index g = env_offset + i (must stay < 2^32).  All in-kernel randomness is Philox4x32-10 with
+ *     key = seed and counter = (g, 64-bit counter, stream id | block << 8); see csrc/philox.cuh.  Results therefore
+ *     do not depend on how envs are sharded over launches, ranks or GPUs.
+ *   - `stats` (nullable) points at EF_STATS_LEN doubles that the kernels ADD to (atomically):
+ *       [0] finished episodes  [1] sum of their lengths  [2] sum of their returns  [3] sum of squared returns
+ *       [4] env-steps executed [5..7] reserved.  Integer-valued entries stay exact below 2^53.
+ *     This vector is what gets all-reduced (NCCL, sum) across GPUs.
+ *   - `err` (nullable) points at EF_ERR_LEN uint32: [0] number of env-steps the reference would have raised on
+ *     (atomicAdd), [1] 1 + global index of one offending env, [2] its table row (cell*4+action) or action value,
+ *     [3] ef_step_error kind.  Offending envs are left untouched (the reference raises before mutating state).
+ */
+#ifndef ENVFORGE_B200_H
+#define ENVFORGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EF_ABI_VERSION 1
+#define EF_STATS_LEN 8
+#define EF_ERR_LEN 4
+
+typedef enum ef_status {
+    EF_OK = 0,
+    EF_ERR_INVALID_ARGUMENT = 1,   /* null/unaligned pointer, bad size, bad descriptor */
+    EF_ERR_CUDA = 2,               /* a CUDA runtime call failed; see ef_last_cuda_error() */
+    EF_ERR_UNSUPPORTED = 3         /* descriptor outside what the kernels support (e.g. > 65536 cells) */
+} ef_status;
+
+typedef enum ef_step_error {
+    EF_STEP_OK = 0,
+    EF_STEP_BAD_ACTION = 1,        /* GridWorld: Action(a) ValueError (grid_world.py:505); bandit: assert (k_armed_bandit.py:186) */
+    EF_STEP_NO_OUTCOMES = 2,       /* GridWorld: "No outcomes defined" ValueError (grid_world.py:508-511), e.g. agent on a wall */
+    EF_STEP_BAD_PROBS = 3          /* GridWorld: numpy choice "probabilities do not sum to 1" (grid_world.py:515) */
+} ef_step_error;
+
+int ef_abi_version(void);
+const char* ef_status_string(int status);
+/* cudaError_t of the most recent failed CUDA call on this host thread (0 if none) and its name. */
+int ef_last_cuda_error(void);
+const char* ef_last_cuda_error_string(void);
+/* SM count / compute capability of the current device. */
+int ef_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GridWorld   (reference: rl_envs_forge/envs/grid_world/grid_world.py)
+ *
+ * The host compiles the reference's dict MDP (build_mdp :245-274) into a flat device table of ef_grid_outcome,
+ * indexed [(cell*4 + action) * n_slots + outcome_index], cell = row*cols + col.  Rows with a single outcome
+ * replicate it over all slots, so one set of thresholds serves the whole table:
+ *     outcome_index = min((r >= thr[0]) + (r >= thr[1]) + (r >= thr[2]), idx_cap)        (n_slots == 4)
+ * which equals numpy's searchsorted(cumsum(p)/cumsum(p)[-1], r * 2^-32, 'right') used by Generator.choice
+ * (grid_world.py:514-515); thr[k] = ceil(cdf_k * 2^32) clipped to 2^32-1, idx_cap = #thresholds below 2^32.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define EF_GRID_DONE 0x1u        /* outcome lands on a terminal state */
+#define EF_GRID_NO_OUTCOMES 0x2u /* row has no MDP entry (reference raises ValueError) */
+#define EF_GRID_BAD_PROBS 0x4u   /* row's probabilities fail numpy's sum-to-1 check (reference raises ValueError) */
+
+typedef struct ef_grid_outcome {
+    uint16_t next;   /* destination cell */
+    uint16_t flags;  /* EF_GRID_* */
+    float reward;
+} ef_grid_outcome;
+
+typedef struct ef_grid_desc {
+    int32_t rows, cols;
+    int32_t n_slots;             /* 1 (every row deterministic) or 4 */
+    int32_t idx_cap;             /* 0..3 */
+    uint32_t thr[3];
+    int32_t start_cell;
+    int32_t episode_limit;       /* <= 0: no limit (episode_length_limit=None) */
+    int32_t table_cells;         /* cells the table covers: 0 or rows*cols, or more when the host appends pseudo-cells
+                                    (an off-grid start_state the reference accepts in reset, grid_world.py:541-548) */
+    const ef_grid_outcome* table; /* device, table_cells*4*n_slots entries, 8-byte aligned */
+} ef_grid_desc;
+
+/* GridWorld.step (:495-528) + GridWorld.reset (:530-551) fused as same-step auto-reset, for n envs.
+ *   pos/ep_len/ep_ret  in/out state: cell index, episode_length_counter, running episode return (fp32).
+ *   action             [n] int32 in {0,1,2,3}, or NULL: uniform random policy from the Philox policy word.
+ *   draw               [n] uint32 injected outcome draws r (u = r*2^-32), or NULL: Philox transition word of step t.
+ *   obs                [n,2] int32 (row, col) AFTER auto-reset (nullable).  final_obs: (row, col) BEFORE it (nullable).
+ *   reward/terminated/truncated  [n] outputs (each nullable).
+ *   autoreset          0: reproduce the reference step-for-step (no reset; terminal self-loops, sticky truncation).
+ */
+int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                      const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset,
+                      int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
+                      double* stats, uint32_t* err, int64_t n, int32_t autoreset, void* stream);
+
+/* K fused steps (t0 .. t0+K-1) with state held in registers and auto-reset always on.
+ *   actions  [K,n] int32 or NULL (random policy).   rewards [K,n] float / flags [K,n] uint8 (bit0 terminated,
+ *   bit1 truncated) or NULL: nothing is written per step and only state + stats leave the kernel. */
+int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                         const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                         float* rewards, uint8_t* flags, double* stats, uint32_t* err, int64_t n, void* stream);
+
+/* GridWorld.reset (:530-551) for all envs (mask == NULL) or those with mask[i] != 0. */
+int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                       int32_t* obs, const uint8_t* mask, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CartPole / PendulumDisk   (reference: rl_envs_forge/envs/inverted_pendulum/{cart_pole/cart_pole.py,
+ * pendulum_disk/pendulum_disk.py}).  fp32 on device; the host derives the constants in float64.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_pendulum_params {
+    float tau;                   /* cart_pole.py:39 / pendulum_disk.py:38 */
+    /* CartPole: c[0]=gravity c[1]=pole_mass_length c[2]=1/total_mass c[3]=length c[4]=4/3 c[5]=mass_pole/total_mass
+     *           c[6]=pole_mass_length/total_mass c[7]=x_threshold (cart_pole.py:56-64, 117-123)
+     * PendulumDisk: c[0]=m*g*l/J c[1]=(b+K^2/R)/J c[2]=K/(R*J) c[3]=15*pi (pendulum_disk.py:58-64, 115-120) */
+    float c[8];
+    float angle_threshold;       /* 0.2 (theta_threshold_radians) | pi */
+    float angle_termination;     /* < 0: None */
+    int32_t reward_mode;         /* 0 discrete, 1 continuous linear, 2 continuous nonlinear */
+    float reward_lo, reward_hi;  /* reward_angle_range */
+    float reward_decay;          /* reward_decay_rate */
+    float reward_inv_span;       /* 1/angle_threshold (linear) */
+    float reward_inv_norm;       /* 1/(1-exp(-decay*angle_threshold)) (nonlinear) */
+    int32_t episode_limit;       /* episode_length_limit */
+    int32_t fixed_init;          /* 1: reset to init_state; 0: U(init_lo, init_hi) per component (_initialize_state) */
+    float init_lo, init_hi;
+    float init_state[4];
+} ef_pendulum_params;
+
+/* CartPole.step (cart_pole.py:107-180) + reset (:91-105) as same-step auto-reset.
+ *   state   [n,4] fp32 (x, x_dot, theta, theta_dot), 16-byte aligned.   action [n] fp32 force, or NULL: U(-3,3) policy.
+ *   obs     [n,4] post-reset observation (nullable; may equal `state`).  final_obs [n,4] pre-reset (nullable).
+ *   acc     [n,2] (x_acc, theta_acc) info values (nullable). */
+int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, const float* action,
+                     uint64_t seed, uint64_t t, uint64_t env_offset, float* obs, float* reward, uint8_t* terminated,
+                     uint8_t* truncated, float* final_obs, float* acc, double* stats, int64_t n, int32_t autoreset,
+                     void* stream);
+int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                        const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                        float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream);
+/* reset: initial state from params (fixed) or Philox STREAM_RESET_USER at counter `epoch`; mask nullable. */
+int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
+                      uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
+
+/* PendulumDisk.step (pendulum_disk.py:108-172) + reset (:94-106).  state [n,2] fp32 (alpha, alpha_dot), 8-byte
+ * aligned; acc [n] alpha_dot_dot (nullable). */
+int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                          const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
+                          float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs, float* acc,
+                          double* stats, int64_t n, int32_t autoreset, void* stream);
+int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                             const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                             float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream);
+int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
+                           uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * KArmedBandit   (reference: rl_envs_forge/envs/k_armed_bandit/k_armed_bandit.py)
+ * Arms are shared by all n bandits; a default arm (family EF_ARM_DEFAULT_NORMAL) has a per-env mean re-derived
+ * in-kernel from Philox STREAM_BANDIT_MEANS (the reference draws it with randn in _create_default_arms :160-165).
+ * Time-varying parameters (Arm.update_param :53-64) are evaluated by the host into `arms[t - t0]`.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef enum ef_arm_family {
+    EF_ARM_NORMAL = 0,      /* p0 mean, p1 std      (Arm.sample :76-79)   */
+    EF_ARM_UNIFORM = 1,     /* p0 low,  p1 high     (:81-84)              */
+    EF_ARM_EXPONENTIAL = 2, /* p0 scale             (:86-88)              */
+    EF_ARM_GAMMA = 3,       /* p0 shape, p1 scale   (:90-97)              */
+    EF_ARM_BETA = 4,        /* p0 a, p1 b           (:99-106)             */
+    EF_ARM_LOGISTIC = 5,    /* p0 loc, p1 scale     (:108-111)            */
+    EF_ARM_WEIBULL = 6,     /* p0 a                 (:113-117)            */
+    EF_ARM_LOGNORMAL = 7,   /* p0 mean, p1 sigma    (:119-122)            */
+    EF_ARM_DEFAULT_NORMAL = 8 /* mean = per-env default mean + p0, std p1 (_create_default_arms :160-165) */
+} ef_arm_family;
+
+typedef struct ef_arm {
+    int32_t family;
+    float p0, p1;
+    int32_t reserved;
+} ef_arm;
+
+/* KArmedBandit.step (:175-200) for n bandits over K consecutive timesteps (K = 1 is the plain step).
+ *   arms     device [K,k] ef_arm: parameters in force when the reward of timestep index t0+j is drawn.
+ *   action   [K,n] int32 or NULL (uniform random arm from the Philox policy word).
+ *   obs      [K,n] int32 (= action, :200) nullable.  reward [K,n] fp32.  (done == 1, truncated == 0 always.)
+ *   t0       number of steps taken since the last reset() -- the counter of the per-(env, step) primitive stream.
+ *            (The reference re-creates RandomState(seed) in reset (:215), so its reward stream replays after a
+ *            reset while `timestep`, which only drives the parameter shift, keeps counting; the host mirrors that
+ *            by restarting t0 at 0 on reset and evaluating `arms` at the true timestep.) */
+int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_t seed,
+                   uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
+                   uint32_t* err, int64_t n, void* stream);
+/* Per-env default-arm means (fp32 [n,k], the values the kernel re-derives); for KArmedBandit.arms / state. */
+int ef_bandit_default_means(int32_t k, uint64_t seed, uint64_t env_offset, float* means, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Episode statistics: reduce per-env running (ep_len, ep_ret) of the envs still in flight into `out[0..3]`
+ * (count, sum len, sum ret, sum ret^2) -- complements `stats`, which only sees finished episodes.
+ * ------------------------------------------------------------------------------------------------------------ */
+int ef_episode_stat_reduce(const int32_t* ep_len, const float* ep_ret, double* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENVFORGE_B200_H */

@@ -303,3 +303,132 @@ def engine_sample(seed, g, t, family, p0, p1):
     else:
         raise ValueError(family)
     return v, prim.consumed
+
+
+# -- vectorised engine-level oracle (same algorithms, N envs at once; checked against `engine_sample`) ------------
+class _VecPrimitives:
+    """Per-env word cursor over the STREAM_BANDIT substream of (env, t); float64 evaluation."""
+
+    def __init__(self, seed, g, t):
+        self.seed, self.g, self.t = seed, np.asarray(g, np.uint64), np.asarray(t, np.uint64)
+        self.n = len(self.g)
+        self.cur = np.zeros(self.n, np.int64)
+        self._blocks = []
+
+    def _words(self, mask):
+        idx = np.nonzero(mask)[0]
+        j, k = self.cur[idx] >> 2, self.cur[idx] & 3
+        need = int(j.max()) + 1 if len(idx) else 0
+        while len(self._blocks) < need:
+            blk = philox.draw_block(self.seed, self.g, self.t, philox.STREAM_BANDIT, block=len(self._blocks))
+            self._blocks.append(np.stack(blk, axis=1))
+        out = np.zeros(self.n, np.uint32)
+        if len(idx):
+            stack = np.stack(self._blocks, axis=0)  # [blocks, n, 4]
+            out[idx] = stack[j, idx, k]
+        self.cur[idx] += 1
+        return out
+
+    def u(self, mask):
+        return philox.u23(self._words(mask))
+
+    def n_(self, mask):
+        u1 = self.u(mask)
+        u2 = self.u(mask)
+        return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+    def std_exp(self, mask):
+        return -np.log(1.0 - self.u(mask))
+
+
+def _vec_std_gamma(pr, shape, active):
+    out = np.zeros(pr.n)
+    pending = active.copy()
+    with np.errstate(all="ignore"):
+        if shape == 1.0:
+            return np.where(active, pr.std_exp(active), 0.0)
+        if shape == 0.0:
+            return out
+        if shape < 1.0:
+            while pending.any():
+                u = pr.u(pending)
+                v = pr.std_exp(pending)
+                low = u <= 1.0 - shape
+                x1 = np.power(u, 1.0 / shape)
+                y = -np.log((1.0 - u) / shape)
+                x2 = np.power(1.0 - shape + shape * y, 1.0 / shape)
+                x = np.where(low, x1, x2)
+                acc = pending & np.where(low, x1 <= v, x2 <= v + y)
+                out[acc] = x[acc]
+                pending &= ~acc
+            return out
+        b = shape - 1.0 / 3.0
+        c = 1.0 / math.sqrt(9.0 * b)
+        while pending.any():
+            x = np.zeros(pr.n)
+            v = np.zeros(pr.n)
+            inner = pending.copy()
+            while inner.any():
+                xn = pr.n_(inner)
+                vn = 1.0 + c * xn
+                x[inner], v[inner] = xn[inner], vn[inner]
+                inner &= ~(vn > 0.0)
+            v = v * v * v
+            u = pr.u(pending)
+            acc = (u < 1.0 - 0.0331 * (x * x) * (x * x)) | (np.log(u) < 0.5 * x * x + b * (1.0 - v + np.log(v)))
+            acc &= pending
+            out[acc] = (b * v)[acc]
+            pending &= ~acc
+    return out
+
+
+def engine_sample_vec(seed, g, t, family, p0, p1=0.0):
+    """Vectorised `engine_sample`: float64 samples for envs g at step counter t (scalar or per-env).  Returns
+    (samples float64 [n], words consumed int64 [n])."""
+    g = np.asarray(g)
+    t = np.broadcast_to(np.asarray(t, np.uint64), g.shape)
+    pr = _VecPrimitives(seed, g, t)
+    all_ = np.ones(pr.n, bool)
+    with np.errstate(all="ignore"):
+        if family == "normal":
+            v = p0 + p1 * pr.n_(all_)
+        elif family == "uniform":
+            v = p0 + (p1 - p0) * pr.u(all_)
+        elif family == "exponential":
+            v = p0 * pr.std_exp(all_)
+        elif family == "gamma":
+            v = p1 * _vec_std_gamma(pr, float(p0), all_)
+        elif family == "beta":
+            a, b = float(p0), float(p1)
+            if a <= 1.0 and b <= 1.0:
+                v = np.zeros(pr.n)
+                pending = all_.copy()
+                while pending.any():
+                    u = pr.u(pending)
+                    w = pr.u(pending)
+                    x = np.power(u, 1.0 / a)
+                    y = np.power(w, 1.0 / b)
+                    acc = pending & (x + y <= 1.0)
+                    pos = acc & (x + y > 0)
+                    v[pos] = (x / (x + y))[pos]
+                    tiny = acc & ~pos
+                    if tiny.any():
+                        lx, ly = np.log(u) / a, np.log(w) / b
+                        lm = np.maximum(lx, ly)
+                        lx, ly = lx - lm, ly - lm
+                        v[tiny] = np.exp(lx - np.log(np.exp(lx) + np.exp(ly)))[tiny]
+                    pending &= ~acc
+            else:
+                ga = _vec_std_gamma(pr, a, all_)
+                gb = _vec_std_gamma(pr, b, all_)
+                v = ga / (ga + gb)
+        elif family == "logistic":
+            u = pr.u(all_)
+            v = p0 + p1 * np.log(u / (1.0 - u))
+        elif family == "weibull":
+            v = np.zeros(pr.n) if p0 == 0.0 else np.power(pr.std_exp(all_), 1.0 / p0)
+        elif family == "lognormal":
+            v = np.exp(p0 + p1 * pr.n_(all_))
+        else:
+            raise ValueError(family)
+    return v, pr.cur.copy()

@@ -1,0 +1,109 @@
+"""ctypes binding of the C-ABI library (include/envforge_b200.h).
+
+There is deliberately NO fallback: if libenvforge_b200.so is missing or fails to load, importing an env class raises.
+The library is built in-tree by `python -m rl_envs_forge_b200._build` (also run by __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libenvforge_b200.so")
+
+EF_STATS_LEN = 8
+EF_ERR_LEN = 4
+EF_ABI_VERSION = 1
+
+EF_GRID_DONE = 0x1
+EF_GRID_NO_OUTCOMES = 0x2
+EF_GRID_BAD_PROBS = 0x4
+
+STEP_ERROR_NAMES = {1: "bad action", 2: "no outcomes defined", 3: "probabilities do not sum to 1"}
+
+ARM_FAMILIES = {"normal": 0, "uniform": 1, "exponential": 2, "gamma": 3, "beta": 4, "logistic": 5, "weibull": 6,
+                "lognormal": 7, "default_normal": 8}
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("n_slots", C.c_int32), ("idx_cap", C.c_int32),
+                ("thr", C.c_uint32 * 3), ("start_cell", C.c_int32), ("episode_limit", C.c_int32),
+                ("table_cells", C.c_int32), ("table", C.c_void_p)]
+
+
+class PendulumParams(C.Structure):
+    _fields_ = [("tau", C.c_float), ("c", C.c_float * 8), ("angle_threshold", C.c_float),
+                ("angle_termination", C.c_float), ("reward_mode", C.c_int32), ("reward_lo", C.c_float),
+                ("reward_hi", C.c_float), ("reward_decay", C.c_float), ("reward_inv_span", C.c_float),
+                ("reward_inv_norm", C.c_float), ("episode_limit", C.c_int32), ("fixed_init", C.c_int32),
+                ("init_lo", C.c_float), ("init_hi", C.c_float), ("init_state", C.c_float * 4)]
+
+
+_P, _I32, _I64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/envforge_b200.h one to one (tests check the symbol list against the header)
+SIGNATURES = {
+    "ef_abi_version": (C.c_int, []),
+    "ef_status_string": (C.c_char_p, [C.c_int]),
+    "ef_last_cuda_error": (C.c_int, []),
+    "ef_last_cuda_error_string": (C.c_char_p, []),
+    "ef_device_info": (C.c_int, [_P, _P, _P]),
+    "ef_gridworld_step": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
+                                    _P, _I64, _I32, _P]),
+    "ef_gridworld_rollout": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P,
+                                       _I64, _P]),
+    "ef_gridworld_reset": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _I64, _P]),
+    "ef_cartpole_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
+                                   _P, _I64, _I32, _P]),
+    "ef_cartpole_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,
+                                      _I64, _P]),
+    "ef_cartpole_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
+    "ef_pendulum_disk_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
+                                        _P, _P, _I64, _I32, _P]),
+    "ef_pendulum_disk_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P,
+                                           _P, _I64, _P]),
+    "ef_pendulum_disk_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
+    "ef_bandit_step": (C.c_int, [_P, _I32, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
+    "ef_bandit_default_means": (C.c_int, [_I32, _U64, _U64, _P, _I64, _P]),
+    "ef_episode_stat_reduce": (C.c_int, [_P, _P, _P, _I64, _P]),
+}
+
+_lib = None
+
+
+class EnvForgeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes library.  Raises EnvForgeError when it is absent -- no fallback path exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EnvForgeError(
+            f"{LIB_PATH} not found. Build it with `python -m rl_envs_forge_b200._build` (needs nvcc). "
+            "rl_envs_forge_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.ef_abi_version()
+    if got != EF_ABI_VERSION:
+        raise EnvForgeError(f"libenvforge_b200.so ABI version {got} != expected {EF_ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status == 0:
+        return
+    lib = load()
+    name = lib.ef_status_string(status).decode()
+    if status == 2:
+        raise EnvForgeError(f"{name}: {lib.ef_last_cuda_error_string().decode()} ({lib.ef_last_cuda_error()})")
+    raise EnvForgeError(name)
+
+
+def ptr(t):
+    """Device (or None) pointer of a torch tensor as an int for ctypes c_void_p."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,211 @@
+// envforge_b200 -- KArmedBandit batched step kernel (sm_100a, fp32 samplers over a Philox primitive stream).
+//
+// Replaces, for N independent bandits, the reference's per-instance
+//   KArmedBandit.step  rl_envs_forge/envs/k_armed_bandit/k_armed_bandit.py:175-200
+//   Arm.sample         rl_envs_forge/envs/k_armed_bandit/k_armed_bandit.py:66-122
+// The reference samples through numpy's legacy RandomState (normal/uniform/exponential/gamma/beta/logistic/weibull/
+// lognormal).  Those algorithms are restated here in fp32 over *primitives*: U(0,1) = u23(word) and N(0,1) = plain
+// Box-Muller of two words, the words being consumed in order from the (env, step) substream kStreamBandit.  The
+// oracle (oracle/bandit.py) feeds the same primitives to the float64 legacy algorithms, so device and oracle differ
+// only by fp32 rounding -- except when an accept/reject comparison of a rejection sampler lands within that rounding
+// (a "flip"), which the parity test counts.
+#include "ef_common.cuh"
+
+namespace ef {
+
+struct BanditArgs {
+    const ef_arm* arms;  // [K, k]
+    int32_t k;
+    const int32_t* action;  // [K, n] or null
+    uint64_t seed, t0, env_offset;
+    int32_t K;
+    int32_t* obs;
+    float* reward;
+    double* stats;
+    uint32_t* err;
+    int64_t n;
+};
+
+struct Primitives {
+    uint64_t seed, t;
+    uint32_t g, consumed;
+    uint4 blk;
+    __device__ __forceinline__ Primitives(uint64_t seed_, uint32_t g_, uint64_t t_) : seed(seed_), t(t_), g(g_), consumed(0) {}
+    __device__ __forceinline__ uint32_t word() {
+        const uint32_t lane = consumed & 3u;
+        if (lane == 0u) blk = draw_block(seed, g, t, kStreamBandit, consumed >> 2);
+        ++consumed;
+        return lane == 0u ? blk.x : lane == 1u ? blk.y : lane == 2u ? blk.z : blk.w;
+    }
+    __device__ __forceinline__ float u() { return u23(word()); }
+    __device__ __forceinline__ float n() {
+        const float u1 = u();
+        const float u2 = u();
+        return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+    __device__ __forceinline__ float std_exp() { return -logf(1.0f - u()); }
+};
+
+constexpr int kMaxRejections = 1024;  // termination guard; P(reaching it) is astronomically small for valid params
+
+__device__ float std_gamma(Primitives& pr, float shape) {
+    if (shape == 1.0f) return pr.std_exp();
+    if (shape == 0.0f) return 0.0f;
+    if (shape < 1.0f) {  // Ahrens-Dieter style (numpy legacy_standard_gamma, shape < 1)
+        const float inv = 1.0f / shape;
+        float x = 0.0f;
+        for (int it = 0; it < kMaxRejections; ++it) {
+            const float u = pr.u();
+            const float v = pr.std_exp();
+            if (u <= 1.0f - shape) {
+                x = powf(u, inv);
+                if (x <= v) return x;
+            } else {
+                const float y = -logf((1.0f - u) / shape);
+                x = powf(1.0f - shape + shape * y, inv);
+                if (x <= v + y) return x;
+            }
+        }
+        return x;
+    }
+    // Marsaglia-Tsang (shape > 1)
+    const float b = shape - 1.0f / 3.0f;
+    const float c = 1.0f / sqrtf(9.0f * b);
+    float v = 1.0f;
+    for (int it = 0; it < kMaxRejections; ++it) {
+        float x;
+        int guard = 0;
+        do {
+            x = pr.n();
+            v = 1.0f + c * x;
+        } while (v <= 0.0f && ++guard < kMaxRejections);
+        v = v * v * v;
+        const float u = pr.u();
+        const float x2 = x * x;
+        if (u < 1.0f - 0.0331f * x2 * x2) return b * v;
+        if (logf(u) < 0.5f * x2 + b * (1.0f - v + logf(v))) return b * v;
+    }
+    return b * v;
+}
+
+__device__ float beta_sample(Primitives& pr, float a, float b) {
+    if (a <= 1.0f && b <= 1.0f) {  // Johnk
+        const float ia = 1.0f / a, ib = 1.0f / b;
+        float x = 0.0f, y = 1.0f;
+        for (int it = 0; it < kMaxRejections; ++it) {
+            const float u = pr.u();
+            const float v = pr.u();
+            x = powf(u, ia);
+            y = powf(v, ib);
+            const float s = x + y;
+            if (s <= 1.0f) {  // u + v > 0 always holds: primitives are strictly positive
+                if (s > 0.0f) return x / s;
+                float lx = logf(u) * ia, ly = logf(v) * ib;
+                const float lm = fmaxf(lx, ly);
+                lx -= lm;
+                ly -= lm;
+                return expf(lx - logf(expf(lx) + expf(ly)));
+            }
+        }
+        return x / (x + y);
+    }
+    const float ga = std_gamma(pr, a);
+    const float gb = std_gamma(pr, b);
+    return ga / (ga + gb);
+}
+
+__device__ __forceinline__ float default_mean(uint64_t seed, uint32_t g, uint32_t arm) {
+    const uint4 w = draw_block(seed, g, arm, kStreamBanditMeans);
+    return sqrtf(-2.0f * logf(u23(w.x))) * cospif(2.0f * u23(w.y));
+}
+
+__device__ float sample_arm(const ef_arm arm, Primitives& pr, uint64_t seed, uint32_t g, uint32_t arm_index) {
+    switch (arm.family) {
+        case EF_ARM_NORMAL: return arm.p0 + arm.p1 * pr.n();
+        case EF_ARM_UNIFORM: return arm.p0 + (arm.p1 - arm.p0) * pr.u();
+        case EF_ARM_EXPONENTIAL: return arm.p0 * pr.std_exp();
+        case EF_ARM_GAMMA: return arm.p1 * std_gamma(pr, arm.p0);
+        case EF_ARM_BETA: return beta_sample(pr, arm.p0, arm.p1);
+        case EF_ARM_LOGISTIC: {
+            const float u = pr.u();
+            return arm.p0 + arm.p1 * logf(u / (1.0f - u));
+        }
+        case EF_ARM_WEIBULL: return arm.p0 == 0.0f ? 0.0f : powf(pr.std_exp(), 1.0f / arm.p0);
+        case EF_ARM_LOGNORMAL: return expf(arm.p0 + arm.p1 * pr.n());
+        default: return (default_mean(seed, g, arm_index) + arm.p0) + arm.p1 * pr.n();  // EF_ARM_DEFAULT_NORMAL
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs a) {
+    EpisodeAcc acc;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        uint4 w = make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < a.K; ++j) {
+            const uint64_t t = a.t0 + static_cast<uint64_t>(j);
+            const int64_t o = static_cast<int64_t>(j) * a.n + i;
+            int32_t act;
+            if (a.action) {
+                act = __ldg(a.action + o);
+            } else {
+                if (j == 0 || !(t & 1)) w = draw_block(a.seed, g, t >> 1, kStreamStep);
+                act = static_cast<int32_t>(__umulhi((t & 1) ? w.w : w.y, static_cast<uint32_t>(a.k)));
+            }
+            if (a.obs) a.obs[o] = act;  // observation = action (k_armed_bandit.py:200)
+            if (static_cast<uint32_t>(act) >= static_cast<uint32_t>(a.k)) {
+                report_error(a.err, g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+                if (a.reward) a.reward[o] = 0.0f;
+                continue;
+            }
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(a.arms) + static_cast<int64_t>(j) * a.k + act);
+            ef_arm arm;
+            arm.family = raw.x;
+            arm.p0 = __int_as_float(raw.y);
+            arm.p1 = __int_as_float(raw.z);
+            arm.reserved = 0;
+            Primitives pr(a.seed, g, t);
+            const float r = sample_arm(arm, pr, a.seed, g, static_cast<uint32_t>(act));
+            if (a.reward) a.reward[o] = r;
+            acc.steps += 1u;
+            acc.finish(1, r);  // every bandit step is a finished one-step episode (done is always True, :198)
+        }
+    }
+    flush_stats(acc, a.stats);
+}
+
+__global__ void __launch_bounds__(kThreads) bandit_means_kernel(int32_t k, uint64_t seed, uint64_t env_offset,
+                                                                float* __restrict__ means, int64_t n) {
+    const int64_t total = n * k;
+    for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < total;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t i = j / k;
+        means[j] = default_mean(seed, static_cast<uint32_t>(env_offset + i), static_cast<uint32_t>(j - i * k));
+    }
+}
+
+}  // namespace ef
+
+using namespace ef;
+
+extern "C" int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_t seed, uint64_t t0,
+                              uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
+                              uint32_t* err, int64_t n, void* stream) {
+    if (!arms || k <= 0 || K < 0 || n < 0 || !aligned(arms, 16)) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    BanditArgs a{};
+    a.arms = arms; a.k = k; a.action = action; a.seed = seed; a.t0 = t0; a.env_offset = env_offset; a.K = K;
+    a.obs = obs; a.reward = reward; a.stats = stats; a.err = err; a.n = n;
+    bandit_step_kernel<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int ef_bandit_default_means(int32_t k, uint64_t seed, uint64_t env_offset, float* means, int64_t n,
+                                       void* stream) {
+    if (k <= 0 || n < 0 || !means) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0) return EF_OK;
+    bandit_means_kernel<<<grid_for(n * k, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(k, seed, env_offset, means, n);
+    return cuda_status(cudaGetLastError());
+}

@@ -1,0 +1,334 @@
+// envforge_b200 -- CartPole / PendulumDisk batched step, fused rollout and reset kernels (sm_100a, fp32).
+//
+// Replaces, for N independent instances, the reference's per-instance
+//   CartPole.step      rl_envs_forge/envs/inverted_pendulum/cart_pole/cart_pole.py:107-180   (+ reset :91-105)
+//   PendulumDisk.step  rl_envs_forge/envs/inverted_pendulum/pendulum_disk/pendulum_disk.py:108-172 (+ reset :94-106)
+// State is one float4 (CartPole: x, x_dot, theta, theta_dot) or float2 (PendulumDisk: alpha, alpha_dot) per env, so a
+// warp moves it with one fully coalesced 128-bit (64-bit) access per lane.  The reference integrates in float64; the
+// device integrates in fp32 with accurate sincosf/division (no fast-math) and is held to 1e-5 relative per step.
+#include "ef_common.cuh"
+
+namespace ef {
+
+struct PendArgs {
+    ef_pendulum_params p;
+    float* state;
+    int32_t* ep_len;
+    float* ep_ret;
+    const float* action;
+    uint64_t seed, t, env_offset;
+    float* obs;
+    float* reward;
+    uint8_t* terminated;
+    uint8_t* truncated;
+    float* final_obs;
+    float* acc;
+    double* stats;
+    int64_t n;
+    int32_t autoreset;
+    int32_t K;
+    uint8_t* flags;
+    const uint8_t* mask;
+};
+
+// (a + pi) floored-mod 2pi - pi with -pi -> +pi (cart_pole.py:84-89).  On (-pi, pi] the map is the identity, which is
+// what the fast path returns; fp32 has no value strictly between pi and 3.14159274f, so |a| >= 3.14159274f is exactly
+// "outside (-pi, pi]".  The rare wrap is evaluated in double like the reference.
+__device__ __forceinline__ float normalize_angle(float a) {
+    if (fabsf(a) < 3.14159274f) return a;
+    constexpr double kPi = 3.141592653589793, kTwoPi = 6.283185307179586;
+    double m = fmod(static_cast<double>(a) + kPi, kTwoPi);
+    if (m < 0.0) m += kTwoPi;
+    double r = m - kPi;
+    if (r == -kPi) r = kPi;
+    return static_cast<float>(r);
+}
+
+__device__ __forceinline__ float angle_reward(const ef_pendulum_params& p, float angle) {
+    if (p.reward_mode == 0) return (p.reward_lo <= angle && angle <= p.reward_hi) ? 1.0f : 0.0f;
+    const float a = fabsf(angle);
+    if (p.reward_mode == 1) return fmaf(-a, p.reward_inv_span, 1.0f);
+    return fmaf(-(1.0f - expf(-p.reward_decay * a)), p.reward_inv_norm, 1.0f);
+}
+
+struct CartPole {
+    static constexpr int DIM = 4;
+    using Vec = float4;
+    static __device__ __forceinline__ Vec init(const ef_pendulum_params& p, uint64_t seed, uint32_t g, uint64_t ctr,
+                                               uint32_t stream) {
+        if (p.fixed_init) return make_float4(p.init_state[0], p.init_state[1], p.init_state[2], p.init_state[3]);
+        const uint4 w = draw_block(seed, g, ctr, stream);
+        const float span = p.init_hi - p.init_lo;
+        return make_float4(uniform_f32(w.x, p.init_lo, span), uniform_f32(w.y, p.init_lo, span),
+                           uniform_f32(w.z, p.init_lo, span), uniform_f32(w.w, p.init_lo, span));
+    }
+    // cart_pole.py:110-143.  Returns the "done" predicate before the truncation override; writes accelerations.
+    static __device__ __forceinline__ bool advance(const ef_pendulum_params& p, Vec& s, float force, float& acc0,
+                                                   float& acc1, float& angle) {
+        float sn, cs;
+        sincosf(s.z, &sn, &cs);
+        // explicit fmaf + -fmad=false: the step and rollout kernels round identically (bit-equal trajectories)
+        const float temp = fmaf(p.c[1] * (s.w * s.w), sn, force) * p.c[2];
+        const float theta_acc = fmaf(p.c[0], sn, -(cs * temp)) / (p.c[3] * fmaf(-(p.c[5] * cs), cs, p.c[4]));
+        const float x_acc = fmaf(-(p.c[6] * theta_acc), cs, temp);
+        s.x = fmaf(p.tau, s.y, s.x);
+        s.y = fmaf(p.tau, x_acc, s.y);
+        s.z = normalize_angle(fmaf(p.tau, s.w, s.z));
+        s.w = fmaf(p.tau, theta_acc, s.w);
+        acc0 = x_acc;
+        acc1 = theta_acc;
+        angle = s.z;
+        bool done = (s.x < -p.c[7]) | (s.x > p.c[7]) | (s.z < -p.angle_threshold) | (s.z > p.angle_threshold);
+        if (p.angle_termination >= 0.0f) done |= fabsf(s.z) > p.angle_termination;
+        return done;
+    }
+    static __device__ __forceinline__ void store_acc(float* acc, int64_t i, float a0, float a1) {
+        reinterpret_cast<float2*>(acc)[i] = make_float2(a0, a1);
+    }
+};
+
+struct PendulumDisk {
+    static constexpr int DIM = 2;
+    using Vec = float2;
+    static __device__ __forceinline__ Vec init(const ef_pendulum_params& p, uint64_t seed, uint32_t g, uint64_t ctr,
+                                               uint32_t stream) {
+        if (p.fixed_init) return make_float2(p.init_state[0], p.init_state[1]);
+        const uint4 w = draw_block(seed, g, ctr, stream);
+        const float span = p.init_hi - p.init_lo;
+        return make_float2(uniform_f32(w.x, p.init_lo, span), uniform_f32(w.y, p.init_lo, span));
+    }
+    // pendulum_disk.py:111-136
+    static __device__ __forceinline__ bool advance(const ef_pendulum_params& p, Vec& s, float u, float& acc0,
+                                                   float& acc1, float& angle) {
+        const float acc = fmaf(p.c[0], sinf(s.x), fmaf(-p.c[1], s.y, p.c[2] * u));
+        s.x = normalize_angle(fmaf(p.tau, s.y, s.x));
+        s.y = fmaf(p.tau, acc, s.y);
+        acc0 = acc;
+        acc1 = 0.0f;
+        angle = s.x;
+        // |alpha| > pi cannot fire after normalisation in the reference either (pendulum_disk.py:128-133)
+        bool done = (s.y < -p.c[3]) | (s.y > p.c[3]);
+        if (p.angle_termination >= 0.0f) done |= fabsf(s.x) > p.angle_termination;
+        return done;
+    }
+    static __device__ __forceinline__ void store_acc(float* acc, int64_t i, float a0, float) { acc[i] = a0; }
+};
+
+// One reference step of one env: returns flags bit0 terminated, bit1 truncated.
+template <class Env>
+__device__ __forceinline__ uint32_t env_step(const ef_pendulum_params& p, typename Env::Vec& s, int32_t& len, float& ret,
+                                             float action, float& reward, float& acc0, float& acc1) {
+    float angle;
+    const bool done = Env::advance(p, s, action, acc0, acc1, angle);
+    reward = angle_reward(p, angle);
+    ret += reward;
+    len += 1;
+    const bool trunc = len >= p.episode_limit;
+    return trunc ? 2u : (done ? 1u : 0u);  // truncation overrides done (cart_pole.py:163-164)
+}
+
+__device__ __forceinline__ float policy_action(uint32_t w) { return uniform_f32(w, -3.0f, 6.0f); }
+
+template <class Env>
+__global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs a) {
+    using Vec = typename Env::Vec;
+    EpisodeAcc acc;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        Vec s = reinterpret_cast<const Vec*>(a.state)[i];
+        int32_t len = a.ep_len[i];
+        float ret = a.ep_ret[i];
+        float act;
+        if (a.action) {
+            act = __ldg(a.action + i);
+        } else {
+            const uint4 w = draw_block(a.seed, g, a.t >> 1, kStreamStep);
+            act = policy_action((a.t & 1) ? w.w : w.y);
+        }
+        float rew, a0, a1;
+        const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
+        acc.steps += 1u;
+        if (a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s;
+        if (a.autoreset && f) {
+            acc.finish(len, ret);
+            s = Env::init(a.p, a.seed, g, a.t, kStreamResetAuto);
+            len = 0;
+            ret = 0.0f;
+        }
+        reinterpret_cast<Vec*>(a.state)[i] = s;
+        a.ep_len[i] = len;
+        a.ep_ret[i] = ret;
+        if (a.obs && a.obs != a.state) reinterpret_cast<Vec*>(a.obs)[i] = s;
+        if (a.reward) a.reward[i] = rew;
+        if (a.terminated) a.terminated[i] = f & 1u;
+        if (a.truncated) a.truncated[i] = (f >> 1) & 1u;
+        if (a.acc) Env::store_acc(a.acc, i, a0, a1);
+    }
+    flush_stats(acc, a.stats);
+}
+
+template <class Env, bool EXT_ACTIONS, bool EMIT>
+__global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendArgs a) {
+    using Vec = typename Env::Vec;
+    EpisodeAcc acc;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t n_round = (a.n + 31) & ~static_cast<int64_t>(31);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < a.n;
+        const int64_t ii = valid ? i : 0;
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + ii);
+        Vec s = reinterpret_cast<const Vec*>(a.state)[ii];
+        int32_t len = a.ep_len[ii];
+        float ret = a.ep_ret[ii];
+        uint4 w = make_uint4(0, 0, 0, 0);
+        for (int k = 0; k < a.K; ++k) {
+            const uint64_t t = a.t + static_cast<uint64_t>(k);
+            float act;
+            if constexpr (EXT_ACTIONS) {
+                act = __ldg(a.action + static_cast<int64_t>(k) * a.n + ii);
+            } else {
+                if (k == 0 || !(t & 1)) w = draw_block(a.seed, g, t >> 1, kStreamStep);
+                act = policy_action((t & 1) ? w.w : w.y);
+            }
+            float rew, a0, a1;
+            const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
+            if constexpr (EMIT) {
+                if (valid) {
+                    if (a.reward) a.reward[static_cast<int64_t>(k) * a.n + i] = rew;
+                    if (a.flags) a.flags[static_cast<int64_t>(k) * a.n + i] = static_cast<uint8_t>(f);
+                }
+            }
+            const bool fin = valid && f;
+            if (__ballot_sync(0xffffffffu, fin)) {  // warp vote: reset path only where some lane finished
+                if (fin) {
+                    acc.finish(len, ret);
+                    s = Env::init(a.p, a.seed, g, t, kStreamResetAuto);
+                    len = 0;
+                    ret = 0.0f;
+                }
+            }
+        }
+        if (valid) {
+            acc.steps += static_cast<uint32_t>(a.K);
+            reinterpret_cast<Vec*>(a.state)[i] = s;
+            a.ep_len[i] = len;
+            a.ep_ret[i] = ret;
+        }
+    }
+    flush_stats(acc, a.stats);
+}
+
+template <class Env>
+__global__ void __launch_bounds__(kThreads) pendulum_reset_kernel(const PendArgs a) {
+    using Vec = typename Env::Vec;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        if (a.mask && !a.mask[i]) continue;
+        reinterpret_cast<Vec*>(a.state)[i] =
+            Env::init(a.p, a.seed, static_cast<uint32_t>(a.env_offset + i), a.t, kStreamResetUser);
+        a.ep_len[i] = 0;
+        a.ep_ret[i] = 0.0f;
+    }
+}
+
+template <class Env>
+static int check_common(const ef_pendulum_params* p, const float* state, const int32_t* ep_len, const float* ep_ret,
+                        uint64_t env_offset, int64_t n) {
+    if (!p || !state || !ep_len || !ep_ret || n < 0) return EF_ERR_INVALID_ARGUMENT;
+    if (!aligned(state, sizeof(typename Env::Vec))) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    return EF_OK;
+}
+
+template <class Env>
+static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, const float* action,
+                     uint64_t seed, uint64_t t, uint64_t env_offset, float* obs, float* reward, uint8_t* terminated,
+                     uint8_t* truncated, float* final_obs, float* acc, double* stats, int64_t n, int32_t autoreset,
+                     void* stream) {
+    if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
+    if (!aligned(obs, sizeof(typename Env::Vec)) || !aligned(final_obs, sizeof(typename Env::Vec)) ||
+        !aligned(acc, Env::DIM == 4 ? 8 : 4))
+        return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0) return EF_OK;
+    PendArgs a{};
+    a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action;
+    a.seed = seed; a.t = t; a.env_offset = env_offset; a.obs = obs; a.reward = reward;
+    a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs; a.acc = acc;
+    a.stats = stats; a.n = n; a.autoreset = autoreset;
+    pendulum_step_kernel<Env><<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return cuda_status(cudaGetLastError());
+}
+
+template <class Env>
+static int rollout_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                        const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                        float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream) {
+    if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
+    if (K < 0) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    PendArgs a{};
+    a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
+    a.stats = stats; a.n = n; a.autoreset = 1;
+    const int grid = grid_for(n, 8);
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
+    if (ext && emit) pendulum_rollout_kernel<Env, true, true><<<grid, kThreads, 0, st>>>(a);
+    else if (ext) pendulum_rollout_kernel<Env, true, false><<<grid, kThreads, 0, st>>>(a);
+    else if (emit) pendulum_rollout_kernel<Env, false, true><<<grid, kThreads, 0, st>>>(a);
+    else pendulum_rollout_kernel<Env, false, false><<<grid, kThreads, 0, st>>>(a);
+    return cuda_status(cudaGetLastError());
+}
+
+template <class Env>
+static int reset_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
+                      uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream) {
+    if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
+    if (n == 0) return EF_OK;
+    PendArgs a{};
+    a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.seed = seed; a.t = epoch;
+    a.env_offset = env_offset; a.mask = mask; a.n = n;
+    pendulum_reset_kernel<Env><<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return cuda_status(cudaGetLastError());
+}
+
+}  // namespace ef
+
+using namespace ef;
+
+extern "C" int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
+                                float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs, float* acc,
+                                double* stats, int64_t n, int32_t autoreset, void* stream) {
+    return step_impl<CartPole>(p, state, ep_len, ep_ret, action, seed, t, env_offset, obs, reward, terminated, truncated,
+                               final_obs, acc, stats, n, autoreset, stream);
+}
+extern "C" int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                   const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                   float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream) {
+    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, n, stream);
+}
+extern "C" int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                 uint64_t seed, uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n,
+                                 void* stream) {
+    return reset_impl<CartPole>(p, state, ep_len, ep_ret, seed, epoch, env_offset, mask, n, stream);
+}
+extern "C" int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                     const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
+                                     float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs,
+                                     float* acc, double* stats, int64_t n, int32_t autoreset, void* stream) {
+    return step_impl<PendulumDisk>(p, state, ep_len, ep_ret, action, seed, t, env_offset, obs, reward, terminated,
+                                   truncated, final_obs, acc, stats, n, autoreset, stream);
+}
+extern "C" int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                        const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset,
+                                        int32_t K, float* rewards, uint8_t* flags, double* stats, int64_t n,
+                                        void* stream) {
+    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, n, stream);
+}
+extern "C" int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                      uint64_t seed, uint64_t epoch, uint64_t env_offset, const uint8_t* mask,
+                                      int64_t n, void* stream) {
+    return reset_impl<PendulumDisk>(p, state, ep_len, ep_ret, seed, epoch, env_offset, mask, n, stream);
+}

@@ -1,0 +1,484 @@
+"""VecGridWorld -- N GridWorld instances stepped by one sm_100a kernel launch.
+
+Drop-in surface for the reference class `GridWorld` (rl_envs_forge/envs/grid_world/grid_world.py): same constructor
+kwargs and defaults (:19-34), same validation errors (validate_args :101-212), `reset` / `step` with batched
+arguments, `action_space` / `observation_space`, `state`, `start_state`, `episode_length_counter`, `mdp`, `P`,
+`add_special_transition`.  What changes: state lives in SoA device buffers (cell index int32, episode length int32,
+episode return fp32), and the dict MDP is compiled into a flat outcome table that the kernels keep in shared memory.
+
+Host-only pieces (`Action`, `validate_args`, `GridSpec`) import without CUDA; `VecGridWorld` needs a B200.
+"""
+import math
+from enum import IntEnum
+
+import numpy as np
+
+from . import _lib, spaces
+from .vec_env import VecEnv
+
+
+class Action(IntEnum):  # grid_world.py:11-15
+    UP = 0
+    RIGHT = 1
+    DOWN = 2
+    LEFT = 3
+
+
+_SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)  # numpy Generator.choice tolerance on sum(p)
+_DEFAULT_REWARDS = {"valid_move": -0.1, "wall_collision": -1, "out_of_bounds": -1, "default": 0.0}
+_DEFAULT_TERMINALS = {(3, 4): 1.0}  # grid_world.py:24
+# outcome slot j >= 1 of intended action a is the j-th action of the enum order with a removed (grid_world.py:348-357)
+_SLIP_ORDER = np.array([[a] + [b for b in range(4) if b != a] for a in range(4)])
+
+
+def _is_cell(x):
+    return isinstance(x, tuple) and len(x) == 2 and all(isinstance(v, int) for v in x)
+
+
+def validate_args(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, seed,
+                  slip_distribution, p_success, episode_length_limit):
+    """Same acceptance rules and messages as the reference's GridWorld.validate_args (grid_world.py:101-212)."""
+    if not isinstance(rows, int) or rows <= 0:
+        raise ValueError("rows must be a positive integer")
+    if not isinstance(cols, int) or cols <= 0:
+        raise ValueError("cols must be a positive integer")
+    if not _is_cell(start_state):
+        raise ValueError("start_state must be a tuple of two integers")
+    if not (isinstance(terminal_states, dict)
+            and all(_is_cell(k) and isinstance(v, (int, float)) for k, v in terminal_states.items())):
+        raise ValueError("terminal_states must be a dictionary with keys as tuples of two integers and values as "
+                         "integers or floats")
+    if walls is not None and not (isinstance(walls, set) and all(_is_cell(w) for w in walls)):
+        raise ValueError("walls must be a set of tuples of two integers or an empty set")
+    if special_transitions is not None and not (
+            isinstance(special_transitions, dict)
+            and all(isinstance(k, tuple) and len(k) == 2 and _is_cell(k[0]) and isinstance(k[1], Action)
+                    and isinstance(v, tuple) and len(v) == 2 and _is_cell(v[0]) and isinstance(v[1], (int, float))
+                    for k, v in special_transitions.items())):
+        raise ValueError(
+            "special_transitions must be a dictionary with keys as tuples where the first element is a tuple of two "
+            "integers and the second element is an Action, and values as tuples where the first element is a tuple of "
+            "two integers and the second element is an integer or float, or an empty dictionary")
+    if rewards is not None and not (
+            isinstance(rewards, dict)
+            and all(isinstance(k, str) and isinstance(v, (int, float)) for k, v in rewards.items())):
+        raise ValueError("rewards must be a dictionary with keys as strings and values as integers or floats, or an "
+                         "empty dictionary")
+    if seed is not None and not isinstance(seed, int):
+        raise ValueError("seed must be an integer or None")
+    if slip_distribution is not None and not (
+            isinstance(slip_distribution, dict)
+            and all(isinstance(k, Action) and isinstance(v, (int, float)) for k, v in slip_distribution.items())):
+        raise ValueError("slip_distribution must be a dictionary with keys as Actions and values as integers or "
+                         "floats, or an empty dictionary")
+    if not isinstance(p_success, (int, float)) or not (0 <= p_success <= 1):
+        raise ValueError("p_success must be a float between 0 and 1")
+    if episode_length_limit is not None and not isinstance(episode_length_limit, int):
+        raise ValueError("episode_length_limit must be an integer or None")
+
+
+class GridSpec:
+    """Host-side compiled form of one GridWorld configuration (shared by all N envs).
+
+    Arrays are indexed by row = cell*4 + action and outcome slot (4 slots; single-outcome rows replicate slot 0):
+        nxt int32 [R,4], reward float64 [R,4], done bool [R,4], count int32 [R] (0 = no MDP entry), bad bool [R]
+    `thr`, `idx_cap`, `n_slots` implement numpy's Generator.choice rule with integer thresholds (see the header).
+    """
+
+    def __init__(self, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
+                 special_transitions=None, rewards=None, p_success=1.0, episode_length_limit=None):
+        self.rows, self.cols = rows, cols
+        self.start_state = start_state
+        self.terminal_states = terminal_states
+        self.walls = walls or set()
+        self.special_transitions = special_transitions or {}
+        self.rewards = rewards or dict(_DEFAULT_REWARDS)
+        self.p_success = p_success
+        self.episode_length_limit = episode_length_limit
+        S = rows * cols
+        if S > 65535:
+            raise ValueError("rl_envs_forge_b200 supports at most 65535 cells per grid (16-bit cell index in the table)")
+        self.n_cells = S
+        self._compile()
+        self._construction_tables = (self.nxt.copy(), self.count.copy(), self.prob_row.copy())
+
+    # -- compiler (vectorised restatement of build_mdp / calculate_outcomes / calculate_transition / calculate_reward) ----
+    def _in_grid(self, cell):
+        return 0 <= cell[0] < self.rows and 0 <= cell[1] < self.cols
+
+    def _cell_index(self, cell):
+        return cell[0] * self.cols + cell[1]
+
+    def _compile(self):
+        rows, cols, S = self.rows, self.cols, self.n_cells
+        r, c = np.divmod(np.arange(S), cols)
+        is_wall = np.zeros(S, bool)
+        for w in self.walls:
+            if self._in_grid(w):
+                is_wall[self._cell_index(w)] = True
+        term_reward = np.zeros(S, np.float64)
+        is_term = np.zeros(S, bool)
+        for t, rew in self.terminal_states.items():
+            if self._in_grid(t):
+                is_term[self._cell_index(t)] = True
+                term_reward[self._cell_index(t)] = rew
+        # default_transition (:379-399), wall => stay (:373-374)
+        tr = np.stack([np.maximum(r - 1, 0), r, np.minimum(r + 1, rows - 1), r], axis=1)
+        tc = np.stack([c, np.minimum(c + 1, cols - 1), c, np.maximum(c - 1, 0)], axis=1)
+        t1 = tr * cols + tc                                   # [S,4] destination of (cell, action)
+        here = np.arange(S)[:, None]
+        t1 = np.where(is_wall[t1], here, t1)
+        # calculate_reward (:467-493): terminal reward, else stay => out_of_bounds, else valid_move
+        rew1 = np.where(is_term[t1], term_reward[t1],
+                        np.where(t1 == here, float(self.rewards.get("out_of_bounds", -1)),
+                                 float(self.rewards.get("valid_move", -0.1))))
+        done1 = is_term[t1]
+        # special transitions replace calculate_transition's answer (:365-369), hence also appear as slip outcomes
+        special_rows = {}
+        for (frm, act), (to, rew) in self.special_transitions.items():
+            if not self._in_grid(frm):
+                continue
+            if not self._in_grid(to):
+                raise ValueError(f"special transition target {to} is outside the {rows}x{cols} grid; the reference "
+                                 "accepts it but can never step from there -- not representable on device")
+            i = self._cell_index(frm)
+            t1[i, int(act)] = self._cell_index(to)
+            rew1[i, int(act)] = rew
+            done1[i, int(act)] = to in self.terminal_states
+            special_rows[i * 4 + int(act)] = True
+        p = float(self.p_success)
+        self.n_slots = 4 if p < 1.0 else 1
+        R = S * 4
+        # outcome slots: slot 0 intended, slots 1..3 the other actions in enum order (:327-359)
+        order = _SLIP_ORDER[None, :, :]                                     # [1,4(action),4(slot)]
+        nxt = np.take_along_axis(t1[:, None, :].repeat(4, 1), order, 2).reshape(R, 4)
+        reward = np.take_along_axis(rew1[:, None, :].repeat(4, 1), order, 2).reshape(R, 4)
+        done = np.take_along_axis(done1[:, None, :].repeat(4, 1), order, 2).reshape(R, 4)
+        count = np.full(R, 4 if p < 1.0 else 1, np.int32)
+        prob_row = np.tile(np.array([p] + [(1.0 - p) / 3.0] * 3), (R, 1))
+        if p >= 1.0:
+            prob_row[:, 1:] = 0.0
+        bad = np.zeros(R, bool)
+        cell_of_row = np.arange(R) // 4
+        # walls have no entry (:247-252); terminals self-loop with reward 0 (:263-265)
+        count[is_wall[cell_of_row]] = 0
+        term_rows = is_term[cell_of_row]  # also for a cell listed as wall AND terminal: the loop at :263 ignores walls
+        count[term_rows] = 1
+        nxt[term_rows] = cell_of_row[term_rows][:, None]
+        reward[term_rows] = 0.0
+        done[term_rows] = True
+        prob_row[term_rows] = [1.0, 0.0, 0.0, 0.0]
+        # specials overwrite their row with one outcome of probability p_success (:268-274)
+        for row in special_rows:
+            a = row % 4
+            i = row // 4
+            count[row] = 1
+            nxt[row] = t1[i, a]
+            reward[row] = rew1[i, a]
+            done[row] = done1[i, a]
+            prob_row[row] = [p, 0.0, 0.0, 0.0]
+            bad[row] = abs(p - 1.0) > _SQRT_EPS
+        single = count == 1
+        nxt[single] = nxt[single][:, :1]
+        reward[single] = reward[single][:, :1]
+        done[single] = done[single][:, :1]
+        self.nxt, self.reward, self.done, self.count, self.bad, self.prob_row = nxt, reward, done, count, bad, prob_row
+        self._set_thresholds()
+
+    def _set_thresholds(self):
+        p = float(self.p_success)
+        if self.n_slots == 1:
+            self.thr, self.idx_cap = (0xFFFFFFFF,) * 3, 0
+            return
+        cdf = np.cumsum(np.array([p] + [(1.0 - p) / 3.0] * 3, np.float64))
+        cdf /= cdf[-1]
+        t = [int(math.ceil(float(cdf[k]) * 2.0 ** 32)) for k in range(3)]   # exact: scaling by 2^32 is exact in binary64
+        self.idx_cap = sum(1 for v in t if v < 2 ** 32)
+        self.thr = tuple(min(v, 0xFFFFFFFF) for v in t)
+
+    # -- runtime patch (:214-243) -----------------------------------------------------------------------------------
+    def add_special_transition(self, from_state, action, to_state=None, reward=None):
+        a = int(action)
+        if to_state is None:  # calculate_next_state(check_special=False) (:432-465)
+            i = self._cell_index(from_state)
+            rr, cc = from_state
+            cand = {0: (max(rr - 1, 0), cc), 1: (rr, min(cc + 1, self.cols - 1)),
+                    2: (min(rr + 1, self.rows - 1), cc), 3: (rr, max(cc - 1, 0))}[a]
+            to_state = from_state if (cand in self.walls or cand == from_state) else cand
+        if reward is None:
+            reward = self.rewards["default"]
+        if not self._in_grid(from_state):
+            return  # the reference stores an unreachable dict entry; nothing to compile
+        if not self._in_grid(to_state):
+            raise ValueError(f"special transition target {to_state} is outside the grid -- not representable on device")
+        row = self._cell_index(from_state) * 4 + a
+        self.count[row] = 1
+        self.nxt[row] = self._cell_index(to_state)
+        self.reward[row] = reward
+        self.done[row] = to_state in self.terminal_states
+        self.prob_row[row] = [self.p_success, 0.0, 0.0, 0.0]
+        self.bad[row] = abs(float(self.p_success) - 1.0) > _SQRT_EPS
+
+    # -- exports ------------------------------------------------------------------------------------------------
+    def mdp_dict(self):
+        """The reference's `mdp` attribute: {((r, c), Action): [(next_state, reward, done, prob), ...]}."""
+        out = {}
+        cols = self.cols
+        for row in np.nonzero(self.count)[0]:
+            cell, a = divmod(int(row), 4)
+            key = ((cell // cols, cell % cols), Action(a))
+            out[key] = [((int(self.nxt[row, k]) // cols, int(self.nxt[row, k]) % cols), float(self.reward[row, k]),
+                         bool(self.done[row, k]), float(self.prob_row[row, k])) for k in range(int(self.count[row]))]
+        return out
+
+    def probability_matrix(self):
+        """create_probability_matrix (:276-300) from the construction-time tables."""
+        nxt, count, prob = self._construction_tables
+        S = self.n_cells
+        P = np.zeros((S, S, 4))
+        rows_idx = np.arange(S * 4)
+        cell, act = rows_idx // 4, rows_idx % 4
+        absorbing = np.zeros(S, bool)
+        for t in self.terminal_states:
+            if self._in_grid(t):
+                absorbing[self._cell_index(t)] = True
+        for w in self.walls:
+            if self._in_grid(w):
+                absorbing[self._cell_index(w)] = True
+        for k in range(4):
+            live = (count > k) & ~absorbing[cell]
+            np.add.at(P, (cell[live], nxt[live, k], act[live]), prob[live, k])
+        idx = np.nonzero(absorbing)[0]
+        P[idx, idx, :] = 1.0
+        return P
+
+    def device_table(self, extra_cells=0):
+        """Packed ef_grid_outcome array (uint32 [entries, 2]): word0 = next | flags << 16, word1 = fp32 reward bits."""
+        R, slots = self.n_cells * 4, self.n_slots
+        flags = self.done[:, :slots].astype(np.uint32) * _lib.EF_GRID_DONE
+        flags |= (self.count == 0)[:, None].astype(np.uint32) * _lib.EF_GRID_NO_OUTCOMES
+        flags |= self.bad[:, None].astype(np.uint32) * _lib.EF_GRID_BAD_PROBS
+        word0 = (self.nxt[:, :slots].astype(np.uint32) & 0xFFFF) | (flags << 16)
+        word1 = self.reward[:, :slots].astype(np.float32).view(np.uint32)
+        tab = np.stack([word0, word1], axis=-1).reshape(R * slots, 2)
+        if extra_cells:
+            pad = np.zeros((extra_cells * 4 * slots, 2), np.uint32)
+            pad[:, 0] = _lib.EF_GRID_NO_OUTCOMES << 16
+            tab = np.concatenate([tab, pad])
+        return np.ascontiguousarray(tab)
+
+
+class VecGridWorld(VecEnv):
+    """N GridWorld instances sharing one configuration.  See module docstring; kwargs as in the reference."""
+
+    def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
+                 special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
+                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False):
+        validate_args(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, seed,
+                      slip_distribution, p_success, episode_length_limit)
+        self.spec = GridSpec(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, p_success,
+                             episode_length_limit)
+        super().__init__(num_envs, device, seed, env_offset, autoreset)
+        torch = self._torch
+        self.rows, self.cols = rows, cols
+        self.start_state = start_state
+        self.terminal_states = terminal_states
+        self.walls = self.spec.walls
+        self.special_transitions = self.spec.special_transitions
+        self.rewards = self.spec.rewards
+        self.p_success = p_success
+        self.slip_distribution = slip_distribution or {a: (1.0 - p_success) / (len(Action) - 1) for a in Action}
+        self.episode_length_limit = episode_length_limit
+        self.strict = bool(strict)
+        self.single_action_space = spaces.Discrete(4)
+        self.single_observation_space = spaces.Tuple((spaces.Discrete(rows), spaces.Discrete(cols)))
+        self.action_space = spaces.Batched(self.single_action_space, num_envs)
+        self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
+        n, dev = self.num_envs, self.device
+        self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._obs = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        self._final_obs = None
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._term = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._P = None
+        self._upload_table()
+        self.reset()
+
+    # -- table ----------------------------------------------------------------------------------------------------
+    def _start_cell(self):
+        s = self.start_state
+        if self.spec._in_grid(s):
+            return self.spec._cell_index(s)
+        return self.spec.n_cells  # pseudo-cell without outcomes: the reference accepts the start and raises on step
+
+    def _upload_table(self):
+        torch = self._torch
+        tab = self.spec.device_table(extra_cells=1)
+        self._table = torch.from_numpy(tab.view(np.int32)).to(self.device)
+        d = _lib.GridDesc()
+        d.rows, d.cols, d.n_slots, d.idx_cap = self.rows, self.cols, self.spec.n_slots, self.spec.idx_cap
+        d.thr[0], d.thr[1], d.thr[2] = self.spec.thr
+        d.start_cell = self._start_cell()
+        d.episode_limit = self.episode_length_limit if self.episode_length_limit is not None else 0
+        d.table_cells = self.spec.n_cells + 1
+        d.table = self._table.data_ptr()
+        self._desc = d
+        # an episode_length_limit <= 0 truncates on every step in the reference (counter >= limit); the kernel's
+        # "<= 0 means None" encoding cannot express that, so refuse it loudly rather than diverge silently.
+        if self.episode_length_limit is not None and self.episode_length_limit <= 0:
+            raise ValueError("episode_length_limit <= 0 is not supported by the device path")
+
+    def add_special_transition(self, from_state, action, to_state=None, reward=None):
+        """Runtime MDP patch (grid_world.py:214-243); recompiles and re-uploads the table."""
+        self.spec.add_special_transition(from_state, action, to_state, reward)
+        self._upload_table()
+
+    @property
+    def mdp(self):
+        return self.spec.mdp_dict()
+
+    @property
+    def P(self):
+        if self._P is None:
+            self._P = self.spec.probability_matrix()
+        return self._P
+
+    # -- reference-style attributes -----------------------------------------------------------------------------------
+    @property
+    def state(self):
+        """int32 [N,2] (row, col) tensor; assignable with a (row, col) tuple, an [N,2] array or tensor."""
+        p = self.pos.to(self._torch.int64)
+        return self._torch.stack([p // self.cols, p % self.cols], dim=1).to(self._torch.int32)
+
+    @state.setter
+    def state(self, value):
+        torch = self._torch
+        v = torch.as_tensor(np.asarray(value) if not torch.is_tensor(value) else value).to(self.device)
+        v = v.reshape(-1, 2).to(torch.int64)
+        if v.shape[0] == 1:
+            v = v.expand(self.num_envs, 2)
+        inside = (v[:, 0] >= 0) & (v[:, 0] < self.rows) & (v[:, 1] >= 0) & (v[:, 1] < self.cols)
+        cell = torch.where(inside, v[:, 0] * self.cols + v[:, 1], torch.full_like(v[:, 0], self.spec.n_cells))
+        self.pos.copy_(cell.to(torch.int32))
+
+    @property
+    def episode_length_counter(self):
+        return self.ep_len
+
+    def get_state(self):
+        return {"pos": self.pos.clone(), "ep_len": self.ep_len.clone(), "ep_ret": self.ep_ret.clone(), "t": self._t}
+
+    def set_state(self, state):
+        self.pos.copy_(state["pos"])
+        self.ep_len.copy_(state["ep_len"])
+        self.ep_ret.copy_(state["ep_ret"])
+        self._t = int(state.get("t", self._t))
+
+    # -- hot path ---------------------------------------------------------------------------------------------------
+    def reset(self, new_start_state=None, *, seed=None, options=None, mask=None):
+        """GridWorld.reset (:530-551) for all envs, or those selected by `mask` ([N] bool/uint8 tensor).
+
+        `seed` re-keys the Philox streams (the reference's reset never reseeds; passing nothing keeps that)."""
+        if new_start_state is not None:
+            if not _is_cell(new_start_state):
+                raise ValueError("new_start_state must be a tuple of two integers")
+            self.start_state = new_start_state
+            self.spec.start_state = new_start_state
+            self._desc.start_cell = self._start_cell()
+        if seed is not None:
+            from .vec_env import resolve_seed
+            self.seed, self._seed = seed, resolve_seed(seed)
+        m = None
+        if mask is not None:
+            m = self._torch.as_tensor(mask, device=self.device).to(self._torch.uint8).contiguous()
+        self._call(self._lib.ef_gridworld_reset, self._desc.start_cell, self.cols, _lib.ptr(self.pos),
+                   _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(self._obs), _lib.ptr(m), self.num_envs)
+        self._reset_epoch += 1
+        obs = self._obs
+        if not self.spec._in_grid(self.start_state):  # off-grid start: report it verbatim like the reference
+            obs = self._torch.tensor(self.start_state, dtype=self._torch.int32, device=self.device).expand(self.num_envs, 2)
+        return obs, {}
+
+    def step(self, actions, draws=None, *, return_final_obs=False):
+        """GridWorld.step (:495-528) for all envs.
+
+        actions  int tensor/array [N] with values in {0,1,2,3} (Action members work at num_envs == 1).  CUDA tensors are
+                 used in place; host arrays take the pinned-staging path and numpy arrays come back.
+        draws    optional uint32-valued [N] injected outcome draws r (u = r * 2**-32); default: Philox.
+        Returns (obs int32 [N,2], reward fp32 [N], terminated bool [N], truncated bool [N], info)."""
+        torch = self._torch
+        host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        n = self.num_envs
+        if host_io:
+            a = np.asarray(actions)
+            if a.shape == ():
+                a = a.reshape(1)
+            act = self._to_device("action", a.astype(np.int32, copy=False), torch.int32, (n,))
+        else:
+            if tuple(actions.shape) != (n,):
+                raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
+            act = actions if actions.dtype == torch.int32 else actions.to(torch.int32)
+            act = act.contiguous()
+        drw = None
+        if draws is not None:
+            if torch.is_tensor(draws) and draws.is_cuda:
+                drw = draws.to(torch.int64).to(torch.int32).contiguous() if draws.dtype != torch.int32 else draws.contiguous()
+            else:
+                d = np.asarray(draws).astype(np.uint32, copy=False).view(np.int32)
+                drw = self._to_device("draw", d, torch.int32, (n,))
+        fobs = None
+        if return_final_obs:
+            if self._final_obs is None:
+                self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+            fobs = self._final_obs
+        self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
+                   _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t, self.env_offset,
+                   _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc),
+                   _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), n, int(self.autoreset))
+        self._t += 1
+        if self.strict:
+            self.check_errors()
+        info = {}
+        if host_io:
+            named = [("obs", self._obs), ("reward", self._reward), ("term", self._term), ("trunc", self._trunc)]
+            if return_final_obs:
+                named.append(("final_obs", fobs))
+            out = self._to_host(named)
+            if return_final_obs:
+                info["final_observation"] = out[4]
+            return out[0], out[1], out[2].astype(bool), out[3].astype(bool), info
+        if return_final_obs:
+            info["final_observation"] = fobs
+        return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
+
+    def rollout(self, K, actions=None, *, return_rewards=False):
+        """K fused steps in one kernel (state in registers, auto-reset on).  actions: CUDA int32 [K,N] or None for the
+        in-kernel uniform random policy.  Returns (rewards fp32 [K,N], flags uint8 [K,N]) if return_rewards else None;
+        episode statistics accumulate in `self.stats` either way."""
+        torch = self._torch
+        n = self.num_envs
+        if actions is not None:
+            if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+                    and tuple(actions.shape) == (K, n)):
+                raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
+            actions = actions.contiguous()
+        rew = flg = None
+        if return_rewards:
+            rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+            flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        self._call(self._lib.ef_gridworld_rollout, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
+                   _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t, self.env_offset, int(K),
+                   _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self.stats), _lib.ptr(self.err), n)
+        self._t += int(K)
+        return (rew, flg) if return_rewards else None
+
+    def _describe_error(self, count, env, detail, kind_id, kind):
+        if kind_id == 1:
+            return f"{detail} is not a valid Action (env {env}; {count} rejected env-step(s))"
+        cell, a = divmod(detail, 4)
+        st = (cell // self.cols, cell % self.cols) if cell < self.spec.n_cells else self.start_state
+        if kind_id == 2:
+            return f"No outcomes defined for state {st} and action {Action(a)!r} (env {env}; {count} rejected env-step(s))"
+        return (f"probabilities do not sum to 1 for state {st} and action {Action(a)!r} "
+                f"(env {env}; {count} rejected env-step(s))")

@@ -1,0 +1,244 @@
+"""VecKArmedBandit -- N k-armed bandits stepped by one sm_100a kernel launch.
+
+Drop-in surface for the reference classes `Arm` and `KArmedBandit`
+(rl_envs_forge/envs/k_armed_bandit/k_armed_bandit.py): `KArmedBandit(k, arm_params, seed)` (:126-153), default normal
+arms with randn means (:160-165), custom arms with index check (:167-173), `step(action)` returning
+`(action, reward, True, False, {})` (:175-200), `reset(seed)` that rebuilds the arms but keeps `timestep` (:202-217),
+`state` (:273-282), and `Arm` with absolute parameter shifts `init + f(t)` (:53-64).
+
+The arm set is shared by all N bandits (default arms have a per-bandit mean re-derived in-kernel from Philox).  User
+`param_functions` are arbitrary Python callables: they are evaluated on the host, per timestep, into the small arm
+table the kernel reads; sampling itself (8 families) runs on the device in fp32.
+"""
+import numpy as np
+
+from . import _lib, spaces
+from .vec_env import VecEnv, resolve_seed
+
+IMPLEMENTED_DISTRIBUTIONS = ["normal", "uniform", "exponential", "gamma", "beta", "logistic", "weibull", "lognormal"]
+
+# family -> ((param name, default or REQUIRED), (second param ...)) in the order packed into ef_arm.p0 / p1 (Arm.sample :66-122)
+_REQUIRED = object()
+_PARAMS = {
+    "normal": (("mean", 0), ("std", 1)),
+    "uniform": (("low", 0), ("high", 1)),
+    "exponential": (("scale", 1),),
+    "gamma": (("shape", _REQUIRED), ("scale", _REQUIRED)),
+    "beta": (("a", _REQUIRED), ("b", _REQUIRED)),
+    "logistic": (("loc", 0), ("scale", 1)),
+    "weibull": (("a", _REQUIRED),),
+    "lognormal": (("mean", 0), ("sigma", 1)),
+}
+_MISSING_MSG = {
+    "gamma": "For gamma distribution, both 'shape' and 'scale' params are required.",
+    "beta": "For beta distribution, both 'a' and 'b' params are required.",
+    "weibull": "For weibull distribution, 'a' param is required.",
+}
+
+
+class Arm:
+    """Host descriptor of one arm (reference `Arm`, :11-64).  Sampling happens on the device."""
+
+    IMPLEMENTED_DISTRIBUTIONS = IMPLEMENTED_DISTRIBUTIONS
+
+    def __init__(self, distribution="normal", param_functions=None, **kwargs):
+        self.distribution = distribution
+        if self.distribution not in self.IMPLEMENTED_DISTRIBUTIONS:
+            raise ValueError(
+                f"Invalid distribution: {self.distribution}. Please use one of {self.IMPLEMENTED_DISTRIBUTIONS}.")
+        self.init_params = kwargs.copy()
+        self.current_params = kwargs.copy()
+        self.param_functions = param_functions if param_functions else []
+        self.per_env_mean = False  # True for default arms: `mean` differs per bandit and lives on the device
+
+    def update_param(self, timestep):
+        for fd in self.param_functions:
+            self.current_params[fd["target_param"]] = self.init_params[fd["target_param"]] + fd["function"](timestep)
+
+    def packed(self):
+        """(family id, p0, p1) as the kernel wants them; raises what Arm.sample / numpy would raise at sample time."""
+        d, p = self.distribution, self.current_params
+        vals = []
+        for name, default in _PARAMS[d]:
+            v = p.get(name) if default is _REQUIRED else p.get(name, default)
+            if v is None and self.per_env_mean and name == "mean":
+                v = 0.0
+            if v is None:
+                raise ValueError(_MISSING_MSG.get(d, f"parameter {name!r} of a {d} arm is None"))
+            vals.append(float(v))
+        vals += [0.0] * (2 - len(vals))
+        p0, p1 = vals
+        # numpy legacy argument checks (RandomState.normal/exponential/gamma/beta/logistic/weibull/lognormal)
+        if d in ("normal", "logistic") and p1 < 0:
+            raise ValueError("scale < 0")
+        if d == "lognormal" and p1 < 0:
+            raise ValueError("sigma < 0")
+        if d == "exponential" and p0 < 0:
+            raise ValueError("scale < 0")
+        if d == "gamma":
+            if p0 < 0:
+                raise ValueError("shape < 0")
+            if p1 < 0:
+                raise ValueError("scale < 0")
+        if d == "beta":
+            if p0 <= 0:
+                raise ValueError("a <= 0")
+            if p1 <= 0:
+                raise ValueError("b <= 0")
+        if d == "weibull" and p0 < 0:
+            raise ValueError("a < 0")
+        if self.per_env_mean:
+            return _lib.ARM_FAMILIES["default_normal"], 0.0, p1
+        return _lib.ARM_FAMILIES[d], p0, p1
+
+
+class VecKArmedBandit(VecEnv):
+    def __init__(self, num_envs=1, k=10, arm_params=None, seed=None, *, device=None, env_offset=0, strict=False):
+        super().__init__(num_envs, device, seed, env_offset, autoreset=True)
+        torch = self._torch
+        self.k = k
+        self.arm_params = arm_params
+        self.timestep = 0
+        self.strict = bool(strict)
+        self._steps_since_reset = 0
+        self.single_action_space = spaces.Discrete(k)
+        self.single_observation_space = spaces.Discrete(1)
+        self.action_space = spaces.Batched(self.single_action_space, num_envs)
+        self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
+        n, dev = self.num_envs, self.device
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._obs = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._done = torch.ones(n, dtype=torch.bool, device=dev)
+        self._trunc = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._zero_obs = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._arm_dev = None
+        self._arm_key = None
+        self.arms = None
+        self._init_arms()
+
+    # -- arms (:155-173) ----------------------------------------------------------------------------------------------
+    def _init_arms(self):
+        self.arms = []
+        for _ in range(self.k):
+            arm = Arm(distribution="normal", mean=None, std=1)
+            arm.per_env_mean = True
+            self.arms.append(arm)
+        if self.arm_params:
+            for idx, params in self.arm_params.items():
+                if idx < 0 or (idx > self.k - 1):
+                    raise ValueError(f"Invalid arm index: {idx}, the arm index range is between 0 and {self.k-1}.")
+                self.arms[idx] = Arm(**params)
+        self._arm_key = None
+
+    @property
+    def default_means(self):
+        """fp32 [N,k] default-arm means (what `np_random.randn(k)` is to one reference instance)."""
+        out = self._torch.empty((self.num_envs, self.k), dtype=self._torch.float32, device=self.device)
+        self._call(self._lib.ef_bandit_default_means, self.k, self._seed, self.env_offset, _lib.ptr(out), self.num_envs)
+        return out
+
+    @property
+    def state(self):
+        return self.timestep, [arm.current_params for arm in self.arms]
+
+    def _arm_table(self, K):
+        """Device [K,k] ef_arm table for timesteps timestep .. timestep+K-1 (parameters in force when sampling)."""
+        torch = self._torch
+        dynamic = any(a.param_functions for a in self.arms)
+        if not dynamic:
+            key = (K, tuple((a.distribution, tuple(sorted(a.current_params.items(), key=lambda kv: kv[0])), a.per_env_mean)
+                            for a in self.arms))
+            if key == self._arm_key and self._arm_dev is not None:
+                return self._arm_dev
+        tab = np.zeros((K, self.k, 4), np.float32)
+        itab = tab.view(np.int32)
+        saved = [dict(a.current_params) for a in self.arms]
+        for j in range(K):
+            if j > 0:  # parameters in force for the (j+1)-th step: shifted by f(timestep + j)
+                for a in self.arms:
+                    a.update_param(self.timestep + j)
+            for i, a in enumerate(self.arms):
+                fam, p0, p1 = a.packed()
+                itab[j, i, 0] = fam
+                tab[j, i, 1], tab[j, i, 2] = p0, p1
+        for a, s in zip(self.arms, saved):
+            a.current_params = s
+        stage = self._pinned("h_arms", (K, self.k, 4), torch.float32)
+        stage.copy_(torch.from_numpy(tab))
+        if self._arm_dev is None or tuple(self._arm_dev.shape) != (K, self.k, 4):
+            self._arm_dev = torch.empty((K, self.k, 4), dtype=torch.float32, device=self.device)
+        self._arm_dev.copy_(stage, non_blocking=True)
+        self._arm_key = None if dynamic else key
+        return self._arm_dev
+
+    # -- hot path ---------------------------------------------------------------------------------------------------
+    def step(self, actions):
+        """KArmedBandit.step (:175-200) for all bandits: (obs = actions, reward fp32 [N], done = True, truncated = False, {})."""
+        torch = self._torch
+        n = self.num_envs
+        host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        if host_io:
+            a = np.asarray(actions).reshape(-1)
+            if self.strict:
+                assert ((0 <= a) & (a < self.k)).all(), "Invalid action, must be between 0 and k-1."
+            act = self._to_device("action", a.astype(np.int32, copy=False), torch.int32, (n,))
+        else:
+            if tuple(actions.shape) != (n,):
+                raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
+            act = (actions if actions.dtype == torch.int32 else actions.to(torch.int32)).contiguous()
+        arms = self._arm_table(1)
+        self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, _lib.ptr(act), self._seed, self._steps_since_reset,
+                   self.env_offset, 1, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self.stats),
+                   _lib.ptr(self.err), n)
+        self._advance(1)
+        if self.strict:
+            try:
+                self.check_errors()
+            except ValueError as e:
+                raise AssertionError("Invalid action, must be between 0 and k-1.") from e
+        if host_io:
+            obs, rew = self._to_host([("obs", self._obs), ("reward", self._reward)])
+            return obs, rew, np.ones(n, bool), np.zeros(n, bool), {}
+        return self._obs, self._reward, self._done, self._trunc, {}
+
+    def rollout(self, K, actions=None):
+        """K consecutive steps in one launch.  actions CUDA int32 [K,N] or None (uniform random arm).  Returns
+        (obs int32 [K,N], reward fp32 [K,N])."""
+        torch = self._torch
+        n = self.num_envs
+        if actions is not None:
+            if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+                    and tuple(actions.shape) == (K, n)):
+                raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
+            actions = actions.contiguous()
+        arms = self._arm_table(K)
+        obs = torch.empty((K, n), dtype=torch.int32, device=self.device)
+        rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+        self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, _lib.ptr(actions), self._seed,
+                   self._steps_since_reset, self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self.stats),
+                   _lib.ptr(self.err), n)
+        self._advance(K)
+        return obs, rew
+
+    def _advance(self, K):
+        self.timestep += K
+        self._steps_since_reset += K
+        self._t += K
+        for arm in self.arms:  # :195-196 -- absolute shift, so one update at the final timestep suffices
+            arm.update_param(self.timestep)
+
+    def reset(self, seed=None):
+        """KArmedBandit.reset (:202-217): re-key the generator, rebuild the arms (parameters back to their initial
+        values); `timestep` is NOT reset.  Returns (zeros int32 [N], {})."""
+        if seed is not None:
+            self.seed = seed
+        # the reference builds RandomState(self.seed): a fixed seed replays the same means and reward stream,
+        # seed=None draws fresh entropy
+        self._seed = resolve_seed(self.seed)
+        self._steps_since_reset = 0
+        self._reset_epoch += 1
+        self._init_arms()
+        return self._zero_obs, {}
+
+    def _describe_error(self, count, env, detail, kind_id, kind):
+        return f"Invalid action {detail}, must be between 0 and k-1 (env {env}; {count} rejected env-step(s))"

@@ -1,0 +1,169 @@
+"""Common host-side plumbing of the vectorised envs: device buffers, stream, statistics, error word, host staging.
+
+PyTorch is used for device memory, streams and torch.distributed only; every transition runs in the sm_100a kernels
+behind the C ABI (rl_envs_forge_b200/_lib.py).  No CPU / PyTorch fallback exists: constructing an env without a CUDA
+device or without the built library raises.
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import EnvForgeError
+
+
+def resolve_seed(seed):
+    """None -> fresh 63-bit entropy (the reference seeds from OS entropy too); ints are taken mod 2^64."""
+    if seed is None:
+        return int.from_bytes(os.urandom(8), "little") >> 1
+    if not isinstance(seed, (int, np.integer)):
+        raise ValueError("seed must be an integer or None")
+    return int(seed) & 0xFFFFFFFFFFFFFFFF
+
+
+def shard_range(num_envs_global, rank, world_size):
+    """Contiguous index range [lo, hi) of `rank`; ranges differ by at most one env and cover [0, N) exactly."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(int(num_envs_global), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+STAT_FIELDS = ("episodes", "length_sum", "return_sum", "return_sq_sum", "env_steps")
+
+
+def stats_to_dict(vec):
+    """EF_STATS_LEN doubles -> readable dict (means derived)."""
+    v = [float(x) for x in vec]
+    d = {k: v[i] for i, k in enumerate(STAT_FIELDS)}
+    n = d["episodes"]
+    d["mean_return"] = d["return_sum"] / n if n else float("nan")
+    d["mean_length"] = d["length_sum"] / n if n else float("nan")
+    return d
+
+
+def all_reduce_stats(stats, group=None):
+    """Sum the statistics vector over all ranks (NCCL over NVLink for CUDA tensors, gloo for CPU tensors).
+
+    This is the only collective of the engine: env instances never exchange data.  No-op without an initialised
+    process group.  Returns the (in-place reduced) tensor."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+class VecEnv:
+    """Base class: owns the SoA buffers shared by all env families (episode counters, stats, error word)."""
+
+    def __init__(self, num_envs, device=None, seed=None, env_offset=0, autoreset=True):
+        import torch
+        if not isinstance(num_envs, (int, np.integer)) or num_envs <= 0:
+            raise ValueError("num_envs must be a positive integer")
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise EnvForgeError("rl_envs_forge_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._torch = torch
+        dev = torch.device("cuda" if device is None else device)
+        if dev.type != "cuda":
+            raise EnvForgeError(f"device must be a CUDA device, got {dev}")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)
+        if self.env_offset < 0 or self.env_offset + self.num_envs > 2 ** 32:
+            raise ValueError("env_offset + num_envs must stay below 2**32")
+        self.autoreset = bool(autoreset)
+        self.seed = seed
+        self._seed = resolve_seed(seed)
+        self._t = 0            # step counter: the Philox time coordinate of the next step
+        self._reset_epoch = 0  # counts explicit resets (Philox coordinate of STREAM_RESET_USER)
+        n = self.num_envs
+        self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(_lib.EF_STATS_LEN, dtype=torch.float64, device=dev)
+        self.err = torch.zeros(_lib.EF_ERR_LEN, dtype=torch.int32, device=dev)
+        self._host = {}
+
+    # -- helpers ---------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, fn, *args):
+        with self._torch.cuda.device(self.device):
+            _lib.check(fn(*args, self._stream()))
+
+    def _pinned(self, name, shape, dtype):
+        t = self._host.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self._torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._host[name] = t
+        return t
+
+    def _to_device(self, name, array, dtype, shape):
+        """Host array -> device tensor through a pinned staging buffer, on the current stream."""
+        torch = self._torch
+        src = torch.as_tensor(np.ascontiguousarray(array))
+        if tuple(src.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(src.shape)}")
+        stage = self._pinned("h_" + name, shape, dtype)
+        stage.copy_(src)
+        dev = self._host.get("d_" + name)
+        if dev is None or tuple(dev.shape) != tuple(shape) or dev.dtype != dtype:
+            dev = torch.empty(shape, dtype=dtype, device=self.device)
+            self._host["d_" + name] = dev
+        dev.copy_(stage, non_blocking=True)
+        return dev
+
+    def _to_host(self, named_tensors):
+        """Device tensors -> numpy arrays through pinned buffers; one stream sync for the whole batch."""
+        torch = self._torch
+        outs = []
+        for name, t in named_tensors:
+            stage = self._pinned("o_" + name, t.shape, t.dtype)
+            stage.copy_(t, non_blocking=True)
+            outs.append(stage)
+        torch.cuda.current_stream(self.device).synchronize()
+        return [o.numpy().copy() for o in outs]
+
+    # -- statistics / errors ---------------------------------------------------------------------------------------
+    def episode_stats(self, all_reduce=False, reset=False):
+        """Finished-episode statistics accumulated on device since construction (or the last reset=True call).
+
+        all_reduce=True sums them over the ranks of the default process group first (one NCCL all-reduce of 64 B)."""
+        vec = self.stats.clone()
+        if all_reduce:
+            all_reduce_stats(vec)
+        if reset:
+            self.stats.zero_()
+        return stats_to_dict(vec.cpu().tolist())
+
+    def running_episode_stats(self):
+        """(count, mean length, mean return) over the episodes currently in flight (device reduction)."""
+        out = self._torch.zeros(_lib.EF_STATS_LEN, dtype=self._torch.float64, device=self.device)
+        self._call(self._lib.ef_episode_stat_reduce, _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(out),
+                   self.num_envs)
+        return stats_to_dict(out.cpu().tolist())
+
+    def check_errors(self, clear=True):
+        """Raise ValueError if any env-step since the last check hit a condition the reference raises on.
+
+        Lazy by design: it costs a device->host read, so the batched path does not call it per step (strict mode does)."""
+        e = [int(x) & 0xFFFFFFFF for x in self.err.cpu().tolist()]
+        if clear and e[0]:
+            self.err.zero_()
+        if e[0]:
+            kind = _lib.STEP_ERROR_NAMES.get(e[3], "unknown")
+            raise ValueError(self._describe_error(e[0], e[1] - 1, e[2], e[3], kind))
+
+    def _describe_error(self, count, env, detail, kind_id, kind):
+        return f"{count} env-step(s) rejected ({kind}); first offender env {env}, detail {detail}"
+
+    @property
+    def step_count(self):
+        return self._t
+
+    def close(self):
+        pass

@@ -1,0 +1,75 @@
+"""The C-ABI library loads without a GPU and exports exactly the entry points include/envforge_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from rl_envs_forge_b200 import _build, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "envforge_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _build.build()
+    return _lib.load()
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ef_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    names = _declared()
+    assert len(names) >= 17
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_status_strings(lib):
+    assert lib.ef_abi_version() == _lib.EF_ABI_VERSION
+    assert lib.ef_status_string(0) == b"EF_OK"
+    assert lib.ef_status_string(1) == b"EF_ERR_INVALID_ARGUMENT"
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.GridDesc) == 48
+    assert _lib.GridDesc.table.offset == 40
+    assert ctypes.sizeof(_lib.PendulumParams) == 4 + 32 + 4 * 4 + 4 * 4 + 4 * 4 + 16  # 100 bytes
+
+
+def test_argument_validation_without_gpu(lib):
+    # null descriptor / null state are rejected before any CUDA call is made
+    assert lib.ef_gridworld_step(None, None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None,
+                                 None, 8, 1, None) == 1
+    d = _lib.GridDesc()
+    assert lib.ef_gridworld_rollout(ctypes.byref(d), None, None, None, None, 0, 0, 0, 4, None, None, None, None, 8,
+                                    None) == 1
+    assert lib.ef_cartpole_step(None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, 8, 1,
+                                None) == 1
+    assert lib.ef_bandit_step(None, 10, None, 0, 0, 0, 1, None, None, None, None, 8, None) == 1
+
+
+def test_no_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import rl_envs_forge_b200 as r
+    for cls in (r.VecGridWorld, r.VecCartPole, r.VecPendulumDisk, r.VecKArmedBandit):
+        with pytest.raises(r.EnvForgeError):
+            cls(4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "rl_envs_forge_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f

@@ -1,0 +1,151 @@
+"""GPU parity tests for KArmedBandit: device fp32 samplers (through the C ABI) vs the float64 legacy-numpy algorithms
+fed the same Philox primitives (oracle/bandit.py).  Actions / observations / timestep: exact.  Rewards: rtol 1e-5 +
+atol 1e-6, except accept/reject flips of the rejection samplers, which are counted."""
+import numpy as np
+import pytest
+
+from oracle import bandit as OB
+from oracle import philox
+from oracle.gen_golden import BANDIT_ARMS
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+CASES = [("normal", (5.0, 1.0)), ("uniform", (4.0, 6.0)), ("exponential", (0.2,)), ("gamma", (9.0, 0.55)),
+         ("gamma", (0.4, 2.0)), ("gamma", (1.0, 2.0)), ("beta", (2.0, 5.0)), ("beta", (0.5, 0.7)),
+         ("logistic", (5.0, 0.3)), ("weibull", (2.0,)), ("weibull", (0.7,)), ("lognormal", (1.6, 0.3))]
+_NAMES = {"normal": ("mean", "std"), "uniform": ("low", "high"), "exponential": ("scale",), "gamma": ("shape", "scale"),
+          "beta": ("a", "b"), "logistic": ("loc", "scale"), "weibull": ("a",), "lognormal": ("mean", "sigma")}
+
+
+def _close(dev, ref):
+    return np.abs(dev.astype(np.float64) - ref) <= RTOL * np.abs(ref) + ATOL
+
+
+@pytest.mark.parametrize("fam,args", CASES)
+def test_family_parity_vs_legacy_numpy_algorithms(fam, args):
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    n, seed = 1 << 18, 77
+    params = dict(distribution=fam, **dict(zip(_NAMES[fam], args)))
+    env = VecKArmedBandit(n, k=1, arm_params={0: params}, seed=seed)
+    flips = 0
+    for t in range(3):
+        obs, rew, done, trunc, _ = env.step(torch.zeros(n, dtype=torch.int32, device="cuda"))
+        ref, _ = OB.engine_sample_vec(seed, np.arange(n), t, fam, args[0], args[1] if len(args) > 1 else 0.0)
+        ok = _close(rew.cpu().numpy(), ref)
+        flips += int((~ok).sum())
+        assert bool(done.all()) and not bool(trunc.any()) and int(obs.abs().sum()) == 0
+    print(f"{fam}{args}: {flips} accept/reject flips in {3 * n} samples")
+    limit = 0 if fam in ("normal", "uniform", "exponential", "logistic", "weibull", "lognormal") else 3 * n * 2e-5
+    assert flips <= limit
+    assert env.timestep == 3
+
+
+def test_config3_mixed_arms_with_shift_16M():
+    """BASELINE config 3: 10 arms (8 families + 2 default normals), absolute parameter shift on arm 0, 2^24 bandits."""
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    n, seed, K = 1 << 24, 123, 3
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items()}
+    arms[0]["param_functions"] = [{"function": lambda t: 0.1 * t, "target_param": "mean"},
+                                  {"function": lambda t: -0.01 * t, "target_param": "std"}]
+    env = VecKArmedBandit(n, k=10, arm_params=arms, seed=seed)
+    sub = np.arange(0, n, 64)                      # the float64 oracle checks a 262144-env subsample
+    means = env.default_means[torch.from_numpy(sub).cuda()].cpu().numpy()
+    flips = 0
+    for t in range(K):
+        act = torch.randint(0, 10, (n,), dtype=torch.int32, device="cuda")
+        obs, rew, done, trunc, _ = env.step(act)
+        assert torch.equal(obs, act) and env.timestep == t + 1
+        a, r = act.cpu().numpy()[sub], rew.cpu().numpy()[sub]
+        ref = np.zeros(len(sub))
+        for arm in range(10):
+            m = a == arm
+            if arm >= 8:
+                mu = OB.default_arm_mean(seed, sub[m], arm)
+                assert np.all(np.abs(means[m, arm] - mu) <= 2e-6 * np.abs(mu) + 1e-6)
+                z, _ = OB.engine_sample_vec(seed, sub[m], t, "normal", 0.0, 1.0)
+                ref[m] = mu + z
+                continue
+            p = dict(BANDIT_ARMS[arm])
+            fam = p.pop("distribution")
+            vals = [float(p[k]) for k in _NAMES[fam]]
+            if arm == 0:                           # reward of step t+1 uses init + f(t) (SURVEY 2.2 ordering)
+                vals = [5 + 0.1 * t, 1 - 0.01 * t]
+            ref[m], _ = OB.engine_sample_vec(seed, sub[m], t, fam, vals[0], vals[1] if len(vals) > 1 else 0.0)
+        flips += int((~_close(r, ref)).sum())
+    print(f"config3: {flips} flips in {K * len(sub)} checked samples")
+    assert flips <= K * len(sub) * 2e-5
+    assert env.arms[0].current_params["mean"] == pytest.approx(5 + 0.1 * K)
+    st = env.episode_stats()
+    assert st["episodes"] == K * n and st["length_sum"] == K * n
+
+
+def test_reset_replays_stream_and_keeps_timestep():
+    """k_armed_bandit.py:202-217: reset rebuilds arms and the generator (fixed seed => identical rewards), timestep survives."""
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    n = 10_000
+    env = VecKArmedBandit(n, k=10, seed=0)
+    act = torch.randint(0, 10, (n,), dtype=torch.int32, device="cuda")
+    r1 = [env.step(act)[1].clone() for _ in range(3)]
+    m1 = env.default_means.clone()
+    obs, info = env.reset()
+    assert int(obs.abs().sum()) == 0 and env.timestep == 3
+    r2 = [env.step(act)[1].clone() for _ in range(3)]
+    assert all(torch.equal(x, y) for x, y in zip(r1, r2)) and torch.equal(m1, env.default_means)
+    env.reset(seed=1)
+    assert not torch.equal(env.step(act)[1], r1[0])
+
+
+def test_rollout_equals_steps_and_random_policy():
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    n, K = 100_003, 9
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items()}
+    arms[0]["param_functions"] = [{"function": lambda t: 0.1 * t, "target_param": "mean"}]
+    a = VecKArmedBandit(n, k=10, arm_params=arms, seed=3)
+    b = VecKArmedBandit(n, k=10, arm_params=arms, seed=3)
+    acts = torch.randint(0, 10, (K, n), dtype=torch.int32, device="cuda")
+    obs, rew = a.rollout(K, acts)
+    for j in range(K):
+        assert torch.equal(b.step(acts[j])[1], rew[j])
+    assert a.timestep == b.timestep == K and a.arms[0].current_params == b.arms[0].current_params
+    obs, rew = a.rollout(4)                        # in-kernel uniform random arm = mulhi(policy word, k)
+    for j in range(4):
+        _, wp = philox.step_words(3, np.arange(n), np.full(n, K + j, np.uint64))
+        want = ((wp.astype(np.uint64) * 10) >> np.uint64(32)).astype(np.int32)
+        assert np.array_equal(obs[j].cpu().numpy(), want)
+
+
+def test_reference_test_suite_on_vec_surface():
+    """tests/envs/k_armed_bandit/test_k_armed_bandit.py at num_envs=1."""
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    with pytest.raises(ValueError):                                                    # test_invalid_arm_index
+        VecKArmedBandit(1, k=3, arm_params={3: dict(distribution="normal", mean=0, std=1)})
+    with pytest.raises(ValueError):                                                    # test_not_implemented_arm
+        VecKArmedBandit(1, k=1, arm_params={0: dict(distribution="cauchy")})
+    env = VecKArmedBandit(1, k=1, seed=0, arm_params={0: dict(distribution="normal", mean=0, std=1, param_functions=[
+        {"function": lambda t: t, "target_param": "mean"}])})
+    for _ in range(10):                                                                # test_linear_param_shift
+        obs, rew, done, trunc, info = env.step(np.array([0]))
+        assert obs[0] == 0 and done[0] and not trunc[0] and info == {}
+    assert env.arms[0].current_params["mean"] == 10 and env.state[0] == 10
+    for fam, args in CASES:                                                            # test_arms_sampling
+        e = VecKArmedBandit(1, k=1, seed=0, arm_params={0: dict(distribution=fam, **dict(zip(_NAMES[fam], args)))})
+        rs = [float(e.step(np.array([0]))[1][0]) for _ in range(20)]
+        assert all(np.isfinite(rs))
+    env = VecKArmedBandit(1, k=10, seed=0, strict=True)
+    with pytest.raises(AssertionError):
+        env.step(np.array([10]))
+    env = VecKArmedBandit(1, k=1, arm_params={0: dict(distribution="gamma", shape=2.0)})
+    with pytest.raises(ValueError):                                                    # missing required parameter
+        env.step(np.array([0]))
+    env = VecKArmedBandit(1, k=1, arm_params={0: dict(distribution="normal", mean=0, std=1, param_functions=[
+        {"function": lambda t: -2.0 * t, "target_param": "std"}])})
+    env.step(np.array([0]))
+    with pytest.raises(ValueError, match="scale < 0"):                                  # numpy's error for std < 0
+        env.step(np.array([0]))
+    assert torch.cuda.is_available()

@@ -1,0 +1,345 @@
+"""GPU parity tests for GridWorld: the CUDA path (through the C ABI) against the reference's golden vectors and the
+oracle restatement, bit-exact (integer state, fp32-cast rewards)."""
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle.gen_golden import CONFIG2_LAYOUT
+from oracle.gridworld import FlatTables, GridWorldPort, vec_step
+from tests._golden import golden_files, grid_kwargs, grid_runtime_specials, load
+
+pytestmark = pytest.mark.gpu
+FILES = golden_files("gridworld")
+
+
+def _vec_kwargs(kw):
+    from rl_envs_forge_b200 import Action
+    kw = dict(kw)
+    if kw.get("special_transitions"):
+        kw["special_transitions"] = {(k[0], Action(int(k[1]))): v for k, v in kw["special_transitions"].items()}
+    return kw
+
+
+def _config2(p):
+    cfg = dict(CONFIG2_LAYOUT, p_success=p)
+    return cfg
+
+
+@pytest.mark.parametrize("path", FILES, ids=lambda p: p.split("gridworld_")[-1][:-4])
+def test_golden_steps_as_batch(path):
+    """Every recorded reference step becomes one env of a batch: same pre-state, action, injected draw."""
+    import torch
+    from rl_envs_forge_b200 import Action, VecGridWorld
+    g = load(path)
+    n = len(g["action"])
+    env = VecGridWorld(n, autoreset=False, **_vec_kwargs(grid_kwargs(g)))
+    for fs, a, ts, r in grid_runtime_specials(g):
+        env.add_special_transition(fs, Action(a), ts, r)
+    env.state = g["pre"]
+    raised = g["raised"] > 0
+    env.ep_len.copy_(torch.from_numpy((g["ep_len"] - (~raised)).astype(np.int32)))
+    r32 = np.floor(g["u"] * 2.0 ** 32).astype(np.uint64).astype(np.uint32)
+    obs, rew, term, trunc, _ = env.step(torch.from_numpy(g["action"].astype(np.int32)).cuda(),
+                                        draws=torch.from_numpy(r32.view(np.int32)).cuda())
+    obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+    ok = ~raised
+    assert np.array_equal(obs[ok], g["post"][ok])
+    assert np.array_equal(obs[raised], g["pre"][raised])          # the reference raises before mutating state
+    assert np.array_equal(rew[ok], g["reward"][ok].astype(np.float32))
+    assert np.array_equal(term[ok], g["done"][ok]) and np.array_equal(trunc[ok], g["trunc"][ok])
+    assert np.array_equal(env.ep_len.cpu().numpy()[ok], g["ep_len"][ok])
+    err = env.err.cpu().numpy()
+    assert int(err[0]) == int(raised.sum())
+    if raised.any():
+        with pytest.raises(ValueError):
+            env.check_errors()
+
+
+@pytest.mark.parametrize("name", ["default", "slip_seed42", "config2_p08", "limit10", "runtime_special"])
+def test_single_env_strict_replay(name):
+    """num_envs=1, autoreset off, strict: the wrapper reproduces the reference trajectory call for call, including
+    the ValueError on cells the reference cannot execute."""
+    from rl_envs_forge_b200 import Action, VecGridWorld
+    g = load([f for f in FILES if f.endswith(f"gridworld_{name}.npz")][0])
+    env = VecGridWorld(1, autoreset=False, strict=True, **_vec_kwargs(grid_kwargs(g)))
+    for fs, a, ts, r in grid_runtime_specials(g):
+        env.add_special_transition(fs, Action(a), ts, r)
+    env.reset()
+    steps = min(400, len(g["action"]))
+    for i in range(steps):
+        assert tuple(env.state.cpu().numpy()[0]) == tuple(g["pre"][i])
+        r32 = np.uint32(np.floor(g["u"][i] * 2.0 ** 32))
+        if g["raised"][i]:
+            with pytest.raises(ValueError):
+                env.step(np.array([g["action"][i]]), draws=np.array([r32]))
+            continue
+        obs, rew, term, trunc, _ = env.step(np.array([g["action"][i]]), draws=np.array([r32]))
+        assert tuple(obs[0]) == tuple(g["post"][i]) and rew[0] == np.float32(g["reward"][i])
+        assert bool(term[0]) == bool(g["done"][i]) and bool(trunc[0]) == bool(g["trunc"][i])
+        if g["done"][i] or g["trunc"][i]:
+            env.reset()
+
+
+def _run_against_oracle(n, steps, p, seed, limit=200, check_every=1, env_offset=0):
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    cfg = _config2(p)
+    cfg["episode_length_limit"] = limit
+    port = GridWorldPort(**cfg)
+    tab = FlatTables(port)
+    env = VecGridWorld(n, seed=seed, env_offset=env_offset, **_vec_kwargs(cfg))
+    pos, ln, ret = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.float32)
+    g = np.arange(n) + env_offset
+    eps = lens = 0
+    rets = 0.0
+    errors = 0
+    for t in range(steps):
+        wt, wp = philox.step_words(seed, g, np.full(n, t, np.uint64))
+        act = (wp >> np.uint32(30)).astype(np.int32)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(act).cuda())
+        o = vec_step(tab, pos, ln, ret, act, wt, limit=limit, start_pos=0, autoreset=True)
+        fin = o["finished"]
+        eps += int(fin.sum()); lens += int(o["final_len"][fin].sum()); rets += float(o["final_ret"][fin].astype(np.float64).sum())
+        errors += int(o["error"].sum())
+        pos, ln, ret = o["pos"], o["ep_len"], o["ep_ret"]
+        if t % check_every == 0 or t == steps - 1:
+            assert np.array_equal(obs.cpu().numpy(), o["obs"]), t
+            assert np.array_equal(rew.cpu().numpy(), o["reward"]), t
+            assert np.array_equal(term.cpu().numpy(), o["terminated"]), t
+            assert np.array_equal(trunc.cpu().numpy(), o["truncated"]), t
+    assert np.array_equal(env.pos.cpu().numpy(), pos)
+    assert np.array_equal(env.ep_len.cpu().numpy(), ln)
+    assert np.array_equal(env.ep_ret.cpu().numpy(), ret)
+    st = env.episode_stats()
+    assert int(st["episodes"]) == eps and int(st["length_sum"]) == lens
+    assert st["return_sum"] == pytest.approx(rets, rel=1e-12, abs=1e-9)
+    assert int(st["env_steps"]) == n * steps - errors
+    assert int(env.err.cpu().numpy()[0]) == errors
+    return env, (pos, ln, ret), (eps, lens, rets)
+
+
+@pytest.mark.parametrize("p", [1.0, 0.8])
+def test_philox_step_matches_oracle_65536_envs(p):
+    """Config 2 (8x8, walls, special transition), device-side Philox outcome draws, auto-reset: bit-exact per step.
+    With p=0.8 the cell ((3,3), UP) is one the reference raises on; it is flagged and left untouched."""
+    _run_against_oracle(65536, 256, p, seed=2024, check_every=1)
+
+
+def test_full_size_config2_1M_envs():
+    """BASELINE config 2 at full size (2^20 envs), 48 steps, both variants, bit-exact against the restatement."""
+    _run_against_oracle(1 << 20, 48, 0.8, seed=5, check_every=8)
+    _run_against_oracle(1 << 20, 24, 1.0, seed=6, check_every=8)
+
+
+@pytest.mark.parametrize("p", [1.0, 0.8])
+def test_rollout_equals_step_sequence(p):
+    """Fused K-step rollout (random Philox policy) == K step() calls fed the same Philox policy words: identical state and
+    identical integer statistics (size-independent property, run at 2^20 envs)."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, K, seed = 1 << 20, 64, 99
+    cfg = _vec_kwargs(_config2(p))
+    a = VecGridWorld(n, seed=seed, **cfg)
+    b = VecGridWorld(n, seed=seed, **cfg)
+    a.rollout(K)
+    for t in range(K):
+        b.step(None_actions(b, t))
+    for x, y in ((a.pos, b.pos), (a.ep_len, b.ep_len), (a.ep_ret, b.ep_ret)):
+        assert torch.equal(x, y)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert sa["episodes"] == sb["episodes"] and sa["length_sum"] == sb["length_sum"] and sa["env_steps"] == sb["env_steps"]
+    assert sa["return_sum"] == pytest.approx(sb["return_sum"], rel=1e-12)
+    assert sa["episodes"] > 0
+    # odd start time and odd K exercise the word-pairing rule
+    a.rollout(7)
+    a.rollout(5)
+    for t in range(K, K + 12):
+        b.step(None_actions(b, t))
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_ret, b.ep_ret)
+
+
+def None_actions(env, t):
+    """Policy word of step t for every env of `env`, as a CUDA int32 action tensor (host twin of the in-kernel policy)."""
+    import torch
+    g = np.arange(env.num_envs) + env.env_offset
+    _, wp = philox.step_words(env._seed, g, np.full(env.num_envs, t, np.uint64))
+    return torch.from_numpy((wp >> np.uint32(30)).astype(np.int32)).cuda()
+
+
+def test_rollout_external_actions_and_emitted_outputs():
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, K, seed = 50_001, 33, 3
+    cfg = _vec_kwargs(_config2(0.8))
+    a = VecGridWorld(n, seed=seed, **cfg)
+    b = VecGridWorld(n, seed=seed, **cfg)
+    acts = torch.randint(0, 4, (K, n), dtype=torch.int32, device="cuda")
+    rew, flg = a.rollout(K, acts, return_rewards=True)
+    for t in range(K):
+        _, r, te, tr, _ = b.step(acts[t])
+        assert torch.equal(rew[t], r)
+        assert torch.equal(flg[t], te.to(torch.uint8) | (tr.to(torch.uint8) << 1))
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    # in-kernel policy == stepping with None actions
+    c = VecGridWorld(n, seed=seed, **cfg)
+    d = VecGridWorld(n, seed=seed, **cfg)
+    c.rollout(9)
+    for t in range(9):
+        d.step(None_actions(d, t))
+    assert torch.equal(c.pos, d.pos)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 33, 257, 1023])
+def test_ragged_sizes_and_tail(n):
+    _run_against_oracle(n, 40, 0.8, seed=n, limit=7)
+
+
+def test_sharding_invariance_env_offset():
+    """Two shards with env_offset reproduce the single-launch result and statistics (Philox is keyed by global index)."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld, shard_range
+    n, K, seed = 100_003, 50, 17
+    cfg = _vec_kwargs(_config2(0.8))
+    whole = VecGridWorld(n, seed=seed, **cfg)
+    whole.rollout(K)
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(n, r, 3)
+        e = VecGridWorld(hi - lo, seed=seed, env_offset=lo, **cfg)
+        e.rollout(K)
+        parts.append(e)
+    assert torch.equal(torch.cat([e.pos for e in parts]), whole.pos)
+    assert torch.equal(torch.cat([e.ep_ret for e in parts]), whole.ep_ret)
+    tot = sum(e.stats for e in parts)
+    assert torch.equal(tot[:2], whole.stats[:2]) and tot[4] == whole.stats[4]
+    assert float(tot[2]) == pytest.approx(float(whole.stats[2]), rel=1e-12)
+
+
+def test_unaligned_views_take_scalar_path():
+    """State tensors that are not 16-byte aligned (views offset by one element) must still be correct."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n = 4099
+    cfg = _vec_kwargs(_config2(0.8))
+    a = VecGridWorld(n, seed=1, **cfg)
+    b = VecGridWorld(n, seed=1, **cfg)
+    for name in ("pos", "ep_len", "ep_ret"):
+        big = torch.zeros(n + 1, dtype=getattr(b, name).dtype, device="cuda")
+        setattr(b, name, big[1:])
+    b.reset()
+    for t in range(30):
+        act = None_actions(a, t)
+        oa = a.step(act)
+        ob = b.step(act)
+        assert all(torch.equal(x, y) for x, y in zip(oa[:4], ob[:4]))
+    assert torch.equal(a.pos, b.pos)
+
+
+def test_large_grid_uses_global_table_path():
+    """200x200 grid: the outcome table (2.5 MB) exceeds shared memory, kernels read it through the read-only path."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    rng = np.random.default_rng(0)
+    walls = {(int(r), int(c)) for r, c in rng.integers(1, 199, (3000, 2))}
+    cfg = dict(rows=200, cols=200, start_state=(0, 0), walls=walls, terminal_states={(199, 199): 5.0},
+               p_success=0.7, episode_length_limit=500)
+    port = GridWorldPort(**cfg)
+    tab = FlatTables(port)
+    n, seed = 20_000, 8
+    env = VecGridWorld(n, seed=seed, **cfg)
+    pos, ln, ret = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.float32)
+    g = np.arange(n)
+    for t in range(60):
+        wt, wp = philox.step_words(seed, g, np.full(n, t, np.uint64))
+        act = (wp >> np.uint32(30)).astype(np.int32)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(act).cuda())
+        o = vec_step(tab, pos, ln, ret, act, wt, limit=500, start_pos=0, autoreset=True)
+        pos, ln, ret = o["pos"], o["ep_len"], o["ep_ret"]
+        assert np.array_equal(obs.cpu().numpy(), o["obs"]) and np.array_equal(rew.cpu().numpy(), o["reward"])
+    env.rollout(40)
+    for t in range(60, 100):
+        wt, wp = philox.step_words(seed, g, np.full(n, t, np.uint64))
+        o = vec_step(tab, pos, ln, ret, (wp >> np.uint32(30)).astype(np.int32), wt, limit=500, start_pos=0, autoreset=True)
+        pos, ln, ret = o["pos"], o["ep_len"], o["ep_ret"]
+    assert np.array_equal(env.pos.cpu().numpy(), pos)
+
+
+def test_reference_test_suite_on_vec_surface():
+    """tests/envs/grid_world/test_grid_world.py re-expressed against VecGridWorld(num_envs=1)."""
+    from rl_envs_forge_b200 import Action, VecGridWorld
+    env = VecGridWorld(1, autoreset=False)
+    assert (env.rows, env.cols, env.start_state) == (5, 5, (0, 0))                      # test_initialization
+    obs, *_ = env.step(np.array([Action.DOWN]))
+    assert tuple(obs[0]) == (1, 0)                                                        # test_actions
+    env = VecGridWorld(1, autoreset=False)
+    assert env.step(np.array([Action.RIGHT]))[1][0] == np.float32(-0.1)                   # test_rewards
+    env.step(np.array([Action.DOWN]))
+    obs, _ = env.reset()
+    assert tuple(obs.cpu().numpy()[0]) == (0, 0)                                          # test_reset
+    env.add_special_transition(from_state=(0, 0), action=Action.DOWN, to_state=(4, 4), reward=0.5)
+    env.state = (0, 0)
+    obs, rew, *_ = env.step(np.array([Action.DOWN]))
+    assert tuple(obs[0]) == (4, 4) and rew[0] == 0.5                                      # test_special_transition
+    env = VecGridWorld(1, autoreset=False, episode_length_limit=10)                       # test_episode_length_limit
+    for i in range(9):
+        assert not env.step(np.array([Action.RIGHT if i % 2 else Action.LEFT]))[3][0]
+    _, _, term, trunc, _ = env.step(np.array([Action.LEFT]))
+    assert trunc[0] and not term[0]
+    _, _, _, trunc, _ = env.step(np.array([Action.LEFT]))
+    assert trunc[0]                                                                       # truncation is sticky past the limit
+    env = VecGridWorld(1, rows=5, cols=5, autoreset=False, strict=True)                   # test_reset_to_new_starting_state
+    obs, _ = env.reset((5, 5))
+    assert tuple(obs.cpu().numpy()[0]) == (5, 5)
+    with pytest.raises(ValueError):                                                       # ...and stepping from there raises
+        env.step(np.array([0]))
+    with pytest.raises(ValueError):
+        env.reset([1, 1])
+    env = VecGridWorld(1, rows=4, cols=4, walls={(1, 1), (2, 2)}, terminal_states={(3, 3): 1.0})
+    assert len(env.mdp) == (16 - 2) * 4                                                   # test_mdp_size
+    env = VecGridWorld(1, rows=3, cols=3, walls={(1, 1)}, terminal_states={(2, 2): 1.0},
+                       special_transitions={((0, 0), Action.RIGHT): ((0, 2), 0.0)})       # test_probability_matrix
+    P = env.P
+    assert P.shape == (9, 9, 4) and P[0, 2, Action.RIGHT] == 1.0 and P[4, 4, 0] == 1.0 and P[8, 8, 1] == 1.0
+    env = VecGridWorld(1, autoreset=False, strict=True)
+    with pytest.raises(ValueError):                                                       # Action(7) raises in the reference
+        env.step(np.array([7]))
+    # terminal self-loop with reward 0 and done=True when auto-reset is off (grid_world.py:263-265)
+    env = VecGridWorld(1, autoreset=False)
+    env.state = (3, 3)
+    obs, rew, term, _, _ = env.step(np.array([Action.RIGHT]))
+    assert tuple(obs[0]) == (3, 4) and rew[0] == 1.0 and term[0]
+    obs, rew, term, _, _ = env.step(np.array([Action.UP]))
+    assert tuple(obs[0]) == (3, 4) and rew[0] == 0.0 and term[0]
+
+
+def test_autoreset_semantics_and_final_observation():
+    import torch
+    from rl_envs_forge_b200 import Action, VecGridWorld
+    env = VecGridWorld(4, autoreset=True)
+    env.state = np.array([[3, 3], [0, 0], [3, 3], [2, 2]])
+    acts = torch.tensor([Action.RIGHT, Action.RIGHT, Action.UP, Action.LEFT], dtype=torch.int32, device="cuda")
+    obs, rew, term, trunc, info = env.step(acts, return_final_obs=True)
+    assert obs.cpu().tolist() == [[0, 0], [0, 1], [2, 3], [2, 1]]                 # env 0 finished -> start state
+    assert info["final_observation"].cpu().tolist() == [[3, 4], [0, 1], [2, 3], [2, 1]]
+    assert term.cpu().tolist() == [True, False, False, False]
+    assert env.ep_len.cpu().tolist() == [0, 1, 1, 1] and env.ep_ret.cpu().tolist()[0] == 0.0
+    st = env.episode_stats()
+    assert st["episodes"] == 1 and st["length_sum"] == 1 and st["return_sum"] == 1.0
+    obs, _ = env.reset(mask=torch.tensor([0, 1, 0, 0], dtype=torch.bool))
+    assert env.ep_len.cpu().tolist() == [0, 0, 1, 1]
+
+
+def test_host_buffer_path_equals_device_path():
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    cfg = _vec_kwargs(_config2(0.8))
+    a = VecGridWorld(10_000, seed=4, **cfg)
+    b = VecGridWorld(10_000, seed=4, **cfg)
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        act = rng.integers(0, 4, 10_000).astype(np.int32)
+        oa = a.step(act)                                   # numpy in -> numpy out through pinned staging
+        ob = b.step(torch.from_numpy(act).cuda())
+        assert isinstance(oa[0], np.ndarray)
+        assert np.array_equal(oa[0], ob[0].cpu().numpy()) and np.array_equal(oa[1], ob[1].cpu().numpy())
+        assert np.array_equal(oa[2], ob[2].cpu().numpy()) and np.array_equal(oa[3], ob[3].cpu().numpy())

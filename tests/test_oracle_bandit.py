@@ -87,3 +87,15 @@ def test_engine_stream_moments():
     assert abs(xs.mean() - 5) < 0.06 and abs(xs.std() - 1) < 0.05
     p = PhiloxPrimitives(1, 0, 0)
     assert 0 < p.u() < 1 and p.consumed == 1
+
+
+@pytest.mark.parametrize("fam,args", CASES)
+def test_vectorised_engine_oracle_matches_scalar(fam, args):
+    from oracle.bandit import engine_sample_vec
+    p0 = float(args[0])
+    p1 = float(args[1]) if len(args) > 1 else 0.0
+    g = np.arange(300) + 1000
+    v, used = engine_sample_vec(42, g, 5, fam, p0, p1)
+    for i in range(0, 300, 7):
+        s, c = engine_sample(42, int(g[i]), 5, fam, p0, p1)
+        assert abs(s - v[i]) <= 4e-16 * abs(s) and c == used[i]  # np.power vs math.pow may differ in the last bit
