@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched-stepping hot path on B200 (contract: see DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this engine (one JSON line on stdout)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's CPU path (oracle port), same line shape
+    torchrun --nproc-per-node N ... bench.py --gpus N ...                # N > 1: one rank per GPU, weak scaling
+
+Workload (BASELINE.json configs[1]): GridWorld 8x8 with walls + terminal states + one special transition,
+p_success = 0.8 (slip transitions), episode_length_limit = 200, 2^20 envs per GPU.  One "step" = one VecGridWorld.step()
+launch over one 2^20-env batch with actions already in HBM.  The batches rotate over 8 independent env sets
+(8 x 44 MB = 352 MB > 126 MB L2) so no launch finds its state in L2.  The K launches are replayed from a captured
+CUDA graph (device-resident step clock), so the host never throttles the stream.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIG2 = dict(rows=8, cols=8, start_state=(0, 0),
+               walls={(1, 1), (1, 2), (2, 5), (3, 5), (4, 5), (6, 2), (6, 3), (5, 6)},
+               terminal_states={(7, 7): 1.0, (0, 7): -1.0}, episode_length_limit=200, p_success=0.8)
+SPECIAL = ((3, 3), 0, (6, 6), 0.5)  # ((3,3), UP) -> (6,6), reward 0.5
+METRIC = "env-steps/sec (GridWorld 8x8 walls+special transitions, batched step, 2^20 envs per GPU)"
+UNIT = "env-steps/s"
+GRID_BYTES_PER_STEP = 42     # read action+pos+ep_len+ep_ret (16 B), write pos+ep_len+ep_ret+obs+reward+flags (26 B)
+CARTPOLE_BYTES_PER_STEP = 74
+WORKLOAD = "gridworld_8x8_walls_special_p0.8_limit200"
+BANDIT_ARMS = {  # BASELINE config 3: the eight families with the parameters of the reference's test_arms_sampling
+    0: dict(distribution="normal", mean=5, std=1), 1: dict(distribution="uniform", low=4, high=6),
+    2: dict(distribution="exponential", scale=0.2), 3: dict(distribution="gamma", shape=9, scale=0.55),
+    4: dict(distribution="logistic", loc=5, scale=0.3), 5: dict(distribution="lognormal", mean=1.6, sigma=0.3),
+    6: dict(distribution="weibull", a=2), 7: dict(distribution="beta", a=2, b=5),
+}
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(kernel):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def _ref_worker(args):
+    """One host process: a per-instance GridWorld stepped the way the reference steps it (dict MDP lookup +
+    numpy Generator.choice per step, reset on done/truncated).  Returns (env_steps, seconds)."""
+    seed, n_steps = args
+    import numpy as np
+    from oracle.gridworld import GridWorldPort
+    port = GridWorldPort(special_transitions={(SPECIAL[0], SPECIAL[1]): (SPECIAL[2], SPECIAL[3])}, **CONFIG2)
+    rng = np.random.default_rng(seed)   # Generator(PCG64), what gym.utils.seeding.np_random builds (grid_world.py:69)
+    actions = np.random.default_rng(seed + 1).integers(0, 4, n_steps)
+    mdp = port.mdp
+    port.reset()
+    done_steps = 0
+    t0 = time.perf_counter()
+    for a in actions:
+        outcomes = mdp.get((port.state, int(a)), [])
+        probs = [o[3] for o in outcomes]
+        try:
+            idx = rng.choice(len(outcomes), p=probs)          # grid_world.py:514-515
+        except ValueError:                                    # the cell the reference raises on ((3,3), UP at p < 1)
+            continue
+        nxt, reward, done, _ = outcomes[idx]
+        port.state = nxt
+        port.episode_length_counter += 1
+        done_steps += 1
+        if done or port.episode_length_counter >= port.episode_length_limit:
+            port.reset()
+    return done_steps, time.perf_counter() - t0
+
+
+def _ref_throughput(n_steps_per_worker, workers, pool):
+    t0 = time.perf_counter()
+    res = pool.map(_ref_worker, [(1000 + i, n_steps_per_worker) for i in range(workers)])
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's per-instance CPU stepping (oracle port; the Python reference itself cannot
+    travel to the GPU box) on all host cores.  One "step" = every worker advancing its env by `sample` transitions."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        # warm-up also calibrates the per-step sample so that the timed K steps take ~args.cpu_seconds in total
+        probe = 4000
+        for _ in range(max(2, min(args.warmup, 3))):
+            n, wall = _ref_throughput(probe, cores, pool)
+        rate_per_worker = max(n / cores / wall, 1.0)
+        sample = int(max(50, min(200_000, args.cpu_seconds * rate_per_worker / max(args.steps, 1))))
+        n, wall = _ref_throughput(sample * args.steps, cores, pool)
+    value = n / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs": cores, "note": "one env per host process, reference-style step loop"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x {sample} transitions per step x {args.steps} steps "
+                                   f"(oracle/gridworld.py GridWorldPort + numpy Generator.choice, reset on done)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------- clock sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append((time.perf_counter(), parts))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, windows):
+        """Median SM clock over samples inside any (t0, t1) window (fallback: all samples), plus active throttle reasons."""
+        def inside(ts):
+            return any(a <= ts <= b for a, b in windows)
+        sel = [p for ts, p in self.samples if inside(ts)] or [p for _, p in self.samples]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        mhz = sorted(float(p[0]) for p in sel if p[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for p in sel for n, v in zip(names, p[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": float(sel[0][1]), "reasons": reasons,
+                "samples": len(sel)}
+
+
+# ------------------------------------------------------------------------------------------------------------ our arm
+def _time_region(torch, dist, world, fn):
+    """barrier + synchronize on both sides, CUDA events on the launching stream; returns (max-over-ranks ms, (t0, t1))."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    start.record()
+    fn()
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w1 = time.perf_counter()
+    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), (w0, w1)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandit, VecPendulumDisk, all_reduce_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: rl_envs_forge_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, R, K, W = args.envs_per_gpu, args.sets, args.steps, args.warmup
+    seed = 20261019
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    spec = {(SPECIAL[0], Action(SPECIAL[1])): (SPECIAL[2], SPECIAL[3])}
+    sets, acts = [], []
+    for r in range(R):
+        env = VecGridWorld(n, seed=seed, special_transitions=spec, env_offset=(rank * R + r) * n, **CONFIG2)
+        env.enable_device_clock()
+        sets.append(env)
+    # A distinct action buffers shared by the sets; launch i uses buffer i % A with A coprime to R, so an env sees a
+    # fresh action every step (a fixed action per env would pin agents against walls / on the rejected cell)
+    A = args.action_buffers
+    acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda") for _ in range(A)]
+    G = R * A  # launches per captured graph: every (set, action buffer) pairing once
+
+    def direct(i):
+        sets[i % R].step(acts[i % A])
+
+    for i in range(G):   # un-timed: module load, allocator
+        direct(i)
+    torch.cuda.synchronize()
+    # one CUDA graph = one round over the R env sets; the tail graph covers K % R launches
+    stream = torch.cuda.Stream()
+    graphs = {}
+    with torch.cuda.stream(stream):
+        for name, count in (("round", G), ("tail", K % G)):
+            if count == 0:
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(count):
+                    direct(i)
+            graphs[name] = g
+    torch.cuda.synchronize()
+
+    def launch_k(k):
+        for _ in range(k // G):
+            graphs["round"].replay()
+        if k % G:
+            if k % G == K % G and "tail" in graphs:
+                graphs["tail"].replay()
+            else:
+                for i in range(k % G):
+                    direct(i)
+
+    launch_k(max(W, 3))  # W warm-up steps (>= 3)
+    torch.cuda.synchronize()
+    before = sum(e.stats[4] for e in sets).clone()
+    tot = torch.zeros(8, dtype=torch.float64, device="cuda")
+
+    def timed():
+        launch_k(K)
+        if world > 1:  # the engine's only collective: sum of the episode statistics (64 B) over NVLink
+            tot.copy_(sum(e.stats for e in sets))
+            all_reduce_stats(tot)
+
+    ms, win_main = _time_region(torch, dist, world, timed)
+    after = sum(e.stats[4] for e in sets).clone()
+    steps_done = after - before
+    if world > 1:
+        dist.all_reduce(steps_done)
+    env_steps = float(steps_done.item())
+    value = env_steps / (ms * 1e-3)
+    launch_us = ms * 1e3 / K
+    peak, peak_src = _peaks()
+    achieved = GRID_BYTES_PER_STEP * n / (launch_us * 1e-6) / 1e9
+    err_count = int(sum(int(e.err[0].item()) & 0xFFFFFFFF for e in sets))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": n * world, "env_sets": R, "action_buffers": A,
+                   "l2": f"inputs larger than L2: {R} rotating env sets x {GRID_BYTES_PER_STEP * n / 1e6:.0f} MB",
+                   "launch": "CUDA graph replay of VecGridWorld.step (device step clock)", "actions": "resident in HBM",
+                   "rejected_env_steps": err_count, "parallelism": f"env-sharded x{world}"},
+        "gpu_launches": K,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": _traffic("gridworld_step_kernel"), "peak_source": peak_src,
+                     "kernel": "ef::gridworld_step_kernel<true,4,4>", "algorithmic_bytes_per_launch": GRID_BYTES_PER_STEP * n,
+                     "avg_launch_us": launch_us},
+    }
+
+    # ---- e2e: the public API with HOST buffers (numpy actions in, numpy results out), copies inside the timed region
+    e2e_env = VecGridWorld(n, seed=seed + 1, special_transitions=spec, env_offset=(world * R + rank) * n, **CONFIG2)
+    h_actions = [np.random.default_rng(i).integers(0, 4, n).astype(np.int32) for i in range(4)]
+    for i in range(3):
+        e2e_env.step(h_actions[i % 4])
+    k_e2e = max(5, min(K, args.e2e_steps))
+    s0 = float(e2e_env.stats[4].item())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for i in range(k_e2e):
+        obs, rew, term, trunc, _ = e2e_env.step(h_actions[i % 4])
+        checksum += float(rew[0])          # touch the host result
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    e2e_steps = torch.tensor([float(e2e_env.stats[4].item()) - s0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_steps)
+    win_e2e = (t0, time.perf_counter())
+    line["e2e"] = {"value": float(e2e_steps.item()) / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": 4 * n,
+                   "d2h_bytes_per_step": 14 * n, "steps": k_e2e,
+                   "api": "VecGridWorld.step(numpy int32[N]) -> numpy (obs, reward, terminated, truncated)"}
+    del e2e_env
+
+    # ---- detail sections (not the headline): fused rollouts and the other env families at their BASELINE configs
+    details = {}
+    if not args.no_details:
+        def ev_time(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(reps):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e) * 1e-3 / reps
+
+        Kr = 64
+        sec = ev_time(lambda: sets[0].rollout(Kr), 10)
+        details["gridworld_rollout_K64_random_policy"] = {"env_steps_per_s": n * Kr / sec, "envs": n}
+        del sets[1:]
+        big = 1 << 22
+        cp = VecCartPole(big, seed=seed, env_offset=rank * big)
+        a_cp = torch.empty(big, device="cuda").uniform_(-3, 3)
+        sec = ev_time(lambda: cp.step(a_cp), 50)
+        details["cartpole_step"] = {"env_steps_per_s": big / sec, "envs": big, "GBps": CARTPOLE_BYTES_PER_STEP * big / sec / 1e9,
+                                    "roofline_frac": CARTPOLE_BYTES_PER_STEP * big / sec / 1e9 / peak}
+        acts64 = torch.empty((Kr, big), device="cuda").uniform_(-3, 3)
+        rew = flg = None
+        sec = ev_time(lambda: cp.rollout(Kr, acts64, return_rewards=True), 5)
+        details["cartpole_rollout_K64_ext_actions_emit"] = {"env_steps_per_s": big * Kr / sec, "envs": big,
+                                                            "GBps": (9 + 48 / Kr) * big * Kr / sec / 1e9}
+        sec = ev_time(lambda: cp.rollout(Kr), 5)
+        details["cartpole_rollout_K64_random_policy"] = {"env_steps_per_s": big * Kr / sec, "envs": big}
+        del cp, acts64
+        pd = VecPendulumDisk(big, seed=seed, env_offset=rank * big)
+        sec = ev_time(lambda: pd.step(a_cp), 50)
+        details["pendulum_disk_step"] = {"env_steps_per_s": big / sec, "envs": big, "GBps": 50 * big / sec / 1e9}
+        sec = ev_time(lambda: pd.rollout(Kr), 5)
+        details["pendulum_disk_rollout_K64_random_policy"] = {"env_steps_per_s": big * Kr / sec, "envs": big}
+        del pd, a_cp
+        nb = 1 << 24
+        bd = VecKArmedBandit(nb, k=10, arm_params={i: dict(p) for i, p in BANDIT_ARMS.items()}, seed=seed,
+                             env_offset=rank * nb)
+        a_b = torch.randint(0, 10, (nb,), dtype=torch.int32, device="cuda")
+        sec = ev_time(lambda: bd.step(a_b), 20)
+        details["bandit_step_10arm_mixed"] = {"env_steps_per_s": nb / sec, "envs": nb, "GBps": 12 * nb / sec / 1e9}
+        del bd, a_b
+        if world > 1:
+            for v in details.values():
+                t = torch.tensor([v["env_steps_per_s"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t)
+                v["env_steps_per_s"] = float(t.item())
+                v["aggregate_over_gpus"] = world
+    line["details"] = details
+
+    if sampler is not None:
+        time.sleep(0.06)
+        sampler.stop()
+        line["clocks"] = sampler.summary([win_main, win_e2e])
+        line["clocks"]["in_timed_region"] = sum(1 for ts, _ in sampler.samples if win_main[0] <= ts <= win_main[1])
+
+    # ---- CPU baseline (rank 0, N = 1 only): the reference-style per-instance loop on the host cores, bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "4",
+                                  "--warmup", "1", "--cpu-seconds", str(args.cpu_seconds)], capture_output=True,
+                                 text=True, timeout=600)
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        except Exception as e:  # keep the GPU numbers even if the host arm fails
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100_000)
+    ap.add_argument("--warmup", type=int, default=2_000)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--sets", type=int, default=8)
+    ap.add_argument("--action-buffers", type=int, default=7)
+    ap.add_argument("--e2e-steps", type=int, default=60)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-details", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -25,6 +25,10 @@
  *   - `err` (nullable) points at EF_ERR_LEN uint32: [0] number of env-steps the reference would have raised on
  *     (atomicAdd), [1] 1 + global index of one offending env, [2] its table row (cell*4+action) or action value,
  *     [3] ef_step_error kind.  Offending envs are left untouched (the reference raises before mutating state).
+ *   - `clock` (nullable) points at 2 uint64 in device memory: clock[0] is ADDED to the `t` / `t0` argument to form
+ *     the Philox time coordinate and is advanced by the kernel itself (by 1 per step call, K per rollout) once all
+ *     its CTAs have read it; clock[1] is scratch (must start at 0).  It exists so a captured CUDA graph can be
+ *     replayed without the host re-baking `t` into the kernel parameters.
  */
 #ifndef ENVFORGE_B200_H
 #define ENVFORGE_B200_H
@@ -104,14 +108,15 @@ typedef struct ef_grid_desc {
 int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
                       const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset,
                       int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
-                      double* stats, uint32_t* err, int64_t n, int32_t autoreset, void* stream);
+                      double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 
 /* K fused steps (t0 .. t0+K-1) with state held in registers and auto-reset always on.
  *   actions  [K,n] int32 or NULL (random policy).   rewards [K,n] float / flags [K,n] uint8 (bit0 terminated,
  *   bit1 truncated) or NULL: nothing is written per step and only state + stats leave the kernel. */
 int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
                          const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                         float* rewards, uint8_t* flags, double* stats, uint32_t* err, int64_t n, void* stream);
+                         float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
+                         void* stream);
 
 /* GridWorld.reset (:530-551) for all envs (mask == NULL) or those with mask[i] != 0. */
 int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos, int32_t* ep_len, float* ep_ret,
@@ -146,11 +151,11 @@ typedef struct ef_pendulum_params {
  *   acc     [n,2] (x_acc, theta_acc) info values (nullable). */
 int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, const float* action,
                      uint64_t seed, uint64_t t, uint64_t env_offset, float* obs, float* reward, uint8_t* terminated,
-                     uint8_t* truncated, float* final_obs, float* acc, double* stats, int64_t n, int32_t autoreset,
-                     void* stream);
+                     uint8_t* truncated, float* final_obs, float* acc, double* stats, uint64_t* clock, int64_t n,
+                     int32_t autoreset, void* stream);
 int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                        float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream);
+                        float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
 /* reset: initial state from params (fixed) or Philox STREAM_RESET_USER at counter `epoch`; mask nullable. */
 int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                       uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
@@ -160,10 +165,10 @@ int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len
 int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                           const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
                           float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs, float* acc,
-                          double* stats, int64_t n, int32_t autoreset, void* stream);
+                          double* stats, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                              const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                             float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream);
+                             float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
 int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                            uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
 

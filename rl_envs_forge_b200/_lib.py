@@ -47,19 +47,19 @@ SIGNATURES = {
     "ef_last_cuda_error_string": (C.c_char_p, []),
     "ef_device_info": (C.c_int, [_P, _P, _P]),
     "ef_gridworld_step": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
-                                    _P, _I64, _I32, _P]),
+                                    _P, _P, _I64, _I32, _P]),
     "ef_gridworld_rollout": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P,
-                                       _I64, _P]),
+                                       _P, _I64, _P]),
     "ef_gridworld_reset": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "ef_cartpole_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
-                                   _P, _I64, _I32, _P]),
+                                   _P, _P, _I64, _I32, _P]),
     "ef_cartpole_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,
-                                      _I64, _P]),
+                                      _P, _I64, _P]),
     "ef_cartpole_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
     "ef_pendulum_disk_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
-                                        _P, _P, _I64, _I32, _P]),
+                                        _P, _P, _P, _I64, _I32, _P]),
     "ef_pendulum_disk_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P,
-                                           _P, _I64, _P]),
+                                           _P, _P, _I64, _P]),
     "ef_pendulum_disk_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
     "ef_bandit_step": (C.c_int, [_P, _I32, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_default_means": (C.c_int, [_I32, _U64, _U64, _P, _I64, _P]),

@@ -163,9 +163,9 @@ class VecPendulumBase(VecEnv):
                 self._acc = torch.zeros((n, self._ACC_DIM), dtype=torch.float32, device=self.device)
             acc = self._acc
         self._call(self._fn_step, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
-                   _lib.ptr(act), self._seed, self._t, self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward),
-                   _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self.stats), n,
-                   int(self.autoreset))
+                   _lib.ptr(act), self._seed, self._t_arg(), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward),
+                   _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self.stats),
+                   _lib.ptr(self._clock), n, int(self.autoreset))
         self._t += 1
         info = {}
         if host_io:
@@ -180,8 +180,8 @@ class VecPendulumBase(VecEnv):
                 info["final_observation"] = out[k]
                 k += 1
             if return_info:
-                info.update(self._info(out[k], out[3].astype(bool), np.asarray(actions).reshape(-1)))
-            return out[0], out[1], out[2].astype(bool), out[3].astype(bool), info
+                info.update(self._info(out[k], out[3].view(np.bool_), np.asarray(actions).reshape(-1)))
+            return out[0], out[1], out[2].view(np.bool_), out[3].view(np.bool_), info
         if return_final_obs:
             info["final_observation"] = fobs
         if return_info:
@@ -203,8 +203,8 @@ class VecPendulumBase(VecEnv):
             rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
         self._call(self._fn_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
-                   _lib.ptr(actions), self._seed, self._t, self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
-                   _lib.ptr(self.stats), n)
+                   _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
+                   _lib.ptr(self.stats), _lib.ptr(self._clock), n)
         self._t += int(K)
         if self._obs is not self._state:
             self._obs.copy_(self._state)

@@ -138,6 +138,7 @@ __device__ float sample_arm(const ef_arm arm, Primitives& pr, uint64_t seed, uin
 
 __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs a) {
     EpisodeAcc acc;
+    ErrorAcc errs;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
             }
             if (a.obs) a.obs[o] = act;  // observation = action (k_armed_bandit.py:200)
             if (static_cast<uint32_t>(act) >= static_cast<uint32_t>(a.k)) {
-                report_error(a.err, g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+                errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
                 if (a.reward) a.reward[o] = 0.0f;
                 continue;
             }
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
         }
     }
     flush_stats(acc, a.stats);
+    flush_errors(errs, a.err);
 }
 
 __global__ void __launch_bounds__(kThreads) bandit_means_kernel(int32_t k, uint64_t seed, uint64_t env_offset,

@@ -110,12 +110,63 @@ __device__ __forceinline__ void flush_stats(const EpisodeAcc& acc, double* __res
     if (threadIdx.x < 5 && s_part[threadIdx.x] != 0.0) atomicAdd(&stats[threadIdx.x], s_part[threadIdx.x]);
 }
 
-__device__ __forceinline__ void report_error(uint32_t* __restrict__ err, uint32_t g, uint32_t detail, uint32_t kind) {
+// Device-resident step clock (optional, for CUDA-graph capture where the host cannot bump `t` between replays):
+// clock[0] = steps already taken, clock[1] = CTA ticket.  Every CTA reads clock[0] when it starts; the CTA that
+// finishes last (ticket == gridDim.x - 1) advances clock[0] by `inc`, i.e. only after all CTAs have read it.
+__device__ __forceinline__ uint64_t clock_read(const unsigned long long* clock) {
+    return clock ? *reinterpret_cast<const volatile unsigned long long*>(clock) : 0ull;
+}
+__device__ __forceinline__ void clock_advance(unsigned long long* clock, unsigned long long inc) {
+    if (clock == nullptr) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&clock[1], 1ull) == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+            clock[1] = 0ull;
+            clock[0] += inc;
+            __threadfence();
+        }
+    }
+}
+
+// Rejected env-steps ("the reference would have raised here") are counted per thread and folded once per CTA, so a
+// batch with many offenders costs one global atomic per CTA instead of one per offender.
+struct ErrorAcc {
+    uint32_t count = 0, g = 0, detail = 0, kind = 0;
+    __device__ __forceinline__ void record(uint32_t g_, uint32_t detail_, uint32_t kind_) {
+        ++count;
+        g = g_;
+        detail = detail_;
+        kind = kind_;
+    }
+};
+
+// All threads of the CTA must call it.  err[0] += offenders of this CTA; the CTA that finds err[0] == 0 also records
+// one offender's (global env index + 1, detail, kind).
+__device__ __forceinline__ void flush_errors(const ErrorAcc& e, uint32_t* __restrict__ err) {
     if (err == nullptr) return;
-    if (atomicAdd(&err[0], 1u) == 0u) {
-        err[1] = g + 1u;
-        err[2] = detail;
-        err[3] = kind;
+    __shared__ uint32_t s_err[4];
+    if (threadIdx.x < 4) s_err[threadIdx.x] = 0u;
+    __syncthreads();
+    const uint32_t mask = __ballot_sync(0xffffffffu, e.count != 0u);
+    if (mask != 0u) {
+        uint32_t c = e.count;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+        if ((threadIdx.x & 31u) == 0u) atomicAdd(&s_err[0], c);
+        if ((threadIdx.x & 31u) == static_cast<uint32_t>(__ffs(mask) - 1)) {  // lowest offending lane of the warp
+            s_err[1] = e.g + 1u;
+            s_err[2] = e.detail;
+            s_err[3] = e.kind;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_err[0] != 0u) {
+        if (atomicAdd(&err[0], s_err[0]) == 0u) {
+            err[1] = s_err[1];
+            err[2] = s_err[2];
+            err[3] = s_err[3];
+        }
     }
 }
 

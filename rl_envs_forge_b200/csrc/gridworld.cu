@@ -40,6 +40,7 @@ struct GridArgs {
     // rollout only
     int32_t K;
     uint8_t* flags;
+    unsigned long long* clock;
 };
 
 template <bool SMEM>
@@ -68,9 +69,9 @@ __device__ __forceinline__ uint32_t outcome_index(const GridArgs& a, uint32_t r)
 template <bool SMEM, int SLOTS>
 __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* __restrict__ tab, uint32_t g,
                                                int32_t& pos, int32_t& len, float& ret, int32_t act, uint32_t r,
-                                               float& reward_out) {
+                                               float& reward_out, ErrorAcc& errs) {
     if (static_cast<uint32_t>(act) > 3u) {
-        report_error(a.err, g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+        errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
         reward_out = 0.0f;
         return 4u;
     }
@@ -79,7 +80,7 @@ __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* _
     const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
     const uint32_t oflags = o.x >> 16;
     if (oflags & (EF_GRID_NO_OUTCOMES | EF_GRID_BAD_PROBS)) {
-        report_error(a.err, g, row, (oflags & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS);
+        errs.record(g, row, (oflags & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS);
         reward_out = 0.0f;
         return 4u;
     }
@@ -96,8 +97,10 @@ template <bool SMEM, int SLOTS, int VEC>
 __global__ void __launch_bounds__(kThreads) gridworld_step_kernel(const GridArgs a) {
     const uint2* __restrict__ tab = stage_table<SMEM>(a);
     EpisodeAcc acc;
+    ErrorAcc errs;
     const int64_t groups = (a.n + VEC - 1) / VEC;
     const bool need_philox = (a.action == nullptr) || (SLOTS == 4 && a.draw == nullptr);
+    const uint64_t t = a.t + clock_read(a.clock);
     for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < groups;
          v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t base = v * VEC;
@@ -138,12 +141,12 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_kernel(const GridArgs
         for (int j = 0; j < VEC; ++j) {
             const uint32_t g = static_cast<uint32_t>(a.env_offset + base + j);
             if (need_philox) {
-                const uint4 w = draw_block(a.seed, g, a.t >> 1, kStreamStep);
-                const uint32_t wt = (a.t & 1) ? w.z : w.x, wp = (a.t & 1) ? w.w : w.y;
+                const uint4 w = draw_block(a.seed, g, t >> 1, kStreamStep);
+                const uint32_t wt = (t & 1) ? w.z : w.x, wp = (t & 1) ? w.w : w.y;
                 if (a.action == nullptr) act[j] = static_cast<int32_t>(wp >> 30);
                 if (SLOTS == 4 && a.draw == nullptr) r[j] = wt;
             }
-            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos[j], len[j], ret[j], act[j], r[j], rew[j]);
+            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos[j], len[j], ret[j], act[j], r[j], rew[j], errs);
             term[j] = f & 1u;
             trunc[j] = (f >> 1) & 1u;
             fobs[2 * j] = pos[j] / a.cols;
@@ -194,6 +197,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_kernel(const GridArgs
         }
     }
     flush_stats(acc, a.stats);
+    flush_errors(errs, a.err);
+    clock_advance(a.clock, 1ull);
 }
 
 // ---- fused K-step rollout -------------------------------------------------------------------------------------------
@@ -203,8 +208,10 @@ template <bool SMEM, int SLOTS, bool EXT_ACTIONS, bool EMIT>
 __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridArgs a) {
     const uint2* __restrict__ tab = stage_table<SMEM>(a);
     EpisodeAcc acc;
+    ErrorAcc errs;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t n_round = (a.n + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
+    const uint64_t t0 = a.t + clock_read(a.clock);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool valid = i < a.n;
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
         uint4 w = make_uint4(0, 0, 0, 0);
         constexpr bool kNeedWords = !EXT_ACTIONS || SLOTS == 4;
         for (int k = 0; k < a.K; ++k) {
-            const uint64_t t = a.t + static_cast<uint64_t>(k);
+            const uint64_t t = t0 + static_cast<uint64_t>(k);
             uint32_t wt = 0, wp = 0;
             if constexpr (kNeedWords) {
                 if (k == 0 || !(t & 1)) w = draw_block(a.seed, g, t >> 1, kStreamStep);
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
             if constexpr (EXT_ACTIONS) act = valid ? __ldg(a.action + static_cast<int64_t>(k) * a.n + i) : 0;
             else act = static_cast<int32_t>(wp >> 30);
             float rew;
-            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, wt, rew);
+            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, wt, rew, errs);
             if constexpr (EMIT) {
                 if (valid) {
                     if (a.reward) a.reward[static_cast<int64_t>(k) * a.n + i] = rew;
@@ -250,6 +257,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
         }
     }
     flush_stats(acc, a.stats);
+    flush_errors(errs, a.err);
+    clock_advance(a.clock, static_cast<unsigned long long>(a.K));
 }
 
 __global__ void __launch_bounds__(kThreads) gridworld_reset_kernel(int32_t start_cell, int32_t cols, int32_t* pos,
@@ -308,8 +317,8 @@ using namespace ef;
 extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
                                  const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t,
                                  uint64_t env_offset, int32_t* obs, float* reward, uint8_t* terminated,
-                                 uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err, int64_t n,
-                                 int32_t autoreset, void* stream) {
+                                 uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
+                                 uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
     if (n < 0 || !pos || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
@@ -319,6 +328,7 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     a.seed = seed; a.t = t; a.env_offset = env_offset;
     a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs;
     a.stats = stats; a.err = err; a.n = n; a.autoreset = autoreset;
+    a.clock = reinterpret_cast<unsigned long long*>(clock);
     const bool vec = aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) && aligned(action, 16) &&
                      aligned(draw, 16) && aligned(obs, 16) && aligned(reward, 16) && aligned(terminated, 4) &&
                      aligned(truncated, 4) && aligned(final_obs, 16);
@@ -338,8 +348,8 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
 
 extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
                                     const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                                    float* rewards, uint8_t* flags, double* stats, uint32_t* err, int64_t n,
-                                    void* stream) {
+                                    float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock,
+                                    int64_t n, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
     if (n < 0 || K < 0 || !pos || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
@@ -348,6 +358,7 @@ extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int3
     a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K;
     a.reward = rewards; a.flags = flags; a.stats = stats; a.err = err; a.n = n; a.autoreset = 1;
+    a.clock = reinterpret_cast<unsigned long long*>(clock);
     const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -29,6 +29,7 @@ struct PendArgs {
     int32_t K;
     uint8_t* flags;
     const uint8_t* mask;
+    unsigned long long* clock;
 };
 
 // (a + pi) floored-mod 2pi - pi with -pi -> +pi (cart_pole.py:84-89).  On (-pi, pi] the map is the identity, which is
@@ -133,6 +134,7 @@ template <class Env>
 __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs a) {
     using Vec = typename Env::Vec;
     EpisodeAcc acc;
+    const uint64_t t = a.t + clock_read(a.clock);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
         if (a.action) {
             act = __ldg(a.action + i);
         } else {
-            const uint4 w = draw_block(a.seed, g, a.t >> 1, kStreamStep);
-            act = policy_action((a.t & 1) ? w.w : w.y);
+            const uint4 w = draw_block(a.seed, g, t >> 1, kStreamStep);
+            act = policy_action((t & 1) ? w.w : w.y);
         }
         float rew, a0, a1;
         const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
         if (a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s;
         if (a.autoreset && f) {
             acc.finish(len, ret);
-            s = Env::init(a.p, a.seed, g, a.t, kStreamResetAuto);
+            s = Env::init(a.p, a.seed, g, t, kStreamResetAuto);
             len = 0;
             ret = 0.0f;
         }
@@ -166,6 +168,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
         if (a.acc) Env::store_acc(a.acc, i, a0, a1);
     }
     flush_stats(acc, a.stats);
+    clock_advance(a.clock, 1ull);
 }
 
 template <class Env, bool EXT_ACTIONS, bool EMIT>
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
     EpisodeAcc acc;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t n_round = (a.n + 31) & ~static_cast<int64_t>(31);
+    const uint64_t t0 = a.t + clock_read(a.clock);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool valid = i < a.n;
         const int64_t ii = valid ? i : 0;
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
         float ret = a.ep_ret[ii];
         uint4 w = make_uint4(0, 0, 0, 0);
         for (int k = 0; k < a.K; ++k) {
-            const uint64_t t = a.t + static_cast<uint64_t>(k);
+            const uint64_t t = t0 + static_cast<uint64_t>(k);
             float act;
             if constexpr (EXT_ACTIONS) {
                 act = __ldg(a.action + static_cast<int64_t>(k) * a.n + ii);
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
         }
     }
     flush_stats(acc, a.stats);
+    clock_advance(a.clock, static_cast<unsigned long long>(a.K));
 }
 
 template <class Env>
@@ -244,8 +249,8 @@ static int check_common(const ef_pendulum_params* p, const float* state, const i
 template <class Env>
 static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, const float* action,
                      uint64_t seed, uint64_t t, uint64_t env_offset, float* obs, float* reward, uint8_t* terminated,
-                     uint8_t* truncated, float* final_obs, float* acc, double* stats, int64_t n, int32_t autoreset,
-                     void* stream) {
+                     uint8_t* truncated, float* final_obs, float* acc, double* stats, uint64_t* clock, int64_t n,
+                     int32_t autoreset, void* stream) {
     if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
     if (!aligned(obs, sizeof(typename Env::Vec)) || !aligned(final_obs, sizeof(typename Env::Vec)) ||
         !aligned(acc, Env::DIM == 4 ? 8 : 4))
@@ -255,7 +260,7 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action;
     a.seed = seed; a.t = t; a.env_offset = env_offset; a.obs = obs; a.reward = reward;
     a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs; a.acc = acc;
-    a.stats = stats; a.n = n; a.autoreset = autoreset;
+    a.stats = stats; a.n = n; a.autoreset = autoreset; a.clock = reinterpret_cast<unsigned long long*>(clock);
     pendulum_step_kernel<Env><<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return cuda_status(cudaGetLastError());
 }
@@ -263,14 +268,14 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
 template <class Env>
 static int rollout_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                        float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream) {
+                        float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream) {
     if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
     if (K < 0) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0 || K == 0) return EF_OK;
     PendArgs a{};
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
-    a.stats = stats; a.n = n; a.autoreset = 1;
+    a.stats = stats; a.n = n; a.autoreset = 1; a.clock = reinterpret_cast<unsigned long long*>(clock);
     const int grid = grid_for(n, 8);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
@@ -300,14 +305,15 @@ using namespace ef;
 extern "C" int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                 const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
                                 float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs, float* acc,
-                                double* stats, int64_t n, int32_t autoreset, void* stream) {
+                                double* stats, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     return step_impl<CartPole>(p, state, ep_len, ep_ret, action, seed, t, env_offset, obs, reward, terminated, truncated,
-                               final_obs, acc, stats, n, autoreset, stream);
+                               final_obs, acc, stats, clock, n, autoreset, stream);
 }
 extern "C" int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                    const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                                   float* rewards, uint8_t* flags, double* stats, int64_t n, void* stream) {
-    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, n, stream);
+                                   float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n,
+                                   void* stream) {
+    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n, stream);
 }
 extern "C" int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                  uint64_t seed, uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n,
@@ -317,15 +323,16 @@ extern "C" int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int3
 extern "C" int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                      const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
                                      float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs,
-                                     float* acc, double* stats, int64_t n, int32_t autoreset, void* stream) {
+                                     float* acc, double* stats, uint64_t* clock, int64_t n, int32_t autoreset,
+                                     void* stream) {
     return step_impl<PendulumDisk>(p, state, ep_len, ep_ret, action, seed, t, env_offset, obs, reward, terminated,
-                                   truncated, final_obs, acc, stats, n, autoreset, stream);
+                                   truncated, final_obs, acc, stats, clock, n, autoreset, stream);
 }
 extern "C" int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset,
-                                        int32_t K, float* rewards, uint8_t* flags, double* stats, int64_t n,
-                                        void* stream) {
-    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, n, stream);
+                                        int32_t K, float* rewards, uint8_t* flags, double* stats, uint64_t* clock,
+                                        int64_t n, void* stream) {
+    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n, stream);
 }
 extern "C" int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                       uint64_t seed, uint64_t epoch, uint64_t env_offset, const uint8_t* mask,

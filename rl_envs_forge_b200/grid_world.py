@@ -433,9 +433,10 @@ class VecGridWorld(VecEnv):
                 self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
             fobs = self._final_obs
         self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
-                   _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t, self.env_offset,
+                   _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
                    _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc),
-                   _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), n, int(self.autoreset))
+                   _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), _lib.ptr(self._clock), n,
+                   int(self.autoreset))
         self._t += 1
         if self.strict:
             self.check_errors()
@@ -447,7 +448,7 @@ class VecGridWorld(VecEnv):
             out = self._to_host(named)
             if return_final_obs:
                 info["final_observation"] = out[4]
-            return out[0], out[1], out[2].astype(bool), out[3].astype(bool), info
+            return out[0], out[1], out[2].view(np.bool_), out[3].view(np.bool_), info
         if return_final_obs:
             info["final_observation"] = fobs
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
@@ -468,8 +469,8 @@ class VecGridWorld(VecEnv):
             rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
         self._call(self._lib.ef_gridworld_rollout, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
-                   _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t, self.env_offset, int(K),
-                   _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self.stats), _lib.ptr(self.err), n)
+                   _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K),
+                   _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self.stats), _lib.ptr(self.err), _lib.ptr(self._clock), n)
         self._t += int(K)
         return (rew, flg) if return_rewards else None
 

@@ -86,6 +86,24 @@ class VecEnv:
         self.stats = torch.zeros(_lib.EF_STATS_LEN, dtype=torch.float64, device=dev)
         self.err = torch.zeros(_lib.EF_ERR_LEN, dtype=torch.int32, device=dev)
         self._host = {}
+        self._clock = None  # optional device-resident step clock (CUDA-graph capture), see enable_device_clock()
+
+    # -- device clock ---------------------------------------------------------------------------------------------
+    def enable_device_clock(self):
+        """Keep the Philox time coordinate in device memory so that step()/rollout() can be captured in a CUDA graph and
+        replayed: the kernels read and advance the clock themselves instead of receiving `t` as a baked-in argument."""
+        if self._clock is None:
+            torch = self._torch
+            self._clock = torch.tensor([self._t, 0], dtype=torch.int64, device=self.device)
+        return self._clock
+
+    def disable_device_clock(self):
+        if self._clock is not None:
+            self._t = int(self._clock[0].item())
+            self._clock = None
+
+    def _t_arg(self):
+        return 0 if self._clock is not None else self._t
 
     # -- helpers ---------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -118,7 +136,10 @@ class VecEnv:
         return dev
 
     def _to_host(self, named_tensors):
-        """Device tensors -> numpy arrays through pinned buffers; one stream sync for the whole batch."""
+        """Device tensors -> numpy arrays through pinned buffers; one stream sync for the whole batch.
+
+        The arrays are views of the pinned staging buffers (no extra host copy): they stay valid until the next
+        host-buffer step() of this env, like the device tensors step() returns on the CUDA path."""
         torch = self._torch
         outs = []
         for name, t in named_tensors:
@@ -126,7 +147,7 @@ class VecEnv:
             stage.copy_(t, non_blocking=True)
             outs.append(stage)
         torch.cuda.current_stream(self.device).synchronize()
-        return [o.numpy().copy() for o in outs]
+        return [o.numpy() for o in outs]
 
     # -- statistics / errors ---------------------------------------------------------------------------------------
     def episode_stats(self, all_reduce=False, reset=False):
@@ -163,7 +184,7 @@ class VecEnv:
 
     @property
     def step_count(self):
-        return self._t
+        return self._t if self._clock is None else int(self._clock[0].item())
 
     def close(self):
         pass

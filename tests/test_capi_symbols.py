@@ -47,12 +47,12 @@ def test_struct_layouts_match_header():
 def test_argument_validation_without_gpu(lib):
     # null descriptor / null state are rejected before any CUDA call is made
     assert lib.ef_gridworld_step(None, None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None,
-                                 None, 8, 1, None) == 1
+                                 None, None, 8, 1, None) == 1
     d = _lib.GridDesc()
-    assert lib.ef_gridworld_rollout(ctypes.byref(d), None, None, None, None, 0, 0, 0, 4, None, None, None, None, 8,
-                                    None) == 1
-    assert lib.ef_cartpole_step(None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, 8, 1,
-                                None) == 1
+    assert lib.ef_gridworld_rollout(ctypes.byref(d), None, None, None, None, 0, 0, 0, 4, None, None, None, None, None,
+                                    8, None) == 1
+    assert lib.ef_cartpole_step(None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, None,
+                                8, 1, None) == 1
     assert lib.ef_bandit_step(None, 10, None, 0, 0, 0, 1, None, None, None, None, 8, None) == 1
 
 
