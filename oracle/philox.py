@@ -8,9 +8,12 @@ the reference (injected through `np_random` shims).  This file restates the publ
 algorithm (Salmon et al., SC'11; Random123) in numpy and is pinned by the Random123 known-answer
 vectors in tests/test_oracle_philox.py.
 
-Stream layout shared with rl_envs_forge_b200/csrc/philox.cuh (keep both in sync):
+Stream layout shared with rl_envs_forge_b200/csrc/ef_common.cuh (keep both in sync):
     key = (seed & 0xffffffff, seed >> 32)
-    ctr = (g, c_lo, c_hi, stream | block << 8)         g = global env index (u32)
+    ctr = (x, c_lo, c_hi, stream | block << 8)
+  per-env streams    (RESET_*, BANDIT*):    x = g (global env index, u32), all four words belong to env g
+  grouped streams    (TRANSITION, POLICY):  x = g >> 2, env g owns word g & 3 -- one Philox call serves four
+                                            consecutive envs, which is what a thread of the step kernels processes
 """
 import numpy as np
 
@@ -21,11 +24,12 @@ W1 = 0xBB67AE85
 MASK32 = np.uint64(0xFFFFFFFF)
 
 # stream ids (ctr[3] low byte)
-STREAM_STEP = 0         # per (env, t>>1): words (0,1) serve even t, (2,3) odd t: [transition draw, policy draw]
+STREAM_TRANSITION = 0   # grouped, per (g>>2, t): word g&3 = transition (outcome) draw of env g at step t
 STREAM_RESET_AUTO = 1   # per (env, t): initial-state draws of the episode that starts after step t
 STREAM_RESET_USER = 2   # per (env, reset epoch): initial-state draws of an explicit reset()
 STREAM_BANDIT = 3       # per (env, t), block j: primitive draws of the arm sampler
-STREAM_BANDIT_MEANS = 4  # per (env, arm//2): default-arm means
+STREAM_BANDIT_MEANS = 4  # per (env, arm): default-arm means
+STREAM_POLICY = 5       # grouped, per (g>>2, t): word g&3 = policy draw (random action) of env g at step t
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -55,12 +59,17 @@ def draw_block(seed, g, counter, stream, block=0):
     return philox4x32_10(np.asarray(g, dtype=np.uint64), c1, c2, c3, seed & 0xFFFFFFFF, seed >> 32)
 
 
+def group_word(seed, g, t, stream):
+    """Word of env g in a grouped stream: word (g & 3) of the block at x = g >> 2, counter t."""
+    g = np.asarray(g, dtype=np.uint64)
+    w = np.stack(draw_block(seed, g >> np.uint64(2), t, stream), axis=-1)
+    lane = (g & np.uint64(3)).astype(np.int64)
+    return np.take_along_axis(w, lane[..., None], axis=-1)[..., 0]
+
+
 def step_words(seed, g, t):
-    """(transition word, policy word) of step index t for envs g -- the pairing rule of STREAM_STEP."""
-    t = np.asarray(t, dtype=np.uint64)
-    w = draw_block(seed, g, t >> np.uint64(1), STREAM_STEP)
-    odd = (t & np.uint64(1)).astype(bool)
-    return np.where(odd, w[2], w[0]), np.where(odd, w[3], w[1])
+    """(transition word, policy word) of step index t for envs g."""
+    return group_word(seed, g, t, STREAM_TRANSITION), group_word(seed, g, t, STREAM_POLICY)
 
 
 def u23(w):

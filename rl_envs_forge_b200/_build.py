@@ -32,26 +32,32 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """Compile and link.  `defines` (e.g. ["EF_STEP_MINBLOCKS=4"]) + `tag` build a tuning variant next to the default
+    library (libenvforge_b200<tag>.so), selected at run time with ENVFORGE_LIB."""
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    lib = LIB[:-3] + tag + ".so"
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = s[:-3] + ".o"
+        o = s[:-3] + tag + ".o"
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = ([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else [])
+                   + ["-c", s, "-o", o])
             if verbose:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-cudart", "static", "-o", LIB] + objs
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tags = [a[6:] for a in sys.argv[1:] if a.startswith("--tag=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, tag=tags[0] if tags else ""))

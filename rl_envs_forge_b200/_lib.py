@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libenvforge_b200.so")
+# ENVFORGE_LIB selects an alternative build of the same library (kernel tuning experiments); default: the in-tree build
+LIB_PATH = os.environ.get("ENVFORGE_LIB") or os.path.join(_HERE, "csrc", "libenvforge_b200.so")
 
 EF_STATS_LEN = 8
 EF_ERR_LEN = 4

@@ -142,7 +142,6 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-        uint4 w = make_uint4(0, 0, 0, 0);
         for (int j = 0; j < a.K; ++j) {
             const uint64_t t = a.t0 + static_cast<uint64_t>(j);
             const int64_t o = static_cast<int64_t>(j) * a.n + i;
@@ -150,8 +149,7 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
             if (a.action) {
                 act = __ldg(a.action + o);
             } else {
-                if (j == 0 || !(t & 1)) w = draw_block(a.seed, g, t >> 1, kStreamStep);
-                act = static_cast<int32_t>(__umulhi((t & 1) ? w.w : w.y, static_cast<uint32_t>(a.k)));
+                act = static_cast<int32_t>(__umulhi(group_word1(a.seed, g, t, kStreamPolicy), static_cast<uint32_t>(a.k)));
             }
             if (a.obs) a.obs[o] = act;  // observation = action (k_armed_bandit.py:200)
             if (static_cast<uint32_t>(act) >= static_cast<uint32_t>(a.k)) {
@@ -172,8 +170,7 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
             acc.finish(1, r);  // every bandit step is a finished one-step episode (done is always True, :198)
         }
     }
-    flush_stats(acc, a.stats);
-    flush_errors(errs, a.err);
+    cta_epilogue(acc, errs, a.stats, a.err, nullptr, 0ull, 0ull);
 }
 
 __global__ void __launch_bounds__(kThreads) bandit_means_kernel(int32_t k, uint64_t seed, uint64_t env_offset,

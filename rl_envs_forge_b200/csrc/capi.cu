@@ -1,4 +1,6 @@
 // envforge_b200 -- version / status / device helpers and the in-flight episode statistics reduction.
+#include <cstdlib>
+
 #include "ef_common.cuh"
 
 namespace ef {
@@ -19,6 +21,11 @@ int sm_count() {
     return cached_sms;
 }
 
+bool pdl_enabled() {
+    static const bool on = (getenv("ENVFORGE_NO_PDL") == nullptr);
+    return on;
+}
+
 __global__ void __launch_bounds__(kThreads) episode_stat_reduce_kernel(const int32_t* __restrict__ ep_len,
                                                                        const float* __restrict__ ep_ret,
                                                                        double* __restrict__ out, int64_t n) {
@@ -26,7 +33,7 @@ __global__ void __launch_bounds__(kThreads) episode_stat_reduce_kernel(const int
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x)
         acc.finish(ep_len[i], ep_ret[i]);
-    flush_stats(acc, out);
+    cta_epilogue(acc, ErrorAcc(), out, nullptr, nullptr, 0ull, 0ull);
 }
 
 }  // namespace ef

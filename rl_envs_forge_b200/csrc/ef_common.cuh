@@ -16,7 +16,7 @@ inline int cuda_status(cudaError_t e) {
     return EF_ERR_CUDA;
 }
 
-inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+__host__ __device__ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // Launch geometry: B200 has 148 SMs; a grid of `per_sm` resident CTAs per SM looping grid-stride keeps every SM
 // busy without a tail wave.  Queried once per process per device (cheap attribute reads, cached in a small table).
@@ -32,13 +32,41 @@ inline int grid_for(int64_t work_items, int per_sm) {
     return static_cast<int>(blocks);
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// Step kernels are launched with the programmatic-stream-serialization attribute: the CTAs of launch i+1 may be
+// scheduled while launch i drains, run their prologue (stage the transition table into shared memory) and then block in
+// pdl_wait() until launch i has completed and its writes are visible.  That hides launch latency and the prologue behind
+// the previous step's tail.  Both instructions are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // false when ENVFORGE_NO_PDL is set (A/B experiments)
+
+template <typename Kernel, typename Args>
+inline int launch_kernel(Kernel kernel, const Args& args, int grid, size_t smem_bytes, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cuda_status(cudaLaunchKernelEx(&cfg, kernel, args));
+}
+
 // ---- Philox4x32-10 ------------------------------------------------------------------------------------------------
-// Stream layout (twin: oracle/philox.py).  key = (seed lo, seed hi); ctr = (g, c_lo, c_hi, stream | block << 8).
-constexpr uint32_t kStreamStep = 0;        // per (env, t>>1): words (0,1) even t, (2,3) odd t = [transition, policy]
+// Stream layout (twin: oracle/philox.py).  key = (seed lo, seed hi); ctr = (x, c_lo, c_hi, stream | block << 8).
+//   per-env streams: x = g (global env index).  Grouped streams: x = g >> 2 and env g owns word g & 3, so the one
+//   Philox call a thread makes serves the four consecutive envs it processes.
+constexpr uint32_t kStreamTransition = 0;  // grouped, per (g>>2, t): outcome draw of env g at step t
 constexpr uint32_t kStreamResetAuto = 1;   // per (env, t): initial state of the episode starting after step t
 constexpr uint32_t kStreamResetUser = 2;   // per (env, reset epoch)
 constexpr uint32_t kStreamBandit = 3;      // per (env, step), block j: sampler primitives
 constexpr uint32_t kStreamBanditMeans = 4; // per (env, arm): default-arm mean
+constexpr uint32_t kStreamPolicy = 5;      // grouped, per (g>>2, t): random-policy draw of env g at step t
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
                                                uint32_t k1) {
@@ -63,6 +91,27 @@ __device__ __forceinline__ uint4 draw_block(uint64_t seed, uint32_t g, uint64_t 
                                             uint32_t block = 0) {
     return philox4x32_10(g, static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32),
                          stream | (block << 8), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+}
+
+// Grouped-stream words of the four consecutive envs g0 .. g0+3 at counter t.  g0 & 3 is the same for every thread of a
+// launch (it equals env_offset & 3), so the second call is a launch-uniform branch taken only for unaligned shards.
+__device__ __forceinline__ void group_words4(uint64_t seed, uint32_t g0, uint64_t t, uint32_t stream, uint32_t (&w)[4]) {
+    const uint4 a = draw_block(seed, g0 >> 2, t, stream);
+    const uint32_t sh = g0 & 3u;
+    if (sh == 0u) {
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else {
+        const uint4 b = draw_block(seed, (g0 >> 2) + 1u, t, stream);
+        const uint32_t all[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = sh == 1u ? all[j + 1] : (sh == 2u ? all[j + 2] : all[j + 3]);
+    }
+}
+
+__device__ __forceinline__ uint32_t group_word1(uint64_t seed, uint32_t g, uint64_t t, uint32_t stream) {
+    const uint4 a = draw_block(seed, g >> 2, t, stream);
+    const uint32_t l = g & 3u;
+    return l == 0u ? a.x : (l == 1u ? a.y : (l == 2u ? a.z : a.w));
 }
 
 // uint32 word -> uniform in (0,1), ((w>>9)+0.5)*2^-23: exact in fp32, and so is 1-u.
@@ -92,45 +141,7 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Block-level fold of the per-thread accumulators into `stats` (one atomicAdd set per CTA).  All threads of the CTA
-// must call it (it synchronises).  `stats` may be null.
-__device__ __forceinline__ void flush_stats(const EpisodeAcc& acc, double* __restrict__ stats) {
-    if (stats == nullptr) return;
-    __shared__ double s_part[5];
-    if (threadIdx.x < 5) s_part[threadIdx.x] = 0.0;
-    __syncthreads();
-    double v[5] = {static_cast<double>(acc.episodes), static_cast<double>(acc.length), acc.ret, acc.ret_sq,
-                   static_cast<double>(acc.steps)};
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-        const double w = warp_sum(v[j]);
-        if ((threadIdx.x & 31) == 0 && w != 0.0) atomicAdd(&s_part[j], w);
-    }
-    __syncthreads();
-    if (threadIdx.x < 5 && s_part[threadIdx.x] != 0.0) atomicAdd(&stats[threadIdx.x], s_part[threadIdx.x]);
-}
-
-// Device-resident step clock (optional, for CUDA-graph capture where the host cannot bump `t` between replays):
-// clock[0] = steps already taken, clock[1] = CTA ticket.  Every CTA reads clock[0] when it starts; the CTA that
-// finishes last (ticket == gridDim.x - 1) advances clock[0] by `inc`, i.e. only after all CTAs have read it.
-__device__ __forceinline__ uint64_t clock_read(const unsigned long long* clock) {
-    return clock ? *reinterpret_cast<const volatile unsigned long long*>(clock) : 0ull;
-}
-__device__ __forceinline__ void clock_advance(unsigned long long* clock, unsigned long long inc) {
-    if (clock == nullptr) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&clock[1], 1ull) == static_cast<unsigned long long>(gridDim.x) - 1ull) {
-            clock[1] = 0ull;
-            clock[0] += inc;
-            __threadfence();
-        }
-    }
-}
-
-// Rejected env-steps ("the reference would have raised here") are counted per thread and folded once per CTA, so a
-// batch with many offenders costs one global atomic per CTA instead of one per offender.
+// Rejected env-steps ("the reference would have raised here") are counted per thread and folded once per CTA.
 struct ErrorAcc {
     uint32_t count = 0, g = 0, detail = 0, kind = 0;
     __device__ __forceinline__ void record(uint32_t g_, uint32_t detail_, uint32_t kind_) {
@@ -141,31 +152,93 @@ struct ErrorAcc {
     }
 };
 
-// All threads of the CTA must call it.  err[0] += offenders of this CTA; the CTA that finds err[0] == 0 also records
-// one offender's (global env index + 1, detail, kind).
-__device__ __forceinline__ void flush_errors(const ErrorAcc& e, uint32_t* __restrict__ err) {
-    if (err == nullptr) return;
-    __shared__ uint32_t s_err[4];
-    if (threadIdx.x < 4) s_err[threadIdx.x] = 0u;
-    __syncthreads();
-    const uint32_t mask = __ballot_sync(0xffffffffu, e.count != 0u);
-    if (mask != 0u) {
-        uint32_t c = e.count;
+// Device-resident step clock (optional, for CUDA-graph capture where the host cannot bump `t` between replays):
+// clock[0] = steps already taken, clock[1] = CTA ticket.  Every CTA reads clock[0] when it starts and then takes a
+// ticket; the CTA holding the last ticket knows every CTA has read the clock and advances it (in the epilogue).  The
+// ticket atomic is issued early so its round trip overlaps the CTA's loads; no fence is needed because a completed load
+// cannot be affected by the later write.
+__device__ __forceinline__ uint64_t clock_read(const unsigned long long* clock) {
+    return clock ? *reinterpret_cast<const volatile unsigned long long*>(clock) : 0ull;
+}
+__device__ __forceinline__ unsigned long long clock_ticket(unsigned long long* clock) {
+    return (clock != nullptr && threadIdx.x == 0) ? atomicAdd(&clock[1], 1ull) : 0ull;
+}
+
+constexpr int kWarpsPerCta = kThreads / 32;
+
+// CTA epilogue: fold the per-thread statistics / error accumulators into global memory with ONE barrier and at most
+// a handful of global reductions per CTA, then advance the device clock if this CTA holds the last ticket.
+// All threads of the CTA must call it.  `stats`, `err`, `clock` may each be null.
+__device__ __forceinline__ void cta_epilogue(const EpisodeAcc& acc, const ErrorAcc& errs, double* __restrict__ stats,
+                                             uint32_t* __restrict__ err, unsigned long long* clock,
+                                             unsigned long long ticket, unsigned long long clock_inc) {
+    __shared__ uint32_t s_u[kWarpsPerCta][3];            // steps, episodes, rejected
+    __shared__ unsigned long long s_len[kWarpsPerCta];
+    __shared__ double s_d[kWarpsPerCta][2];              // return, return^2
+    __shared__ uint32_t s_e[kWarpsPerCta][3];            // one offender per warp: g + 1, detail, kind
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t steps = __reduce_add_sync(0xffffffffu, acc.steps);
+    const uint32_t eps = __reduce_add_sync(0xffffffffu, acc.episodes);
+    const uint32_t rejected = __reduce_add_sync(0xffffffffu, errs.count);
+    unsigned long long len = 0ull;
+    double r = 0.0, r2 = 0.0;
+    if (eps) {  // warp-uniform: floating sums only where some lane finished an episode
+        len = acc.length;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-        if ((threadIdx.x & 31u) == 0u) atomicAdd(&s_err[0], c);
-        if ((threadIdx.x & 31u) == static_cast<uint32_t>(__ffs(mask) - 1)) {  // lowest offending lane of the warp
-            s_err[1] = e.g + 1u;
-            s_err[2] = e.detail;
-            s_err[3] = e.kind;
+        for (int o = 16; o > 0; o >>= 1) len += __shfl_down_sync(0xffffffffu, len, o);
+        r = warp_sum(acc.ret);
+        r2 = warp_sum(acc.ret_sq);
+    }
+    if (rejected) {
+        const uint32_t mask = __ballot_sync(0xffffffffu, errs.count != 0u);
+        if (lane == static_cast<uint32_t>(__ffs(mask) - 1)) {
+            s_e[warp][0] = errs.g + 1u;
+            s_e[warp][1] = errs.detail;
+            s_e[warp][2] = errs.kind;
         }
     }
+    if (lane == 0u) {
+        s_u[warp][0] = steps;
+        s_u[warp][1] = eps;
+        s_u[warp][2] = rejected;
+        s_len[warp] = len;
+        s_d[warp][0] = r;
+        s_d[warp][1] = r2;
+    }
     __syncthreads();
-    if (threadIdx.x == 0 && s_err[0] != 0u) {
-        if (atomicAdd(&err[0], s_err[0]) == 0u) {
-            err[1] = s_err[1];
-            err[2] = s_err[2];
-            err[3] = s_err[3];
+    if (threadIdx.x == 0) {
+        unsigned long long t_steps = 0ull, t_eps = 0ull, t_len = 0ull;
+        uint32_t t_rej = 0u, first = kWarpsPerCta;
+        double t_r = 0.0, t_r2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) {
+            t_steps += s_u[w][0];
+            t_eps += s_u[w][1];
+            if (s_u[w][2] != 0u && first == kWarpsPerCta) first = w;
+            t_rej += s_u[w][2];
+            t_len += s_len[w];
+            t_r += s_d[w][0];
+            t_r2 += s_d[w][1];
+        }
+        if (stats != nullptr) {
+            if (t_eps) {
+                atomicAdd(&stats[0], static_cast<double>(t_eps));
+                atomicAdd(&stats[1], static_cast<double>(t_len));
+                atomicAdd(&stats[2], t_r);
+                atomicAdd(&stats[3], t_r2);
+            }
+            if (t_steps) atomicAdd(&stats[4], static_cast<double>(t_steps));
+        }
+        if (err != nullptr && t_rej != 0u) {
+            if (atomicAdd(&err[0], t_rej) == 0u) {
+                err[1] = s_e[first][0];
+                err[2] = s_e[first][1];
+                err[3] = s_e[first][2];
+            }
+        }
+        if (clock != nullptr && ticket == static_cast<unsigned long long>(gridDim.x) - 1ull) {
+            clock[1] = 0ull;
+            clock[0] += clock_inc;
         }
     }
 }

@@ -8,8 +8,9 @@
 //   r (uint32 draw) -> outcome index by integer thresholds -> one 8-byte shared-memory load -> state update.
 //
 // Memory behaviour (the step kernel is HBM-bound): per env 16 B read (action, pos, ep_len, ep_ret) and 26 B
-// written (pos, ep_len, ep_ret, obs[2], reward, terminated, truncated) = 42 B; all traffic is 128-bit vector
-// loads/stores, four envs per thread, grid-stride over a grid sized to the SM count.
+// written (pos, ep_len, ep_ret, obs[2], reward, terminated, truncated) = 42 B.  A thread owns four consecutive envs:
+// every access is a 128-bit vector load/store (flags: one 32-bit store), and one Philox4x32 call yields the four
+// outcome draws.  Grid-stride over a grid sized to the SM count; the table (8 KB for 8x8) is staged once per CTA.
 #include "ef_common.cuh"
 
 namespace ef {
@@ -18,6 +19,7 @@ struct GridArgs {
     const uint2* table;  // ef_grid_outcome as raw 8-byte words: x = next | flags << 16, y = reward bits
     int32_t table_len;   // entries
     int32_t cols;
+    uint32_t cols_magic; // ceil(2^32 / cols): row = umulhi(cell, magic), exact for cell < 65536 (cols > 1)
     uint32_t thr0, thr1, thr2;
     int32_t idx_cap;
     int32_t start_cell;
@@ -47,7 +49,13 @@ template <bool SMEM>
 __device__ __forceinline__ const uint2* stage_table(const GridArgs& a) {
     extern __shared__ __align__(16) uint2 s_table[];
     if constexpr (SMEM) {
-        for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) s_table[i] = __ldg(a.table + i);
+        if (aligned(a.table, 16)) {  // table_len is a multiple of 4 entries: copy two 8-byte entries per access
+            const uint4* src = reinterpret_cast<const uint4*>(a.table);
+            uint4* dst = reinterpret_cast<uint4*>(s_table);
+            for (int i = threadIdx.x; i < (a.table_len >> 1); i += blockDim.x) dst[i] = __ldg(src + i);
+        } else {
+            for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) s_table[i] = __ldg(a.table + i);
+        }
         __syncthreads();
         return s_table;
     } else {
@@ -55,17 +63,12 @@ __device__ __forceinline__ const uint2* stage_table(const GridArgs& a) {
     }
 }
 
-template <int SLOTS>
-__device__ __forceinline__ uint32_t outcome_index(const GridArgs& a, uint32_t r) {
-    if constexpr (SLOTS == 1) {
-        return 0u;
-    } else {
-        const uint32_t idx = (r >= a.thr0) + (r >= a.thr1) + (r >= a.thr2);
-        return min(idx, static_cast<uint32_t>(a.idx_cap));
-    }
+__device__ __forceinline__ int2 cell_to_obs(const GridArgs& a, int32_t cell) {
+    const int32_t row = a.cols == 1 ? cell : static_cast<int32_t>(__umulhi(static_cast<uint32_t>(cell), a.cols_magic));
+    return make_int2(row, cell - row * a.cols);
 }
 
-// One transition of one env.  Returns flags: bit0 terminated, bit1 truncated, bit2 error (state untouched).
+// One transition of one env.  Returns bit0 terminated, bit1 truncated, bit2 rejected (state untouched).
 template <bool SMEM, int SLOTS>
 __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* __restrict__ tab, uint32_t g,
                                                int32_t& pos, int32_t& len, float& ret, int32_t act, uint32_t r,
@@ -76,7 +79,11 @@ __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* _
         return 4u;
     }
     const uint32_t row = static_cast<uint32_t>(pos) * 4u + static_cast<uint32_t>(act);
-    const uint32_t slot = row * SLOTS + outcome_index<SLOTS>(a, r);
+    uint32_t slot = row;
+    if constexpr (SLOTS == 4) {
+        const uint32_t idx = (r >= a.thr0) + (r >= a.thr1) + (r >= a.thr2);
+        slot = row * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
+    }
     const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
     const uint32_t oflags = o.x >> 16;
     if (oflags & (EF_GRID_NO_OUTCOMES | EF_GRID_BAD_PROBS)) {
@@ -92,173 +99,397 @@ __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* _
     return (oflags & EF_GRID_DONE) | trunc;
 }
 
-// ---- step -------------------------------------------------------------------------------------------------------------
-template <bool SMEM, int SLOTS, int VEC>
-__global__ void __launch_bounds__(kThreads) gridworld_step_kernel(const GridArgs a) {
-    const uint2* __restrict__ tab = stage_table<SMEM>(a);
-    EpisodeAcc acc;
-    ErrorAcc errs;
-    const int64_t groups = (a.n + VEC - 1) / VEC;
-    const bool need_philox = (a.action == nullptr) || (SLOTS == 4 && a.draw == nullptr);
-    const uint64_t t = a.t + clock_read(a.clock);
-    for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < groups;
-         v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t base = v * VEC;
-        int32_t pos[VEC], len[VEC], act[VEC];
-        float ret[VEC];
-        uint32_t r[VEC];
-        const bool full = (VEC == 4) && (base + VEC <= a.n);
-        if (full) {  // 128-bit loads
-            const int4 p4 = *reinterpret_cast<const int4*>(a.pos + base);
-            const int4 l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
-            const float4 r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
-            pos[0] = p4.x; pos[1] = p4.y; pos[2] = p4.z; pos[3] = p4.w;
-            len[0] = l4.x; len[1] = l4.y; len[2] = l4.z; len[3] = l4.w;
-            ret[0] = r4.x; ret[1] = r4.y; ret[2] = r4.z; ret[3] = r4.w;
-            if (a.action) {
-                const int4 a4 = __ldg(reinterpret_cast<const int4*>(a.action + base));
-                act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
-            }
-            if (SLOTS == 4 && a.draw) {
-                const uint4 d4 = __ldg(reinterpret_cast<const uint4*>(a.draw + base));
-                r[0] = d4.x; r[1] = d4.y; r[2] = d4.z; r[3] = d4.w;
-            }
-        } else {
+// Branch-free transition of the four envs a thread owns (hot path of both kernels).  Rejected env-steps (bad action,
+// row without outcomes, row failing numpy's probability check) are handled as data: the state update is masked out and
+// the bit lands in `bad`; the caller records them in a rare branch.  Byte j of `term` / `trunc` is env j's flag.
+struct Quad {
+    int32_t pos[4], len[4];
+    float ret[4], rew[4];
+    uint32_t term, trunc, bad, rows[4];
+};
+
+template <bool SMEM, int SLOTS>
+__device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __restrict__ tab, Quad& q,
+                                            const int32_t (&act)[4], const uint32_t (&r)[4]) {
+    q.term = q.trunc = q.bad = 0u;
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const bool ok = base + j < a.n;
-                pos[j] = ok ? a.pos[base + j] : 0;
-                len[j] = ok ? a.ep_len[base + j] : 0;
-                ret[j] = ok ? a.ep_ret[base + j] : 0.0f;
-                act[j] = (ok && a.action) ? __ldg(a.action + base + j) : 0;
-                r[j] = (ok && SLOTS == 4 && a.draw) ? __ldg(a.draw + base + j) : 0u;
-            }
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t ua = static_cast<uint32_t>(act[j]);
+        const uint32_t row = static_cast<uint32_t>(q.pos[j]) * 4u + (ua & 3u);
+        uint32_t slot = row;
+        if constexpr (SLOTS == 4) {
+            const uint32_t idx = (r[j] >= a.thr0) + (r[j] >= a.thr1) + (r[j] >= a.thr2);
+            slot = row * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
         }
-        int32_t obs[2 * VEC], fobs[2 * VEC];
-        float rew[VEC];
-        uint8_t term[VEC], trunc[VEC];
+        const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
+        const bool bad = (ua > 3u) | ((o.x & ((EF_GRID_NO_OUTCOMES | EF_GRID_BAD_PROBS) << 16)) != 0u);
+        q.rows[j] = ua > 3u ? ua : row;
+        q.rew[j] = bad ? 0.0f : __uint_as_float(o.y);
+        q.pos[j] = bad ? q.pos[j] : static_cast<int32_t>(o.x & 0xffffu);
+        q.ret[j] += q.rew[j];
+        q.len[j] += bad ? 0 : 1;
+        const bool dn = !bad & ((o.x & (EF_GRID_DONE << 16)) != 0u);
+        const bool tr = !bad & (a.limit > 0) & (q.len[j] >= a.limit);
+        q.term |= static_cast<uint32_t>(dn) << (8 * j);
+        q.trunc |= static_cast<uint32_t>(tr) << (8 * j);
+        q.bad |= static_cast<uint32_t>(bad) << j;
+    }
+}
+
+// Rare path: classify and record the rejected env-steps of a quad (arguments by value: keeps the quad in registers).
+template <bool SMEM, int SLOTS>
+__device__ __noinline__ uint4 record_bad4(const uint2* __restrict__ tab, uint32_t bad, uint32_t g0, uint4 rows, int4 act) {
+    uint32_t e_count = 0u, e_g = 0u, e_detail = 0u, e_kind = 0u;
+    const uint32_t rw[4] = {rows.x, rows.y, rows.z, rows.w};
+    const int32_t ac[4] = {act.x, act.y, act.z, act.w};
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            const uint32_t g = static_cast<uint32_t>(a.env_offset + base + j);
-            if (need_philox) {
-                const uint4 w = draw_block(a.seed, g, t >> 1, kStreamStep);
-                const uint32_t wt = (t & 1) ? w.z : w.x, wp = (t & 1) ? w.w : w.y;
-                if (a.action == nullptr) act[j] = static_cast<int32_t>(wp >> 30);
-                if (SLOTS == 4 && a.draw == nullptr) r[j] = wt;
-            }
-            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos[j], len[j], ret[j], act[j], r[j], rew[j], errs);
-            term[j] = f & 1u;
-            trunc[j] = (f >> 1) & 1u;
-            fobs[2 * j] = pos[j] / a.cols;
-            fobs[2 * j + 1] = pos[j] - fobs[2 * j] * a.cols;
-            const bool valid = base + j < a.n;
-            if (valid && !(f & 4u)) acc.steps += 1u;
-            if (a.autoreset && (f & 3u) && valid) {
-                acc.finish(len[j], ret[j]);
-                pos[j] = a.start_cell;
-                len[j] = 0;
-                ret[j] = 0.0f;
-                obs[2 * j] = a.start_cell / a.cols;
-                obs[2 * j + 1] = a.start_cell - obs[2 * j] * a.cols;
-            } else {
-                obs[2 * j] = fobs[2 * j];
-                obs[2 * j + 1] = fobs[2 * j + 1];
-            }
-        }
-        if (full) {  // 128-bit stores
-            *reinterpret_cast<int4*>(a.pos + base) = make_int4(pos[0], pos[1], pos[2], pos[3]);
-            *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(len[0], len[1], len[2], len[3]);
-            *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(ret[0], ret[1], ret[2], ret[3]);
-            if (a.obs) {
-                *reinterpret_cast<int4*>(a.obs + 2 * base) = make_int4(obs[0], obs[1], obs[2], obs[3]);
-                *reinterpret_cast<int4*>(a.obs + 2 * base + 4) = make_int4(obs[4], obs[5], obs[6], obs[7]);
-            }
-            if (a.final_obs) {
-                *reinterpret_cast<int4*>(a.final_obs + 2 * base) = make_int4(fobs[0], fobs[1], fobs[2], fobs[3]);
-                *reinterpret_cast<int4*>(a.final_obs + 2 * base + 4) = make_int4(fobs[4], fobs[5], fobs[6], fobs[7]);
-            }
-            if (a.reward) *reinterpret_cast<float4*>(a.reward + base) = make_float4(rew[0], rew[1], rew[2], rew[3]);
-            if (a.terminated) *reinterpret_cast<uchar4*>(a.terminated + base) = make_uchar4(term[0], term[1], term[2], term[3]);
-            if (a.truncated) *reinterpret_cast<uchar4*>(a.truncated + base) = make_uchar4(trunc[0], trunc[1], trunc[2], trunc[3]);
+    for (int j = 0; j < 4; ++j) {
+        if (!((bad >> j) & 1u)) continue;
+        ++e_count;
+        e_g = g0 + j;
+        if (static_cast<uint32_t>(ac[j]) > 3u) {
+            e_detail = static_cast<uint32_t>(ac[j]);
+            e_kind = EF_STEP_BAD_ACTION;
         } else {
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                if (base + j >= a.n) break;
-                const int64_t i = base + j;
-                a.pos[i] = pos[j];
-                a.ep_len[i] = len[j];
-                a.ep_ret[i] = ret[j];
-                if (a.obs) { a.obs[2 * i] = obs[2 * j]; a.obs[2 * i + 1] = obs[2 * j + 1]; }
-                if (a.final_obs) { a.final_obs[2 * i] = fobs[2 * j]; a.final_obs[2 * i + 1] = fobs[2 * j + 1]; }
-                if (a.reward) a.reward[i] = rew[j];
-                if (a.terminated) a.terminated[i] = term[j];
-                if (a.truncated) a.truncated[i] = trunc[j];
-            }
+            const uint2 o = SMEM ? tab[rw[j] * SLOTS] : __ldg(tab + rw[j] * SLOTS);
+            e_detail = rw[j];
+            e_kind = ((o.x >> 16) & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS;
         }
     }
-    flush_stats(acc, a.stats);
-    flush_errors(errs, a.err);
-    clock_advance(a.clock, 1ull);
+    return make_uint4(e_count, e_g, e_detail, e_kind);
+}
+
+// Auto-reset + statistics of the finished envs of a quad (fin = byte-wise finished bits).
+__device__ __forceinline__ void finish4(const GridArgs& a, Quad& q, uint32_t fin, EpisodeAcc& acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if ((fin >> (8 * j)) & 1u) {
+            acc.finish(q.len[j], q.ret[j]);
+            q.pos[j] = a.start_cell;
+            q.len[j] = 0;
+            q.ret[j] = 0.0f;
+        }
+    }
+}
+
+// Inputs of one quad (four consecutive envs), loaded with 128-bit accesses.
+struct QuadIn {
+    int4 p4, l4, a4;
+    float4 r4;
+};
+
+__device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, bool philox_act) {
+    QuadIn in;
+    in.p4 = *reinterpret_cast<const int4*>(a.pos + base);
+    in.l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
+    in.r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
+    in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
+    return in;
+}
+
+// One step of a full quad: draws, branch-free transitions, auto-reset, 128-bit stores.
+template <bool SMEM, int SLOTS>
+__device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
+                                          uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
+                                          ErrorAcc& errs) {
+    Quad q;
+    int32_t act[4] = {in.a4.x, in.a4.y, in.a4.z, in.a4.w};
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
+    q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
+    q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
+    if (philox_act) {
+        uint32_t w[4];
+        group_words4(a.seed, g0, t, kStreamPolicy, w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(w[j] >> 30);
+    }
+#if EF_EXPERIMENT & 1  // timing experiments only: no Philox
+    r[0] = g0 * 2654435761u; r[1] = r[0] + 0x9E3779B9u; r[2] = r[1] + 0x9E3779B9u; r[3] = r[2] + 0x9E3779B9u;
+#else
+    if constexpr (SLOTS == 4) group_words4(a.seed, g0, t, kStreamTransition, r);
+#endif
+#if EF_EXPERIMENT & 2  // timing experiments only: no table walk
+    q.term = q.trunc = q.bad = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { q.pos[j] = (q.pos[j] + act[j]) & 63; q.len[j] += 1; q.rew[j] = __uint_as_float(r[j] >> 9); q.ret[j] += q.rew[j]; q.rows[j] = 0; }
+#else
+    transition4<SMEM, SLOTS>(a, tab, q, act, r);
+#endif
+    if (q.bad) {
+        const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_uint4(q.rows[0], q.rows[1], q.rows[2], q.rows[3]),
+                                                 make_int4(act[0], act[1], act[2], act[3]));
+        errs.count += e.x;
+        errs.g = e.y;
+        errs.detail = e.z;
+        errs.kind = e.w;
+    }
+    acc.steps += 4u - __popc(q.bad);
+    if (a.final_obs) {  // pre-reset observation, only materialised on request
+        int4* o = reinterpret_cast<int4*>(a.final_obs + 2 * base);
+        const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
+        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
+        const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
+        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
+    }
+    const uint32_t fin = a.autoreset ? (q.term | q.trunc) : 0u;
+    if (fin) finish4(a, q, fin, acc);
+    *reinterpret_cast<int4*>(a.pos + base) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
+    *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
+    *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
+    if (a.obs) {  // observation after auto-reset = (row, col) of the stored position
+        int4* o = reinterpret_cast<int4*>(a.obs + 2 * base);
+        const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
+        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
+        const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
+        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
+    }
+    if (a.reward) *reinterpret_cast<float4*>(a.reward + base) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
+    if (a.terminated) *reinterpret_cast<uint32_t*>(a.terminated + base) = q.term;
+    if (a.truncated) *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
+}
+
+#ifndef EF_STEP_MINBLOCKS
+#define EF_STEP_MINBLOCKS 2  // resident CTAs per SM the step kernel is compiled for (register cap 65536 / (256 * this))
+#endif
+#ifndef EF_EXPERIMENT
+#define EF_EXPERIMENT 0
+#endif
+#ifndef EF_STEP_Q
+#define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
+#endif
+
+// ---- step -------------------------------------------------------------------------------------------------------------
+// Vector kernel (all pointers 16-byte aligned, Philox or no outcome draws).  The batch is cut into one contiguous chunk of
+// quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
+// (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
+// load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
+template <bool SMEM, int SLOTS>
+__global__ void __launch_bounds__(kThreads, EF_STEP_MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
+#if EF_EXPERIMENT & 4
+    const uint2* __restrict__ tab = a.table;
+#else
+    const uint2* __restrict__ tab = stage_table<SMEM>(a);  // prologue: independent of the previous launch
+#endif
+    pdl_launch_dependents();
+    pdl_wait();                                            // previous launch complete, its writes visible
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint64_t t = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
+    const bool philox_act = a.action == nullptr;
+    const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
+    const int64_t per_cta = (quads + gridDim.x - 1) / gridDim.x;
+    const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
+    const int64_t q_end = min(q_begin + per_cta, quads);
+    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(EF_STEP_Q) * kThreads) {
+        QuadIn in[EF_STEP_Q];
+#pragma unroll
+        for (int j = 0; j < EF_STEP_Q; ++j) {
+            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+            if (v < q_end) in[j] = load_quad(a, v * 4, philox_act);
+        }
+#pragma unroll
+        for (int j = 0; j < EF_STEP_Q; ++j) {
+            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+            if (v < q_end)
+                step_quad<SMEM, SLOTS>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in[j], philox_act,
+                                       acc, errs);
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < (a.n & 3)) {  // ragged tail: at most three envs
+        const int64_t i = (quads << 2) + threadIdx.x;
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        int32_t pos = a.pos[i], len = a.ep_len[i];
+        float ret = a.ep_ret[i], rew;
+        const int32_t act = philox_act ? static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30)
+                                       : __ldg(a.action + i);
+        uint32_t r = 0u;
+        if constexpr (SLOTS == 4) r = group_word1(a.seed, g, t, kStreamTransition);
+        const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, r, rew, errs);
+        if (!(f & 4u)) acc.steps += 1u;
+        if (a.final_obs) {
+            const int2 fo = cell_to_obs(a, pos);
+            a.final_obs[2 * i] = fo.x;
+            a.final_obs[2 * i + 1] = fo.y;
+        }
+        if (a.autoreset && (f & 3u)) {
+            acc.finish(len, ret);
+            pos = a.start_cell;
+            len = 0;
+            ret = 0.0f;
+        }
+        a.pos[i] = pos;
+        a.ep_len[i] = len;
+        a.ep_ret[i] = ret;
+        if (a.obs) {
+            const int2 ob = cell_to_obs(a, pos);
+            a.obs[2 * i] = ob.x;
+            a.obs[2 * i + 1] = ob.y;
+        }
+        if (a.reward) a.reward[i] = rew;
+        if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
+        if (a.truncated) a.truncated[i] = static_cast<uint8_t>((f >> 1) & 1u);
+    }
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
+}
+
+// Scalar kernel: one env per thread, any alignment, optional injected outcome draws (parity tests, unaligned views).
+template <bool SMEM, int SLOTS>
+__global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const GridArgs a) {
+    const uint2* __restrict__ tab = stage_table<SMEM>(a);
+    pdl_launch_dependents();
+    pdl_wait();
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint64_t t = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
+    const bool philox_act = a.action == nullptr;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        int32_t pos = a.pos[i], len = a.ep_len[i];
+        float ret = a.ep_ret[i], rew;
+        const int32_t act = philox_act ? static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30)
+                                       : __ldg(a.action + i);
+        uint32_t r = 0u;
+        if constexpr (SLOTS == 4) r = a.draw ? __ldg(a.draw + i) : group_word1(a.seed, g, t, kStreamTransition);
+        const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, r, rew, errs);
+        if (!(f & 4u)) acc.steps += 1u;
+        if (a.final_obs) {
+            const int2 fo = cell_to_obs(a, pos);
+            a.final_obs[2 * i] = fo.x;
+            a.final_obs[2 * i + 1] = fo.y;
+        }
+        if (a.autoreset && (f & 3u)) {
+            acc.finish(len, ret);
+            pos = a.start_cell;
+            len = 0;
+            ret = 0.0f;
+        }
+        a.pos[i] = pos;
+        a.ep_len[i] = len;
+        a.ep_ret[i] = ret;
+        if (a.obs) {
+            const int2 ob = cell_to_obs(a, pos);
+            a.obs[2 * i] = ob.x;
+            a.obs[2 * i + 1] = ob.y;
+        }
+        if (a.reward) a.reward[i] = rew;
+        if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
+        if (a.truncated) a.truncated[i] = static_cast<uint8_t>((f >> 1) & 1u);
+    }
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
 }
 
 // ---- fused K-step rollout -------------------------------------------------------------------------------------------
-// One env per thread, state in registers for all K steps.  A warp votes (ballot) on "any lane finished an episode";
-// the reset / statistics path runs only in warps where the vote is non-zero.
+// A thread keeps FOUR consecutive envs in registers for all K steps (one Philox call per step yields their four outcome
+// draws, one more their four random actions; the four table walks are independent, which gives the scheduler ILP).
+// A warp votes (ballot) on "any of my lanes finished an episode this step"; the reset / statistics path is skipped by
+// warps where nobody did.  State is read and written once per launch (24 B / K per env-step).
 template <bool SMEM, int SLOTS, bool EXT_ACTIONS, bool EMIT>
 __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridArgs a) {
     const uint2* __restrict__ tab = stage_table<SMEM>(a);
+    pdl_launch_dependents();
+    pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t n_round = (a.n + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
+    const int64_t groups = (a.n + 3) / 4;
+    const int64_t groups_round = (groups + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
     const uint64_t t0 = a.t + clock_read(a.clock);
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < a.n;
-        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-        int32_t pos = valid ? a.pos[i] : a.start_cell;
-        int32_t len = valid ? a.ep_len[i] : 0;
-        float ret = valid ? a.ep_ret[i] : 0.0f;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        constexpr bool kNeedWords = !EXT_ACTIONS || SLOTS == 4;
+    const unsigned long long ticket = clock_ticket(a.clock);
+    const bool vec_ok = aligned(a.pos, 16) && aligned(a.ep_len, 16) && aligned(a.ep_ret, 16);
+    for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < groups_round; v += stride) {
+        const int64_t base = v * 4;
+        const uint32_t g0 = static_cast<uint32_t>(a.env_offset + base);
+        Quad q;
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) valid[j] = base + j < a.n;
+        const bool full = valid[3] && vec_ok;
+        if (full) {
+            const int4 p4 = *reinterpret_cast<const int4*>(a.pos + base);
+            const int4 l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
+            const float4 r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
+            q.pos[0] = p4.x; q.pos[1] = p4.y; q.pos[2] = p4.z; q.pos[3] = p4.w;
+            q.len[0] = l4.x; q.len[1] = l4.y; q.len[2] = l4.z; q.len[3] = l4.w;
+            q.ret[0] = r4.x; q.ret[1] = r4.y; q.ret[2] = r4.z; q.ret[3] = r4.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                q.pos[j] = valid[j] ? a.pos[base + j] : a.start_cell;
+                q.len[j] = valid[j] ? a.ep_len[base + j] : 0;
+                q.ret[j] = valid[j] ? a.ep_ret[base + j] : 0.0f;
+            }
+        }
+        // lanes past the end of the batch (only in the last, ragged quad) carry dummy envs: masks keep them out of
+        // statistics, errors and stores
+        const uint32_t valid_bytes = (valid[0] ? 0x1u : 0u) | (valid[1] ? 0x100u : 0u) | (valid[2] ? 0x10000u : 0u) |
+                                     (valid[3] ? 0x1000000u : 0u);
+        const uint32_t valid_bits = (valid[0] ? 1u : 0u) | (valid[1] ? 2u : 0u) | (valid[2] ? 4u : 0u) | (valid[3] ? 8u : 0u);
+        const bool act_vec = EXT_ACTIONS && valid[3] && ((a.n & 3) == 0) && aligned(a.action, 16);
         for (int k = 0; k < a.K; ++k) {
             const uint64_t t = t0 + static_cast<uint64_t>(k);
-            uint32_t wt = 0, wp = 0;
-            if constexpr (kNeedWords) {
-                if (k == 0 || !(t & 1)) w = draw_block(a.seed, g, t >> 1, kStreamStep);
-                wt = (t & 1) ? w.z : w.x;
-                wp = (t & 1) ? w.w : w.y;
+            const int64_t o = static_cast<int64_t>(k) * a.n + base;
+            uint32_t wt[4] = {0u, 0u, 0u, 0u};
+            int32_t act[4];
+            if constexpr (SLOTS == 4) group_words4(a.seed, g0, t, kStreamTransition, wt);
+            if constexpr (EXT_ACTIONS) {
+                if (act_vec) {
+                    const int4 a4 = __ldg(reinterpret_cast<const int4*>(a.action + o));
+                    act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) act[j] = valid[j] ? __ldg(a.action + o + j) : 0;
+                }
+            } else {
+                uint32_t wp[4];
+                group_words4(a.seed, g0, t, kStreamPolicy, wp);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(wp[j] >> 30);
             }
-            int32_t act;
-            if constexpr (EXT_ACTIONS) act = valid ? __ldg(a.action + static_cast<int64_t>(k) * a.n + i) : 0;
-            else act = static_cast<int32_t>(wp >> 30);
-            float rew;
-            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, wt, rew, errs);
+            transition4<SMEM, SLOTS>(a, tab, q, act, wt);
+            q.bad &= valid_bits;
+            if (q.bad) {
+                    const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_uint4(q.rows[0], q.rows[1], q.rows[2], q.rows[3]),
+                                                             make_int4(act[0], act[1], act[2], act[3]));
+                    errs.count += e.x;
+                    errs.g = e.y;
+                    errs.detail = e.z;
+                    errs.kind = e.w;
+                }
+            acc.steps += __popc(valid_bits) - __popc(q.bad);
             if constexpr (EMIT) {
-                if (valid) {
-                    if (a.reward) a.reward[static_cast<int64_t>(k) * a.n + i] = rew;
-                    if (a.flags) a.flags[static_cast<int64_t>(k) * a.n + i] = static_cast<uint8_t>(f & 3u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (valid[j]) {
+                        if (a.reward) a.reward[o + j] = q.rew[j];
+                        if (a.flags) a.flags[o + j] = static_cast<uint8_t>(((q.term >> (8 * j)) & 1u) | (((q.trunc >> (8 * j)) & 1u) << 1));
+                    }
                 }
             }
-            if (valid && !(f & 4u)) acc.steps += 1u;
-            const bool fin = valid && (f & 3u);
-            if (__ballot_sync(0xffffffffu, fin)) {
-                if (fin) {
-                    acc.finish(len, ret);
-                    pos = a.start_cell;
-                    len = 0;
-                    ret = 0.0f;
-                }
+            const uint32_t fin = (q.term | q.trunc) & valid_bytes;
+            if (__ballot_sync(0xffffffffu, fin != 0u)) {  // warp vote: skip the reset path where nobody finished
+                if (fin) finish4(a, q, fin, acc);
             }
         }
-        if (valid) {
-            a.pos[i] = pos;
-            a.ep_len[i] = len;
-            a.ep_ret[i] = ret;
+        if (full) {
+            *reinterpret_cast<int4*>(a.pos + base) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
+            *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
+            *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (valid[j]) {
+                    a.pos[base + j] = q.pos[j];
+                    a.ep_len[base + j] = q.len[j];
+                    a.ep_ret[base + j] = q.ret[j];
+                }
+            }
         }
     }
-    flush_stats(acc, a.stats);
-    flush_errors(errs, a.err);
-    clock_advance(a.clock, static_cast<unsigned long long>(a.K));
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, static_cast<unsigned long long>(a.K));
 }
 
 __global__ void __launch_bounds__(kThreads) gridworld_reset_kernel(int32_t start_cell, int32_t cols, int32_t* pos,
@@ -283,13 +514,14 @@ static int fill_args(const ef_grid_desc* g, GridArgs& a) {
     if (g->rows <= 0 || g->cols <= 0 || (g->n_slots != 1 && g->n_slots != 4)) return EF_ERR_INVALID_ARGUMENT;
     const int64_t cells = static_cast<int64_t>(g->rows) * g->cols;
     if (cells > 65536) return EF_ERR_UNSUPPORTED;
-    if (g->start_cell < 0 || g->start_cell >= (g->table_cells > 0 ? g->table_cells : cells) || g->idx_cap < 0 || g->idx_cap > 3) return EF_ERR_INVALID_ARGUMENT;
-    if (!aligned(g->table, 8)) return EF_ERR_INVALID_ARGUMENT;
-    a.table = reinterpret_cast<const uint2*>(g->table);
     const int64_t tcells = g->table_cells > 0 ? g->table_cells : cells;
     if (tcells < cells || tcells > 65536) return EF_ERR_INVALID_ARGUMENT;
+    if (g->start_cell < 0 || g->start_cell >= tcells || g->idx_cap < 0 || g->idx_cap > 3) return EF_ERR_INVALID_ARGUMENT;
+    if (!aligned(g->table, 8)) return EF_ERR_INVALID_ARGUMENT;
+    a.table = reinterpret_cast<const uint2*>(g->table);
     a.table_len = static_cast<int32_t>(tcells * 4 * g->n_slots);
     a.cols = g->cols;
+    a.cols_magic = g->cols > 1 ? static_cast<uint32_t>(((1ull << 32) + g->cols - 1) / static_cast<uint64_t>(g->cols)) : 0u;
     a.thr0 = g->thr[0];
     a.thr1 = g->thr[1];
     a.thr2 = g->thr[2];
@@ -306,8 +538,7 @@ static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStr
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
         if (e != cudaSuccess) return cuda_status(e);
     }
-    kernel<<<grid, kThreads, bytes, stream>>>(a);
-    return cuda_status(cudaGetLastError());
+    return launch_kernel(kernel, a, grid, bytes, stream);
 }
 
 }  // namespace ef
@@ -329,15 +560,15 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs;
     a.stats = stats; a.err = err; a.n = n; a.autoreset = autoreset;
     a.clock = reinterpret_cast<unsigned long long*>(clock);
-    const bool vec = aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) && aligned(action, 16) &&
-                     aligned(draw, 16) && aligned(obs, 16) && aligned(reward, 16) && aligned(terminated, 4) &&
+    const bool vec = draw == nullptr && aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) &&
+                     aligned(action, 16) && aligned(obs, 16) && aligned(reward, 16) && aligned(terminated, 4) &&
                      aligned(truncated, 4) && aligned(final_obs, 16);
     const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid_v = grid_for((n + 3) / 4, 4), grid_s = grid_for(n, 8);
+    const int grid_v = grid_for((n + 3) / 4, EF_STEP_MINBLOCKS), grid_s = grid_for(n, 8);
 #define EF_DISPATCH(SM, SL)                                                                                   \
-    return vec ? launch(gridworld_step_kernel<SM, SL, 4>, a, SM, grid_v, st)                                   \
-               : launch(gridworld_step_kernel<SM, SL, 1>, a, SM, grid_s, st)
+    return vec ? launch(gridworld_step_kernel<SM, SL>, a, SM, grid_v, st)                                      \
+               : launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st)
     if (smem) {
         if (grid->n_slots == 1) { EF_DISPATCH(true, 1); } else { EF_DISPATCH(true, 4); }
     } else {
@@ -362,7 +593,7 @@ extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int3
     const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid_r = grid_for(n, 8);
+    const int grid_r = grid_for((n + 3) / 4, 8);
 #define EF_DISPATCH2(SM, SL)                                                                                  \
     do {                                                                                                      \
         if (ext && emit) return launch(gridworld_rollout_kernel<SM, SL, true, true>, a, SM, grid_r, st);     \

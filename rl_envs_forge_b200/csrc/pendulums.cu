@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
     using Vec = typename Env::Vec;
     EpisodeAcc acc;
     const uint64_t t = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
@@ -145,8 +146,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
         if (a.action) {
             act = __ldg(a.action + i);
         } else {
-            const uint4 w = draw_block(a.seed, g, t >> 1, kStreamStep);
-            act = policy_action((t & 1) ? w.w : w.y);
+            act = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
         }
         float rew, a0, a1;
         const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
@@ -167,8 +167,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
         if (a.truncated) a.truncated[i] = (f >> 1) & 1u;
         if (a.acc) Env::store_acc(a.acc, i, a0, a1);
     }
-    flush_stats(acc, a.stats);
-    clock_advance(a.clock, 1ull);
+    cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, 1ull);
 }
 
 template <class Env, bool EXT_ACTIONS, bool EMIT>
@@ -178,6 +177,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t n_round = (a.n + 31) & ~static_cast<int64_t>(31);
     const uint64_t t0 = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool valid = i < a.n;
         const int64_t ii = valid ? i : 0;
@@ -185,15 +185,13 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
         Vec s = reinterpret_cast<const Vec*>(a.state)[ii];
         int32_t len = a.ep_len[ii];
         float ret = a.ep_ret[ii];
-        uint4 w = make_uint4(0, 0, 0, 0);
         for (int k = 0; k < a.K; ++k) {
             const uint64_t t = t0 + static_cast<uint64_t>(k);
             float act;
             if constexpr (EXT_ACTIONS) {
                 act = __ldg(a.action + static_cast<int64_t>(k) * a.n + ii);
             } else {
-                if (k == 0 || !(t & 1)) w = draw_block(a.seed, g, t >> 1, kStreamStep);
-                act = policy_action((t & 1) ? w.w : w.y);
+                act = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
             }
             float rew, a0, a1;
             const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
@@ -220,8 +218,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
             a.ep_ret[i] = ret;
         }
     }
-    flush_stats(acc, a.stats);
-    clock_advance(a.clock, static_cast<unsigned long long>(a.K));
+    cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, static_cast<unsigned long long>(a.K));
 }
 
 template <class Env>

@@ -19,18 +19,20 @@ def test_known_answers():
 
 def test_vectorised_matches_scalar():
     g = np.arange(1000, dtype=np.uint64)
-    w = philox.draw_block(0x123456789ABCDEF, g, 77, philox.STREAM_STEP)
+    w = philox.draw_block(0x123456789ABCDEF, g, 77, philox.STREAM_BANDIT)
     for i in (0, 1, 500, 999):
-        s = philox.draw_block(0x123456789ABCDEF, i, 77, philox.STREAM_STEP)
+        s = philox.draw_block(0x123456789ABCDEF, i, 77, philox.STREAM_BANDIT)
         assert all(int(w[k][i]) == int(s[k]) for k in range(4))
 
 
-def test_step_words_pairing():
-    g = np.arange(16)
+def test_step_words_grouping():
+    g = np.arange(3, 35)
     for t in (0, 1, 2, 3, 2 ** 33 + 5):
-        a, b = philox.step_words(9, g, np.full(16, t, np.uint64))
-        w = philox.draw_block(9, g, t >> 1, philox.STREAM_STEP)
-        assert (a == w[2 * (t & 1)]).all() and (b == w[2 * (t & 1) + 1]).all()
+        a, b = philox.step_words(9, g, np.full(len(g), t, np.uint64))
+        for i, gi in enumerate(g):
+            wt = philox.draw_block(9, int(gi) >> 2, t, philox.STREAM_TRANSITION)
+            wp = philox.draw_block(9, int(gi) >> 2, t, philox.STREAM_POLICY)
+            assert int(a[i]) == int(wt[int(gi) & 3]) and int(b[i]) == int(wp[int(gi) & 3])
 
 
 def test_u23_open_interval_and_fp32_exact():
