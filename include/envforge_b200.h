@@ -74,6 +74,8 @@ int ef_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
  *     outcome_index = min((r >= thr[0]) + (r >= thr[1]) + (r >= thr[2]), idx_cap)        (n_slots == 4)
  * which equals numpy's searchsorted(cumsum(p)/cumsum(p)[-1], r * 2^-32, 'right') used by Generator.choice
  * (grid_world.py:514-515); thr[k] = ceil(cdf_k * 2^32) clipped to 2^32-1, idx_cap = #thresholds below 2^32.
+ * Rows the reference cannot execute carry EF_GRID_NO_OUTCOMES / EF_GRID_BAD_PROBS in every slot and MUST be compiled
+ * inert: next = the row's own cell, reward = 0, EF_GRID_DONE clear (the kernels apply them and mask the step counter).
  * ------------------------------------------------------------------------------------------------------------ */
 #define EF_GRID_DONE 0x1u        /* outcome lands on a terminal state */
 #define EF_GRID_NO_OUTCOMES 0x2u /* row has no MDP entry (reference raises ValueError) */

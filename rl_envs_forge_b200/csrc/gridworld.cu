@@ -99,62 +99,58 @@ __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* _
     return (oflags & EF_GRID_DONE) | trunc;
 }
 
-// Branch-free transition of the four envs a thread owns (hot path of both kernels).  Rejected env-steps (bad action,
-// row without outcomes, row failing numpy's probability check) are handled as data: the state update is masked out and
-// the bit lands in `bad`; the caller records them in a rare branch.  Byte j of `term` / `trunc` is env j's flag.
+// Branch-free transition of the four envs a thread owns (hot path of both kernels).  The host compiles rejected rows
+// (no outcomes / probabilities that fail numpy's check) as inert entries -- next = own cell, reward 0, not done -- so
+// applying one changes nothing but the step counter, which is masked with the row's flag bits.  Bit j of `bad` marks
+// env j as rejected; byte j of `term` / `trunc` is env j's flag.  Actions must already be known to lie in 0..3 (the
+// callers route quads with an out-of-range action through the generic `transition`).
 struct Quad {
     int32_t pos[4], len[4];
     float ret[4], rew[4];
-    uint32_t term, trunc, bad, rows[4];
+    uint32_t term, trunc, bad;
 };
 
 template <bool SMEM, int SLOTS>
 __device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __restrict__ tab, Quad& q,
                                             const int32_t (&act)[4], const uint32_t (&r)[4]) {
     q.term = q.trunc = q.bad = 0u;
+    const int32_t limit = a.limit > 0 ? a.limit : 0x7fffffff;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t ua = static_cast<uint32_t>(act[j]);
-        const uint32_t row = static_cast<uint32_t>(q.pos[j]) * 4u + (ua & 3u);
-        uint32_t slot = row;
+        uint32_t slot = static_cast<uint32_t>(q.pos[j]) * 4u + static_cast<uint32_t>(act[j]);
         if constexpr (SLOTS == 4) {
             const uint32_t idx = (r[j] >= a.thr0) + (r[j] >= a.thr1) + (r[j] >= a.thr2);
-            slot = row * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
+            slot = slot * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
         }
         const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
-        const bool bad = (ua > 3u) | ((o.x & ((EF_GRID_NO_OUTCOMES | EF_GRID_BAD_PROBS) << 16)) != 0u);
-        q.rows[j] = ua > 3u ? ua : row;
-        q.rew[j] = bad ? 0.0f : __uint_as_float(o.y);
-        q.pos[j] = bad ? q.pos[j] : static_cast<int32_t>(o.x & 0xffffu);
+        const uint32_t ok = ((o.x >> 17) & 3u) == 0u ? 1u : 0u;  // 0 for a rejected (inert) row
+        q.rew[j] = __uint_as_float(o.y);
+        q.pos[j] = static_cast<int32_t>(o.x & 0xffffu);
         q.ret[j] += q.rew[j];
-        q.len[j] += bad ? 0 : 1;
-        const bool dn = !bad & ((o.x & (EF_GRID_DONE << 16)) != 0u);
-        const bool tr = !bad & (a.limit > 0) & (q.len[j] >= a.limit);
-        q.term |= static_cast<uint32_t>(dn) << (8 * j);
-        q.trunc |= static_cast<uint32_t>(tr) << (8 * j);
-        q.bad |= static_cast<uint32_t>(bad) << j;
+        q.len[j] += static_cast<int32_t>(ok);
+        const uint32_t tr = (q.len[j] >= limit ? 1u : 0u) & ok;
+        q.term |= ((o.x >> 16) & 1u) << (8 * j);
+        q.trunc |= tr << (8 * j);
+        q.bad |= (ok ^ 1u) << j;
     }
 }
 
-// Rare path: classify and record the rejected env-steps of a quad (arguments by value: keeps the quad in registers).
+// Rare path: classify and record the rejected env-steps of a quad (a rejected env keeps its position, so the row can
+// be rebuilt from the post-step state).  Arguments by value: keeps the quad in registers.
 template <bool SMEM, int SLOTS>
-__device__ __noinline__ uint4 record_bad4(const uint2* __restrict__ tab, uint32_t bad, uint32_t g0, uint4 rows, int4 act) {
+__device__ __noinline__ uint4 record_bad4(const uint2* __restrict__ tab, uint32_t bad, uint32_t g0, int4 pos, int4 act) {
     uint32_t e_count = 0u, e_g = 0u, e_detail = 0u, e_kind = 0u;
-    const uint32_t rw[4] = {rows.x, rows.y, rows.z, rows.w};
+    const int32_t ps[4] = {pos.x, pos.y, pos.z, pos.w};
     const int32_t ac[4] = {act.x, act.y, act.z, act.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (!((bad >> j) & 1u)) continue;
         ++e_count;
         e_g = g0 + j;
-        if (static_cast<uint32_t>(ac[j]) > 3u) {
-            e_detail = static_cast<uint32_t>(ac[j]);
-            e_kind = EF_STEP_BAD_ACTION;
-        } else {
-            const uint2 o = SMEM ? tab[rw[j] * SLOTS] : __ldg(tab + rw[j] * SLOTS);
-            e_detail = rw[j];
-            e_kind = ((o.x >> 16) & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS;
-        }
+        const uint32_t row = static_cast<uint32_t>(ps[j]) * 4u + static_cast<uint32_t>(ac[j]);
+        const uint2 o = SMEM ? tab[row * SLOTS] : __ldg(tab + row * SLOTS);
+        e_detail = row;
+        e_kind = ((o.x >> 16) & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS;
     }
     return make_uint4(e_count, e_g, e_detail, e_kind);
 }
@@ -180,10 +176,17 @@ struct QuadIn {
 
 __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, bool philox_act) {
     QuadIn in;
+#if EF_STREAMING
+    in.p4 = __ldcs(reinterpret_cast<const int4*>(a.pos + base));
+    in.l4 = __ldcs(reinterpret_cast<const int4*>(a.ep_len + base));
+    in.r4 = __ldcs(reinterpret_cast<const float4*>(a.ep_ret + base));
+    in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.action + base));
+#else
     in.p4 = *reinterpret_cast<const int4*>(a.pos + base);
     in.l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
     in.r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
     in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
+#endif
     return in;
 }
 
@@ -212,19 +215,35 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #if EF_EXPERIMENT & 2  // timing experiments only: no table walk
     q.term = q.trunc = q.bad = 0u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { q.pos[j] = (q.pos[j] + act[j]) & 63; q.len[j] += 1; q.rew[j] = __uint_as_float(r[j] >> 9); q.ret[j] += q.rew[j]; q.rows[j] = 0; }
+    for (int j = 0; j < 4; ++j) { q.pos[j] = (q.pos[j] + act[j]) & 63; q.len[j] += 1; q.rew[j] = __uint_as_float(r[j] >> 9); q.ret[j] += q.rew[j]; }
 #else
     transition4<SMEM, SLOTS>(a, tab, q, act, r);
 #endif
-    if (q.bad) {
-        const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_uint4(q.rows[0], q.rows[1], q.rows[2], q.rows[3]),
+    uint32_t rejected = 0u;
+    if (((act[0] | act[1] | act[2] | act[3]) & ~3) != 0) {
+        // some action is outside 0..3 (the reference raises ValueError in Action(action)): redo the quad one env at a
+        // time through the checking path, from the loaded state
+        q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
+        q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
+        q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
+        q.term = q.trunc = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g0 + j, q.pos[j], q.len[j], q.ret[j], act[j], r[j], q.rew[j], errs);
+            q.term |= (f & 1u) << (8 * j);
+            q.trunc |= ((f >> 1) & 1u) << (8 * j);
+            rejected += (f >> 2) & 1u;
+        }
+    } else if (q.bad) {
+        const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]),
                                                  make_int4(act[0], act[1], act[2], act[3]));
         errs.count += e.x;
         errs.g = e.y;
         errs.detail = e.z;
         errs.kind = e.w;
+        rejected = e.x;
     }
-    acc.steps += 4u - __popc(q.bad);
+    acc.steps += 4u - rejected;
     if (a.final_obs) {  // pre-reset observation, only materialised on request
         int4* o = reinterpret_cast<int4*>(a.final_obs + 2 * base);
         const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
@@ -234,19 +253,25 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
     }
     const uint32_t fin = a.autoreset ? (q.term | q.trunc) : 0u;
     if (fin) finish4(a, q, fin, acc);
-    *reinterpret_cast<int4*>(a.pos + base) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
-    *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
-    *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
+#if EF_STREAMING
+#define EF_ST(ptr, val) __stcs(ptr, val)
+#else
+#define EF_ST(ptr, val) (*(ptr) = (val))
+#endif
+    EF_ST(reinterpret_cast<int4*>(a.pos + base), make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]));
+    EF_ST(reinterpret_cast<int4*>(a.ep_len + base), make_int4(q.len[0], q.len[1], q.len[2], q.len[3]));
+    EF_ST(reinterpret_cast<float4*>(a.ep_ret + base), make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]));
     if (a.obs) {  // observation after auto-reset = (row, col) of the stored position
         int4* o = reinterpret_cast<int4*>(a.obs + 2 * base);
         const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
-        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
+        EF_ST(o, make_int4(o0.x, o0.y, o1.x, o1.y));
         const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
-        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
+        EF_ST(o + 1, make_int4(o2.x, o2.y, o3.x, o3.y));
     }
-    if (a.reward) *reinterpret_cast<float4*>(a.reward + base) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
-    if (a.terminated) *reinterpret_cast<uint32_t*>(a.terminated + base) = q.term;
-    if (a.truncated) *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
+    if (a.reward) EF_ST(reinterpret_cast<float4*>(a.reward + base), make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]));
+    if (a.terminated) EF_ST(reinterpret_cast<uint32_t*>(a.terminated + base), q.term);
+    if (a.truncated) EF_ST(reinterpret_cast<uint32_t*>(a.truncated + base), q.trunc);
+#undef EF_ST
 }
 
 #ifndef EF_STEP_MINBLOCKS
@@ -254,6 +279,9 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #endif
 #ifndef EF_EXPERIMENT
 #define EF_EXPERIMENT 0
+#endif
+#ifndef EF_STREAMING
+#define EF_STREAMING 0  // 1: evict-first cache hints on the state/outputs streams
 #endif
 #ifndef EF_STEP_Q
 #define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
@@ -449,17 +477,32 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
 #pragma unroll
                 for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(wp[j] >> 30);
             }
-            transition4<SMEM, SLOTS>(a, tab, q, act, wt);
-            q.bad &= valid_bits;
-            if (q.bad) {
-                    const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_uint4(q.rows[0], q.rows[1], q.rows[2], q.rows[3]),
+            uint32_t rejected = 0u;
+            if (EXT_ACTIONS && ((act[0] | act[1] | act[2] | act[3]) & ~3) != 0) {  // out-of-range action: checking path
+                q.term = q.trunc = q.bad = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ErrorAcc scratch;
+                    const uint32_t f = transition<SMEM, SLOTS>(a, tab, g0 + j, q.pos[j], q.len[j], q.ret[j], act[j], wt[j],
+                                                               q.rew[j], valid[j] ? errs : scratch);
+                    q.term |= (f & 1u) << (8 * j);
+                    q.trunc |= ((f >> 1) & 1u) << (8 * j);
+                    rejected += valid[j] ? ((f >> 2) & 1u) : 0u;
+                }
+            } else {
+                transition4<SMEM, SLOTS>(a, tab, q, act, wt);
+                q.bad &= valid_bits;
+                if (q.bad) {
+                    const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]),
                                                              make_int4(act[0], act[1], act[2], act[3]));
                     errs.count += e.x;
                     errs.g = e.y;
                     errs.detail = e.z;
                     errs.kind = e.w;
+                    rejected = e.x;
                 }
-            acc.steps += __popc(valid_bits) - __popc(q.bad);
+            }
+            acc.steps += __popc(valid_bits) - rejected;
             if constexpr (EMIT) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

@@ -255,15 +255,22 @@ class GridSpec:
     def device_table(self, extra_cells=0):
         """Packed ef_grid_outcome array (uint32 [entries, 2]): word0 = next | flags << 16, word1 = fp32 reward bits."""
         R, slots = self.n_cells * 4, self.n_slots
-        flags = self.done[:, :slots].astype(np.uint32) * _lib.EF_GRID_DONE
+        rejected = (self.count == 0) | self.bad
+        # rejected rows are compiled INERT (next = own cell, reward 0, not done): the branch-free kernel path applies
+        # them and only masks the step counter; the flags let it report them (the reference raises on these rows)
+        own = (np.arange(R) // 4)[:, None]
+        nxt = np.where(rejected[:, None], own, self.nxt[:, :slots])
+        reward = np.where(rejected[:, None], 0.0, self.reward[:, :slots])
+        flags = (self.done[:, :slots] & ~rejected[:, None]).astype(np.uint32) * _lib.EF_GRID_DONE
         flags |= (self.count == 0)[:, None].astype(np.uint32) * _lib.EF_GRID_NO_OUTCOMES
-        flags |= self.bad[:, None].astype(np.uint32) * _lib.EF_GRID_BAD_PROBS
-        word0 = (self.nxt[:, :slots].astype(np.uint32) & 0xFFFF) | (flags << 16)
-        word1 = self.reward[:, :slots].astype(np.float32).view(np.uint32)
+        flags |= (self.bad & (self.count != 0))[:, None].astype(np.uint32) * _lib.EF_GRID_BAD_PROBS
+        word0 = (nxt.astype(np.uint32) & 0xFFFF) | (flags << 16)
+        word1 = reward.astype(np.float32).view(np.uint32)
         tab = np.stack([word0, word1], axis=-1).reshape(R * slots, 2)
         if extra_cells:
             pad = np.zeros((extra_cells * 4 * slots, 2), np.uint32)
-            pad[:, 0] = _lib.EF_GRID_NO_OUTCOMES << 16
+            cells = self.n_cells + np.arange(extra_cells * 4 * slots) // (4 * slots)
+            pad[:, 0] = (cells.astype(np.uint32) & 0xFFFF) | (_lib.EF_GRID_NO_OUTCOMES << 16)
             tab = np.concatenate([tab, pad])
         return np.ascontiguousarray(tab)
 
