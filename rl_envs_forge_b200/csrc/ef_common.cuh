@@ -95,17 +95,24 @@ __device__ __forceinline__ uint4 draw_block(uint64_t seed, uint32_t g, uint64_t 
 
 // Grouped-stream words of the four consecutive envs g0 .. g0+3 at counter t.  g0 & 3 is the same for every thread of a
 // launch (it equals env_offset & 3), so the second call is a launch-uniform branch taken only for unaligned shards.
-__device__ __forceinline__ void group_words4(uint64_t seed, uint32_t g0, uint64_t t, uint32_t stream, uint32_t (&w)[4]) {
+// Unaligned shard (env_offset & 3 != 0): the quad straddles two Philox blocks.  Kept out of line: it is launch-uniformly
+// rare and would otherwise double the code size of every unrolled call site.
+static __device__ __noinline__ uint4 group_words4_unaligned(uint64_t seed, uint32_t g0, uint64_t t, uint32_t stream) {
     const uint4 a = draw_block(seed, g0 >> 2, t, stream);
+    const uint4 b = draw_block(seed, (g0 >> 2) + 1u, t, stream);
     const uint32_t sh = g0 & 3u;
-    if (sh == 0u) {
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    } else {
-        const uint4 b = draw_block(seed, (g0 >> 2) + 1u, t, stream);
-        const uint32_t all[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t all[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = sh == 1u ? all[j + 1] : (sh == 2u ? all[j + 2] : all[j + 3]);
-    }
+    for (int j = 0; j < 4; ++j) w[j] = sh == 1u ? all[j + 1] : (sh == 2u ? all[j + 2] : all[j + 3]);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ void group_words4(uint64_t seed, uint32_t g0, uint64_t t, uint32_t stream, uint32_t (&w)[4]) {
+    uint4 a;
+    if ((g0 & 3u) == 0u) a = draw_block(seed, g0 >> 2, t, stream);
+    else a = group_words4_unaligned(seed, g0, t, stream);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
 }
 
 __device__ __forceinline__ uint32_t group_word1(uint64_t seed, uint32_t g, uint64_t t, uint32_t stream) {

@@ -283,6 +283,23 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #ifndef EF_STREAMING
 #define EF_STREAMING 0  // 1: evict-first cache hints on the state/outputs streams
 #endif
+// Large batches (measured on B200 at 4M / 16M envs: Q=4, 2 CTAs/SM resident, dynamic CTA scheduling reaches 0.95 of the
+// measured HBM peak; Q=1..2 with 3-4 CTAs/SM or a persistent grid are 10-25 % slower)
+#ifndef EF_STEP_BIG_Q
+#define EF_STEP_BIG_Q 4
+#endif
+#ifndef EF_STEP_BIG_MINBLOCKS
+#define EF_STEP_BIG_MINBLOCKS 2
+#endif
+#ifndef EF_STEP_BIG_GRID_PER_SM
+#define EF_STEP_BIG_GRID_PER_SM 64
+#endif
+#ifndef EF_STEP_GRID_PER_SM
+#define EF_STEP_GRID_PER_SM EF_STEP_MINBLOCKS  // grid cap in CTAs per SM
+#endif
+#ifndef EF_FORCE_GLOBAL_TABLE
+#define EF_FORCE_GLOBAL_TABLE 0  // experiment: read the table through L1 instead of staging it in shared memory
+#endif
 #ifndef EF_STEP_Q
 #define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
 #endif
@@ -292,8 +309,8 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 // quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
 // (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
 // load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
-template <bool SMEM, int SLOTS>
-__global__ void __launch_bounds__(kThreads, EF_STEP_MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
+template <bool SMEM, int SLOTS, int Q, int MINBLOCKS>
+__global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
 #if EF_EXPERIMENT & 4
     const uint2* __restrict__ tab = a.table;
 #else
@@ -310,15 +327,15 @@ __global__ void __launch_bounds__(kThreads, EF_STEP_MINBLOCKS) gridworld_step_ke
     const int64_t per_cta = (quads + gridDim.x - 1) / gridDim.x;
     const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t q_end = min(q_begin + per_cta, quads);
-    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(EF_STEP_Q) * kThreads) {
-        QuadIn in[EF_STEP_Q];
+    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
+        QuadIn in[Q];
 #pragma unroll
-        for (int j = 0; j < EF_STEP_Q; ++j) {
+        for (int j = 0; j < Q; ++j) {
             const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
             if (v < q_end) in[j] = load_quad(a, v * 4, philox_act);
         }
 #pragma unroll
-        for (int j = 0; j < EF_STEP_Q; ++j) {
+        for (int j = 0; j < Q; ++j) {
             const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
             if (v < q_end)
                 step_quad<SMEM, SLOTS>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in[j], philox_act,
@@ -606,12 +623,19 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     const bool vec = draw == nullptr && aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) &&
                      aligned(action, 16) && aligned(obs, 16) && aligned(reward, 16) && aligned(terminated, 4) &&
                      aligned(truncated, 4) && aligned(final_obs, 16);
-    const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
+    const bool smem = !EF_FORCE_GLOBAL_TABLE && static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid_v = grid_for((n + 3) / 4, EF_STEP_MINBLOCKS), grid_s = grid_for(n, 8);
-#define EF_DISPATCH(SM, SL)                                                                                   \
-    return vec ? launch(gridworld_step_kernel<SM, SL>, a, SM, grid_v, st)                                      \
-               : launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st)
+    // Small batches (one pass fits the resident grid): EF_STEP_Q quads per thread, all loads in flight, persistent grid.
+    // Large batches: fewer quads per thread, more resident warps, CTAs scheduled dynamically over many passes.
+    const int64_t quads = (n + 3) / 4;
+    const bool small = quads <= static_cast<int64_t>(sm_count()) * EF_STEP_GRID_PER_SM * kThreads * EF_STEP_Q;
+    const int grid_v = grid_for((quads + EF_STEP_Q - 1) / EF_STEP_Q, EF_STEP_GRID_PER_SM);
+    const int grid_b = grid_for((quads + EF_STEP_BIG_Q - 1) / EF_STEP_BIG_Q, EF_STEP_BIG_GRID_PER_SM);
+    const int grid_s = grid_for(n, 8);
+#define EF_DISPATCH(SM, SL)                                                                                              \
+    if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                      \
+    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS>, a, SM, grid_v, st)                  \
+                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS>, a, SM, grid_b, st)
     if (smem) {
         if (grid->n_slots == 1) { EF_DISPATCH(true, 1); } else { EF_DISPATCH(true, 4); }
     } else {

@@ -130,92 +130,167 @@ __device__ __forceinline__ uint32_t env_step(const ef_pendulum_params& p, typena
 
 __device__ __forceinline__ float policy_action(uint32_t w) { return uniform_f32(w, -3.0f, 6.0f); }
 
+#ifndef EF_PEND_GRID_PER_SM
+#define EF_PEND_GRID_PER_SM 64  // measured on B200 at 4M envs: 64 (one pass, dynamic CTA scheduling) beats a persistent 3/SM grid by 20-25 %
+#endif
+#ifndef EF_PEND_ROLLOUT_GRID_PER_SM
+#define EF_PEND_ROLLOUT_GRID_PER_SM 8
+#endif
+#ifndef EF_PEND_U
+#define EF_PEND_U 4  // envs per thread whose loads are issued before any of them is stepped (memory-level parallelism)
+#endif
+
+// Step kernel (HBM-bound).  The batch is cut into one contiguous chunk per CTA; a thread issues the loads of EF_PEND_U
+// envs (stride = CTA size, so every access of a warp is contiguous) before stepping them, which keeps ~4x more bytes in
+// flight per SM than one env per thread.
 template <class Env>
 __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs a) {
     using Vec = typename Env::Vec;
+    pdl_launch_dependents();
+    pdl_wait();
     EpisodeAcc acc;
     const uint64_t t = a.t + clock_read(a.clock);
     const unsigned long long ticket = clock_ticket(a.clock);
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-        Vec s = reinterpret_cast<const Vec*>(a.state)[i];
-        int32_t len = a.ep_len[i];
-        float ret = a.ep_ret[i];
-        float act;
-        if (a.action) {
-            act = __ldg(a.action + i);
-        } else {
-            act = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
+    int64_t per_cta = (a.n + gridDim.x - 1) / gridDim.x;
+    per_cta = (per_cta + kThreads - 1) / kThreads * kThreads;  // keeps every CTA's chunk 256-env aligned
+    const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_cta;
+    const int64_t end = min(begin + per_cta, a.n);
+    for (int64_t chunk = begin; chunk < end; chunk += static_cast<int64_t>(EF_PEND_U) * kThreads) {
+        Vec s[EF_PEND_U];
+        int32_t len[EF_PEND_U];
+        float ret[EF_PEND_U], act[EF_PEND_U];
+#pragma unroll
+        for (int j = 0; j < EF_PEND_U; ++j) {
+            const int64_t i = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+            if (i < end) {
+                s[j] = reinterpret_cast<const Vec*>(a.state)[i];
+                len[j] = a.ep_len[i];
+                ret[j] = a.ep_ret[i];
+                act[j] = a.action ? __ldg(a.action + i) : 0.0f;
+            }
         }
-        float rew, a0, a1;
-        const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
-        acc.steps += 1u;
-        if (a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s;
-        if (a.autoreset && f) {
-            acc.finish(len, ret);
-            s = Env::init(a.p, a.seed, g, t, kStreamResetAuto);
-            len = 0;
-            ret = 0.0f;
+#pragma unroll
+        for (int j = 0; j < EF_PEND_U; ++j) {
+            const int64_t i = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+            if (i >= end) continue;
+            const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+            if (!a.action) act[j] = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
+            float rew, a0, a1;
+            const uint32_t f = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew, a0, a1);
+            acc.steps += 1u;
+            if (a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s[j];
+            if (a.autoreset && f) {
+                acc.finish(len[j], ret[j]);
+                s[j] = Env::init(a.p, a.seed, g, t, kStreamResetAuto);
+                len[j] = 0;
+                ret[j] = 0.0f;
+            }
+            reinterpret_cast<Vec*>(a.state)[i] = s[j];
+            a.ep_len[i] = len[j];
+            a.ep_ret[i] = ret[j];
+            if (a.obs && a.obs != a.state) reinterpret_cast<Vec*>(a.obs)[i] = s[j];
+            if (a.reward) a.reward[i] = rew;
+            if (a.terminated) a.terminated[i] = f & 1u;
+            if (a.truncated) a.truncated[i] = (f >> 1) & 1u;
+            if (a.acc) Env::store_acc(a.acc, i, a0, a1);
         }
-        reinterpret_cast<Vec*>(a.state)[i] = s;
-        a.ep_len[i] = len;
-        a.ep_ret[i] = ret;
-        if (a.obs && a.obs != a.state) reinterpret_cast<Vec*>(a.obs)[i] = s;
-        if (a.reward) a.reward[i] = rew;
-        if (a.terminated) a.terminated[i] = f & 1u;
-        if (a.truncated) a.truncated[i] = (f >> 1) & 1u;
-        if (a.acc) Env::store_acc(a.acc, i, a0, a1);
     }
     cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, 1ull);
 }
 
+// Fused K-step rollout.  A thread keeps FOUR consecutive envs in registers for all K steps: one Philox call per step
+// yields their four policy draws, external actions / emitted rewards move as one 128-bit access per step, and the four
+// independent integrations give the FP32 pipes instruction-level parallelism.  A warp ballot skips the reset path in
+// warps where no lane finished an episode this step.
 template <class Env, bool EXT_ACTIONS, bool EMIT>
 __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendArgs a) {
     using Vec = typename Env::Vec;
+    pdl_launch_dependents();
+    pdl_wait();
     EpisodeAcc acc;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    const int64_t n_round = (a.n + 31) & ~static_cast<int64_t>(31);
+    const int64_t quads = (a.n + 3) / 4;
+    const int64_t quads_round = (quads + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
     const uint64_t t0 = a.t + clock_read(a.clock);
     const unsigned long long ticket = clock_ticket(a.clock);
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < a.n;
-        const int64_t ii = valid ? i : 0;
-        const uint32_t g = static_cast<uint32_t>(a.env_offset + ii);
-        Vec s = reinterpret_cast<const Vec*>(a.state)[ii];
-        int32_t len = a.ep_len[ii];
-        float ret = a.ep_ret[ii];
+    const bool io_vec = ((a.n & 3) == 0) && aligned(a.action, 16) && aligned(a.reward, 16) && aligned(a.flags, 4);
+    for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < quads_round; v += stride) {
+        const int64_t base = v * 4;
+        const uint32_t g0 = static_cast<uint32_t>(a.env_offset + base);
+        Vec s[4];
+        int32_t len[4];
+        float ret[4];
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            valid[j] = base + j < a.n;
+            const int64_t i = valid[j] ? base + j : 0;
+            s[j] = reinterpret_cast<const Vec*>(a.state)[i];
+            len[j] = a.ep_len[i];
+            ret[j] = a.ep_ret[i];
+        }
+        const bool full = valid[3] && io_vec;
         for (int k = 0; k < a.K; ++k) {
             const uint64_t t = t0 + static_cast<uint64_t>(k);
-            float act;
+            const int64_t o = static_cast<int64_t>(k) * a.n + base;
+            float act[4];
             if constexpr (EXT_ACTIONS) {
-                act = __ldg(a.action + static_cast<int64_t>(k) * a.n + ii);
+                if (full) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(a.action + o));
+                    act[0] = a4.x; act[1] = a4.y; act[2] = a4.z; act[3] = a4.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) act[j] = valid[j] ? __ldg(a.action + o + j) : 0.0f;
+                }
             } else {
-                act = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
+                uint32_t w[4];
+                group_words4(a.seed, g0, t, kStreamPolicy, w);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) act[j] = policy_action(w[j]);
             }
-            float rew, a0, a1;
-            const uint32_t f = env_step<Env>(a.p, s, len, ret, act, rew, a0, a1);
+            float rew[4];
+            uint32_t f[4];
+            bool any_fin = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a0, a1;
+                f[j] = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew[j], a0, a1);
+                any_fin |= valid[j] && f[j];
+            }
             if constexpr (EMIT) {
-                if (valid) {
-                    if (a.reward) a.reward[static_cast<int64_t>(k) * a.n + i] = rew;
-                    if (a.flags) a.flags[static_cast<int64_t>(k) * a.n + i] = static_cast<uint8_t>(f);
+                if (full) {
+                    if (a.reward) *reinterpret_cast<float4*>(a.reward + o) = make_float4(rew[0], rew[1], rew[2], rew[3]);
+                    if (a.flags) *reinterpret_cast<uint32_t*>(a.flags + o) = f[0] | (f[1] << 8) | (f[2] << 16) | (f[3] << 24);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (valid[j]) {
+                            if (a.reward) a.reward[o + j] = rew[j];
+                            if (a.flags) a.flags[o + j] = static_cast<uint8_t>(f[j]);
+                        }
+                    }
                 }
             }
-            const bool fin = valid && f;
-            if (__ballot_sync(0xffffffffu, fin)) {  // warp vote: reset path only where some lane finished
-                if (fin) {
-                    acc.finish(len, ret);
-                    s = Env::init(a.p, a.seed, g, t, kStreamResetAuto);
-                    len = 0;
-                    ret = 0.0f;
+            if (__ballot_sync(0xffffffffu, any_fin)) {  // warp vote: reset path only where some lane finished
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (valid[j] && f[j]) {
+                        acc.finish(len[j], ret[j]);
+                        s[j] = Env::init(a.p, a.seed, g0 + j, t, kStreamResetAuto);
+                        len[j] = 0;
+                        ret[j] = 0.0f;
+                    }
                 }
             }
         }
-        if (valid) {
-            acc.steps += static_cast<uint32_t>(a.K);
-            reinterpret_cast<Vec*>(a.state)[i] = s;
-            a.ep_len[i] = len;
-            a.ep_ret[i] = ret;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (valid[j]) {
+                acc.steps += static_cast<uint32_t>(a.K);
+                reinterpret_cast<Vec*>(a.state)[base + j] = s[j];
+                a.ep_len[base + j] = len[j];
+                a.ep_ret[base + j] = ret[j];
+            }
         }
     }
     cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, static_cast<unsigned long long>(a.K));
@@ -258,8 +333,8 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
     a.seed = seed; a.t = t; a.env_offset = env_offset; a.obs = obs; a.reward = reward;
     a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs; a.acc = acc;
     a.stats = stats; a.n = n; a.autoreset = autoreset; a.clock = reinterpret_cast<unsigned long long*>(clock);
-    pendulum_step_kernel<Env><<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
-    return cuda_status(cudaGetLastError());
+    return launch_kernel(pendulum_step_kernel<Env>, a, grid_for((n + EF_PEND_U - 1) / EF_PEND_U, EF_PEND_GRID_PER_SM), 0,
+                         static_cast<cudaStream_t>(stream));
 }
 
 template <class Env>
@@ -273,14 +348,13 @@ static int rollout_impl(const ef_pendulum_params* p, float* state, int32_t* ep_l
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
     a.stats = stats; a.n = n; a.autoreset = 1; a.clock = reinterpret_cast<unsigned long long*>(clock);
-    const int grid = grid_for(n, 8);
+    const int grid = grid_for((n + 3) / 4, EF_PEND_ROLLOUT_GRID_PER_SM);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
-    if (ext && emit) pendulum_rollout_kernel<Env, true, true><<<grid, kThreads, 0, st>>>(a);
-    else if (ext) pendulum_rollout_kernel<Env, true, false><<<grid, kThreads, 0, st>>>(a);
-    else if (emit) pendulum_rollout_kernel<Env, false, true><<<grid, kThreads, 0, st>>>(a);
-    else pendulum_rollout_kernel<Env, false, false><<<grid, kThreads, 0, st>>>(a);
-    return cuda_status(cudaGetLastError());
+    if (ext && emit) return launch_kernel(pendulum_rollout_kernel<Env, true, true>, a, grid, 0, st);
+    if (ext) return launch_kernel(pendulum_rollout_kernel<Env, true, false>, a, grid, 0, st);
+    if (emit) return launch_kernel(pendulum_rollout_kernel<Env, false, true>, a, grid, 0, st);
+    return launch_kernel(pendulum_rollout_kernel<Env, false, false>, a, grid, 0, st);
 }
 
 template <class Env>
