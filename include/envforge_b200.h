@@ -112,6 +112,21 @@ int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, f
                       int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
                       double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 
+/* Stream-exact variant of ef_gridworld_step: the outcome draw of env i comes from ITS OWN numpy-compatible generator,
+ * Generator(PCG64(SeedSequence(seed_i))) as built by gym.utils.seeding.np_random (grid_world.py:69) and consumed by
+ * Generator.choice (:515), so a batch seeded with the reference's seeds reproduces the reference's trajectories without
+ * injected draws.
+ *   rng_state / rng_inc  [n,2] uint64 (high word, low word) PCG64 state / increment, 16-byte aligned; state is updated.
+ *   thr53 / idx_cap53    host pointer to 3 thresholds T_k = ceil(cdf_k * 2^53) and the index cap: with
+ *                        m = next_uint64 >> 11, outcome_index = min(sum(m >= T_k), idx_cap53)  (ignored for n_slots == 1,
+ *                        where a draw is still consumed, as the reference does).
+ * Rejected env-steps consume no draw (the reference raises before drawing). */
+int ef_gridworld_step_pcg64(const ef_grid_desc* grid, const uint64_t* thr53, int32_t idx_cap53, int32_t* pos,
+                            int32_t* ep_len, float* ep_ret, uint64_t* rng_state, const uint64_t* rng_inc,
+                            const int32_t* action, uint64_t env_offset, int32_t* obs, float* reward, uint8_t* terminated,
+                            uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err, int64_t n,
+                            int32_t autoreset, void* stream);
+
 /* K fused steps (t0 .. t0+K-1) with state held in registers and auto-reset always on.
  *   actions  [K,n] int32 or NULL (random policy).   rewards [K,n] float / flags [K,n] uint8 (bit0 terminated,
  *   bit1 truncated) or NULL: nothing is written per step and only state + stats leave the kernel. */

@@ -427,6 +427,96 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
     cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
 }
 
+// ---- stream-exact step (numpy PCG64 per env) ------------------------------------------------------------------------
+// `GridWorld(seed=s)` draws one Generator.random() double per successful step from Generator(PCG64(SeedSequence(s)))
+// (grid_world.py:69, :515).  Here every env carries that generator's 128-bit state and increment; a step advances it
+// (state = state * MULT + inc, XSL-RR output) and compares m = raw >> 11 against 53-bit integer thresholds, which is
+// numpy's searchsorted(cdf, m * 2^-53, 'right').  Rejected steps do not consume a draw, like the reference (it raises
+// before calling choice / inside choice before drawing).
+struct Pcg64Args {
+    unsigned long long thr[3];
+    int32_t idx_cap;
+    ulonglong2* rng_state;      // x = high word, y = low word
+    const ulonglong2* rng_inc;
+};
+
+template <bool SMEM, int SLOTS>
+__global__ void __launch_bounds__(kThreads) gridworld_step_pcg64_kernel(const GridArgs a, const Pcg64Args r) {
+    const uint2* __restrict__ tab = stage_table<SMEM>(a);
+    pdl_launch_dependents();
+    pdl_wait();
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    constexpr unsigned long long kMultHi = 0x2360ED051FC65DA4ull, kMultLo = 0x4385DF649FCCF645ull;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        int32_t pos = a.pos[i], len = a.ep_len[i];
+        float ret = a.ep_ret[i], rew = 0.0f;
+        const int32_t act = __ldg(a.action + i);
+        uint32_t f = 0u;
+        if (static_cast<uint32_t>(act) > 3u) {
+            errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+            f = 4u;
+        } else {
+            const uint32_t row = static_cast<uint32_t>(pos) * 4u + static_cast<uint32_t>(act);
+            const uint2 probe = SMEM ? tab[row * SLOTS] : __ldg(tab + row * SLOTS);  // every slot of a row carries its flags
+            if ((probe.x >> 16) & (EF_GRID_NO_OUTCOMES | EF_GRID_BAD_PROBS)) {
+                errs.record(g, row, ((probe.x >> 16) & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS);
+                f = 4u;
+            } else {
+                ulonglong2 st = r.rng_state[i];
+                const ulonglong2 inc = r.rng_inc[i];
+                // 128-bit LCG step
+                unsigned long long lo = st.y * kMultLo;
+                unsigned long long hi = __umul64hi(st.y, kMultLo) + st.x * kMultLo + st.y * kMultHi;
+                lo += inc.y;
+                hi += inc.x + (lo < inc.y ? 1ull : 0ull);
+                r.rng_state[i] = make_ulonglong2(hi, lo);
+                const unsigned long long x = hi ^ lo;
+                const unsigned rot = static_cast<unsigned>(hi >> 58);
+                const unsigned long long raw = (x >> rot) | (x << ((64u - rot) & 63u));
+                const unsigned long long m = raw >> 11;
+                uint32_t idx = 0u;
+                if constexpr (SLOTS == 4) {
+                    idx = (m >= r.thr[0]) + (m >= r.thr[1]) + (m >= r.thr[2]);
+                    idx = min(idx, static_cast<uint32_t>(r.idx_cap));
+                }
+                const uint2 o = SMEM ? tab[row * SLOTS + idx] : __ldg(tab + row * SLOTS + idx);
+                pos = static_cast<int32_t>(o.x & 0xffffu);
+                rew = __uint_as_float(o.y);
+                ret += rew;
+                len += 1;
+                f = ((o.x >> 16) & EF_GRID_DONE) | ((a.limit > 0 && len >= a.limit) ? 2u : 0u);
+                acc.steps += 1u;
+            }
+        }
+        if (a.final_obs) {
+            const int2 fo = cell_to_obs(a, pos);
+            a.final_obs[2 * i] = fo.x;
+            a.final_obs[2 * i + 1] = fo.y;
+        }
+        if (a.autoreset && (f & 3u)) {
+            acc.finish(len, ret);
+            pos = a.start_cell;
+            len = 0;
+            ret = 0.0f;
+        }
+        a.pos[i] = pos;
+        a.ep_len[i] = len;
+        a.ep_ret[i] = ret;
+        if (a.obs) {
+            const int2 ob = cell_to_obs(a, pos);
+            a.obs[2 * i] = ob.x;
+            a.obs[2 * i + 1] = ob.y;
+        }
+        if (a.reward) a.reward[i] = rew;
+        if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
+        if (a.truncated) a.truncated[i] = static_cast<uint8_t>((f >> 1) & 1u);
+    }
+    cta_epilogue(acc, errs, a.stats, a.err, nullptr, 0ull, 0ull);
+}
+
 // ---- fused K-step rollout -------------------------------------------------------------------------------------------
 // A thread keeps FOUR consecutive envs in registers for all K steps (one Philox call per step yields their four outcome
 // draws, one more their four random actions; the four table walks are independent, which gives the scheduler ILP).
@@ -642,6 +732,48 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
         if (grid->n_slots == 1) { EF_DISPATCH(false, 1); } else { EF_DISPATCH(false, 4); }
     }
 #undef EF_DISPATCH
+}
+
+extern "C" int ef_gridworld_step_pcg64(const ef_grid_desc* grid, const uint64_t* thr53, int32_t idx_cap53, int32_t* pos,
+                                       int32_t* ep_len, float* ep_ret, uint64_t* rng_state, const uint64_t* rng_inc,
+                                       const int32_t* action, uint64_t env_offset, int32_t* obs, float* reward,
+                                       uint8_t* terminated, uint8_t* truncated, int32_t* final_obs, double* stats,
+                                       uint32_t* err, int64_t n, int32_t autoreset, void* stream) {
+    GridArgs a{};
+    if (int s = fill_args(grid, a)) return s;
+    if (n < 0 || !pos || !ep_len || !ep_ret || !rng_state || !rng_inc || !action || !thr53) return EF_ERR_INVALID_ARGUMENT;
+    if (!aligned(rng_state, 16) || !aligned(rng_inc, 16) || idx_cap53 < 0 || idx_cap53 > 3) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0) return EF_OK;
+    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action; a.env_offset = env_offset;
+    a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs;
+    a.stats = stats; a.err = err; a.n = n; a.autoreset = autoreset;
+    Pcg64Args r{};
+    r.thr[0] = thr53[0]; r.thr[1] = thr53[1]; r.thr[2] = thr53[2];
+    r.idx_cap = idx_cap53;
+    r.rng_state = reinterpret_cast<ulonglong2*>(rng_state);
+    r.rng_inc = reinterpret_cast<const ulonglong2*>(rng_inc);
+    const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
+    const size_t bytes = smem ? static_cast<size_t>(a.table_len) * sizeof(uint2) : 0;
+    const int grid_s = grid_for(n, 8);
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define EF_DISPATCH3(SM, SL)                                                                                          \
+    do {                                                                                                              \
+        auto kernel = gridworld_step_pcg64_kernel<SM, SL>;                                                            \
+        if (bytes > 48 * 1024) {                                                                                      \
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                                       static_cast<int>(bytes));                                      \
+            if (e != cudaSuccess) return cuda_status(e);                                                              \
+        }                                                                                                             \
+        kernel<<<grid_s, kThreads, bytes, st>>>(a, r);                                                                \
+        return cuda_status(cudaGetLastError());                                                                       \
+    } while (0)
+    if (smem) {
+        if (grid->n_slots == 1) EF_DISPATCH3(true, 1); else EF_DISPATCH3(true, 4);
+    } else {
+        if (grid->n_slots == 1) EF_DISPATCH3(false, 1); else EF_DISPATCH3(false, 4);
+    }
+#undef EF_DISPATCH3
 }
 
 extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,

@@ -280,7 +280,17 @@ class VecGridWorld(VecEnv):
 
     def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
                  special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
-                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False):
+                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox"):
+        """`rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
+        `rng="pcg64"`: every env owns the generator the reference would build for it,
+        Generator(PCG64(SeedSequence(seed_i))) with seed_i = seed + global env index (or `seed` given as a sequence of
+        N ints): `VecGridWorld(1, seed=s, rng="pcg64")` reproduces `GridWorld(seed=s)` draw for draw."""
+        seed_list = None
+        if rng not in ("philox", "pcg64"):
+            raise ValueError("rng must be 'philox' or 'pcg64'")
+        if rng == "pcg64" and seed is not None and not isinstance(seed, int):
+            seed_list = [int(x) for x in seed]
+            seed = seed_list[0] if seed_list else None
         validate_args(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, seed,
                       slip_distribution, p_success, episode_length_limit)
         self.spec = GridSpec(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, p_success,
@@ -303,12 +313,34 @@ class VecGridWorld(VecEnv):
         self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
         n, dev = self.num_envs, self.device
         self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
-        self._obs = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        # the four per-step outputs live back to back in ONE allocation (16-byte aligned sections), so the host-buffer
+        # path brings them back with a single device->host copy
+        pad = lambda b: (b + 15) // 16 * 16  # noqa: E731
+        o_rew, o_term, o_trunc = pad(8 * n), pad(8 * n) + pad(4 * n), pad(8 * n) + pad(4 * n) + pad(n)
+        self._out_bytes = o_trunc + pad(n)
+        self._out = torch.zeros(self._out_bytes, dtype=torch.uint8, device=dev)
+        self._out_sections = (o_rew, o_term, o_trunc)
+        self._obs = self._out[:8 * n].view(torch.int32).view(n, 2)
+        self._reward = self._out[o_rew:o_rew + 4 * n].view(torch.float32)
+        self._term = self._out[o_term:o_term + n]
+        self._trunc = self._out[o_trunc:o_trunc + n]
         self._final_obs = None
-        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
-        self._term = torch.zeros(n, dtype=torch.uint8, device=dev)
-        self._trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._P = None
+        self.rng = rng
+        self._rng_state = self._rng_inc = None
+        if rng == "pcg64":
+            from . import pcg64
+            if seed_list is None:
+                base = self._seed if seed is None else int(seed)
+                seed_list = [base + self.env_offset + i for i in range(n)]
+            if len(seed_list) != n:
+                raise ValueError(f"seed sequence must hold {n} integers")
+            st, inc = pcg64.pcg64_initial_state(seed_list)
+            self._rng_state = torch.from_numpy(st.view(np.int64)).to(dev)
+            self._rng_inc = torch.from_numpy(inc.view(np.int64)).to(dev)
+            thr, cap = pcg64.thresholds53(p_success)
+            self._thr53 = (_lib.C.c_uint64 * 3)(*thr)
+            self._cap53 = cap
         self._upload_table()
         self.reset()
 
@@ -417,7 +449,9 @@ class VecGridWorld(VecEnv):
         torch = self._torch
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
         n = self.num_envs
-        if host_io:
+        if host_io and torch.is_tensor(actions):      # CPU torch tensor (pinned => zero-copy staging)
+            act = self._to_device("action", actions.reshape(-1).to(torch.int32), torch.int32, (n,))
+        elif host_io:
             a = np.asarray(actions)
             if a.shape == ():
                 a = a.reshape(1)
@@ -439,23 +473,35 @@ class VecGridWorld(VecEnv):
             if self._final_obs is None:
                 self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
             fobs = self._final_obs
-        self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
-                   _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
-                   _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc),
-                   _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), _lib.ptr(self._clock), n,
-                   int(self.autoreset))
+        if self.rng == "pcg64":
+            if drw is not None:
+                raise ValueError("injected draws are not available with rng='pcg64' (each env owns its generator)")
+            self._call(self._lib.ef_gridworld_step_pcg64, self._desc, self._thr53, self._cap53, _lib.ptr(self.pos),
+                       _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(self._rng_state), _lib.ptr(self._rng_inc),
+                       _lib.ptr(act), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term),
+                       _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), n,
+                       int(self.autoreset))
+        else:
+            self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
+                       _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
+                       _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc),
+                       _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), _lib.ptr(self._clock), n,
+                       int(self.autoreset))
         self._t += 1
         if self.strict:
             self.check_errors()
         info = {}
         if host_io:
-            named = [("obs", self._obs), ("reward", self._reward), ("term", self._term), ("trunc", self._trunc)]
+            named = [("out", self._out)]
             if return_final_obs:
                 named.append(("final_obs", fobs))
             out = self._to_host(named)
             if return_final_obs:
-                info["final_observation"] = out[4]
-            return out[0], out[1], out[2].view(np.bool_), out[3].view(np.bool_), info
+                info["final_observation"] = out[1]
+            buf = out[0]
+            o_rew, o_term, o_trunc = self._out_sections
+            return (buf[:8 * n].view(np.int32).reshape(n, 2), buf[o_rew:o_rew + 4 * n].view(np.float32),
+                    buf[o_term:o_term + n].view(np.bool_), buf[o_trunc:o_trunc + n].view(np.bool_), info)
         if return_final_obs:
             info["final_observation"] = fobs
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
@@ -466,6 +512,8 @@ class VecGridWorld(VecEnv):
         episode statistics accumulate in `self.stats` either way."""
         torch = self._torch
         n = self.num_envs
+        if self.rng == "pcg64":
+            raise NotImplementedError("rollout() uses the Philox streams; rng='pcg64' supports step() only")
         if actions is not None:
             if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
                     and tuple(actions.shape) == (K, n)):

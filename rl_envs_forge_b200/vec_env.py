@@ -121,13 +121,17 @@ class VecEnv:
         return t
 
     def _to_device(self, name, array, dtype, shape):
-        """Host array -> device tensor through a pinned staging buffer, on the current stream."""
+        """Host array -> device tensor on the current stream.  A pinned CPU torch tensor of the right dtype is copied
+        directly (DMA from the caller's buffer); anything else goes through a pinned staging buffer first."""
         torch = self._torch
-        src = torch.as_tensor(np.ascontiguousarray(array))
+        src = array if torch.is_tensor(array) else torch.as_tensor(np.ascontiguousarray(array))
         if tuple(src.shape) != tuple(shape):
             raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(src.shape)}")
-        stage = self._pinned("h_" + name, shape, dtype)
-        stage.copy_(src)
+        if src.is_pinned() and src.dtype == dtype and src.is_contiguous():
+            stage = src
+        else:
+            stage = self._pinned("h_" + name, shape, dtype)
+            stage.copy_(src)
         dev = self._host.get("d_" + name)
         if dev is None or tuple(dev.shape) != tuple(shape) or dev.dtype != dtype:
             dev = torch.empty(shape, dtype=dtype, device=self.device)

@@ -343,3 +343,59 @@ def test_host_buffer_path_equals_device_path():
         assert isinstance(oa[0], np.ndarray)
         assert np.array_equal(oa[0], ob[0].cpu().numpy()) and np.array_equal(oa[1], ob[1].cpu().numpy())
         assert np.array_equal(oa[2], ob[2].cpu().numpy()) and np.array_equal(oa[3], ob[3].cpu().numpy())
+
+
+# ---- stream-exact mode: rng="pcg64" -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["default", "slip_seed42", "config2_p1", "config2_p08", "p0", "random02", "random08"])
+def test_pcg64_mode_reproduces_reference_trajectories_without_injection(name):
+    """`VecGridWorld(1, seed=s, rng="pcg64")` fed the recorded actions reproduces the trajectory the UNMODIFIED reference
+    produced with GridWorld(seed=s) and its own numpy generator: same states, rewards, flags -- no draws injected."""
+    from rl_envs_forge_b200 import VecGridWorld
+    g = load([f for f in FILES if f.endswith(f"gridworld_{name}.npz")][0])
+    env = VecGridWorld(1, seed=int(g["seed"]), rng="pcg64", autoreset=False, strict=True, **_vec_kwargs(grid_kwargs(g)))
+    env.reset()
+    for i in range(min(600, len(g["action"]))):
+        assert tuple(env.state.cpu().numpy()[0]) == tuple(g["pre"][i]), i
+        if g["raised"][i]:
+            with pytest.raises(ValueError):
+                env.step(np.array([g["action"][i]]))
+            continue
+        obs, rew, term, trunc, _ = env.step(np.array([g["action"][i]]))
+        assert tuple(obs[0]) == tuple(g["post"][i]) and rew[0] == np.float32(g["reward"][i]), i
+        assert bool(term[0]) == bool(g["done"][i]) and bool(trunc[0]) == bool(g["trunc"][i])
+        if g["done"][i] or g["trunc"][i]:
+            env.reset()
+
+
+def test_pcg64_mode_batch_matches_numpy_generators():
+    """N envs with seeds s, s+1, ...: each follows the port driven by ITS numpy Generator(PCG64(SeedSequence(seed)))."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, steps, base = 512, 120, 1000
+    cfg = _config2(0.8)
+    env = VecGridWorld(n, seed=base, rng="pcg64", **_vec_kwargs(cfg))
+    ports = [GridWorldPort(**cfg) for _ in range(n)]
+    gens = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(base + i))) for i in range(n)]
+    arng = np.random.default_rng(5)
+    for p in ports:
+        p.reset()
+    for t in range(steps):
+        act = arng.integers(0, 4, n).astype(np.int32)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(act).cuda())
+        obs, rew, term, trunc = obs.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy(), trunc.cpu().numpy()
+        for i, p in enumerate(ports):
+            outs = p.mdp.get((p.state, int(act[i])), [])
+            try:
+                idx = gens[i].choice(len(outs), p=[o[3] for o in outs])
+            except ValueError:
+                assert tuple(obs[i]) == p.state and not term[i] and not trunc[i]
+                continue
+            nxt, r, d, _ = outs[idx]
+            p.state = nxt
+            p.episode_length_counter += 1
+            tr = p.episode_length_counter >= p.episode_length_limit
+            assert rew[i] == np.float32(r) and bool(term[i]) == d and bool(trunc[i]) == tr, (t, i)
+            if d or tr:
+                p.reset()                                  # device auto-reset: same-step reset observation
+            assert tuple(obs[i]) == p.state, (t, i)
+    assert int(env.err.cpu().numpy()[0]) > 0               # the ((3,3), UP) cell was hit and rejected without a draw
