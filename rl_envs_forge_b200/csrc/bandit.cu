@@ -26,24 +26,53 @@ struct BanditArgs {
     int64_t n;
 };
 
+// Primitive stream of one (env, step).  The first Philox block and the transcendental-heavy values every family starts
+// from (first normal, first uniform, first exponential) are computed up front by ALL lanes of the warp, outside the
+// per-family switch: lanes of a warp usually hold different families, and anything inside the switch is serialised
+// across them.  The values are exactly those the lazy path would produce (same words, same formulas, same order).
 struct Primitives {
     uint64_t seed, t;
     uint32_t g, consumed;
     uint4 blk;
-    __device__ __forceinline__ Primitives(uint64_t seed_, uint32_t g_, uint64_t t_) : seed(seed_), t(t_), g(g_), consumed(0) {}
+    float u0, u1, u2, n0, e0;
+    __device__ __forceinline__ Primitives(uint64_t seed_, uint32_t g_, uint64_t t_) : seed(seed_), t(t_), g(g_), consumed(0) {
+        blk = draw_block(seed, g, t, kStreamBandit, 0);
+        u0 = u23(blk.x);
+        u1 = u23(blk.y);
+        u2 = u23(blk.z);
+        n0 = sqrtf(-2.0f * logf(u0)) * cospif(2.0f * u1);
+        e0 = -logf(1.0f - u0);
+    }
     __device__ __forceinline__ uint32_t word() {
         const uint32_t lane = consumed & 3u;
-        if (lane == 0u) blk = draw_block(seed, g, t, kStreamBandit, consumed >> 2);
+        if (lane == 0u && consumed != 0u) blk = draw_block(seed, g, t, kStreamBandit, consumed >> 2);
         ++consumed;
         return lane == 0u ? blk.x : lane == 1u ? blk.y : lane == 2u ? blk.z : blk.w;
     }
-    __device__ __forceinline__ float u() { return u23(word()); }
-    __device__ __forceinline__ float n() {
-        const float u1 = u();
-        const float u2 = u();
-        return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    __device__ __forceinline__ float u() {
+        if (consumed < 3u) {
+            const float v = consumed == 0u ? u0 : (consumed == 1u ? u1 : u2);
+            ++consumed;
+            return v;
+        }
+        return u23(word());
     }
-    __device__ __forceinline__ float std_exp() { return -logf(1.0f - u()); }
+    __device__ __forceinline__ float n() {
+        if (consumed == 0u) {
+            consumed = 2u;
+            return n0;
+        }
+        const float a = u();
+        const float b = u();
+        return sqrtf(-2.0f * logf(a)) * cospif(2.0f * b);
+    }
+    __device__ __forceinline__ float std_exp() {
+        if (consumed == 0u) {
+            consumed = 1u;
+            return e0;
+        }
+        return -logf(1.0f - u());
+    }
 };
 
 constexpr int kMaxRejections = 1024;  // termination guard; P(reaching it) is astronomically small for valid params
