@@ -18,13 +18,16 @@
  *   - Global env index g = env_offset + i (must stay < 2^32).  All in-kernel randomness is Philox4x32-10 with
  *     key = seed and counter = (g, 64-bit counter, stream id | block << 8); see csrc/philox.cuh.  Results therefore
  *     do not depend on how envs are sharded over launches, ranks or GPUs.
- *   - `stats` (nullable) points at EF_STATS_LEN doubles that the kernels ADD to (atomically):
+ *   - `stats` (nullable) points at EF_STATS_REPLICAS x EF_STATS_STRIDE doubles that the kernels ADD to (atomically).
+ *     Replica r lives at stats + r * EF_STATS_STRIDE; a CTA adds into replica (blockIdx.x % EF_STATS_REPLICAS) so that
+ *     CTAs finishing together do not serialise on one L2 atomic unit.  The statistics are the SUM over replicas of
  *       [0] finished episodes  [1] sum of their lengths  [2] sum of their returns  [3] sum of squared returns
- *       [4] env-steps executed [5..7] reserved.  Integer-valued entries stay exact below 2^53.
- *     This vector is what gets all-reduced (NCCL, sum) across GPUs.
- *   - `err` (nullable) points at EF_ERR_LEN uint32: [0] number of env-steps the reference would have raised on
- *     (atomicAdd), [1] 1 + global index of one offending env, [2] its table row (cell*4+action) or action value,
- *     [3] ef_step_error kind.  Offending envs are left untouched (the reference raises before mutating state).
+ *       [4] env-steps executed [5..] reserved.  Integer-valued entries stay exact below 2^53.
+ *     The (summed) vector is what gets all-reduced (NCCL, sum) across GPUs.
+ *   - `err` (nullable) points at EF_ERR_LEN uint32, 8-byte aligned: [0] number of env-steps the reference would have
+ *     raised on (atomic add); [1] reserved; [2..3] one 64-bit word describing the offender with the largest global index
+ *     (atomic max): (1 + global env index) << 32 | ef_step_error kind << 24 | detail (24 bits: table row cell*4+action,
+ *     or the action value).  Offending envs are left untouched (the reference raises before mutating state).
  *   - `clock` (nullable) points at 2 uint64 in device memory: clock[0] is ADDED to the `t` / `t0` argument to form
  *     the Philox time coordinate and is advanced by the kernel itself (by 1 per step call, K per rollout) once all
  *     its CTAs have read it; clock[1] is scratch (must start at 0).  It exists so a captured CUDA graph can be
@@ -41,6 +44,8 @@ extern "C" {
 
 #define EF_ABI_VERSION 1
 #define EF_STATS_LEN 8
+#define EF_STATS_REPLICAS 32
+#define EF_STATS_STRIDE 16
 #define EF_ERR_LEN 4
 
 typedef enum ef_status {

@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ENVFORGE_LIB") or os.path.join(_HERE, "csrc", "libenvforge_b200.so")
 
 EF_STATS_LEN = 8
+EF_STATS_REPLICAS = 32
+EF_STATS_STRIDE = 16
 EF_ERR_LEN = 4
 EF_ABI_VERSION = 1
 

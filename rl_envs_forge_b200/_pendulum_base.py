@@ -164,7 +164,7 @@ class VecPendulumBase(VecEnv):
             acc = self._acc
         self._call(self._fn_step, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
                    _lib.ptr(act), self._seed, self._t_arg(), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward),
-                   _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self.stats),
+                   _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self._stats_raw),
                    _lib.ptr(self._clock), n, int(self.autoreset))
         self._t += 1
         info = {}
@@ -204,7 +204,7 @@ class VecPendulumBase(VecEnv):
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
         self._call(self._fn_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
                    _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
-                   _lib.ptr(self.stats), _lib.ptr(self._clock), n)
+                   _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n)
         self._t += int(K)
         if self._obs is not self._state:
             self._obs.copy_(self._state)

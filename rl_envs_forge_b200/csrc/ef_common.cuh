@@ -57,6 +57,13 @@ inline int launch_kernel(Kernel kernel, const Args& args, int grid, size_t smem_
     return cuda_status(cudaLaunchKernelEx(&cfg, kernel, args));
 }
 
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that hold no registers while in flight -------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- Philox4x32-10 ------------------------------------------------------------------------------------------------
 // Stream layout (twin: oracle/philox.py).  key = (seed lo, seed hi); ctr = (x, c_lo, c_hi, stream | block << 8).
 //   per-env streams: x = g (global env index).  Grouped streams: x = g >> 2 and env g owns word g & 3, so the one
@@ -228,20 +235,23 @@ __device__ __forceinline__ void cta_epilogue(const EpisodeAcc& acc, const ErrorA
             t_r2 += s_d[w][1];
         }
         if (stats != nullptr) {
+            // CTAs finish together and would serialise on one L2 atomic unit if they all added into the same five
+            // addresses (measured: 1.5 us per launch at 296 CTAs): spread them over EF_STATS_REPLICAS copies of the vector
+            double* mine = stats + static_cast<size_t>(blockIdx.x % EF_STATS_REPLICAS) * EF_STATS_STRIDE;
             if (t_eps) {
-                atomicAdd(&stats[0], static_cast<double>(t_eps));
-                atomicAdd(&stats[1], static_cast<double>(t_len));
-                atomicAdd(&stats[2], t_r);
-                atomicAdd(&stats[3], t_r2);
+                atomicAdd(&mine[0], static_cast<double>(t_eps));
+                atomicAdd(&mine[1], static_cast<double>(t_len));
+                atomicAdd(&mine[2], t_r);
+                atomicAdd(&mine[3], t_r2);
             }
-            if (t_steps) atomicAdd(&stats[4], static_cast<double>(t_steps));
+            if (t_steps) atomicAdd(&mine[4], static_cast<double>(t_steps));
         }
-        if (err != nullptr && t_rej != 0u) {
-            if (atomicAdd(&err[0], t_rej) == 0u) {
-                err[1] = s_e[first][0];
-                err[2] = s_e[first][1];
-                err[3] = s_e[first][2];
-            }
+        if (err != nullptr && t_rej != 0u) {  // no returning atomics: count by RED.ADD, offender by RED.MAX on a packed word
+            atomicAdd(&err[0], t_rej);
+            const unsigned long long packed = (static_cast<unsigned long long>(s_e[first][0]) << 32) |
+                                              (static_cast<unsigned long long>(s_e[first][2] & 0xffu) << 24) |
+                                              static_cast<unsigned long long>(s_e[first][1] & 0xffffffu);
+            atomicMax(reinterpret_cast<unsigned long long*>(err + 2), packed);
         }
         if (clock != nullptr && ticket == static_cast<unsigned long long>(gridDim.x) - 1ull) {
             clock[1] = 0ull;

@@ -280,6 +280,9 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #ifndef EF_EXPERIMENT
 #define EF_EXPERIMENT 0
 #endif
+#ifndef EF_STEP_ASYNC
+#define EF_STEP_ASYNC 0  // 1: stage inputs with cp.async into shared memory instead of registers
+#endif
 #ifndef EF_STREAMING
 #define EF_STREAMING 0  // 1: evict-first cache hints on the state/outputs streams
 #endif
@@ -327,7 +330,43 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     const int64_t per_cta = (quads + gridDim.x - 1) / gridDim.x;
     const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t q_end = min(q_begin + per_cta, quads);
+#if EF_STEP_ASYNC
+    // Inputs are staged with cp.async (LDGSTS) into per-thread shared-memory slots instead of registers: the loads of all Q
+    // quads are in flight without holding 16 registers each, which lets more CTAs be resident during the compute phase.
+    // A thread only reads back its own slots, so cp.async.wait_all suffices (no CTA barrier).
+    uint4* stage = reinterpret_cast<uint4*>(const_cast<uint2*>(tab) + (SMEM ? a.table_len : 0));
+#endif
     for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
+#if EF_STEP_ASYNC
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+            if (v < q_end) {
+                uint4* slot = stage + (j * 4) * kThreads + threadIdx.x;
+                cp_async16(slot, a.pos + v * 4);
+                cp_async16(slot + kThreads, a.ep_len + v * 4);
+                cp_async16(slot + 2 * kThreads, a.ep_ret + v * 4);
+                if (!philox_act) cp_async16(slot + 3 * kThreads, a.action + v * 4);
+            }
+        }
+        cp_async_wait_all();
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
+            if (v < q_end) {
+                const uint4* slot = stage + (j * 4) * kThreads + threadIdx.x;
+                QuadIn in;
+                const uint4 p = slot[0], l = slot[kThreads], r = slot[2 * kThreads];
+                const uint4 c = philox_act ? make_uint4(0, 0, 0, 0) : slot[3 * kThreads];
+                in.p4 = make_int4(p.x, p.y, p.z, p.w);
+                in.l4 = make_int4(l.x, l.y, l.z, l.w);
+                in.r4 = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+                in.a4 = make_int4(c.x, c.y, c.z, c.w);
+                step_quad<SMEM, SLOTS>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in, philox_act, acc,
+                                       errs);
+            }
+        }
+#else
         QuadIn in[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
@@ -341,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
                 step_quad<SMEM, SLOTS>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in[j], philox_act,
                                        acc, errs);
         }
+#endif
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x < (a.n & 3)) {  // ragged tail: at most three envs
         const int64_t i = (quads << 2) + threadIdx.x;
@@ -376,7 +416,11 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
         if (a.truncated) a.truncated[i] = static_cast<uint8_t>((f >> 1) & 1u);
     }
+#if EF_EXPERIMENT & 32  // keep the accumulation alive, skip the CTA epilogue
+    if (acc.episodes == 0xFFFFFFFFu && a.stats) { a.stats[0] = acc.ret + acc.ret_sq + static_cast<double>(acc.length + acc.steps + errs.count + ticket); }
+#elif !(EF_EXPERIMENT & 8)
     cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
+#endif
 }
 
 // Scalar kernel: one env per thread, any alignment, optional injected outcome draws (parity tests, unaligned views).
@@ -682,8 +726,8 @@ static int fill_args(const ef_grid_desc* g, GridArgs& a) {
 }
 
 template <typename Kernel>
-static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStream_t stream) {
-    const size_t bytes = smem ? static_cast<size_t>(a.table_len) * sizeof(uint2) : 0;
+static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStream_t stream, size_t extra_smem = 0) {
+    const size_t bytes = (smem ? static_cast<size_t>(a.table_len) * sizeof(uint2) : 0) + extra_smem;
     if (bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
         if (e != cudaSuccess) return cuda_status(e);
@@ -724,8 +768,10 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     const int grid_s = grid_for(n, 8);
 #define EF_DISPATCH(SM, SL)                                                                                              \
     if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                      \
-    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS>, a, SM, grid_v, st)                  \
-                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS>, a, SM, grid_b, st)
+    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS>, a, SM, grid_v, st,                  \
+                          EF_STEP_ASYNC ? size_t(EF_STEP_Q) * 4 * kThreads * 16 : 0)                                       \
+                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS>, a, SM, grid_b, st,          \
+                          EF_STEP_ASYNC ? size_t(EF_STEP_BIG_Q) * 4 * kThreads * 16 : 0)
     if (smem) {
         if (grid->n_slots == 1) { EF_DISPATCH(true, 1); } else { EF_DISPATCH(true, 4); }
     } else {

@@ -479,13 +479,13 @@ class VecGridWorld(VecEnv):
             self._call(self._lib.ef_gridworld_step_pcg64, self._desc, self._thr53, self._cap53, _lib.ptr(self.pos),
                        _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(self._rng_state), _lib.ptr(self._rng_inc),
                        _lib.ptr(act), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term),
-                       _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), n,
+                       _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err), n,
                        int(self.autoreset))
         else:
             self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
                        _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
                        _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc),
-                       _lib.ptr(fobs), _lib.ptr(self.stats), _lib.ptr(self.err), _lib.ptr(self._clock), n,
+                       _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n,
                        int(self.autoreset))
         self._t += 1
         if self.strict:
@@ -525,7 +525,7 @@ class VecGridWorld(VecEnv):
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
         self._call(self._lib.ef_gridworld_rollout, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
                    _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K),
-                   _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self.stats), _lib.ptr(self.err), _lib.ptr(self._clock), n)
+                   _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
         self._t += int(K)
         return (rew, flg) if return_rewards else None
 

@@ -188,7 +188,7 @@ class VecKArmedBandit(VecEnv):
             act = (actions if actions.dtype == torch.int32 else actions.to(torch.int32)).contiguous()
         arms = self._arm_table(1)
         self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, _lib.ptr(act), self._seed, self._steps_since_reset,
-                   self.env_offset, 1, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self.stats),
+                   self.env_offset, 1, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._stats_raw),
                    _lib.ptr(self.err), n)
         self._advance(1)
         if self.strict:
@@ -215,7 +215,7 @@ class VecKArmedBandit(VecEnv):
         obs = torch.empty((K, n), dtype=torch.int32, device=self.device)
         rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
         self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, _lib.ptr(actions), self._seed,
-                   self._steps_since_reset, self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self.stats),
+                   self._steps_since_reset, self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self._stats_raw),
                    _lib.ptr(self.err), n)
         self._advance(K)
         return obs, rew

@@ -83,7 +83,8 @@ class VecEnv:
         n = self.num_envs
         self.ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ep_ret = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.stats = torch.zeros(_lib.EF_STATS_LEN, dtype=torch.float64, device=dev)
+        # statistics accumulators: EF_STATS_REPLICAS copies (CTAs spread their atomics), summed on read -- see `stats`
+        self._stats_raw = torch.zeros(_lib.EF_STATS_REPLICAS * _lib.EF_STATS_STRIDE, dtype=torch.float64, device=dev)
         self.err = torch.zeros(_lib.EF_ERR_LEN, dtype=torch.int32, device=dev)
         self._host = {}
         self._clock = None  # optional device-resident step clock (CUDA-graph capture), see enable_device_clock()
@@ -154,22 +155,28 @@ class VecEnv:
         return [o.numpy() for o in outs]
 
     # -- statistics / errors ---------------------------------------------------------------------------------------
+    @property
+    def stats(self):
+        """float64 [EF_STATS_LEN] device tensor: the statistics vector (sum over the replicas the kernels add into)."""
+        return self._stats_raw.view(_lib.EF_STATS_REPLICAS, _lib.EF_STATS_STRIDE)[:, :_lib.EF_STATS_LEN].sum(dim=0)
+
     def episode_stats(self, all_reduce=False, reset=False):
         """Finished-episode statistics accumulated on device since construction (or the last reset=True call).
 
         all_reduce=True sums them over the ranks of the default process group first (one NCCL all-reduce of 64 B)."""
-        vec = self.stats.clone()
+        vec = self.stats
         if all_reduce:
             all_reduce_stats(vec)
         if reset:
-            self.stats.zero_()
+            self._stats_raw.zero_()
         return stats_to_dict(vec.cpu().tolist())
 
     def running_episode_stats(self):
         """(count, mean length, mean return) over the episodes currently in flight (device reduction)."""
-        out = self._torch.zeros(_lib.EF_STATS_LEN, dtype=self._torch.float64, device=self.device)
+        out = self._torch.zeros(_lib.EF_STATS_REPLICAS * _lib.EF_STATS_STRIDE, dtype=self._torch.float64, device=self.device)
         self._call(self._lib.ef_episode_stat_reduce, _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(out),
                    self.num_envs)
+        out = out.view(_lib.EF_STATS_REPLICAS, _lib.EF_STATS_STRIDE)[:, :_lib.EF_STATS_LEN].sum(dim=0)
         return stats_to_dict(out.cpu().tolist())
 
     def check_errors(self, clear=True):
@@ -180,8 +187,10 @@ class VecEnv:
         if clear and e[0]:
             self.err.zero_()
         if e[0]:
-            kind = _lib.STEP_ERROR_NAMES.get(e[3], "unknown")
-            raise ValueError(self._describe_error(e[0], e[1] - 1, e[2], e[3], kind))
+            packed = e[2] | (e[3] << 32)      # (1 + global env index) << 32 | kind << 24 | detail
+            env, kind_id, detail = (packed >> 32) - 1, (packed >> 24) & 0xFF, packed & 0xFFFFFF
+            kind = _lib.STEP_ERROR_NAMES.get(kind_id, "unknown")
+            raise ValueError(self._describe_error(e[0], env, detail, kind_id, kind))
 
     def _describe_error(self, count, env, detail, kind_id, kind):
         return f"{count} env-step(s) rejected ({kind}); first offender env {env}, detail {detail}"

@@ -399,3 +399,41 @@ def test_pcg64_mode_batch_matches_numpy_generators():
                 p.reset()                                  # device auto-reset: same-step reset observation
             assert tuple(obs[i]) == p.state, (t, i)
     assert int(env.err.cpu().numpy()[0]) > 0               # the ((3,3), UP) cell was hit and rejected without a draw
+
+
+def test_cuda_graph_replay_with_device_clock_equals_eager_steps():
+    """enable_device_clock(): a captured CUDA graph of step() launches can be replayed and keeps advancing the Philox time
+    coordinate on the device -- state, outputs and statistics equal the eager run with host-side step counting."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, seed, per_graph, replays = 70_001, 31, 5, 6
+    cfg = _vec_kwargs(_config2(0.8))
+    eager = VecGridWorld(n, seed=seed, **cfg)
+    graphed = VecGridWorld(n, seed=seed, **cfg)
+    acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda") for _ in range(per_graph)]
+    graphed.step(acts[0])                       # warm-up launch outside capture (module load), mirrored on the eager env
+    eager.step(acts[0])
+    graphed.enable_device_clock()
+    stream = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(g, stream=stream):
+            for a in acts:
+                graphed.step(a)
+    torch.cuda.synchronize()
+    # capture does not execute: bring the eager env to the same point (nothing yet), then replay
+    for _ in range(replays):
+        g.replay()
+        for a in acts:
+            out_e = eager.step(a)
+    torch.cuda.synchronize()
+    assert graphed.step_count == 1 + per_graph * replays == eager.step_count
+    assert torch.equal(graphed.pos, eager.pos) and torch.equal(graphed.ep_len, eager.ep_len)
+    assert torch.equal(graphed.ep_ret, eager.ep_ret)
+    assert torch.equal(graphed._obs, out_e[0]) and torch.equal(graphed._reward, out_e[1])
+    sg, se = graphed.episode_stats(), eager.episode_stats()
+    assert sg["episodes"] == se["episodes"] > 0 and sg["length_sum"] == se["length_sum"] and sg["env_steps"] == se["env_steps"]
+    graphed.disable_device_clock()
+    graphed.step(acts[0])
+    eager.step(acts[0])
+    assert torch.equal(graphed.pos, eager.pos)
