@@ -437,3 +437,59 @@ def test_cuda_graph_replay_with_device_clock_equals_eager_steps():
     graphed.step(acts[0])
     eager.step(acts[0])
     assert torch.equal(graphed.pos, eager.pos)
+
+
+def test_empty_batch_is_a_noop_through_the_c_abi():
+    """n = 0 (empty input): every entry point returns EF_OK without touching memory."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld, _lib
+    env = VecGridWorld(8, **_vec_kwargs(_config2(0.8)))
+    lib = _lib.load()
+    before = env.pos.clone()
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.ef_gridworld_step(env._desc, env.pos.data_ptr(), env.ep_len.data_ptr(), env.ep_ret.data_ptr(), None, None,
+                                 1, 0, 0, None, None, None, None, None, None, None, None, 0, 1, st) == 0
+    assert lib.ef_gridworld_rollout(env._desc, env.pos.data_ptr(), env.ep_len.data_ptr(), env.ep_ret.data_ptr(), None,
+                                    1, 0, 0, 16, None, None, None, None, None, 0, st) == 0
+    assert lib.ef_gridworld_rollout(env._desc, env.pos.data_ptr(), env.ep_len.data_ptr(), env.ep_ret.data_ptr(), None,
+                                    1, 0, 0, 0, None, None, None, None, None, 8, st) == 0     # K = 0
+    assert lib.ef_gridworld_reset(0, 8, env.pos.data_ptr(), env.ep_len.data_ptr(), env.ep_ret.data_ptr(), None, None, 0, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(env.pos, before)
+    # negative sizes / out-of-range global index are rejected, not launched
+    assert lib.ef_gridworld_step(env._desc, env.pos.data_ptr(), env.ep_len.data_ptr(), env.ep_ret.data_ptr(), None, None,
+                                 1, 0, 0, None, None, None, None, None, None, None, None, -1, 1, st) == 1
+    assert lib.ef_gridworld_step(env._desc, env.pos.data_ptr(), env.ep_len.data_ptr(), env.ep_ret.data_ptr(), None, None,
+                                 1, 0, 2 ** 32 - 4, None, None, None, None, None, None, None, None, 8, 1, st) == 1
+
+
+def test_maximum_grid_size_65535_cells():
+    """Largest supported grid (255 x 257 = 65535 cells, 16-bit cell index; 8 MB outcome table read through L1/L2)."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    rows, cols = 255, 257
+    rng = np.random.default_rng(3)
+    walls = {(int(r), int(c)) for r, c in zip(rng.integers(1, rows - 1, 4000), rng.integers(1, cols - 1, 4000))}
+    cfg = dict(rows=rows, cols=cols, start_state=(0, 0), walls=walls, terminal_states={(rows - 1, cols - 1): 3.0, (0, cols - 1): -2.0},
+               p_success=0.6, episode_length_limit=50)
+    port = GridWorldPort(**cfg)
+    tab = FlatTables(port)
+    n, seed = 30_000, 12
+    env = VecGridWorld(n, seed=seed, **cfg)
+    # scatter the agents over the whole grid (incl. the last row / column) so large cell indices are exercised
+    free = np.array([r * cols + c for r in range(rows) for c in range(cols) if (r, c) not in walls and (r, c) not in cfg["terminal_states"]])
+    pos = rng.choice(free, n)
+    env.state = np.stack([pos // cols, pos % cols], axis=1)
+    pos = pos.astype(np.int64)
+    ln, ret = np.zeros(n, np.int32), np.zeros(n, np.float32)
+    g = np.arange(n)
+    for t in range(25):
+        wt, wp = philox.step_words(seed, g, np.full(n, t, np.uint64))
+        act = (wp >> np.uint32(30)).astype(np.int32)
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(act).cuda())
+        o = vec_step(tab, pos, ln, ret, act, wt, limit=50, start_pos=0, autoreset=True)
+        pos, ln, ret = o["pos"], o["ep_len"], o["ep_ret"]
+        assert np.array_equal(obs.cpu().numpy(), o["obs"]) and np.array_equal(rew.cpu().numpy(), o["reward"])
+        assert np.array_equal(term.cpu().numpy(), o["terminated"])
+    with pytest.raises(ValueError):
+        VecGridWorld(4, rows=256, cols=256)        # 65536 cells: one more than the 16-bit table index allows
