@@ -7,7 +7,8 @@
  * that advances N independent instances held as structure-of-arrays device buffers.
  *
  * Conventions
- *   - Plain C types only.  Every buffer is DEVICE memory owned by the caller (PyTorch in the shipped host code);
+ *   - Plain C types only.  Every buffer is DEVICE memory (pinned host memory for the h_ arguments of the *_step_host
+ *     entry points) owned by the caller (PyTorch in the shipped host code);
  *     the library never allocates, frees or retains device memory and keeps no global state.  Descriptor structs
  *     (ef_grid_desc, ef_pendulum_params, ef_bandit_desc) are small HOST structs passed by pointer and copied into
  *     kernel parameters; pointers inside them are device pointers.
@@ -237,6 +238,49 @@ int ef_bandit_default_means(int32_t k, uint64_t seed, uint64_t env_offset, float
  * (count, sum len, sum ret, sum ret^2) -- complements `stats`, which only sees finished episodes.
  * ------------------------------------------------------------------------------------------------------------ */
 int ef_episode_stat_reduce(const int32_t* ep_len, const float* ep_ret, double* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-buffer step: the call a host-side actor makes once per step (the reference's `env.step(action)` with the
+ * action and the results in HOST memory: grid_world.py:495, cart_pole.py:107, pendulum_disk.py:108,
+ * k_armed_bandit.py:175).  Same kernels and same results as the device-buffer entry points above; what is added is
+ * the PCIe plumbing.  The batch is cut into `chunks` contiguous index ranges (starts are multiples of 1024 envs, global
+ * env index = env_offset + start, so chunking never changes a result) and pipelined:
+ *     actions of chunk c+1 cross PCIe host->device  ||  kernel of chunk c+1  ||  outputs of chunk c cross device->host
+ *   h_*   PINNED (page-locked, UVA-addressable) host buffers of the whole batch.  h_action is read, the others written.
+ *   d_*   device buffers of the whole batch the kernels write before the copy engine drains them (caller-owned
+ *         scratch).  An output is skipped when either its d_ or h_ pointer is NULL.
+ *   d_action  device staging buffer [n] or NULL.  NULL: the step kernel reads the actions directly from h_action
+ *         (zero-copy over PCIe); non-NULL: each chunk's actions are first copied by the copy engine.
+ *   The call is asynchronous; when `stream` has been synchronised the h_ outputs are valid.  There is no `clock`
+ *   argument: a host-buffer step is not graph-replayable (its `t` is a plain argument).
+ * ef_host_pipe holds two copy streams and the events that order them; it owns no device memory.  Create it once per
+ * env set on the device it is used on; not thread-safe (one in-flight step per pipe).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_host_pipe ef_host_pipe;
+int ef_host_pipe_create(ef_host_pipe** pipe);
+int ef_host_pipe_destroy(ef_host_pipe* pipe);
+
+int ef_gridworld_step_host(ef_host_pipe* pipe, const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                           const int32_t* h_action, int32_t* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,
+                           int32_t* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+                           int32_t* d_final_obs, int32_t* h_obs, float* h_reward, uint8_t* h_terminated,
+                           uint8_t* h_truncated, int32_t* h_final_obs, double* stats, uint32_t* err, int64_t n,
+                           int32_t autoreset, int32_t chunks, void* stream);
+int ef_cartpole_step_host(ef_host_pipe* pipe, const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                          const float* h_action, float* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,
+                          float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated, float* d_final_obs,
+                          float* d_acc, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                          float* h_final_obs, float* h_acc, double* stats, int64_t n, int32_t autoreset, int32_t chunks,
+                          void* stream);
+int ef_pendulum_disk_step_host(ef_host_pipe* pipe, const ef_pendulum_params* p, float* state, int32_t* ep_len,
+                               float* ep_ret, const float* h_action, float* d_action, uint64_t seed, uint64_t t,
+                               uint64_t env_offset, float* d_obs, float* d_reward, uint8_t* d_terminated,
+                               uint8_t* d_truncated, float* d_final_obs, float* d_acc, float* h_obs, float* h_reward,
+                               uint8_t* h_terminated, uint8_t* h_truncated, float* h_final_obs, float* h_acc,
+                               double* stats, int64_t n, int32_t autoreset, int32_t chunks, void* stream);
+int ef_bandit_step_host(ef_host_pipe* pipe, const ef_arm* arms, int32_t k, const int32_t* h_action, int32_t* d_action,
+                        uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t* d_obs, float* d_reward, int32_t* h_obs,
+                        float* h_reward, double* stats, uint32_t* err, int64_t n, int32_t chunks, void* stream);
 
 #ifdef __cplusplus
 }

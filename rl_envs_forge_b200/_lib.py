@@ -69,6 +69,15 @@ SIGNATURES = {
     "ef_bandit_step": (C.c_int, [_P, _I32, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_default_means": (C.c_int, [_I32, _U64, _U64, _P, _I64, _P]),
     "ef_episode_stat_reduce": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "ef_host_pipe_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "ef_host_pipe_destroy": (C.c_int, [_P]),
+    "ef_gridworld_step_host": (C.c_int, [_P, C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 10
+                               + [_P, _P, _I64, _I32, _I32, _P]),
+    "ef_cartpole_step_host": (C.c_int, [_P, C.POINTER(PendulumParams), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 12
+                              + [_P, _I64, _I32, _I32, _P]),
+    "ef_pendulum_disk_step_host": (C.c_int, [_P, C.POINTER(PendulumParams), _P, _P, _P, _P, _P, _U64, _U64, _U64]
+                                   + [_P] * 12 + [_P, _I64, _I32, _I32, _P]),
+    "ef_bandit_step_host": (C.c_int, [_P, _P, _I32, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
 }
 
 _lib = None

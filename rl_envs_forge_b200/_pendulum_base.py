@@ -41,6 +41,7 @@ class VecPendulumBase(VecEnv):
         self._fn_step = getattr(self._lib, self._FN + "_step")
         self._fn_rollout = getattr(self._lib, self._FN + "_rollout")
         self._fn_reset = getattr(self._lib, self._FN + "_reset")
+        self._fn_step_host = getattr(self._lib, self._FN + "_step_host")
         self.reset()
 
     # -- params -------------------------------------------------------------------------------------------------
@@ -139,11 +140,26 @@ class VecPendulumBase(VecEnv):
         torch = self._torch
         n = self.num_envs
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        mode = self.host_transport if host_io else None
+        if mode == "pipelined" and self._clock is not None:
+            mode = "staged"
+        zero_copy = mode == "zerocopy"
         if host_io:
-            a = np.asarray(actions)
-            if self.strict and a.dtype == np.float64:
-                raise AssertionError("float64 actions invalid: not castable to float32")
-            act = self._to_device("action", a.reshape(-1).astype(np.float32, copy=False), torch.float32, (n,))
+            if torch.is_tensor(actions):
+                a = actions.reshape(-1)
+                if self.strict:
+                    self._check_actions_strict(a)
+                a = a.to(torch.float32)
+            else:
+                a = np.asarray(actions)
+                if self.strict and a.dtype == np.float64:
+                    raise AssertionError("float64 actions invalid: not castable to float32")
+                a = a.reshape(-1).astype(np.float32, copy=False)
+                if self.strict:
+                    self._check_actions_strict(torch.from_numpy(a))
+            h_act = self._host_in("action", a, torch.float32, (n,))
+            p_act = (_lib.ptr(self._to_device("action", h_act, torch.float32, (n,))) if mode == "staged"
+                     else h_act.data_ptr())
         else:
             act = actions.reshape(-1)
             if act.shape[0] != n:
@@ -151,36 +167,68 @@ class VecPendulumBase(VecEnv):
             if self.strict:
                 self._check_actions_strict(act)
             act = act.to(torch.float32).contiguous()
-        if self.strict and host_io:
-            self._check_actions_strict(act)
+            p_act = _lib.ptr(act)
         fobs = acc = None
-        if return_final_obs:
-            if self._final_obs is None:
-                self._final_obs = torch.zeros((n, self.DIM), dtype=torch.float32, device=self.device)
-            fobs = self._final_obs
-        if return_info:
-            if self._acc is None:
-                self._acc = torch.zeros((n, self._ACC_DIM), dtype=torch.float32, device=self.device)
-            acc = self._acc
-        self._call(self._fn_step, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
-                   _lib.ptr(act), self._seed, self._t_arg(), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward),
-                   _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self._stats_raw),
-                   _lib.ptr(self._clock), n, int(self.autoreset))
+        if zero_copy:
+            # outputs are written by the kernel straight into pinned host memory (UVA pointers): no staging copies
+            obs = self._pinned("o_obs", (n, self.DIM), torch.float32)
+            rew = self._pinned("o_reward", (n,), torch.float32)
+            term = self._pinned("o_term", (n,), torch.uint8)
+            trunc = self._pinned("o_trunc", (n,), torch.uint8)
+            if return_final_obs:
+                fobs = self._pinned("o_final_obs", (n, self.DIM), torch.float32)
+            if return_info:
+                acc = self._pinned("o_acc", (n, self._ACC_DIM), torch.float32)
+        else:
+            obs, rew, term, trunc = self._obs, self._reward, self._term, self._trunc
+            if return_final_obs:
+                if self._final_obs is None:
+                    self._final_obs = torch.zeros((n, self.DIM), dtype=torch.float32, device=self.device)
+                fobs = self._final_obs
+            if return_info:
+                if self._acc is None:
+                    self._acc = torch.zeros((n, self._ACC_DIM), dtype=torch.float32, device=self.device)
+                acc = self._acc
+        if mode == "pipelined":
+            # ef_*_step_host: chunked; kernels write the device buffers, the copy engine drains them into pinned memory
+            hosts = [self._pinned("o_obs", (n, self.DIM), torch.float32), self._pinned("o_reward", (n,), torch.float32),
+                     self._pinned("o_term", (n,), torch.uint8), self._pinned("o_trunc", (n,), torch.uint8),
+                     self._pinned("o_final_obs", (n, self.DIM), torch.float32) if return_final_obs else None,
+                     self._pinned("o_acc", (n, self._ACC_DIM), torch.float32) if return_info else None]
+            d_act = _lib.ptr(self._device_scratch("action", (n,), torch.float32)) if self.host_stage_actions else None
+            with torch.cuda.device(self.device):
+                _lib.check(self._fn_step_host(
+                    self._pipe(), self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), p_act,
+                    d_act, self._seed, self._t, self.env_offset, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(term),
+                    _lib.ptr(trunc), _lib.ptr(fobs), _lib.ptr(acc), *[_lib.ptr(h) for h in hosts],
+                    _lib.ptr(self._stats_raw), n, int(self.autoreset), self.host_chunks, self._stream()))
+            obs, rew, term, trunc, fobs, acc = hosts
+        else:
+            self._call(self._fn_step, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
+                       p_act, self._seed, self._t_arg(), self.env_offset, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(term),
+                       _lib.ptr(trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n,
+                       int(self.autoreset))
         self._t += 1
         info = {}
         if host_io:
-            named = [("obs", self._obs), ("reward", self._reward), ("term", self._term), ("trunc", self._trunc)]
-            if return_final_obs:
-                named.append(("final_obs", fobs))
-            if return_info:
-                named.append(("acc", acc))
-            out = self._to_host(named)
+            if mode != "staged":
+                torch.cuda.current_stream(self.device).synchronize()
+                out = [t.numpy() for t in (obs, rew, term, trunc)]
+                out += [fobs.numpy()] if return_final_obs else []
+                out += [acc.numpy()] if return_info else []
+            else:
+                named = [("obs", self._obs), ("reward", self._reward), ("term", self._term), ("trunc", self._trunc)]
+                if return_final_obs:
+                    named.append(("final_obs", fobs))
+                if return_info:
+                    named.append(("acc", acc))
+                out = self._to_host(named)
             k = 4
             if return_final_obs:
                 info["final_observation"] = out[k]
                 k += 1
             if return_info:
-                info.update(self._info(out[k], out[3].view(np.bool_), np.asarray(actions).reshape(-1)))
+                info.update(self._info(out[k], out[3].view(np.bool_), h_act.numpy()))
             return out[0], out[1], out[2].view(np.bool_), out[3].view(np.bool_), info
         if return_final_obs:
             info["final_observation"] = fobs

@@ -277,6 +277,7 @@ class GridSpec:
 
 class VecGridWorld(VecEnv):
     """N GridWorld instances sharing one configuration.  See module docstring; kwargs as in the reference."""
+    _HOST_TRANSPORT = "staged"   # the one-pass persistent step kernel serialises its PCIe reads and writes: DMA wins
 
     def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
                  special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
@@ -448,19 +449,28 @@ class VecGridWorld(VecEnv):
         Returns (obs int32 [N,2], reward fp32 [N], terminated bool [N], truncated bool [N], info)."""
         torch = self._torch
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        mode = self.host_transport if host_io else None
+        if mode == "pipelined" and (self.rng == "pcg64" or draws is not None or self._clock is not None):
+            mode = "staged"     # the pipelined entry point covers the plain Philox step only
+        zero_copy = mode == "zerocopy"
         n = self.num_envs
-        if host_io and torch.is_tensor(actions):      # CPU torch tensor (pinned => zero-copy staging)
-            act = self._to_device("action", actions.reshape(-1).to(torch.int32), torch.int32, (n,))
-        elif host_io:
-            a = np.asarray(actions)
-            if a.shape == ():
-                a = a.reshape(1)
-            act = self._to_device("action", a.astype(np.int32, copy=False), torch.int32, (n,))
+        if host_io:
+            if torch.is_tensor(actions):      # CPU torch tensor (pinned int32 => used in place)
+                a = actions.reshape(-1).to(torch.int32)
+            else:
+                a = np.asarray(actions)
+                a = (a.reshape(1) if a.shape == () else a).astype(np.int32, copy=False)
+            h_act = self._host_in("action", a, torch.int32, (n,))
+            if mode == "staged":
+                p_act = _lib.ptr(self._to_device("action", h_act, torch.int32, (n,)))
+            else:
+                p_act = h_act.data_ptr()
         else:
             if tuple(actions.shape) != (n,):
                 raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
             act = actions if actions.dtype == torch.int32 else actions.to(torch.int32)
             act = act.contiguous()
+            p_act = _lib.ptr(act)
         drw = None
         if draws is not None:
             if torch.is_tensor(draws) and draws.is_cuda:
@@ -470,36 +480,63 @@ class VecGridWorld(VecEnv):
                 drw = self._to_device("draw", d, torch.int32, (n,))
         fobs = None
         if return_final_obs:
-            if self._final_obs is None:
-                self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
-            fobs = self._final_obs
-        if self.rng == "pcg64":
+            if zero_copy:
+                fobs = self._pinned("o_final_obs", (n, 2), torch.int32)
+            else:
+                if self._final_obs is None:
+                    self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+                fobs = self._final_obs
+        o_rew, o_term, o_trunc = self._out_sections
+        if zero_copy:
+            # the kernel stores obs/reward/flags straight into pinned host memory (UVA pointer): no staging copy
+            h_out = self._pinned("o_out", (self._out_bytes,), torch.uint8)
+            base = h_out.data_ptr()
+        else:
+            base = self._out.data_ptr()
+        p_obs, p_rew, p_term, p_trunc = base, base + o_rew, base + o_term, base + o_trunc
+        if mode == "pipelined":
+            h_out = self._pinned("o_out", (self._out_bytes,), torch.uint8)
+            hb = h_out.data_ptr()
+            d_act = _lib.ptr(self._device_scratch("action", (n,), torch.int32)) if self.host_stage_actions else None
+            h_fobs = self._pinned("o_final_obs", (n, 2), torch.int32) if return_final_obs else None
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.ef_gridworld_step_host(
+                    self._pipe(), self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), p_act, d_act,
+                    self._seed, self._t, self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term),
+                    _lib.ptr(self._trunc), _lib.ptr(fobs), hb, hb + o_rew, hb + o_term, hb + o_trunc, _lib.ptr(h_fobs),
+                    _lib.ptr(self._stats_raw), _lib.ptr(self.err), n, int(self.autoreset), self.host_chunks, self._stream()))
+            if return_final_obs:
+                fobs = h_fobs
+        elif self.rng == "pcg64":
             if drw is not None:
                 raise ValueError("injected draws are not available with rng='pcg64' (each env owns its generator)")
             self._call(self._lib.ef_gridworld_step_pcg64, self._desc, self._thr53, self._cap53, _lib.ptr(self.pos),
                        _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(self._rng_state), _lib.ptr(self._rng_inc),
-                       _lib.ptr(act), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term),
-                       _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err), n,
-                       int(self.autoreset))
+                       p_act, self.env_offset, p_obs, p_rew, p_term, p_trunc, _lib.ptr(fobs), _lib.ptr(self._stats_raw),
+                       _lib.ptr(self.err), n, int(self.autoreset))
         else:
             self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
-                       _lib.ptr(self.ep_ret), _lib.ptr(act), _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
-                       _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc),
-                       _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n,
-                       int(self.autoreset))
+                       _lib.ptr(self.ep_ret), p_act, _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
+                       p_obs, p_rew, p_term, p_trunc, _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err),
+                       _lib.ptr(self._clock), n, int(self.autoreset))
         self._t += 1
         if self.strict:
             self.check_errors()
         info = {}
         if host_io:
-            named = [("out", self._out)]
-            if return_final_obs:
-                named.append(("final_obs", fobs))
-            out = self._to_host(named)
-            if return_final_obs:
-                info["final_observation"] = out[1]
-            buf = out[0]
-            o_rew, o_term, o_trunc = self._out_sections
+            if mode != "staged":
+                torch.cuda.current_stream(self.device).synchronize()
+                buf = h_out.numpy()
+                if return_final_obs:
+                    info["final_observation"] = fobs.numpy()
+            else:
+                named = [("out", self._out)]
+                if return_final_obs:
+                    named.append(("final_obs", fobs))
+                out = self._to_host(named)
+                if return_final_obs:
+                    info["final_observation"] = out[1]
+                buf = out[0]
             return (buf[:8 * n].view(np.int32).reshape(n, 2), buf[o_rew:o_rew + 4 * n].view(np.float32),
                     buf[o_term:o_term + n].view(np.bool_), buf[o_trunc:o_trunc + n].view(np.bool_), info)
         if return_final_obs:

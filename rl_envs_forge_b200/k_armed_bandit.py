@@ -177,19 +177,39 @@ class VecKArmedBandit(VecEnv):
         torch = self._torch
         n = self.num_envs
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        mode = self.host_transport if host_io else None
+        obs, rew = self._obs, self._reward
         if host_io:
-            a = np.asarray(actions).reshape(-1)
+            a = (actions.numpy() if torch.is_tensor(actions) else np.asarray(actions)).reshape(-1)
             if self.strict:
                 assert ((0 <= a) & (a < self.k)).all(), "Invalid action, must be between 0 and k-1."
-            act = self._to_device("action", a.astype(np.int32, copy=False), torch.int32, (n,))
+            src = actions.reshape(-1) if torch.is_tensor(actions) and actions.dtype == torch.int32 else a.astype(np.int32, copy=False)
+            h_act = self._host_in("action", src, torch.int32, (n,))
+            if mode == "staged":
+                p_act = _lib.ptr(self._to_device("action", h_act, torch.int32, (n,)))
+            else:   # the kernel reads the actions from pinned host memory directly
+                p_act = h_act.data_ptr()
+                h_obs = self._pinned("o_obs", (n,), torch.int32)
+                h_rew = self._pinned("o_reward", (n,), torch.float32)
+                if mode == "zerocopy":   # ... and writes obs + reward there too
+                    obs, rew = h_obs, h_rew
         else:
             if tuple(actions.shape) != (n,):
                 raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
             act = (actions if actions.dtype == torch.int32 else actions.to(torch.int32)).contiguous()
+            p_act = _lib.ptr(act)
         arms = self._arm_table(1)
-        self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, _lib.ptr(act), self._seed, self._steps_since_reset,
-                   self.env_offset, 1, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._stats_raw),
-                   _lib.ptr(self.err), n)
+        if mode == "pipelined":
+            d_act = _lib.ptr(self._device_scratch("action", (n,), torch.int32)) if self.host_stage_actions else None
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.ef_bandit_step_host(
+                    self._pipe(), _lib.ptr(arms), self.k, p_act, d_act, self._seed, self._steps_since_reset, self.env_offset,
+                    _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(h_obs), _lib.ptr(h_rew), _lib.ptr(self._stats_raw),
+                    _lib.ptr(self.err), n, self.host_chunks, self._stream()))
+            obs, rew = h_obs, h_rew
+        else:
+            self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, p_act, self._seed, self._steps_since_reset,
+                       self.env_offset, 1, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self._stats_raw), _lib.ptr(self.err), n)
         self._advance(1)
         if self.strict:
             try:
@@ -197,6 +217,9 @@ class VecKArmedBandit(VecEnv):
             except ValueError as e:
                 raise AssertionError("Invalid action, must be between 0 and k-1.") from e
         if host_io:
+            if mode != "staged":
+                torch.cuda.current_stream(self.device).synchronize()
+                return obs.numpy(), rew.numpy(), np.ones(n, bool), np.zeros(n, bool), {}
             obs, rew = self._to_host([("obs", self._obs), ("reward", self._reward)])
             return obs, rew, np.ones(n, bool), np.zeros(n, bool), {}
         return self._obs, self._reward, self._done, self._trunc, {}

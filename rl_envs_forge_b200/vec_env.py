@@ -57,6 +57,8 @@ def all_reduce_stats(stats, group=None):
 class VecEnv:
     """Base class: owns the SoA buffers shared by all env families (episode counters, stats, error word)."""
 
+    _HOST_TRANSPORT = "zerocopy"   # default host-buffer transport of the family (see __init__)
+
     def __init__(self, num_envs, device=None, seed=None, env_offset=0, autoreset=True):
         import torch
         if not isinstance(num_envs, (int, np.integer)) or num_envs <= 0:
@@ -87,6 +89,20 @@ class VecEnv:
         self._stats_raw = torch.zeros(_lib.EF_STATS_REPLICAS * _lib.EF_STATS_STRIDE, dtype=torch.float64, device=dev)
         self.err = torch.zeros(_lib.EF_ERR_LEN, dtype=torch.int32, device=dev)
         self._host = {}
+        # how step() moves HOST buffers (numpy / CPU tensors in, numpy out):
+        #   "staged"    copy-engine H2D -> one kernel -> D2H, serialised
+        #   "zerocopy"  one launch that reads the actions from and writes the outputs to pinned host memory itself
+        #   "pipelined" ef_*_step_host: the batch is cut into `host_chunks` ranges; the kernel of a chunk reads its actions
+        #               straight from pinned host memory while the copy engine drains the previous chunk's outputs
+        # The default is per env family, chosen from measurements on B200 / PCIe Gen5 (profiles/r01_host_transport.md):
+        # the link moves ~50 GB/s in total whichever way the bytes are scheduled, so the fewest operations win.
+        # ENVFORGE_HOST_TRANSPORT / ENVFORGE_HOST_CHUNKS override the defaults for A/B timing.
+        self.host_transport = os.environ.get("ENVFORGE_HOST_TRANSPORT", self._HOST_TRANSPORT)
+        if self.host_transport not in ("pipelined", "zerocopy", "staged"):
+            raise ValueError("host_transport must be 'pipelined', 'zerocopy' or 'staged'")
+        self.host_chunks = int(os.environ.get("ENVFORGE_HOST_CHUNKS", "4"))
+        self.host_stage_actions = False   # pipelined: True = copy-engine H2D of the actions instead of zero-copy reads
+        self._pipe_handle = None
         self._clock = None  # optional device-resident step clock (CUDA-graph capture), see enable_device_clock()
 
     # -- device clock ---------------------------------------------------------------------------------------------
@@ -114,6 +130,22 @@ class VecEnv:
         with self._torch.cuda.device(self.device):
             _lib.check(fn(*args, self._stream()))
 
+    def _pipe(self):
+        """Lazily created ef_host_pipe (two copy streams + events) of the pipelined host-buffer step."""
+        if self._pipe_handle is None:
+            h = _lib.C.c_void_p()
+            with self._torch.cuda.device(self.device):
+                _lib.check(self._lib.ef_host_pipe_create(_lib.C.byref(h)))
+            self._pipe_handle = h
+        return self._pipe_handle
+
+    def _device_scratch(self, name, shape, dtype):
+        t = self._host.get("d_" + name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self._torch.empty(shape, dtype=dtype, device=self.device)
+            self._host["d_" + name] = t
+        return t
+
     def _pinned(self, name, shape, dtype):
         t = self._host.get(name)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
@@ -121,18 +153,23 @@ class VecEnv:
             self._host[name] = t
         return t
 
-    def _to_device(self, name, array, dtype, shape):
-        """Host array -> device tensor on the current stream.  A pinned CPU torch tensor of the right dtype is copied
-        directly (DMA from the caller's buffer); anything else goes through a pinned staging buffer first."""
+    def _host_in(self, name, array, dtype, shape):
+        """Host array -> pinned CPU tensor of `dtype`/`shape`.  A pinned torch tensor of the right dtype is used as is (the
+        device reads the caller's buffer); anything else is copied into a pinned staging buffer first."""
         torch = self._torch
         src = array if torch.is_tensor(array) else torch.as_tensor(np.ascontiguousarray(array))
         if tuple(src.shape) != tuple(shape):
             raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(src.shape)}")
         if src.is_pinned() and src.dtype == dtype and src.is_contiguous():
-            stage = src
-        else:
-            stage = self._pinned("h_" + name, shape, dtype)
-            stage.copy_(src)
+            return src
+        stage = self._pinned("h_" + name, shape, dtype)
+        stage.copy_(src)
+        return stage
+
+    def _to_device(self, name, array, dtype, shape):
+        """Host array -> device tensor on the current stream (copy-engine DMA from pinned memory)."""
+        torch = self._torch
+        stage = self._host_in(name, array, dtype, shape)
         dev = self._host.get("d_" + name)
         if dev is None or tuple(dev.shape) != tuple(shape) or dev.dtype != dtype:
             dev = torch.empty(shape, dtype=dtype, device=self.device)
@@ -200,4 +237,13 @@ class VecEnv:
         return self._t if self._clock is None else int(self._clock[0].item())
 
     def close(self):
-        pass
+        if getattr(self, "_pipe_handle", None) is not None:
+            self._torch.cuda.current_stream(self.device).synchronize()
+            self._lib.ef_host_pipe_destroy(self._pipe_handle)
+            self._pipe_handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -54,6 +54,10 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ef_cartpole_step(None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, None,
                                 8, 1, None) == 1
     assert lib.ef_bandit_step(None, 10, None, 0, 0, 0, 1, None, None, None, None, 8, None) == 1
+    # host-buffer entry points: a missing pipe / host action buffer is rejected up front
+    assert lib.ef_bandit_step_host(None, None, 10, None, None, 0, 0, 0, None, None, None, None, None, None, 8, 4, None) == 1
+    assert lib.ef_gridworld_step_host(None, ctypes.byref(d), *([None] * 5), 0, 0, 0, *([None] * 12), 8, 1, 4, None) == 1
+    assert lib.ef_host_pipe_create(None) == 1 and lib.ef_host_pipe_destroy(None) == 0
 
 
 def test_no_fallback_without_cuda():

@@ -149,3 +149,20 @@ def test_reference_test_suite_on_vec_surface():
     with pytest.raises(ValueError, match="scale < 0"):                                  # numpy's error for std < 0
         env.step(np.array([0]))
     assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("transport", ["pipelined", "pipelined+h2d", "zerocopy", "staged"])
+def test_host_buffer_path_equals_device_path(transport):
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    n = 5003
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items()}
+    a, b = VecKArmedBandit(n, k=10, arm_params=arms, seed=5), VecKArmedBandit(n, k=10, arm_params=arms, seed=5)
+    a.host_transport, a.host_stage_actions, a.host_chunks = transport.split("+")[0], transport.endswith("+h2d"), 3
+    rng = np.random.default_rng(2)
+    for _ in range(5):
+        act = rng.integers(0, 10, n).astype(np.int32)
+        oa, ob = a.step(act), b.step(torch.from_numpy(act).cuda())
+        assert isinstance(oa[1], np.ndarray)
+        assert np.array_equal(oa[0], ob[0].cpu().numpy()) and np.array_equal(oa[1], ob[1].cpu().numpy())
+        assert oa[2].all() and not oa[3].any()

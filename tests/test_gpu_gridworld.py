@@ -329,20 +329,28 @@ def test_autoreset_semantics_and_final_observation():
     assert env.ep_len.cpu().tolist() == [0, 0, 1, 1]
 
 
-def test_host_buffer_path_equals_device_path():
+@pytest.mark.parametrize("transport", ["pipelined", "pipelined+h2d", "zerocopy", "staged"])
+def test_host_buffer_path_equals_device_path(transport):
+    """numpy / pinned actions in -> numpy out.  "zerocopy": the step kernel reads and writes pinned host memory itself;
+    "staged": copy-engine H2D, kernel, D2H.  Both must equal the device-tensor path bit for bit."""
     import torch
     from rl_envs_forge_b200 import VecGridWorld
     cfg = _vec_kwargs(_config2(0.8))
-    a = VecGridWorld(10_000, seed=4, **cfg)
-    b = VecGridWorld(10_000, seed=4, **cfg)
+    n = 10_001                                             # ragged tail included
+    a = VecGridWorld(n, seed=4, **cfg)
+    a.host_transport, a.host_stage_actions, a.host_chunks = transport.split("+")[0], transport.endswith("+h2d"), 3
+    b = VecGridWorld(n, seed=4, **cfg)
     rng = np.random.default_rng(0)
-    for _ in range(20):
-        act = rng.integers(0, 4, 10_000).astype(np.int32)
-        oa = a.step(act)                                   # numpy in -> numpy out through pinned staging
-        ob = b.step(torch.from_numpy(act).cuda())
-        assert isinstance(oa[0], np.ndarray)
+    for i in range(20):
+        act = rng.integers(0, 4, n).astype(np.int32)
+        src = torch.from_numpy(act).pin_memory() if i % 2 else act   # caller-pinned buffers are used in place
+        oa = a.step(src, return_final_obs=True)
+        ob = b.step(torch.from_numpy(act).cuda(), return_final_obs=True)
+        assert isinstance(oa[0], np.ndarray) and oa[0].dtype == np.int32 and oa[2].dtype == np.bool_
         assert np.array_equal(oa[0], ob[0].cpu().numpy()) and np.array_equal(oa[1], ob[1].cpu().numpy())
         assert np.array_equal(oa[2], ob[2].cpu().numpy()) and np.array_equal(oa[3], ob[3].cpu().numpy())
+        assert np.array_equal(oa[4]["final_observation"], ob[4]["final_observation"].cpu().numpy())
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
 
 
 # ---- stream-exact mode: rng="pcg64" -----------------------------------------------------------------------------------

@@ -261,3 +261,25 @@ def test_reference_test_suite_on_vec_surface():
     _, _, term, trunc, _ = env.step(np.array([0.0], np.float32))
     assert term[0] and not trunc[0]
     assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "pendulumdisk"])
+@pytest.mark.parametrize("transport", ["pipelined", "pipelined+h2d", "zerocopy", "staged"])
+def test_host_buffer_path_equals_device_path(kind, transport):
+    """numpy actions in -> numpy out; the zero-copy transport (kernel reads/writes pinned host memory) and the staged
+    one (copy engines) must both equal the device-tensor path bit for bit."""
+    import torch
+    Vec, _, _, dim = _cls(kind)
+    n = 4099
+    a, b = Vec(n, seed=9, episode_length_limit=7), Vec(n, seed=9, episode_length_limit=7)
+    a.host_transport, a.host_stage_actions, a.host_chunks = transport.split("+")[0], transport.endswith("+h2d"), 3
+    rng = np.random.default_rng(1)
+    for i in range(12):
+        act = rng.uniform(-3, 3, n).astype(np.float32)
+        oa = a.step(act.reshape(n, 1) if i % 2 else act, return_final_obs=True, return_info=True)
+        ob = b.step(torch.from_numpy(act).cuda(), return_final_obs=True, return_info=True)
+        assert isinstance(oa[0], np.ndarray) and oa[0].shape == (n, dim) and oa[2].dtype == np.bool_
+        for x, y in zip(oa[:4], ob[:4]):
+            assert np.array_equal(x, y.cpu().numpy())
+        assert np.array_equal(oa[4]["final_observation"], ob[4]["final_observation"].cpu().numpy())
+    assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len)
