@@ -9,6 +9,9 @@
 // oracle (oracle/bandit.py) feeds the same primitives to the float64 legacy algorithms, so device and oracle differ
 // only by fp32 rounding -- except when an accept/reject comparison of a rejection sampler lands within that rounding
 // (a "flip"), which the parity test counts.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ef_common.cuh"
 
 namespace ef {
@@ -75,9 +78,34 @@ struct Primitives {
     }
 };
 
+// The same primitive stream, evaluated on demand.  Used by the family-sorted kernel, where the lanes of a warp hold the
+// same family and nothing needs hoisting; word for word and formula for formula identical to `Primitives`.
+struct LazyPrimitives {
+    uint64_t seed, t;
+    uint32_t g, consumed;
+    uint4 blk;
+    __device__ __forceinline__ LazyPrimitives(uint64_t seed_, uint32_t g_, uint64_t t_) : seed(seed_), t(t_), g(g_), consumed(0) {
+        blk = draw_block(seed, g, t, kStreamBandit, 0);
+    }
+    __device__ __forceinline__ uint32_t word() {
+        const uint32_t lane = consumed & 3u;
+        if (lane == 0u && consumed != 0u) blk = draw_block(seed, g, t, kStreamBandit, consumed >> 2);
+        ++consumed;
+        return lane == 0u ? blk.x : lane == 1u ? blk.y : lane == 2u ? blk.z : blk.w;
+    }
+    __device__ __forceinline__ float u() { return u23(word()); }
+    __device__ __forceinline__ float n() {
+        const float a = u();
+        const float b = u();
+        return sqrtf(-2.0f * logf(a)) * cospif(2.0f * b);
+    }
+    __device__ __forceinline__ float std_exp() { return -logf(1.0f - u()); }
+};
+
 constexpr int kMaxRejections = 1024;  // termination guard; P(reaching it) is astronomically small for valid params
 
-__device__ float std_gamma(Primitives& pr, float shape) {
+template <typename P>
+__device__ float std_gamma(P& pr, float shape) {
     if (shape == 1.0f) return pr.std_exp();
     if (shape == 0.0f) return 0.0f;
     if (shape < 1.0f) {  // Ahrens-Dieter style (numpy legacy_standard_gamma, shape < 1)
@@ -117,7 +145,8 @@ __device__ float std_gamma(Primitives& pr, float shape) {
     return b * v;
 }
 
-__device__ float beta_sample(Primitives& pr, float a, float b) {
+template <typename P>
+__device__ float beta_sample(P& pr, float a, float b) {
     if (a <= 1.0f && b <= 1.0f) {  // Johnk
         const float ia = 1.0f / a, ib = 1.0f / b;
         float x = 0.0f, y = 1.0f;
@@ -148,7 +177,8 @@ __device__ __forceinline__ float default_mean(uint64_t seed, uint32_t g, uint32_
     return sqrtf(-2.0f * logf(u23(w.x))) * cospif(2.0f * u23(w.y));
 }
 
-__device__ float sample_arm(const ef_arm arm, Primitives& pr, uint64_t seed, uint32_t g, uint32_t arm_index) {
+template <typename P>
+__device__ float sample_arm(const ef_arm arm, P& pr, uint64_t seed, uint32_t g, uint32_t arm_index) {
     switch (arm.family) {
         case EF_ARM_NORMAL: return arm.p0 + arm.p1 * pr.n();
         case EF_ARM_UNIFORM: return arm.p0 + (arm.p1 - arm.p0) * pr.u();
@@ -202,6 +232,136 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
     cta_epilogue(acc, errs, a.stats, a.err, nullptr, 0ull, 0ull);
 }
 
+// ---- family-sorted step kernel ---------------------------------------------------------------------------------------
+// The eight samplers share almost no code, so a warp whose lanes hold different families executes them one after the
+// other (measured on the plain kernel with 10 mixed arms: 11.2 of 32 lanes active per instruction).  A reward is a pure
+// function of (global env index, step, action, arm parameters), so the order in which a CTA evaluates its envs is free:
+// this kernel takes a tile of kTile consecutive envs, bins them by sampler code path in shared memory (warp-aggregated
+// counting sort), evaluates them in sorted order -- the 32 lanes of a warp then run the same sampler -- and writes the
+// rewards back through shared memory so global stores stay coalesced.  Results are bit-identical to the plain kernel.
+constexpr int kItemsPerThread = 8;
+constexpr int kTile = kThreads * kItemsPerThread;  // 2048 envs per tile; local index fits 12 bits
+constexpr int kBins = 16;
+constexpr int kSortedCtasPerSm = 3;               // 80 registers x 256 threads: three resident CTAs per SM
+constexpr uint32_t kBinSkip = 15u;                 // out-of-range env or rejected action: not evaluated
+constexpr int32_t kSortedMaxArms = 1 << 20;        // action is packed next to the 12-bit local index
+
+__device__ __forceinline__ ef_arm load_arm(const ef_arm* __restrict__ arms, int64_t index) {
+    const int4 raw = __ldg(reinterpret_cast<const int4*>(arms) + index);
+    ef_arm arm;
+    arm.family = raw.x;
+    arm.p0 = __int_as_float(raw.y);
+    arm.p1 = __int_as_float(raw.z);
+    arm.reserved = 0;
+    return arm;
+}
+
+// Code-path bin of an arm: the family, with the samplers that branch on their parameters split further.
+__device__ __forceinline__ uint32_t arm_bin(const ef_arm& arm) {
+    const uint32_t f = static_cast<uint32_t>(arm.family);
+    if (f == EF_ARM_GAMMA) return arm.p0 > 1.0f ? 3u : (arm.p0 == 1.0f ? 2u : (arm.p0 == 0.0f ? 1u : 9u));
+    if (f == EF_ARM_BETA) {
+        if (arm.p0 <= 1.0f && arm.p1 <= 1.0f) return 10u;                 // Johnk
+        return (arm.p0 > 1.0f && arm.p1 > 1.0f) ? 4u : 11u;               // two Marsaglia-Tsang gammas / mixed
+    }
+    return f <= 8u ? f : 12u;
+}
+
+__global__ void __launch_bounds__(kThreads, kSortedCtasPerSm) bandit_step_sorted_kernel(const BanditArgs a) {
+    __shared__ uint32_t s_cnt[kBins], s_base[kBins];
+    __shared__ uint32_t s_sorted[kTile];   // action << 12 | local index, ordered by bin
+    __shared__ float s_rew[kTile];
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint32_t lane = threadIdx.x & 31u;
+    const int64_t tiles = (a.n + kTile - 1) / kTile;
+    const int64_t units = tiles * a.K;
+    for (int64_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        const int j = static_cast<int>(unit / tiles);
+        const int64_t base_i = (unit - static_cast<int64_t>(j) * tiles) * kTile;
+        const uint64_t t = a.t0 + static_cast<uint64_t>(j);
+        const ef_arm* __restrict__ arms = a.arms + static_cast<int64_t>(j) * a.k;
+        if (threadIdx.x < kBins) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        // phase 1: actions in (coalesced), observations out, bin + rank of every env of the tile
+        uint32_t key_rank[kItemsPerThread];
+        int32_t acts[kItemsPerThread];
+#pragma unroll
+        for (int it = 0; it < kItemsPerThread; ++it) {
+            const uint32_t l = static_cast<uint32_t>(it) * kThreads + threadIdx.x;
+            const int64_t i = base_i + l;
+            uint32_t key = kBinSkip;
+            int32_t act = 0;
+            if (i < a.n) {
+                const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+                const int64_t o = static_cast<int64_t>(j) * a.n + i;
+                act = a.action ? __ldg(a.action + o)
+                               : static_cast<int32_t>(__umulhi(group_word1(a.seed, g, t, kStreamPolicy),
+                                                               static_cast<uint32_t>(a.k)));
+                if (a.obs) a.obs[o] = act;  // observation = action (k_armed_bandit.py:200)
+                if (static_cast<uint32_t>(act) >= static_cast<uint32_t>(a.k)) {
+                    errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+                    s_rew[l] = 0.0f;
+                } else {
+                    key = arm_bin(load_arm(arms, act));
+                }
+            }
+            // warp-aggregated counting: lanes with the same bin elect a leader that reserves their slots at once
+            const uint32_t peers = __match_any_sync(0xffffffffu, key);
+            const uint32_t leader = static_cast<uint32_t>(__ffs(peers) - 1);
+            uint32_t first = 0u;
+            if (lane == leader && key != kBinSkip) first = atomicAdd(&s_cnt[key], static_cast<uint32_t>(__popc(peers)));
+            first = __shfl_sync(0xffffffffu, first, leader);
+            key_rank[it] = key | ((first + static_cast<uint32_t>(__popc(peers & ((1u << lane) - 1u)))) << 4);
+            acts[it] = act;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive prefix over the bins (one warp)
+            const uint32_t c = lane < kBins ? s_cnt[lane] : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < kBins; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= static_cast<uint32_t>(o)) incl += v;
+            }
+            if (lane < kBins) s_base[lane] = incl - c;
+        }
+        __syncthreads();
+        const uint32_t total = s_base[kBinSkip];  // envs to evaluate = everything in the bins below the skip bin
+#pragma unroll
+        for (int it = 0; it < kItemsPerThread; ++it) {
+            const uint32_t key = key_rank[it] & 15u;
+            if (key != kBinSkip)
+                s_sorted[s_base[key] + (key_rank[it] >> 4)] =
+                    (static_cast<uint32_t>(acts[it]) << 12) | (static_cast<uint32_t>(it) * kThreads + threadIdx.x);
+        }
+        __syncthreads();
+        // phase 2: evaluate in sorted order -- consecutive lanes run the same sampler
+        for (uint32_t p = threadIdx.x; p < total; p += kThreads) {
+            const uint32_t rec = s_sorted[p];
+            const uint32_t l = rec & 0xfffu, act = rec >> 12;
+            const uint32_t g = static_cast<uint32_t>(a.env_offset + base_i + l);
+            LazyPrimitives pr(a.seed, g, t);
+            const float r = sample_arm(load_arm(arms, act), pr, a.seed, g, act);
+            s_rew[l] = r;
+            acc.steps += 1u;
+            acc.finish(1, r);  // every bandit step is a finished one-step episode (done is always True, :198)
+        }
+        __syncthreads();
+        // phase 3: rewards out (coalesced)
+        if (a.reward) {
+#pragma unroll
+            for (int it = 0; it < kItemsPerThread; ++it) {
+                const uint32_t l = static_cast<uint32_t>(it) * kThreads + threadIdx.x;
+                const int64_t i = base_i + l;
+                if (i < a.n) a.reward[static_cast<int64_t>(j) * a.n + i] = s_rew[l];
+            }
+        }
+        __syncthreads();
+    }
+    cta_epilogue(acc, errs, a.stats, a.err, nullptr, 0ull, 0ull);
+}
+
 __global__ void __launch_bounds__(kThreads) bandit_means_kernel(int32_t k, uint64_t seed, uint64_t env_offset,
                                                                 float* __restrict__ means, int64_t n) {
     const int64_t total = n * k;
@@ -225,7 +385,14 @@ extern "C" int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* acti
     BanditArgs a{};
     a.arms = arms; a.k = k; a.action = action; a.seed = seed; a.t0 = t0; a.env_offset = env_offset; a.K = K;
     a.obs = obs; a.reward = reward; a.stats = stats; a.err = err; a.n = n;
-    bandit_step_kernel<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    const bool unsorted = getenv("ENVFORGE_BANDIT_UNSORTED") != nullptr;  // A/B + parity switch: the plain kernel
+    if (k <= kSortedMaxArms && !unsorted) {
+        const int64_t units = (n + kTile - 1) / kTile * K;
+        const int grid = static_cast<int>(std::min<int64_t>(units, static_cast<int64_t>(sm_count()) * kSortedCtasPerSm));
+        bandit_step_sorted_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    } else {
+        bandit_step_kernel<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    }
     return cuda_status(cudaGetLastError());
 }
 

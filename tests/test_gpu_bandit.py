@@ -166,3 +166,33 @@ def test_host_buffer_path_equals_device_path(transport):
         assert isinstance(oa[1], np.ndarray)
         assert np.array_equal(oa[0], ob[0].cpu().numpy()) and np.array_equal(oa[1], ob[1].cpu().numpy())
         assert oa[2].all() and not oa[3].any()
+
+
+def test_family_sorted_kernel_is_bit_identical_to_plain_kernel(monkeypatch):
+    """The default kernel evaluates a CTA's tile in sampler-sorted order; the plain one-env-per-thread kernel
+    (ENVFORGE_BANDIT_UNSORTED=1) must give the same bits: step, K-step rollout, random policy, rejected actions, ragged n."""
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items()}
+    arms[8] = dict(distribution="gamma", shape=0.4, scale=2.0)
+    arms[9] = dict(distribution="beta", a=0.5, b=0.7)
+    arms[10] = dict(distribution="gamma", shape=1.0, scale=2.0)
+    arms[11] = dict(distribution="beta", a=0.5, b=3.0)
+    for n in (1, 31, 2047, 2049, 100_003):
+        outs = []
+        for unsorted in (False, True):
+            if unsorted:
+                monkeypatch.setenv("ENVFORGE_BANDIT_UNSORTED", "1")
+            else:
+                monkeypatch.delenv("ENVFORGE_BANDIT_UNSORTED", raising=False)
+            env = VecKArmedBandit(n, k=14, arm_params=arms, seed=11)
+            act = torch.from_numpy(np.random.default_rng(n).integers(0, 14, n).astype(np.int32)).cuda()
+            act[::97] = 14                                    # rejected: "Invalid action" in the reference
+            o1, r1, *_ = env.step(act)
+            o2, r2 = env.rollout(3)                           # in-kernel random policy
+            a3 = torch.from_numpy(np.random.default_rng(n + 1).integers(0, 14, (2, n)).astype(np.int32)).cuda()
+            o3, r3 = env.rollout(2, a3)
+            outs.append([x.clone() for x in (o1, r1, o2, r2, o3, r3)] + [env.err[:1].clone(), env.stats[:2].clone(), env.stats[4].clone()])   # (which offender err[2:] names is kernel-specific)
+        for x, y in zip(*outs):
+            assert torch.equal(x, y)
+        assert int(outs[0][6][0]) == (n + 96) // 97
