@@ -107,6 +107,10 @@ typedef struct ef_grid_desc {
 
 /* GridWorld.step (:495-528) + GridWorld.reset (:530-551) fused as same-step auto-reset, for n envs.
  *   pos/ep_len/ep_ret  in/out state: cell index, episode_length_counter, running episode return (fp32).
+ *                      PACKED LAYOUT: ep_len may be NULL in every GridWorld entry point; `pos` then holds one 32-bit word
+ *                      per env, cell in bits 0-15 and episode_length_counter in bits 16-31 (8 fewer bytes moved per
+ *                      env-step).  Accepted only where the counter cannot pass 65535: autoreset != 0 and
+ *                      0 < episode_limit <= 65535; EF_ERR_INVALID_ARGUMENT otherwise.
  *   action             [n] int32 in {0,1,2,3}, or NULL: uniform random policy from the Philox policy word.
  *   draw               [n] uint32 injected outcome draws r (u = r*2^-32), or NULL: Philox transition word of step t.
  *   obs                [n,2] int32 (row, col) AFTER auto-reset (nullable).  final_obs: (row, col) BEFORE it (nullable).

@@ -11,6 +11,10 @@
 // written (pos, ep_len, ep_ret, obs[2], reward, terminated, truncated) = 42 B.  A thread owns four consecutive envs:
 // every access is a 128-bit vector load/store (flags: one 32-bit store), and one Philox4x32 call yields the four
 // outcome draws.  Grid-stride over a grid sized to the SM count; the table (8 KB for 8x8) is staged once per CTA.
+//
+// Packed state (ep_len == NULL): position and episode_length_counter share one 32-bit word per env, cell in bits 0-15
+// and the counter in bits 16-31.  Possible whenever the counter cannot exceed 65535 (auto-reset on, 0 < limit <= 65535;
+// cells are < 65536 by construction of the table), it removes 8 of the 42 bytes an env-step moves.
 #include "ef_common.cuh"
 
 namespace ef {
@@ -66,6 +70,42 @@ __device__ __forceinline__ const uint2* stage_table(const GridArgs& a) {
 __device__ __forceinline__ int2 cell_to_obs(const GridArgs& a, int32_t cell) {
     const int32_t row = a.cols == 1 ? cell : static_cast<int32_t>(__umulhi(static_cast<uint32_t>(cell), a.cols_magic));
     return make_int2(row, cell - row * a.cols);
+}
+
+// Scalar state access in either layout (see "Packed state" above).
+__device__ __forceinline__ void load_state1(const GridArgs& a, int64_t i, int32_t& pos, int32_t& len) {
+    if (a.ep_len) {
+        pos = a.pos[i];
+        len = a.ep_len[i];
+    } else {
+        const uint32_t w = static_cast<uint32_t>(a.pos[i]);
+        pos = static_cast<int32_t>(w & 0xffffu);
+        len = static_cast<int32_t>(w >> 16);
+    }
+}
+__device__ __forceinline__ void store_state1(const GridArgs& a, int64_t i, int32_t pos, int32_t len) {
+    if (a.ep_len) {
+        a.pos[i] = pos;
+        a.ep_len[i] = len;
+    } else {
+        a.pos[i] = static_cast<int32_t>(static_cast<uint32_t>(pos) | (static_cast<uint32_t>(len) << 16));
+    }
+}
+__device__ __forceinline__ void unpack4(const int4 w, int32_t (&pos)[4], int32_t (&len)[4]) {
+    const uint32_t v[4] = {static_cast<uint32_t>(w.x), static_cast<uint32_t>(w.y), static_cast<uint32_t>(w.z),
+                           static_cast<uint32_t>(w.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        pos[j] = static_cast<int32_t>(v[j] & 0xffffu);
+        len[j] = static_cast<int32_t>(v[j] >> 16);
+    }
+}
+__device__ __forceinline__ int4 pack4(const int32_t (&pos)[4], const int32_t (&len)[4]) {
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = static_cast<uint32_t>(pos[j]) | (static_cast<uint32_t>(len[j]) << 16);
+    return make_int4(static_cast<int32_t>(v[0]), static_cast<int32_t>(v[1]), static_cast<int32_t>(v[2]),
+                     static_cast<int32_t>(v[3]));
 }
 
 // One transition of one env.  Returns bit0 terminated, bit1 truncated, bit2 rejected (state untouched).
@@ -178,12 +218,12 @@ __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, boo
     QuadIn in;
 #if EF_STREAMING
     in.p4 = __ldcs(reinterpret_cast<const int4*>(a.pos + base));
-    in.l4 = __ldcs(reinterpret_cast<const int4*>(a.ep_len + base));
+    in.l4 = a.ep_len ? __ldcs(reinterpret_cast<const int4*>(a.ep_len + base)) : make_int4(0, 0, 0, 0);
     in.r4 = __ldcs(reinterpret_cast<const float4*>(a.ep_ret + base));
     in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.action + base));
 #else
     in.p4 = *reinterpret_cast<const int4*>(a.pos + base);
-    in.l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
+    in.l4 = a.ep_len ? *reinterpret_cast<const int4*>(a.ep_len + base) : make_int4(0, 0, 0, 0);
     in.r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
     in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
 #endif
@@ -198,8 +238,13 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
     Quad q;
     int32_t act[4] = {in.a4.x, in.a4.y, in.a4.z, in.a4.w};
     uint32_t r[4] = {0u, 0u, 0u, 0u};
-    q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
-    q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
+    const bool packed = a.ep_len == nullptr;
+    if (packed) {
+        unpack4(in.p4, q.pos, q.len);
+    } else {
+        q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
+        q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
+    }
     q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
     if (philox_act) {
         uint32_t w[4];
@@ -223,8 +268,12 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
     if (((act[0] | act[1] | act[2] | act[3]) & ~3) != 0) {
         // some action is outside 0..3 (the reference raises ValueError in Action(action)): redo the quad one env at a
         // time through the checking path, from the loaded state
-        q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
-        q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
+        if (packed) {
+            unpack4(in.p4, q.pos, q.len);
+        } else {
+            q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
+            q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
+        }
         q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
         q.term = q.trunc = 0u;
 #pragma unroll
@@ -258,8 +307,12 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #else
 #define EF_ST(ptr, val) (*(ptr) = (val))
 #endif
-    EF_ST(reinterpret_cast<int4*>(a.pos + base), make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]));
-    EF_ST(reinterpret_cast<int4*>(a.ep_len + base), make_int4(q.len[0], q.len[1], q.len[2], q.len[3]));
+    if (packed) {
+        EF_ST(reinterpret_cast<int4*>(a.pos + base), pack4(q.pos, q.len));
+    } else {
+        EF_ST(reinterpret_cast<int4*>(a.pos + base), make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]));
+        EF_ST(reinterpret_cast<int4*>(a.ep_len + base), make_int4(q.len[0], q.len[1], q.len[2], q.len[3]));
+    }
     EF_ST(reinterpret_cast<float4*>(a.ep_ret + base), make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]));
     if (a.obs) {  // observation after auto-reset = (row, col) of the stored position
         int4* o = reinterpret_cast<int4*>(a.obs + 2 * base);
@@ -344,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
             if (v < q_end) {
                 uint4* slot = stage + (j * 4) * kThreads + threadIdx.x;
                 cp_async16(slot, a.pos + v * 4);
-                cp_async16(slot + kThreads, a.ep_len + v * 4);
+                if (a.ep_len) cp_async16(slot + kThreads, a.ep_len + v * 4);
                 cp_async16(slot + 2 * kThreads, a.ep_ret + v * 4);
                 if (!philox_act) cp_async16(slot + 3 * kThreads, a.action + v * 4);
             }
@@ -385,7 +438,8 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x < (a.n & 3)) {  // ragged tail: at most three envs
         const int64_t i = (quads << 2) + threadIdx.x;
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-        int32_t pos = a.pos[i], len = a.ep_len[i];
+        int32_t pos, len;
+        load_state1(a, i, pos, len);
         float ret = a.ep_ret[i], rew;
         const int32_t act = philox_act ? static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30)
                                        : __ldg(a.action + i);
@@ -404,8 +458,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
             len = 0;
             ret = 0.0f;
         }
-        a.pos[i] = pos;
-        a.ep_len[i] = len;
+        store_state1(a, i, pos, len);
         a.ep_ret[i] = ret;
         if (a.obs) {
             const int2 ob = cell_to_obs(a, pos);
@@ -437,7 +490,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-        int32_t pos = a.pos[i], len = a.ep_len[i];
+        int32_t pos, len;
+        load_state1(a, i, pos, len);
         float ret = a.ep_ret[i], rew;
         const int32_t act = philox_act ? static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30)
                                        : __ldg(a.action + i);
@@ -456,8 +510,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
             len = 0;
             ret = 0.0f;
         }
-        a.pos[i] = pos;
-        a.ep_len[i] = len;
+        store_state1(a, i, pos, len);
         a.ep_ret[i] = ret;
         if (a.obs) {
             const int2 ob = cell_to_obs(a, pos);
@@ -495,7 +548,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_pcg64_kernel(const Gr
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-        int32_t pos = a.pos[i], len = a.ep_len[i];
+        int32_t pos, len;
+        load_state1(a, i, pos, len);
         float ret = a.ep_ret[i], rew = 0.0f;
         const int32_t act = __ldg(a.action + i);
         uint32_t f = 0u;
@@ -546,8 +600,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_pcg64_kernel(const Gr
             len = 0;
             ret = 0.0f;
         }
-        a.pos[i] = pos;
-        a.ep_len[i] = len;
+        store_state1(a, i, pos, len);
         a.ep_ret[i] = ret;
         if (a.obs) {
             const int2 ob = cell_to_obs(a, pos);
@@ -578,6 +631,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
     const int64_t groups_round = (groups + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
     const uint64_t t0 = a.t + clock_read(a.clock);
     const unsigned long long ticket = clock_ticket(a.clock);
+    const bool packed = a.ep_len == nullptr;
     const bool vec_ok = aligned(a.pos, 16) && aligned(a.ep_len, 16) && aligned(a.ep_ret, 16);
     for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < groups_round; v += stride) {
         const int64_t base = v * 4;
@@ -589,16 +643,21 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
         const bool full = valid[3] && vec_ok;
         if (full) {
             const int4 p4 = *reinterpret_cast<const int4*>(a.pos + base);
-            const int4 l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
             const float4 r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
-            q.pos[0] = p4.x; q.pos[1] = p4.y; q.pos[2] = p4.z; q.pos[3] = p4.w;
-            q.len[0] = l4.x; q.len[1] = l4.y; q.len[2] = l4.z; q.len[3] = l4.w;
+            if (packed) {
+                unpack4(p4, q.pos, q.len);
+            } else {
+                const int4 l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
+                q.pos[0] = p4.x; q.pos[1] = p4.y; q.pos[2] = p4.z; q.pos[3] = p4.w;
+                q.len[0] = l4.x; q.len[1] = l4.y; q.len[2] = l4.z; q.len[3] = l4.w;
+            }
             q.ret[0] = r4.x; q.ret[1] = r4.y; q.ret[2] = r4.z; q.ret[3] = r4.w;
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                q.pos[j] = valid[j] ? a.pos[base + j] : a.start_cell;
-                q.len[j] = valid[j] ? a.ep_len[base + j] : 0;
+                q.pos[j] = a.start_cell;
+                q.len[j] = 0;
+                if (valid[j]) load_state1(a, base + j, q.pos[j], q.len[j]);
                 q.ret[j] = valid[j] ? a.ep_ret[base + j] : 0.0f;
             }
         }
@@ -669,15 +728,18 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
             }
         }
         if (full) {
-            *reinterpret_cast<int4*>(a.pos + base) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
-            *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
+            if (packed) {
+                *reinterpret_cast<int4*>(a.pos + base) = pack4(q.pos, q.len);
+            } else {
+                *reinterpret_cast<int4*>(a.pos + base) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
+                *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
+            }
             *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (valid[j]) {
-                    a.pos[base + j] = q.pos[j];
-                    a.ep_len[base + j] = q.len[j];
+                    store_state1(a, base + j, q.pos[j], q.len[j]);
                     a.ep_ret[base + j] = q.ret[j];
                 }
             }
@@ -693,8 +755,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_reset_kernel(int32_t start
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         if (mask && !mask[i]) continue;
-        pos[i] = start_cell;
-        ep_len[i] = 0;
+        pos[i] = start_cell;              // packed layout (ep_len == NULL): counter bits are zero
+        if (ep_len) ep_len[i] = 0;
         ep_ret[i] = 0.0f;
         if (obs) { obs[2 * i] = r0; obs[2 * i + 1] = c0; }
     }
@@ -725,6 +787,9 @@ static int fill_args(const ef_grid_desc* g, GridArgs& a) {
     return EF_OK;
 }
 
+// Packed state (ep_len == NULL) needs a counter that provably stays below 2^16: auto-reset on and 0 < limit <= 65535.
+static bool packed_ok(const GridArgs& a, int32_t autoreset) { return autoreset != 0 && a.limit > 0 && a.limit <= 65535; }
+
 template <typename Kernel>
 static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStream_t stream, size_t extra_smem = 0) {
     const size_t bytes = (smem ? static_cast<size_t>(a.table_len) * sizeof(uint2) : 0) + extra_smem;
@@ -746,7 +811,8 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
                                  uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
-    if (n < 0 || !pos || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (n < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (!ep_len && !packed_ok(a, autoreset)) return EF_ERR_INVALID_ARGUMENT;
     if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0) return EF_OK;
     a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action; a.draw = draw;
@@ -787,7 +853,8 @@ extern "C" int ef_gridworld_step_pcg64(const ef_grid_desc* grid, const uint64_t*
                                        uint32_t* err, int64_t n, int32_t autoreset, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
-    if (n < 0 || !pos || !ep_len || !ep_ret || !rng_state || !rng_inc || !action || !thr53) return EF_ERR_INVALID_ARGUMENT;
+    if (n < 0 || !pos || !ep_ret || !rng_state || !rng_inc || !action || !thr53) return EF_ERR_INVALID_ARGUMENT;
+    if (!ep_len && !packed_ok(a, autoreset)) return EF_ERR_INVALID_ARGUMENT;
     if (!aligned(rng_state, 16) || !aligned(rng_inc, 16) || idx_cap53 < 0 || idx_cap53 > 3) return EF_ERR_INVALID_ARGUMENT;
     if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0) return EF_OK;
@@ -828,7 +895,8 @@ extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int3
                                     int64_t n, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
-    if (n < 0 || K < 0 || !pos || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (n < 0 || K < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (!ep_len && !packed_ok(a, 1)) return EF_ERR_INVALID_ARGUMENT;
     if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0 || K == 0) return EF_OK;
     a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
@@ -856,7 +924,7 @@ extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int3
 
 extern "C" int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos, int32_t* ep_len, float* ep_ret,
                                   int32_t* obs, const uint8_t* mask, int64_t n, void* stream) {
-    if (n < 0 || cols <= 0 || start_cell < 0 || !pos || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (n < 0 || cols <= 0 || start_cell < 0 || start_cell > 65535 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0) return EF_OK;
     gridworld_reset_kernel<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         start_cell, cols, pos, ep_len, ep_ret, obs, mask, n);

@@ -136,7 +136,7 @@ extern "C" int ef_gridworld_step_host(ef_host_pipe* pipe, const ef_grid_desc* gr
                              {d_truncated, h_truncated, 1}, {d_final_obs, h_final_obs, 8}};
     return run_host_pipe(pipe, h_action, d_action, 4, outs, 5, n, chunks, static_cast<cudaStream_t>(stream),
                          [&](int64_t off, int64_t cnt, const void* in) {
-                             return ef_gridworld_step(grid, pos + off, ep_len + off, ep_ret + off,
+                             return ef_gridworld_step(grid, pos + off, at(ep_len, off), ep_ret + off,
                                                       static_cast<const int32_t*>(in), nullptr, seed, t, env_offset + off,
                                                       at(d_obs, off, 2), at(d_reward, off), at(d_terminated, off),
                                                       at(d_truncated, off), at(d_final_obs, off, 2), stats, err, nullptr,

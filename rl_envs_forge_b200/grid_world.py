@@ -281,11 +281,21 @@ class VecGridWorld(VecEnv):
 
     def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
                  special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
-                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox"):
+                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox",
+                 state_layout="auto"):
         """`rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
         `rng="pcg64"`: every env owns the generator the reference would build for it,
         Generator(PCG64(SeedSequence(seed_i))) with seed_i = seed + global env index (or `seed` given as a sequence of
         N ints): `VecGridWorld(1, seed=s, rng="pcg64")` reproduces `GridWorld(seed=s)` draw for draw."""
+        if state_layout not in ("auto", "packed", "split"):
+            raise ValueError("state_layout must be 'auto', 'packed' or 'split'")
+        can_pack = (bool(autoreset) and isinstance(episode_length_limit, (int, np.integer))
+                    and 0 < episode_length_limit <= 65535)
+        if state_layout == "packed" and not can_pack:
+            raise ValueError("state_layout='packed' needs autoreset=True and 0 < episode_length_limit <= 65535")
+        # packed: cell (bits 0-15) and episode_length_counter (bits 16-31) share one int32 per env -- 8 fewer bytes per
+        # env-step through HBM; `pos` / `ep_len` stay available as (computed) properties
+        self._packed = can_pack and state_layout != "split"
         seed_list = None
         if rng not in ("philox", "pcg64"):
             raise ValueError("rng must be 'philox' or 'pcg64'")
@@ -313,7 +323,10 @@ class VecGridWorld(VecEnv):
         self.action_space = spaces.Batched(self.single_action_space, num_envs)
         self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
         n, dev = self.num_envs, self.device
-        self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
+        if self._packed:
+            self._pl = torch.zeros(n, dtype=torch.int32, device=dev)
+        else:
+            self._pos_split = torch.zeros(n, dtype=torch.int32, device=dev)
         # the four per-step outputs live back to back in ONE allocation (16-byte aligned sections), so the host-buffer
         # path brings them back with a single device->host copy
         pad = lambda b: (b + 15) // 16 * 16  # noqa: E731
@@ -344,6 +357,65 @@ class VecGridWorld(VecEnv):
             self._cap53 = cap
         self._upload_table()
         self.reset()
+
+    # -- state layout ---------------------------------------------------------------------------------------------
+    def _state_ptrs(self):
+        """(pos, ep_len) arguments of the C ABI: the packed word and NULL, or the two split arrays."""
+        if self._packed:
+            return self._pl.data_ptr(), None
+        return self._pos_split.data_ptr(), self._ep_len_split.data_ptr()
+
+    @property
+    def pos(self):
+        """int32 [N] cell index (row * cols + col).  Split layout: the live tensor; packed layout: a computed copy --
+        assign (`env.pos = t`) to write."""
+        return (self._pl & 0xFFFF) if self._packed else self._pos_split
+
+    @pos.setter
+    def pos(self, value):
+        v = self._torch.as_tensor(value, device=self.device).to(self._torch.int32)
+        if self._packed:
+            self._pl.copy_((self._pl & -65536) | (v & 0xFFFF))
+        else:
+            self._pos_split.copy_(v)
+
+    @property
+    def ep_len(self):
+        """int32 [N] episode_length_counter (see `pos` for the layout caveat)."""
+        return ((self._pl >> 16) & 0xFFFF) if self.__dict__.get("_packed") else self._ep_len_split
+
+    @ep_len.setter
+    def ep_len(self, value):
+        if "_ep_len_given" not in self.__dict__:   # first assignment: VecEnv.__init__ hands over the tensor it allocated
+            self._ep_len_given = True
+            if not self._packed:
+                self._ep_len_split = value
+            return
+        v = self._torch.as_tensor(value, device=self.device).to(self._torch.int32)
+        if self._packed:
+            if bool((v < 0).any()) or bool((v > 65535).any()):
+                raise ValueError("packed state layout holds episode_length_counter in 16 bits")
+            self._pl.copy_((self._pl & 0xFFFF) | (v << 16))
+        else:
+            self._ep_len_split.copy_(v)
+
+    @property
+    def autoreset(self):
+        return self._autoreset
+
+    @autoreset.setter
+    def autoreset(self, value):
+        self._autoreset = bool(value)
+        if not self._autoreset:
+            self._leave_packed_layout()
+
+    def _leave_packed_layout(self):
+        """Needed once auto-reset is switched off: the episode counter is then unbounded."""
+        if self._packed and "_pl" in self.__dict__:
+            pos, ln = self.pos.clone(), self.ep_len.clone()
+            self._packed = False
+            self._pos_split, self._ep_len_split = pos, ln
+            del self._pl
 
     # -- table ----------------------------------------------------------------------------------------------------
     def _start_cell(self):
@@ -400,7 +472,7 @@ class VecGridWorld(VecEnv):
             v = v.expand(self.num_envs, 2)
         inside = (v[:, 0] >= 0) & (v[:, 0] < self.rows) & (v[:, 1] >= 0) & (v[:, 1] < self.cols)
         cell = torch.where(inside, v[:, 0] * self.cols + v[:, 1], torch.full_like(v[:, 0], self.spec.n_cells))
-        self.pos.copy_(cell.to(torch.int32))
+        self.pos = cell.to(torch.int32)
 
     @property
     def episode_length_counter(self):
@@ -410,8 +482,8 @@ class VecGridWorld(VecEnv):
         return {"pos": self.pos.clone(), "ep_len": self.ep_len.clone(), "ep_ret": self.ep_ret.clone(), "t": self._t}
 
     def set_state(self, state):
-        self.pos.copy_(state["pos"])
-        self.ep_len.copy_(state["ep_len"])
+        self.pos = state["pos"]
+        self.ep_len = state["ep_len"]
         self.ep_ret.copy_(state["ep_ret"])
         self._t = int(state.get("t", self._t))
 
@@ -432,8 +504,7 @@ class VecGridWorld(VecEnv):
         m = None
         if mask is not None:
             m = self._torch.as_tensor(mask, device=self.device).to(self._torch.uint8).contiguous()
-        self._call(self._lib.ef_gridworld_reset, self._desc.start_cell, self.cols, _lib.ptr(self.pos),
-                   _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(self._obs), _lib.ptr(m), self.num_envs)
+        self._call(self._lib.ef_gridworld_reset, self._desc.start_cell, self.cols, *self._state_ptrs(), _lib.ptr(self.ep_ret), _lib.ptr(self._obs), _lib.ptr(m), self.num_envs)
         self._reset_epoch += 1
         obs = self._obs
         if not self.spec._in_grid(self.start_state):  # off-grid start: report it verbatim like the reference
@@ -501,7 +572,7 @@ class VecGridWorld(VecEnv):
             h_fobs = self._pinned("o_final_obs", (n, 2), torch.int32) if return_final_obs else None
             with torch.cuda.device(self.device):
                 _lib.check(self._lib.ef_gridworld_step_host(
-                    self._pipe(), self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), p_act, d_act,
+                    self._pipe(), self._desc, *self._state_ptrs(), _lib.ptr(self.ep_ret), p_act, d_act,
                     self._seed, self._t, self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term),
                     _lib.ptr(self._trunc), _lib.ptr(fobs), hb, hb + o_rew, hb + o_term, hb + o_trunc, _lib.ptr(h_fobs),
                     _lib.ptr(self._stats_raw), _lib.ptr(self.err), n, int(self.autoreset), self.host_chunks, self._stream()))
@@ -510,12 +581,11 @@ class VecGridWorld(VecEnv):
         elif self.rng == "pcg64":
             if drw is not None:
                 raise ValueError("injected draws are not available with rng='pcg64' (each env owns its generator)")
-            self._call(self._lib.ef_gridworld_step_pcg64, self._desc, self._thr53, self._cap53, _lib.ptr(self.pos),
-                       _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(self._rng_state), _lib.ptr(self._rng_inc),
+            self._call(self._lib.ef_gridworld_step_pcg64, self._desc, self._thr53, self._cap53, *self._state_ptrs(), _lib.ptr(self.ep_ret), _lib.ptr(self._rng_state), _lib.ptr(self._rng_inc),
                        p_act, self.env_offset, p_obs, p_rew, p_term, p_trunc, _lib.ptr(fobs), _lib.ptr(self._stats_raw),
                        _lib.ptr(self.err), n, int(self.autoreset))
         else:
-            self._call(self._lib.ef_gridworld_step, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
+            self._call(self._lib.ef_gridworld_step, self._desc, *self._state_ptrs(),
                        _lib.ptr(self.ep_ret), p_act, _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
                        p_obs, p_rew, p_term, p_trunc, _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err),
                        _lib.ptr(self._clock), n, int(self.autoreset))
@@ -560,7 +630,7 @@ class VecGridWorld(VecEnv):
         if return_rewards:
             rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
-        self._call(self._lib.ef_gridworld_rollout, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len),
+        self._call(self._lib.ef_gridworld_rollout, self._desc, *self._state_ptrs(),
                    _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K),
                    _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
         self._t += int(K)

@@ -54,6 +54,15 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ef_cartpole_step(None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, None,
                                 8, 1, None) == 1
     assert lib.ef_bandit_step(None, 10, None, 0, 0, 0, 1, None, None, None, None, 8, None) == 1
+    # packed GridWorld state (ep_len == NULL) is only accepted with auto-reset on and 0 < episode_limit <= 65535
+    d.rows = d.cols = 2
+    d.n_slots, d.table = 1, 0x1000
+    fake = ctypes.c_void_p(0x2000)
+    for limit, autoreset, want in ((0, 1, 1), (70000, 1, 1), (10, 0, 1), (10, 1, 0)):
+        d.episode_limit = limit
+        got = lib.ef_gridworld_step(ctypes.byref(d), fake, None, fake, None, None, 0, 0, 0, None, None, None, None, None,
+                                    None, None, None, 0, autoreset, None)          # n == 0: returns before any launch
+        assert got == want, (limit, autoreset, got)
     # host-buffer entry points: a missing pipe / host action buffer is rejected up front
     assert lib.ef_bandit_step_host(None, None, 10, None, None, 0, 0, 0, None, None, None, None, None, None, 8, 4, None) == 1
     assert lib.ef_gridworld_step_host(None, ctypes.byref(d), *([None] * 5), 0, 0, 0, *([None] * 12), 8, 1, 4, None) == 1

@@ -37,7 +37,7 @@ def test_golden_steps_as_batch(path):
         env.add_special_transition(fs, Action(a), ts, r)
     env.state = g["pre"]
     raised = g["raised"] > 0
-    env.ep_len.copy_(torch.from_numpy((g["ep_len"] - (~raised)).astype(np.int32)))
+    env.ep_len = torch.from_numpy((g["ep_len"] - (~raised)).astype(np.int32))
     r32 = np.floor(g["u"] * 2.0 ** 32).astype(np.uint64).astype(np.uint32)
     obs, rew, term, trunc, _ = env.step(torch.from_numpy(g["action"].astype(np.int32)).cuda(),
                                         draws=torch.from_numpy(r32.view(np.int32)).cuda())
@@ -501,3 +501,52 @@ def test_maximum_grid_size_65535_cells():
         assert np.array_equal(term.cpu().numpy(), o["terminated"])
     with pytest.raises(ValueError):
         VecGridWorld(4, rows=256, cols=256)        # 65536 cells: one more than the 16-bit table index allows
+
+
+# ---- packed state layout ----------------------------------------------------------------------------------------------
+def test_packed_state_layout_equals_split_layout():
+    """cell | episode_length_counter << 16 in one word per env (8 fewer bytes per env-step) must not change a bit:
+    step (vector + scalar + pcg64), fused rollout, masked reset, state accessors, and leaving the layout."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    cfg = _vec_kwargs(_config2(0.8))
+    n = 20_003
+    for rng_mode in ("philox", "pcg64"):
+        a = VecGridWorld(n, seed=6, rng=rng_mode, **cfg)
+        b = VecGridWorld(n, seed=6, rng=rng_mode, state_layout="split", **cfg)
+        assert a._packed and not b._packed
+        gen = np.random.default_rng(3)
+        for i in range(260):                                   # past the 200-step limit: truncations + auto-resets
+            act = torch.from_numpy(gen.integers(0, 4, n).astype(np.int32)).cuda()
+            oa, ob = a.step(act, return_final_obs=True), b.step(act, return_final_obs=True)
+            for x, y in zip(oa[:4], ob[:4]):
+                assert torch.equal(x, y), i
+            assert torch.equal(oa[4]["final_observation"], ob[4]["final_observation"])
+            if i == 100:
+                m = torch.from_numpy(gen.integers(0, 2, n).astype(np.uint8)).cuda()
+                a.reset(mask=m)
+                b.reset(mask=m)
+        assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+        assert int(a.ep_len.max()) > 100
+        if rng_mode == "philox":
+            draws = torch.from_numpy(gen.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.int32)).cuda()
+            act = torch.from_numpy(gen.integers(0, 4, n).astype(np.int32)).cuda()
+            for x, y in zip(a.step(act, draws=draws)[:4], b.step(act, draws=draws)[:4]):   # scalar kernel
+                assert torch.equal(x, y)
+            a.rollout(37)
+            b.rollout(37)
+            ra, rb = a.rollout(5, return_rewards=True), b.rollout(5, return_rewards=True)
+            assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+            assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+        assert torch.equal(a.stats, b.stats) and torch.equal(a.err[:1], b.err[:1])
+        assert a.running_episode_stats() == b.running_episode_stats()
+        # accessors: get/set state round trip, state setter, leaving the packed layout when auto-reset goes off
+        st = b.get_state()
+        a.set_state(st)
+        assert torch.equal(a.pos, st["pos"]) and torch.equal(a.ep_len, st["ep_len"])
+        a.state = (2, 3)
+        assert int(a.pos.min()) == int(a.pos.max()) == 2 * 8 + 3 and torch.equal(a.ep_len, st["ep_len"])
+        a.autoreset = False
+        assert not a._packed and torch.equal(a.ep_len, st["ep_len"])
+    with pytest.raises(ValueError):
+        VecGridWorld(4, state_layout="packed")                 # no episode limit: the counter is unbounded
