@@ -238,6 +238,51 @@ int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_
 int ef_bandit_default_means(int32_t k, uint64_t seed, uint64_t env_offset, float* means, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * ACML envs   (reference: rl_envs_forge/envs/acml/{gambler_problem/gambler_problem.py, car_rental/car_rental.py})
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_gambler_params {
+    int32_t goal_amount;      /* gambler_problem.py:24 */
+    int32_t start_capital;    /* :26, the state reset() restores (:75) */
+    int32_t episode_limit;    /* <= 0: none (the reference has none; > 0 adds truncation for auto-reset users) */
+    int32_t reserved;
+    uint64_t win_threshold;   /* ceil(win_probability * 2^32) in [0, 2^32]: `np.random.rand() < p` (:51) on u = r*2^-32 */
+} ef_gambler_params;
+
+/* GamblersProblem.step (:36-66) + reset (:68-76) as same-step auto-reset, for n envs.
+ *   state    [n] int32 capital (in/out).   action [n] int32 bet, or NULL: uniform legal bet 0..min(s, goal-s).
+ *   draw     [n] uint32 injected draws r (u = r*2^-32), or NULL: Philox transition word of step t.
+ *   obs      [n] int32 capital after auto-reset; final_obs before it; reward in {0, 1}; truncated only with a limit.
+ *   A bet outside [0, goal_amount] is the reference's `assert self.action_space.contains(action)` (:46): counted in
+ *   `err` (EF_STEP_BAD_ACTION), env untouched.  A bet above the capital is legal in the reference and here. */
+int ef_gambler_step(const ef_gambler_params* p, int32_t* state, int32_t* ep_len, float* ep_ret, const int32_t* action,
+                    const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, int32_t* obs, float* reward,
+                    uint8_t* terminated, uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
+                    uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
+int ef_gambler_reset(int32_t start_capital, int32_t* state, int32_t* ep_len, float* ep_ret, int32_t* obs,
+                     const uint8_t* mask, int64_t n, void* stream);
+
+typedef struct ef_car_rental_params {
+    int32_t max_cars, max_move_cars, rental_credit, move_car_cost;   /* car_rental.py:12-19 */
+    int32_t episode_limit;    /* <= 0: none (the reference never ends an episode) */
+    int32_t init_equal;       /* reset option: 0 "random" (uniform 0..max_cars per location), 1 "equal" (:134-142) */
+    double lam[4];            /* request_lambda[0], request_lambda[1], return_lambda[0], return_lambda[1]; each < 10 */
+    double exp_neg_lam[4];    /* exp(-lam[j]) as the host's libm computes it (numpy's random_poisson_mult does the same) */
+} ef_car_rental_params;
+
+/* JacksCarRental.step (:106-121) for n envs: move cars (:54-74), then four legacy-numpy Poisson draws (scipy.stats.
+ * poisson.rvs, :89-92) by the multiplication method in FP64 over the Philox stream STREAM_ACML of (env, t).
+ *   state  [n,2] int32 (cars at A, cars at B), 8-byte aligned.   action [n] int32 raw action (0 .. 2*max_move_cars; the
+ *   reference does not validate it and neither does the kernel), or NULL: uniform random.
+ *   obs / final_obs [n,2]; reward = rentals * credit - |action - max_move| * cost; terminated == 0 always.
+ * EF_ERR_UNSUPPORTED for a lam >= 10 (numpy switches to the PTRS sampler there). */
+int ef_car_rental_step(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,
+                       const int32_t* action, uint64_t seed, uint64_t t, uint64_t env_offset, int32_t* obs, float* reward,
+                       uint8_t* terminated, uint8_t* truncated, int32_t* final_obs, double* stats, uint64_t* clock,
+                       int64_t n, int32_t autoreset, void* stream);
+int ef_car_rental_reset(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
+                        uint64_t epoch, uint64_t env_offset, int32_t* obs, const uint8_t* mask, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Episode statistics: reduce per-env running (ep_len, ep_ret) of the envs still in flight into `out[0..3]`
  * (count, sum len, sum ret, sum ret^2) -- complements `stats`, which only sees finished episodes.
  * ------------------------------------------------------------------------------------------------------------ */

@@ -196,9 +196,83 @@ def pendulum_case(R, cls_name, name, kw, n_steps, action_seed, init_seed):
     print(cls_name, name, "episodes", int((out["done"] | out["trunc"]).sum()), "done", int(out["done"].sum()))
 
 
+def gambler_case(R, name, kw, n_steps, seed):
+    """GamblersProblem trajectory under np.random.seed(seed): the uniform each step consumed is read from a clone of the
+    global RandomState just before the step."""
+    np.random.seed(seed)
+    env = R.GamblersProblem(**kw)
+    arng = np.random.default_rng(seed + 1000)
+    rec = dict(pre=[], action=[], u=[], post=[], reward=[], done=[])
+    for i in range(n_steps):
+        pre = env.state
+        # mostly legal bets, sometimes above the capital (the reference only asserts action <= goal_amount), and a few
+        # steps taken from a finished state (the reference keeps stepping)
+        hi = pre if arng.random() < 0.8 else kw.get("goal_amount", 100)
+        a = int(arng.integers(0, max(hi, 0) + 1))
+        clone = np.random.RandomState()
+        clone.set_state(np.random.get_state())
+        u = clone.random_sample()
+        obs, r, d, t, _ = env.step(a)
+        assert t is False
+        rec["pre"].append(pre); rec["action"].append(a); rec["u"].append(u); rec["post"].append(obs)
+        rec["reward"].append(r); rec["done"].append(d)
+        if d and arng.random() < 0.7:
+            env.reset()
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["config"] = json.dumps(kw)
+    out["numpy_version"] = np.__version__
+    np.savez_compressed(os.path.join(OUT, f"gambler_{name}.npz"), **out)
+    print("gambler", name, "done", int(out["done"].sum()), "wins", int(out["reward"].sum()))
+
+
+def car_rental_case(R, name, kw, n_steps, seed):
+    """JacksCarRental trajectory: construct, np.random.seed(seed), reset("equal") (draws nothing), then n_steps steps.
+    A replay needs only RandomState(seed): every double the four scipy poisson.rvs calls of a step consume comes from it."""
+    env = R.JacksCarRental(**kw)
+    np.random.seed(seed)
+    env.reset("equal")
+    arng = np.random.default_rng(seed + 2000)
+    n_act = 2 * kw.get("max_move_cars", 5) + 1
+    rec = dict(pre=[], action=[], post=[], reward=[])
+    for _ in range(n_steps):
+        pre = env.state
+        a = int(arng.integers(0, n_act))
+        obs, r, d, t, _ = env.step(a)
+        assert d is False and t is False
+        rec["pre"].append(pre); rec["action"].append(a); rec["post"].append(obs); rec["reward"].append(r)
+    out = {k: np.array(v) for k, v in rec.items()}
+    out["config"] = json.dumps(kw)
+    out["seed"] = seed
+    out["numpy_version"] = np.__version__
+    import scipy
+    out["scipy_version"] = scipy.__version__
+    small = R.JacksCarRental(max_cars=4, max_move_cars=2, request_lambda=[2, 2], return_lambda=[2, 2])
+    mdp = small.build_mdp()                                      # test_car_rental.py fixture config (seconds)
+    keys = sorted(mdp)
+    out["mdp_keys"] = np.array([[k[0][0], k[0][1], k[1]] for k in keys])
+    out["mdp_next"] = np.array([mdp[k][0] for k in keys])
+    out["mdp_reward"] = np.array([mdp[k][1] for k in keys])
+    np.savez_compressed(os.path.join(OUT, f"carrental_{name}.npz"), **out)
+    print("carrental", name, "mean reward", float(np.mean(out["reward"])))
+
+
+def acml_cases(R):
+    gambler_case(R, "default", dict(goal_amount=100, win_probability=0.4, start_capital=10), 4000, seed=21)  # test fixture
+    gambler_case(R, "fair_small", dict(goal_amount=16, win_probability=0.5, start_capital=3), 3000, seed=22)
+    gambler_case(R, "sure_win", dict(goal_amount=30, win_probability=1.0, start_capital=1), 300, seed=23)
+    car_rental_case(R, "default", dict(), 3000, seed=31)
+    car_rental_case(R, "small", dict(max_cars=4, max_move_cars=2, request_lambda=[2, 2], return_lambda=[2, 2]), 3000, seed=32)
+    car_rental_case(R, "zero_lambda", dict(max_cars=10, max_move_cars=3, request_lambda=[0, 9.5], return_lambda=[1, 0],
+                                           rental_credit=7, move_car_cost=3), 2000, seed=33)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
+    import sys
+    if "acml" in sys.argv[1:]:
+        acml_cases(R)
+        return
     # -- GridWorld ---------------------------------------------------------------------------------------
     gridworld_case(R, "default", dict(), 3000, seed=0, action_seed=0)                        # BASELINE config 1
     gridworld_case(R, "slip_seed42", dict(p_success=0.5), 3000, seed=42, action_seed=1)       # test_grid_world.py:20-22
@@ -228,6 +302,8 @@ def main():
     pendulum_case(R, "PendulumDisk", "continuous", dict(continuous_reward=True, tau=0.01, episode_length_limit=50), 1500, 8, 9)
     pendulum_case(R, "PendulumDisk", "nonlinear_angle", dict(continuous_reward=True, nonlinear_reward=True,
                                                               reward_decay_rate=30.0, angle_termination=2.0), 1500, 10, 11)
+    # -- ACML envs ------------------------------------------------------------------
+    acml_cases(R)
 
 
 if __name__ == "__main__":

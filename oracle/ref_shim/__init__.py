@@ -22,7 +22,7 @@ def reference_available() -> bool:
 
 
 def load_reference():
-    """Return a namespace with the four reference env classes, imported from REFERENCE_ROOT."""
+    """Return a namespace with the reference env classes of the hot path, imported from REFERENCE_ROOT."""
     if not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     for name in ("gymnasium", "matplotlib", "pygame", "seaborn"):
@@ -46,4 +46,7 @@ def load_reference():
     ns.KArmedBandit, ns.Arm = kb.KArmedBandit, kb.Arm
     ns.CartPole = cp.CartPole
     ns.PendulumDisk = pd.PendulumDisk
+    gp = importlib.import_module("rl_envs_forge.envs.acml.gambler_problem.gambler_problem")
+    cr = importlib.import_module("rl_envs_forge.envs.acml.car_rental.car_rental")
+    ns.GamblersProblem, ns.JacksCarRental = gp.GamblersProblem, cr.JacksCarRental
     return ns

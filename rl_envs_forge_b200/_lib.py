@@ -40,6 +40,17 @@ class PendulumParams(C.Structure):
                 ("init_lo", C.c_float), ("init_hi", C.c_float), ("init_state", C.c_float * 4)]
 
 
+class GamblerParams(C.Structure):
+    _fields_ = [("goal_amount", C.c_int32), ("start_capital", C.c_int32), ("episode_limit", C.c_int32),
+                ("reserved", C.c_int32), ("win_threshold", C.c_uint64)]
+
+
+class CarRentalParams(C.Structure):
+    _fields_ = [("max_cars", C.c_int32), ("max_move_cars", C.c_int32), ("rental_credit", C.c_int32),
+                ("move_car_cost", C.c_int32), ("episode_limit", C.c_int32), ("init_equal", C.c_int32),
+                ("lam", C.c_double * 4), ("exp_neg_lam", C.c_double * 4)]
+
+
 _P, _I32, _I64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
 
 # name -> (restype, argtypes); mirrors include/envforge_b200.h one to one (tests check the symbol list against the header)
@@ -69,6 +80,12 @@ SIGNATURES = {
     "ef_bandit_step": (C.c_int, [_P, _I32, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_default_means": (C.c_int, [_I32, _U64, _U64, _P, _I64, _P]),
     "ef_episode_stat_reduce": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "ef_gambler_step": (C.c_int, [C.POINTER(GamblerParams), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
+                                  _P, _P, _I64, _I32, _P]),
+    "ef_gambler_reset": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I64, _P]),
+    "ef_car_rental_step": (C.c_int, [C.POINTER(CarRentalParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
+                                     _P, _P, _I64, _I32, _P]),
+    "ef_car_rental_reset": (C.c_int, [C.POINTER(CarRentalParams), _P, _P, _P, _U64, _U64, _U64, _P, _P, _I64, _P]),
     "ef_host_pipe_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ef_host_pipe_destroy": (C.c_int, [_P]),
     "ef_gridworld_step_host": (C.c_int, [_P, C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 10

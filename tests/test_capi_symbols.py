@@ -41,6 +41,8 @@ def test_version_and_status_strings(lib):
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.GridDesc) == 48
     assert _lib.GridDesc.table.offset == 40
+    assert ctypes.sizeof(_lib.GamblerParams) == 24 and _lib.GamblerParams.win_threshold.offset == 16
+    assert ctypes.sizeof(_lib.CarRentalParams) == 88 and _lib.CarRentalParams.lam.offset == 24
     assert ctypes.sizeof(_lib.PendulumParams) == 4 + 32 + 4 * 4 + 4 * 4 + 4 * 4 + 16  # 100 bytes
 
 
@@ -74,7 +76,8 @@ def test_no_fallback_without_cuda():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     import rl_envs_forge_b200 as r
-    for cls in (r.VecGridWorld, r.VecCartPole, r.VecPendulumDisk, r.VecKArmedBandit):
+    for cls in (r.VecGridWorld, r.VecCartPole, r.VecPendulumDisk, r.VecKArmedBandit, r.VecGamblersProblem,
+                r.VecJacksCarRental):
         with pytest.raises(r.EnvForgeError):
             cls(4)
 
