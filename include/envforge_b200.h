@@ -283,6 +283,44 @@ int ef_car_rental_reset(const ef_car_rental_params* p, int32_t* state, int32_t* 
                         uint64_t epoch, uint64_t env_offset, int32_t* obs, const uint8_t* mask, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Labyrinth   (reference: rl_envs_forge/envs/labyrinth/labyrinth.py; maze generation stays on the host)
+ * A maze is its finished grid (uint8 [rows*cols], WALL = 0, anything else walkable; constants.py:12-16) plus a start
+ * and a target cell (cell = row * cols + col) -- `Labyrinth.maze.{grid, start_position, target_position}`.  n players
+ * walk n_mazes mazes: player i uses maze maze_index[i], or (env_offset + i) % n_mazes when maze_index is NULL.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct ef_labyrinth_desc {
+    int32_t rows, cols, n_mazes;
+    int32_t vision_range;            /* state_vision_range (labyrinth.py:20); <= 0: None = the full state matrix */
+    int32_t episode_limit;           /* <= 0: none (the reference never truncates) */
+    float neutral_reward;            /* reward_schema (:103-108): -0.01 */
+    float wall_collision_reward;     /* -1 */
+    float target_reached_reward;     /* 10 */
+    const uint8_t* grids;            /* device [n_mazes, rows*cols] */
+    const int32_t* maze_index;       /* device [n] or NULL */
+    const int32_t* start_cell;       /* device [n_mazes] */
+    const int32_t* target_cell;      /* device [n_mazes] */
+} ef_labyrinth_desc;
+
+/* Labyrinth.step (:245-288) for n players, with same-step auto-reset to the maze's start cell (the reference's own
+ * reset() generates a NEW maze, :342-363 -- host work; same-maze reset is its reset(same_seed=True)).
+ *   pos      [n] int32 player cell (in/out).   action [n] int32 in {0 UP, 1 RIGHT, 2 DOWN, 3 LEFT}, NULL: random policy.
+ *   obs      uint8 [n, rows*cols] (build_state_matrix :210-215: grid, TARGET = 2 at the target, PLAYER = 4 on top) or
+ *            [n, (2v+1)^2] (build_state_around_the_player :217-243, WALL outside the maze); after auto-reset.  Nullable.
+ *   final_obs  the same view before auto-reset (nullable).  reward: wall_collision on a blocked move (position kept),
+ *            target_reached when the move lands on the target (terminated = 1), neutral otherwise.
+ *   An action outside 0..3 is the reference's ValueError in Action(action): counted in `err`, player untouched. */
+int ef_labyrinth_step(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_len, float* ep_ret, const int32_t* action,
+                      uint64_t seed, uint64_t t, uint64_t env_offset, uint8_t* obs, float* reward, uint8_t* terminated,
+                      uint8_t* truncated, uint8_t* final_obs, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
+                      int32_t autoreset, void* stream);
+/* Labyrinth.state (:195-208) for n players: renders `obs` from the current positions, touches nothing else. */
+int ef_labyrinth_observe(const ef_labyrinth_desc* maze, const int32_t* pos, uint64_t env_offset, uint8_t* obs, int64_t n,
+                         void* stream);
+/* Player back to the start cell of its maze, counters cleared; mask nullable. */
+int ef_labyrinth_reset(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_len, float* ep_ret, uint64_t env_offset,
+                       const uint8_t* mask, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Episode statistics: reduce per-env running (ep_len, ep_ret) of the envs still in flight into `out[0..3]`
  * (count, sum len, sum ret, sum ret^2) -- complements `stats`, which only sees finished episodes.
  * ------------------------------------------------------------------------------------------------------------ */

@@ -256,6 +256,48 @@ def car_rental_case(R, name, kw, n_steps, seed):
     print("carrental", name, "mean reward", float(np.mean(out["reward"])))
 
 
+def labyrinth_case(R, name, kw, n_steps, action_seed):
+    """Labyrinth trajectory on a maze generated by the reference: every step's pre/post position, reward, done and the
+    full observation are recorded.  A finished episode continues from the start position on the SAME maze
+    (`set_state`; the reference's own reset() would generate a new maze, which is host work outside the stepping path)."""
+    env = R.Labyrinth(**kw)
+    rng = np.random.default_rng(action_seed)
+    grid = np.array(env.maze.grid, np.uint8)
+    start, target = tuple(env.maze.start_position), tuple(env.maze.target_position)
+    free = [(r, c) for r in range(env.rows) for c in range(env.cols) if grid[r, c] != 0 and (r, c) != target]
+    rec = dict(pre=[], action=[], post=[], reward=[], done=[], obs=[], info=[])
+    for i in range(n_steps):
+        if i % 40 == 39:                                   # visit the whole maze, the target's neighbourhood included
+            near = [p for p in free if abs(p[0] - target[0]) + abs(p[1] - target[1]) == 1]
+            env.set_state(near[rng.integers(len(near))] if near and rng.random() < 0.5 else free[rng.integers(len(free))])
+        pre = env.player.position
+        a = int(rng.integers(0, 4))
+        obs, r, d, t, info = env.step(a)
+        assert t is False
+        rec["pre"].append(pre); rec["action"].append(a); rec["post"].append(env.player.position)
+        rec["reward"].append(r); rec["done"].append(d); rec["obs"].append(np.array(obs, np.uint8))
+        rec["info"].append({"": 0, "Invalid move!": 1, "Reached the target!": 2}[info.get("info", "")])
+        if d:
+            env.set_state(start)
+    out = {k: np.array(v) for k, v in rec.items()}
+    out.update(grid=grid, start=np.array(start), target=np.array(target), config=json.dumps(kw),
+               initial_obs=np.array(R.Labyrinth(**kw).state, np.uint8))
+    np.savez_compressed(os.path.join(OUT, f"labyrinth_{name}.npz"), **out)
+    print("labyrinth", name, grid.shape, "done", int(out["done"].sum()), "bumps", int((out["info"] == 1).sum()))
+
+
+# "donut" rooms are left out: room.py:228 calls random.randint with a float bound, a TypeError on Python >= 3.12
+_ROOMS = ["rectangle", "oval", "t_shape", "l_shape", "triangle"]
+
+
+def labyrinth_cases(R):
+    labyrinth_case(R, "10x10_full", dict(rows=10, cols=10, seed=1, room_types=_ROOMS), 1500, 1)
+    labyrinth_case(R, "20x20_full", dict(rows=20, cols=20, seed=42, room_types=_ROOMS), 1500, 2)                # test_labyrinth.py:222-233
+    labyrinth_case(R, "12x17_vision2", dict(rows=12, cols=17, seed=7, state_vision_range=2, room_types=_ROOMS), 1500, 3)
+    labyrinth_case(R, "30x30_vision3", dict(rows=30, cols=30, seed=42, state_vision_range=3, room_types=_ROOMS), 1500, 4)   # :215-220
+    labyrinth_case(R, "16x16_vision1", dict(rows=16, cols=16, seed=9, state_vision_range=1, room_types=_ROOMS), 800, 5)
+
+
 def acml_cases(R):
     gambler_case(R, "default", dict(goal_amount=100, win_probability=0.4, start_capital=10), 4000, seed=21)  # test fixture
     gambler_case(R, "fair_small", dict(goal_amount=16, win_probability=0.5, start_capital=3), 3000, seed=22)
@@ -270,8 +312,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
     import sys
-    if "acml" in sys.argv[1:]:
-        acml_cases(R)
+    if "acml" in sys.argv[1:] or "labyrinth" in sys.argv[1:]:
+        if "acml" in sys.argv[1:]:
+            acml_cases(R)
+        if "labyrinth" in sys.argv[1:]:
+            labyrinth_cases(R)
         return
     # -- GridWorld ---------------------------------------------------------------------------------------
     gridworld_case(R, "default", dict(), 3000, seed=0, action_seed=0)                        # BASELINE config 1
@@ -304,6 +349,8 @@ def main():
                                                               reward_decay_rate=30.0, angle_termination=2.0), 1500, 10, 11)
     # -- ACML envs ------------------------------------------------------------------
     acml_cases(R)
+    # -- Labyrinth stepping on reference-generated mazes ------------------------------
+    labyrinth_cases(R)
 
 
 if __name__ == "__main__":

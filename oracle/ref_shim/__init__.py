@@ -49,4 +49,6 @@ def load_reference():
     gp = importlib.import_module("rl_envs_forge.envs.acml.gambler_problem.gambler_problem")
     cr = importlib.import_module("rl_envs_forge.envs.acml.car_rental.car_rental")
     ns.GamblersProblem, ns.JacksCarRental = gp.GamblersProblem, cr.JacksCarRental
+    lb = importlib.import_module("rl_envs_forge.envs.labyrinth.labyrinth")
+    ns.Labyrinth = lb.Labyrinth
     return ns

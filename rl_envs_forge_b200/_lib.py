@@ -51,6 +51,13 @@ class CarRentalParams(C.Structure):
                 ("lam", C.c_double * 4), ("exp_neg_lam", C.c_double * 4)]
 
 
+class LabyrinthDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("n_mazes", C.c_int32), ("vision_range", C.c_int32),
+                ("episode_limit", C.c_int32), ("neutral_reward", C.c_float), ("wall_collision_reward", C.c_float),
+                ("target_reached_reward", C.c_float), ("grids", C.c_void_p), ("maze_index", C.c_void_p),
+                ("start_cell", C.c_void_p), ("target_cell", C.c_void_p)]
+
+
 _P, _I32, _I64, _U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
 
 # name -> (restype, argtypes); mirrors include/envforge_b200.h one to one (tests check the symbol list against the header)
@@ -86,6 +93,10 @@ SIGNATURES = {
     "ef_car_rental_step": (C.c_int, [C.POINTER(CarRentalParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
                                      _P, _P, _I64, _I32, _P]),
     "ef_car_rental_reset": (C.c_int, [C.POINTER(CarRentalParams), _P, _P, _P, _U64, _U64, _U64, _P, _P, _I64, _P]),
+    "ef_labyrinth_step": (C.c_int, [C.POINTER(LabyrinthDesc), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P, _P,
+                                    _P, _I64, _I32, _P]),
+    "ef_labyrinth_observe": (C.c_int, [C.POINTER(LabyrinthDesc), _P, _U64, _P, _I64, _P]),
+    "ef_labyrinth_reset": (C.c_int, [C.POINTER(LabyrinthDesc), _P, _P, _P, _U64, _P, _I64, _P]),
     "ef_host_pipe_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "ef_host_pipe_destroy": (C.c_int, [_P]),
     "ef_gridworld_step_host": (C.c_int, [_P, C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 10
