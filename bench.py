@@ -199,6 +199,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
+    from rl_envs_forge_b200 import VecGamblersProblem, VecJacksCarRental, VecLabyrinth
     from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandit, VecPendulumDisk, all_reduce_stats
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -398,6 +399,35 @@ def run_ours(args):
         sec = ev_time(lambda: bd.step(a_b), 20)
         details["bandit_step_10arm_mixed"] = {"env_steps_per_s": nb / sec, "envs": nb, "GBps": 12 * nb / sec / 1e9}
         del bd, a_b
+        # ---- ACML envs and Labyrinth stepping
+        ng = 1 << 24        # 30 B of buffers per env: well past the 126 MB L2
+        gm = VecGamblersProblem(ng, goal_amount=100, win_probability=0.4, start_capital=10, seed=seed, env_offset=rank * ng)
+        a_g = torch.randint(0, 11, (ng,), dtype=torch.int32, device="cuda")
+        sec = ev_time(lambda: gm.step(a_g), 50)
+        details["gambler_step"] = {"env_steps_per_s": ng / sec, "envs": ng, "GBps": 42 * ng / sec / 1e9,
+                                   "roofline_frac": 42 * ng / sec / 1e9 / peak}
+        del gm, a_g
+        ng = 1 << 22
+        cr = VecJacksCarRental(ng, seed=seed, env_offset=rank * ng)
+        a_c = torch.randint(0, 11, (ng,), dtype=torch.int32, device="cuda")
+        sec = ev_time(lambda: cr.step(a_c), 20)
+        details["car_rental_step"] = {"env_steps_per_s": ng / sec, "envs": ng, "GBps": 54 * ng / sec / 1e9,
+                                      "note": "four FP64 legacy-numpy Poisson draws per env-step: issue-bound"}
+        del cr, a_c
+        lrng = np.random.default_rng(5)
+        nl, side, mz = 1 << 19, 32, 64
+        lgr = (lrng.random((mz, side, side)) > 0.3).astype(np.uint8)
+        lgr[:, 0, 0] = lgr[:, side - 1, side - 1] = 1
+        lstart, ltgt = np.zeros((mz, 2), np.int64), np.full((mz, 2), side - 1, np.int64)
+        a_l = torch.randint(0, 4, (nl,), dtype=torch.int32, device="cuda")
+        for vis, key, obytes in ((None, "labyrinth_step_32x32_full_obs", side * side), (3, "labyrinth_step_32x32_vision3", 49)):
+            lb = VecLabyrinth(nl, lgr, lstart, ltgt, state_vision_range=vis, seed=seed, env_offset=rank * nl)
+            sec = ev_time(lambda: lb.step(a_l), 20)
+            per_env = 4 + 12 + 12 + 4 + 2 + obytes          # action, state r/w, reward, flags, observation
+            details[key] = {"env_steps_per_s": nl / sec, "envs": nl, "mazes": mz, "GBps": per_env * nl / sec / 1e9,
+                            "roofline_frac": per_env * nl / sec / 1e9 / peak, "bytes_per_env_step": per_env}
+            del lb
+        del a_l
         if world > 1:
             for v in details.values():
                 t = torch.tensor([v["env_steps_per_s"]], dtype=torch.float64, device="cuda")

@@ -213,19 +213,36 @@ struct DoubleStream {
     }
 };
 
-constexpr int kMaxPoissonTrips = 4096;  // termination guard; lam < 10 makes more than ~60 trips astronomically unlikely
+constexpr int kMaxPoissonTrips = 4096;  // termination guard; lam < 10 makes more than ~100 trips astronomically unlikely
 
-// numpy legacy random_poisson, lam < 10: multiplication method (lam == 0 returns 0 without drawing).
-__device__ __forceinline__ int32_t poisson_mult(DoubleStream& ds, double lam, double enlam) {
-    if (lam == 0.0) return 0;
-    int32_t x = 0;
+// The four Poisson draws of one step -- numpy legacy random_poisson, lam < 10: multiplication method (X = number of
+// uniforms whose running product stays above exp(-lam); lam == 0 returns 0 without drawing) -- evaluated as ONE loop over
+// the double stream.  The doubles are consumed in exactly the reference's order (requests A until the product drops, then
+// requests B, returns A, returns B); what the single loop buys is that every lane of a warp draws in lock step, so the
+// Philox block behind two consecutive doubles is generated by all lanes together instead of once per divergent branch,
+// and a warp runs max(sum of trips) iterations instead of sum(max of trips).
+__device__ __forceinline__ int4 poisson4(DoubleStream& ds, const CarArgs& a) {
+    int32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+    const uint32_t skip = (a.lam[0] == 0.0 ? 1u : 0u) | (a.lam[1] == 0.0 ? 2u : 0u) | (a.lam[2] == 0.0 ? 4u : 0u) |
+                          (a.lam[3] == 0.0 ? 8u : 0u);  // stages that return 0 without drawing
+    int stage = 0;
+    while (stage < 4 && ((skip >> stage) & 1u)) ++stage;
     double prod = 1.0;
-    for (int it = 0; it < kMaxPoissonTrips; ++it) {
+    for (int it = 0; it < kMaxPoissonTrips && stage < 4; ++it) {
         prod *= ds.next();
-        if (prod > enlam) ++x;
-        else break;
+        const double e = stage == 0 ? a.enlam[0] : (stage == 1 ? a.enlam[1] : (stage == 2 ? a.enlam[2] : a.enlam[3]));
+        if (prod > e) {
+            x0 += stage == 0;
+            x1 += stage == 1;
+            x2 += stage == 2;
+            x3 += stage == 3;
+        } else {
+            prod = 1.0;
+            ++stage;
+            while (stage < 4 && ((skip >> stage) & 1u)) ++stage;
+        }
     }
-    return x;
+    return make_int4(x0, x1, x2, x3);
 }
 
 __device__ __forceinline__ int2 car_initial_state(const CarArgs& a, uint32_t g, uint64_t counter, uint32_t stream) {
@@ -259,10 +276,8 @@ __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs
         const int32_t cost = mag * a.move_cost;
         // _simulate_rentals_and_returns (:76-104): requests A, requests B, returns A, returns B -- in that order
         DoubleStream ds(a.seed, g, t);
-        const int32_t req_a = poisson_mult(ds, a.lam[0], a.enlam[0]);
-        const int32_t req_b = poisson_mult(ds, a.lam[1], a.enlam[1]);
-        const int32_t ret_a = poisson_mult(ds, a.lam[2], a.enlam[2]);
-        const int32_t ret_b = poisson_mult(ds, a.lam[3], a.enlam[3]);
+        const int4 draws = poisson4(ds, a);
+        const int32_t req_a = draws.x, req_b = draws.y, ret_a = draws.z, ret_b = draws.w;
         const int32_t rent_a = min(ca, req_a), rent_b = min(cb, req_b);
         const float rew = static_cast<float>((rent_a + rent_b) * a.credit - cost);
         ca = min(ca - rent_a + ret_a, a.max_cars);

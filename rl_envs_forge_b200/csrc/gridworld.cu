@@ -15,6 +15,8 @@
 // Packed state (ep_len == NULL): position and episode_length_counter share one 32-bit word per env, cell in bits 0-15
 // and the counter in bits 16-31.  Possible whenever the counter cannot exceed 65535 (auto-reset on, 0 < limit <= 65535;
 // cells are < 65536 by construction of the table), it removes 8 of the 42 bytes an env-step moves.
+#include <algorithm>
+
 #include "ef_common.cuh"
 
 namespace ef {
@@ -339,13 +341,14 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #ifndef EF_STREAMING
 #define EF_STREAMING 0  // 1: evict-first cache hints on the state/outputs streams
 #endif
-// Large batches (measured on B200 at 4M / 16M envs: Q=4, 2 CTAs/SM resident, dynamic CTA scheduling reaches 0.95 of the
-// measured HBM peak; Q=1..2 with 3-4 CTAs/SM or a persistent grid are 10-25 % slower)
+// Large batches, dynamic CTA scheduling.  Measured on B200 with the packed state layout (34 B moved per env-step), us per
+// launch at 4M / 16M envs: Q=2 x 3 CTAs/SM 28.9 / 105.1 (adopted), Q=4 x 2 32.8 / 110.4, Q=3 x 2 32.5 / 115.3,
+// Q=1 x 4 31.4 / 116.6, Q=2 x 4 36.5 / 125.9, Q=4 x 3 40.5 / 135.2 (the last two spill registers).
 #ifndef EF_STEP_BIG_Q
-#define EF_STEP_BIG_Q 4
+#define EF_STEP_BIG_Q 2
 #endif
 #ifndef EF_STEP_BIG_MINBLOCKS
-#define EF_STEP_BIG_MINBLOCKS 2
+#define EF_STEP_BIG_MINBLOCKS 3
 #endif
 #ifndef EF_STEP_BIG_GRID_PER_SM
 #define EF_STEP_BIG_GRID_PER_SM 64
@@ -829,7 +832,11 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     // Large batches: fewer quads per thread, more resident warps, CTAs scheduled dynamically over many passes.
     const int64_t quads = (n + 3) / 4;
     const bool small = quads <= static_cast<int64_t>(sm_count()) * EF_STEP_GRID_PER_SM * kThreads * EF_STEP_Q;
-    const int grid_v = grid_for((quads + EF_STEP_Q - 1) / EF_STEP_Q, EF_STEP_GRID_PER_SM);
+    // One-pass grid: spread the quads over ALL resident CTA slots (at least a warp's worth each) rather than filling
+    // CTAs to Q * 256 quads -- 2^20 envs would otherwise make 256 full CTAs, leaving 40 of the 148 SMs with one CTA and
+    // 108 with two, and the launch lasts as long as the doubly loaded SMs.
+    const int grid_v = static_cast<int>(std::max<int64_t>(
+        1, std::min<int64_t>(static_cast<int64_t>(sm_count()) * EF_STEP_GRID_PER_SM, (quads + 31) / 32)));
     const int grid_b = grid_for((quads + EF_STEP_BIG_Q - 1) / EF_STEP_BIG_Q, EF_STEP_BIG_GRID_PER_SM);
     const int grid_s = grid_for(n, 8);
 #define EF_DISPATCH(SM, SL)                                                                                              \

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Run one env family's kernel a few times (for ncu / quick timing).
-    python tools/run_kernel.py --env cartpole|pendulum|gridworld|bandit --mode step|rollout|rollout_ext --n N --reps R [--K 64]"""
+    python tools/run_kernel.py --env cartpole|pendulum|gridworld|bandit|gambler|carrental|labyrinth|labyrinth_vision --mode step|rollout|rollout_ext --n N --reps R [--K 64]"""
 import argparse
 import os
 import sys
@@ -8,7 +8,10 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandit, VecPendulumDisk  # noqa: E402
+import numpy as np  # noqa: E402
+
+from rl_envs_forge_b200 import (Action, VecCartPole, VecGamblersProblem, VecGridWorld, VecJacksCarRental,  # noqa: E402
+                                VecKArmedBandit, VecLabyrinth, VecPendulumDisk)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--env", default="cartpole")
@@ -37,6 +40,19 @@ for s in range(a.sets):
                          episode_length_limit=200, seed=1, env_offset=s * n)
         act = torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda")
         ext = torch.randint(0, 4, (K, n), dtype=torch.int32, device="cuda") if a.mode == "rollout_ext" else None
+    elif a.env == "gambler":
+        e = VecGamblersProblem(n, goal_amount=100, win_probability=0.4, start_capital=10, seed=1, env_offset=s * n)
+        act, ext = torch.randint(0, 11, (n,), dtype=torch.int32, device="cuda"), None
+    elif a.env == "carrental":
+        e = VecJacksCarRental(n, seed=1, env_offset=s * n)
+        act, ext = torch.randint(0, 11, (n,), dtype=torch.int32, device="cuda"), None
+    elif a.env in ("labyrinth", "labyrinth_vision"):
+        rng = np.random.default_rng(5)
+        grids = (rng.random((64, 32, 32)) > 0.3).astype(np.uint8)
+        grids[:, 0, 0] = grids[:, 31, 31] = 1
+        e = VecLabyrinth(n, grids, np.zeros((64, 2), np.int64), np.full((64, 2), 31), seed=1, env_offset=s * n,
+                         state_vision_range=3 if a.env == "labyrinth_vision" else None)
+        act, ext = torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda"), None
     else:
         arms = {0: dict(distribution="normal", mean=5, std=1), 1: dict(distribution="uniform", low=4, high=6),
                 2: dict(distribution="exponential", scale=0.2), 3: dict(distribution="gamma", shape=9, scale=0.55),
