@@ -122,6 +122,18 @@ int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, f
                       int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
                       double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 
+/* ef_gridworld_step for a batch that mixes several grid LAYOUTS (walls / terminal states / special transitions / start
+ * state differ per layout; rows, cols, n_slots, thresholds and episode_limit are shared): `grid->table` holds n_layouts
+ * consecutive tables of table_cells*4*n_slots entries each, env i walks table layout_index[i] (or
+ * (env_offset + i) % n_layouts when layout_index is NULL) and auto-resets to start_cells[layout] (grid->start_cell is
+ * ignored).  All layouts are staged in shared memory when they fit (96 KB), else looked up through L1/L2.
+ * One env per thread; every other argument as in ef_gridworld_step. */
+int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
+                              const int32_t* start_cells, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                              const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset,
+                              int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
+                              double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
+
 /* Stream-exact variant of ef_gridworld_step: the outcome draw of env i comes from ITS OWN numpy-compatible generator,
  * Generator(PCG64(SeedSequence(seed_i))) as built by gym.utils.seeding.np_random (grid_world.py:69) and consumed by
  * Generator.choice (:515), so a batch seeded with the reference's seeds reproduces the reference's trajectories without

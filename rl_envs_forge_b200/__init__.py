@@ -7,7 +7,7 @@ Each class mirrors the constructor kwargs / reset / step surface of the referenc
 sm_100a CUDA kernels behind the C ABI declared in include/envforge_b200.h.  There is no CPU fallback.
 """
 from ._lib import EnvForgeError, LIB_PATH  # noqa: F401
-from .grid_world import Action, GridSpec, VecGridWorld  # noqa: F401
+from .grid_world import Action, GridSpec, VecGridWorld, VecGridWorldLayouts  # noqa: F401
 from .k_armed_bandit import Arm, VecKArmedBandit  # noqa: F401
 from .cart_pole import VecCartPole  # noqa: F401
 from .pendulum_disk import VecPendulumDisk  # noqa: F401

@@ -45,6 +45,11 @@ struct GridArgs {
     uint32_t* err;
     int64_t n;
     int32_t autoreset;
+    // several layouts in one batch (scalar step kernel only): `table` holds n_layouts consecutive tables of layout_len
+    // entries; env i uses layout[i], or (env_offset + i) % n_layouts when layout is null; start_cells[l] replaces start_cell
+    const int32_t* layout;
+    const int32_t* start_cells;
+    int32_t n_layouts, layout_len;
     // rollout only
     int32_t K;
     uint8_t* flags;
@@ -500,7 +505,14 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
                                        : __ldg(a.action + i);
         uint32_t r = 0u;
         if constexpr (SLOTS == 4) r = a.draw ? __ldg(a.draw + i) : group_word1(a.seed, g, t, kStreamTransition);
-        const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, r, rew, errs);
+        const uint2* __restrict__ tab_i = tab;
+        int32_t start = a.start_cell;
+        if (a.start_cells) {  // launch-uniform: several layouts in the batch -- this env's own table and start cell
+            const int32_t lay = a.layout ? __ldg(a.layout + i) : static_cast<int32_t>(g % static_cast<uint32_t>(a.n_layouts));
+            tab_i = tab + static_cast<int64_t>(lay) * a.layout_len;
+            start = __ldg(a.start_cells + lay);
+        }
+        const uint32_t f = transition<SMEM, SLOTS>(a, tab_i, g, pos, len, ret, act, r, rew, errs);
         if (!(f & 4u)) acc.steps += 1u;
         if (a.final_obs) {
             const int2 fo = cell_to_obs(a, pos);
@@ -509,7 +521,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
         }
         if (a.autoreset && (f & 3u)) {
             acc.finish(len, ret);
-            pos = a.start_cell;
+            pos = start;
             len = 0;
             ret = 0.0f;
         }
@@ -851,6 +863,39 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
         if (grid->n_slots == 1) { EF_DISPATCH(false, 1); } else { EF_DISPATCH(false, 4); }
     }
 #undef EF_DISPATCH
+}
+
+extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
+                                         const int32_t* start_cells, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                         const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t,
+                                         uint64_t env_offset, int32_t* obs, float* reward, uint8_t* terminated,
+                                         uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
+                                         uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+    GridArgs a{};
+    if (int s = fill_args(grid, a)) return s;
+    if (n_layouts < 1 || !start_cells || n < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (static_cast<int64_t>(a.table_len) * n_layouts > (1ll << 30)) return EF_ERR_UNSUPPORTED;
+    if (!ep_len && !packed_ok(a, autoreset)) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0) return EF_OK;
+    a.layout = layout_index; a.start_cells = start_cells; a.n_layouts = n_layouts; a.layout_len = a.table_len;
+    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action; a.draw = draw;
+    a.seed = seed; a.t = t; a.env_offset = env_offset;
+    a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs;
+    a.stats = stats; a.err = err; a.n = n; a.autoreset = autoreset;
+    a.clock = reinterpret_cast<unsigned long long*>(clock);
+    // the staged table is all layouts back to back when that fits in shared memory, else every lookup goes through L1/L2
+    const int64_t total = static_cast<int64_t>(a.table_len) * n_layouts;
+    const bool smem = static_cast<size_t>(total) * sizeof(uint2) <= kMaxSmemTable;
+    a.table_len = static_cast<int32_t>(total);  // what stage_table copies
+    const int grid_s = grid_for(n, 8);
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (smem) {
+        if (grid->n_slots == 1) return launch(gridworld_step_scalar_kernel<true, 1>, a, true, grid_s, st);
+        return launch(gridworld_step_scalar_kernel<true, 4>, a, true, grid_s, st);
+    }
+    if (grid->n_slots == 1) return launch(gridworld_step_scalar_kernel<false, 1>, a, false, grid_s, st);
+    return launch(gridworld_step_scalar_kernel<false, 4>, a, false, grid_s, st);
 }
 
 extern "C" int ef_gridworld_step_pcg64(const ef_grid_desc* grid, const uint64_t* thr53, int32_t idx_cap53, int32_t* pos,

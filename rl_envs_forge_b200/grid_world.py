@@ -14,7 +14,7 @@ from enum import IntEnum
 import numpy as np
 
 from . import _lib, spaces
-from .vec_env import VecEnv
+from .vec_env import VecEnv, resolve_seed
 
 
 class Action(IntEnum):  # grid_world.py:11-15
@@ -645,3 +645,180 @@ class VecGridWorld(VecEnv):
             return f"No outcomes defined for state {st} and action {Action(a)!r} (env {env}; {count} rejected env-step(s))"
         return (f"probabilities do not sum to 1 for state {st} and action {Action(a)!r} "
                 f"(env {env}; {count} rejected env-step(s))")
+
+
+class VecGridWorldLayouts(VecEnv):
+    """N GridWorld instances spread over several LAYOUTS in one batch (per-env heterogeneous grids).
+
+    `layouts` is a list of dicts with the per-layout reference kwargs `start_state`, `terminal_states`, `walls`,
+    `special_transitions` (each optional, reference defaults); `rows`, `cols`, `rewards`, `p_success`,
+    `episode_length_limit` are shared, so one set of outcome thresholds serves every table.  Env i walks layout
+    `layout_index[i]`, default `(env_offset + i) % len(layouts)`.  Each layout is compiled by the same table compiler as
+    `VecGridWorld` (`GridSpec`, i.e. grid_world.py:245-274 and friends); `mdp_of(l)` / `P_of(l)` export them.
+    One launch steps the whole mixed batch (`ef_gridworld_step_layouts`); fused rollouts and the PCG64 stream mode are
+    per-layout features of `VecGridWorld`."""
+    _HOST_TRANSPORT = "staged"
+
+    def __init__(self, num_envs, layouts, rows=5, cols=5, rewards=None, p_success=1.0, episode_length_limit=None, *,
+                 layout_index=None, device=None, seed=None, env_offset=0, autoreset=True, strict=False):
+        if not layouts:
+            raise ValueError("layouts must hold at least one layout dict")
+        self.specs = []
+        for lay in layouts:
+            unknown = set(lay) - {"start_state", "terminal_states", "walls", "special_transitions"}
+            if unknown:
+                raise ValueError(f"unknown per-layout keys {sorted(unknown)}")
+            kw = dict(start_state=lay.get("start_state", (0, 0)), terminal_states=lay.get("terminal_states", _DEFAULT_TERMINALS),
+                      walls=lay.get("walls"), special_transitions=lay.get("special_transitions"))
+            validate_args(rows, cols, kw["start_state"], kw["terminal_states"], kw["walls"], kw["special_transitions"],
+                          rewards, seed, None, p_success, episode_length_limit)
+            self.specs.append(GridSpec(rows, cols, kw["start_state"], kw["terminal_states"], kw["walls"],
+                                       kw["special_transitions"], rewards, p_success, episode_length_limit))
+        if episode_length_limit is not None and episode_length_limit <= 0:
+            raise ValueError("episode_length_limit <= 0 is not supported by the device path")
+        super().__init__(num_envs, device, seed, env_offset, autoreset)
+        torch = self._torch
+        self.rows, self.cols, self.p_success, self.episode_length_limit = rows, cols, p_success, episode_length_limit
+        self.n_layouts = len(self.specs)
+        self.strict = bool(strict)
+        self.single_action_space = spaces.Discrete(4)
+        self.single_observation_space = spaces.Tuple((spaces.Discrete(rows), spaces.Discrete(cols)))
+        self.action_space = spaces.Batched(self.single_action_space, num_envs)
+        self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
+        n, dev = self.num_envs, self.device
+        self._layout_index = None
+        if layout_index is not None:
+            li = np.asarray(layout_index, np.int64).reshape(-1)
+            if li.shape[0] != n or (li < 0).any() or (li >= self.n_layouts).any():
+                raise ValueError(f"layout_index must hold {n} values in 0..{self.n_layouts - 1}")
+            self._layout_index = torch.from_numpy(li.astype(np.int32)).to(dev)
+        self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._obs = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._term = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._final_obs = None
+        self._upload_tables()
+        self.reset()
+
+    def _upload_tables(self):
+        torch = self._torch
+        S = self.rows * self.cols
+        starts = []
+        for sp in self.specs:
+            s = sp.start_state
+            starts.append(sp._cell_index(s) if sp._in_grid(s) else S)   # pseudo-cell S: the reference raises on step
+        tabs = np.concatenate([sp.device_table(extra_cells=1) for sp in self.specs])
+        self._table = torch.from_numpy(tabs.view(np.int32)).to(self.device)
+        self._start_cells = torch.from_numpy(np.array(starts, np.int32)).to(self.device)
+        sp0 = self.specs[0]
+        d = _lib.GridDesc()
+        d.rows, d.cols, d.n_slots, d.idx_cap = self.rows, self.cols, sp0.n_slots, sp0.idx_cap
+        d.thr[0], d.thr[1], d.thr[2] = sp0.thr
+        d.start_cell = 0
+        d.episode_limit = self.episode_length_limit if self.episode_length_limit is not None else 0
+        d.table_cells = S + 1
+        d.table = self._table.data_ptr()
+        self._desc = d
+
+    def layout_of_env(self):
+        """int64 [N] layout index of every env (host array)."""
+        if self._layout_index is not None:
+            return self._layout_index.cpu().numpy().astype(np.int64)
+        return (self.env_offset + np.arange(self.num_envs, dtype=np.int64)) % self.n_layouts
+
+    def mdp_of(self, layout):
+        return self.specs[layout].mdp_dict()
+
+    def P_of(self, layout):
+        return self.specs[layout].probability_matrix()
+
+    def add_special_transition(self, layout, from_state, action, to_state=None, reward=None):
+        self.specs[layout].add_special_transition(from_state, action, to_state, reward)
+        self._upload_tables()
+
+    @property
+    def state(self):
+        p = self.pos.to(self._torch.int64)
+        return self._torch.stack([p // self.cols, p % self.cols], dim=1).to(self._torch.int32)
+
+    @property
+    def episode_length_counter(self):
+        return self.ep_len
+
+    def get_state(self):
+        return {"pos": self.pos.clone(), "ep_len": self.ep_len.clone(), "ep_ret": self.ep_ret.clone(), "t": self._t}
+
+    def set_state(self, state):
+        self.pos.copy_(state["pos"])
+        self.ep_len.copy_(state["ep_len"])
+        self.ep_ret.copy_(state["ep_ret"])
+        self._t = int(state.get("t", self._t))
+
+    def reset(self, *, seed=None, mask=None):
+        """Every env (or those selected by `mask`) back to the start state of ITS layout (grid_world.py:530-551)."""
+        torch = self._torch
+        if seed is not None:
+            self.seed, self._seed = seed, resolve_seed(seed)
+        lay = torch.from_numpy(self.layout_of_env()).to(self.device)
+        start = self._start_cells[lay]
+        if mask is None:
+            self.pos.copy_(start)
+            self.ep_len.zero_()
+            self.ep_ret.zero_()
+        else:
+            m = torch.as_tensor(mask, device=self.device).bool()
+            self.pos.copy_(torch.where(m, start, self.pos))
+            self.ep_len.masked_fill_(m, 0)
+            self.ep_ret.masked_fill_(m, 0.0)
+        self._reset_epoch += 1
+        return self.state, {}
+
+    def step(self, actions, draws=None, *, return_final_obs=False):
+        """GridWorld.step (:495-528) for the whole mixed batch; arguments and returns as `VecGridWorld.step`."""
+        torch, n = self._torch, self.num_envs
+        host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        if host_io:
+            a = actions.reshape(-1).to(torch.int32) if torch.is_tensor(actions) else \
+                np.asarray(actions).reshape(-1).astype(np.int32, copy=False)
+            act = self._to_device("action", self._host_in("action", a, torch.int32, (n,)), torch.int32, (n,))
+        else:
+            if tuple(actions.shape) != (n,):
+                raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
+            act = (actions if actions.dtype == torch.int32 else actions.to(torch.int32)).contiguous()
+        drw = None
+        if draws is not None:
+            if torch.is_tensor(draws) and draws.is_cuda:
+                drw = (draws if draws.dtype == torch.int32 else draws.to(torch.int64).to(torch.int32)).contiguous()
+            else:
+                drw = self._to_device("draw", np.asarray(draws).astype(np.uint32, copy=False).view(np.int32), torch.int32, (n,))
+        fobs = None
+        if return_final_obs:
+            if self._final_obs is None:
+                self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+            fobs = self._final_obs
+        self._call(self._lib.ef_gridworld_step_layouts, self._desc, self.n_layouts, _lib.ptr(self._layout_index),
+                   _lib.ptr(self._start_cells), _lib.ptr(self.pos), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(act),
+                   _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward),
+                   _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err),
+                   _lib.ptr(self._clock), n, int(self.autoreset))
+        self._t += 1
+        if self.strict:
+            self.check_errors()
+        info = {}
+        if host_io:
+            named = [("obs", self._obs), ("reward", self._reward), ("term", self._term), ("trunc", self._trunc)]
+            out = self._to_host(named + ([("final_obs", fobs)] if return_final_obs else []))
+            if return_final_obs:
+                info["final_observation"] = out[4]
+            return out[0], out[1], out[2].view(np.bool_), out[3].view(np.bool_), info
+        if return_final_obs:
+            info["final_observation"] = fobs
+        return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
+
+    def _describe_error(self, count, env, detail, kind_id, kind):
+        if kind_id == 1:
+            return f"{detail} is not a valid Action (env {env}; {count} rejected env-step(s))"
+        cell, a = divmod(detail, 4)
+        return (f"{'No outcomes defined' if kind_id == 2 else 'probabilities do not sum to 1'} for state "
+                f"{(cell // self.cols, cell % self.cols)} and action {Action(a)!r} (env {env}; {count} rejected env-step(s))")
