@@ -50,6 +50,7 @@ struct GridArgs {
     const int32_t* layout;
     const int32_t* start_cells;
     int32_t n_layouts, layout_len;
+    int64_t quads_per_cta;  // vector step kernel: contiguous quads per CTA
     // rollout only
     int32_t K;
     uint8_t* flags;
@@ -115,6 +116,16 @@ __device__ __forceinline__ int4 pack4(const int32_t (&pos)[4], const int32_t (&l
                      static_cast<int32_t>(v[3]));
 }
 
+// Outcome index = number of thresholds <= r, i.e. (r >= thr0) + (r >= thr1) + (r >= thr2), computed without predicate
+// registers: the high word of the 64-bit difference r - thr is 0xffffffff exactly when r < thr.  (The comparison form
+// made ptxas spill predicates into a general register in the 16-envs-per-thread step kernel.)
+__device__ __forceinline__ uint32_t outcome_index(const GridArgs& a, uint32_t r) {
+    const uint32_t b0 = static_cast<uint32_t>((static_cast<uint64_t>(r) - a.thr0) >> 32);
+    const uint32_t b1 = static_cast<uint32_t>((static_cast<uint64_t>(r) - a.thr1) >> 32);
+    const uint32_t b2 = static_cast<uint32_t>((static_cast<uint64_t>(r) - a.thr2) >> 32);
+    return 3u + b0 + b1 + b2;
+}
+
 // One transition of one env.  Returns bit0 terminated, bit1 truncated, bit2 rejected (state untouched).
 template <bool SMEM, int SLOTS>
 __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* __restrict__ tab, uint32_t g,
@@ -128,7 +139,7 @@ __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* _
     const uint32_t row = static_cast<uint32_t>(pos) * 4u + static_cast<uint32_t>(act);
     uint32_t slot = row;
     if constexpr (SLOTS == 4) {
-        const uint32_t idx = (r >= a.thr0) + (r >= a.thr1) + (r >= a.thr2);
+        const uint32_t idx = outcome_index(a, r);
         slot = row * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
     }
     const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
@@ -166,7 +177,7 @@ __device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __re
     for (int j = 0; j < 4; ++j) {
         uint32_t slot = static_cast<uint32_t>(q.pos[j]) * 4u + static_cast<uint32_t>(act[j]);
         if constexpr (SLOTS == 4) {
-            const uint32_t idx = (r[j] >= a.thr0) + (r[j] >= a.thr1) + (r[j] >= a.thr2);
+            const uint32_t idx = outcome_index(a, r[j]);
             slot = slot * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
         }
         const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     const unsigned long long ticket = clock_ticket(a.clock);
     const bool philox_act = a.action == nullptr;
     const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
-    const int64_t per_cta = (quads + gridDim.x - 1) / gridDim.x;
+    const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
     const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t q_end = min(q_begin + per_cta, quads);
 #if EF_STEP_ASYNC
@@ -851,6 +862,8 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
         1, std::min<int64_t>(static_cast<int64_t>(sm_count()) * EF_STEP_GRID_PER_SM, (quads + 31) / 32)));
     const int grid_b = grid_for((quads + EF_STEP_BIG_Q - 1) / EF_STEP_BIG_Q, EF_STEP_BIG_GRID_PER_SM);
     const int grid_s = grid_for(n, 8);
+    const int grid_used = small ? grid_v : grid_b;
+    a.quads_per_cta = ((n >> 2) + grid_used - 1) / grid_used;  // full quads only; the ragged tail is handled separately
 #define EF_DISPATCH(SM, SL)                                                                                              \
     if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                      \
     return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS>, a, SM, grid_v, st,                  \
