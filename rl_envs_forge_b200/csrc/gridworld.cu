@@ -51,6 +51,7 @@ struct GridArgs {
     const int32_t* start_cells;
     int32_t n_layouts, layout_len;
     int64_t quads_per_cta;  // vector step kernel: contiguous quads per CTA
+    PhiloxKeys rk;          // vector step kernel: round keys of `seed`
     // rollout only
     int32_t K;
     uint8_t* flags;
@@ -266,14 +267,14 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
     q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
     if (philox_act) {
         uint32_t w[4];
-        group_words4(a.seed, g0, t, kStreamPolicy, w);
+        group_words4_rk(a.rk, a.seed, g0, t, kStreamPolicy, w);
 #pragma unroll
         for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(w[j] >> 30);
     }
 #if EF_EXPERIMENT & 1  // timing experiments only: no Philox
     r[0] = g0 * 2654435761u; r[1] = r[0] + 0x9E3779B9u; r[2] = r[1] + 0x9E3779B9u; r[3] = r[2] + 0x9E3779B9u;
 #else
-    if constexpr (SLOTS == 4) group_words4(a.seed, g0, t, kStreamTransition, r);
+    if constexpr (SLOTS == 4) group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, r);
 #endif
 #if EF_EXPERIMENT & 2  // timing experiments only: no table walk
     q.term = q.trunc = q.bad = 0u;
@@ -439,18 +440,20 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
             }
         }
 #else
+        // 32-bit bookkeeping inside the chunk (a CTA's share is far below 2^31 quads); 64-bit only for the addresses
         QuadIn in[Q];
+        const uint32_t left = static_cast<uint32_t>(min(q_end - chunk, static_cast<int64_t>(Q) * kThreads));
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
-            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-            if (v < q_end) in[j] = load_quad(a, v * 4, philox_act);
+            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+            if (local < left) in[j] = load_quad(a, (chunk + local) * 4, philox_act);
         }
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
-            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-            if (v < q_end)
-                step_quad<SMEM, SLOTS>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in[j], philox_act,
-                                       acc, errs);
+            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+            if (local < left)
+                step_quad<SMEM, SLOTS>(a, tab, (chunk + local) * 4, static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t,
+                                       in[j], philox_act, acc, errs);
         }
 #endif
     }
@@ -864,6 +867,7 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     const int grid_s = grid_for(n, 8);
     const int grid_used = small ? grid_v : grid_b;
     a.quads_per_cta = ((n >> 2) + grid_used - 1) / grid_used;  // full quads only; the ragged tail is handled separately
+    a.rk = philox_round_keys(seed);
 #define EF_DISPATCH(SM, SL)                                                                                              \
     if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                      \
     return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS>, a, SM, grid_v, st,                  \
