@@ -233,31 +233,36 @@ struct QuadIn {
     float4 r4;
 };
 
+// PACKED: the state word layout is known at compile time (ep_len == NULL).  FAST: the common call shape is known at
+// compile time -- actions given, obs / reward / terminated / truncated all requested, no final_obs, auto-reset on -- so
+// the launch-uniform null checks and their branches disappear from the instruction stream.
+template <bool PACKED, bool FAST>
 __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, bool philox_act) {
     QuadIn in;
 #if EF_STREAMING
     in.p4 = __ldcs(reinterpret_cast<const int4*>(a.pos + base));
-    in.l4 = a.ep_len ? __ldcs(reinterpret_cast<const int4*>(a.ep_len + base)) : make_int4(0, 0, 0, 0);
+    in.l4 = PACKED ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.ep_len + base));
     in.r4 = __ldcs(reinterpret_cast<const float4*>(a.ep_ret + base));
     in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.action + base));
 #else
     in.p4 = *reinterpret_cast<const int4*>(a.pos + base);
-    in.l4 = a.ep_len ? *reinterpret_cast<const int4*>(a.ep_len + base) : make_int4(0, 0, 0, 0);
+    if constexpr (PACKED) in.l4 = make_int4(0, 0, 0, 0);
+    else in.l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
     in.r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
-    in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
+    in.a4 = (!FAST && philox_act) ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
 #endif
     return in;
 }
 
 // One step of a full quad: draws, branch-free transitions, auto-reset, 128-bit stores.
-template <bool SMEM, int SLOTS>
+template <bool SMEM, int SLOTS, bool PACKED, bool FAST>
 __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
                                           uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
                                           ErrorAcc& errs) {
     Quad q;
     int32_t act[4] = {in.a4.x, in.a4.y, in.a4.z, in.a4.w};
     uint32_t r[4] = {0u, 0u, 0u, 0u};
-    const bool packed = a.ep_len == nullptr;
+    constexpr bool packed = PACKED;
     if (packed) {
         unpack4(in.p4, q.pos, q.len);
     } else {
@@ -265,7 +270,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
     }
     q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
-    if (philox_act) {
+    if (!FAST && philox_act) {
         uint32_t w[4];
         group_words4_rk(a.rk, a.seed, g0, t, kStreamPolicy, w);
 #pragma unroll
@@ -312,14 +317,14 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         rejected = e.x;
     }
     acc.steps += 4u - rejected;
-    if (a.final_obs) {  // pre-reset observation, only materialised on request
+    if (!FAST && a.final_obs) {  // pre-reset observation, only materialised on request
         int4* o = reinterpret_cast<int4*>(a.final_obs + 2 * base);
         const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
         o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
         const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
         o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
     }
-    const uint32_t fin = a.autoreset ? (q.term | q.trunc) : 0u;
+    const uint32_t fin = (FAST || a.autoreset) ? (q.term | q.trunc) : 0u;
     if (fin) finish4(a, q, fin, acc);
 #if EF_STREAMING
 #define EF_ST(ptr, val) __stcs(ptr, val)
@@ -333,16 +338,16 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         EF_ST(reinterpret_cast<int4*>(a.ep_len + base), make_int4(q.len[0], q.len[1], q.len[2], q.len[3]));
     }
     EF_ST(reinterpret_cast<float4*>(a.ep_ret + base), make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]));
-    if (a.obs) {  // observation after auto-reset = (row, col) of the stored position
+    if (FAST || a.obs) {  // observation after auto-reset = (row, col) of the stored position
         int4* o = reinterpret_cast<int4*>(a.obs + 2 * base);
         const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
         EF_ST(o, make_int4(o0.x, o0.y, o1.x, o1.y));
         const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
         EF_ST(o + 1, make_int4(o2.x, o2.y, o3.x, o3.y));
     }
-    if (a.reward) EF_ST(reinterpret_cast<float4*>(a.reward + base), make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]));
-    if (a.terminated) EF_ST(reinterpret_cast<uint32_t*>(a.terminated + base), q.term);
-    if (a.truncated) EF_ST(reinterpret_cast<uint32_t*>(a.truncated + base), q.trunc);
+    if (FAST || a.reward) EF_ST(reinterpret_cast<float4*>(a.reward + base), make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]));
+    if (FAST || a.terminated) EF_ST(reinterpret_cast<uint32_t*>(a.terminated + base), q.term);
+    if (FAST || a.truncated) EF_ST(reinterpret_cast<uint32_t*>(a.truncated + base), q.trunc);
 #undef EF_ST
 }
 
@@ -385,7 +390,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 // quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
 // (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
 // load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
-template <bool SMEM, int SLOTS, int Q, int MINBLOCKS>
+template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST>
 __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
 #if EF_EXPERIMENT & 4
     const uint2* __restrict__ tab = a.table;
@@ -398,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     ErrorAcc errs;
     const uint64_t t = a.t + clock_read(a.clock);
     const unsigned long long ticket = clock_ticket(a.clock);
-    const bool philox_act = a.action == nullptr;
+    const bool philox_act = FAST ? false : a.action == nullptr;
     const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
     const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
     const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
@@ -435,8 +440,8 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
                 in.l4 = make_int4(l.x, l.y, l.z, l.w);
                 in.r4 = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
                 in.a4 = make_int4(c.x, c.y, c.z, c.w);
-                step_quad<SMEM, SLOTS>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in, philox_act, acc,
-                                       errs);
+                step_quad<SMEM, SLOTS, PACKED, FAST>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in,
+                                                     philox_act, acc, errs);
             }
         }
 #else
@@ -446,14 +451,15 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left) in[j] = load_quad(a, (chunk + local) * 4, philox_act);
+            if (local < left) in[j] = load_quad<PACKED, FAST>(a, (chunk + local) * 4, philox_act);
         }
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
             if (local < left)
-                step_quad<SMEM, SLOTS>(a, tab, (chunk + local) * 4, static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t,
-                                       in[j], philox_act, acc, errs);
+                step_quad<SMEM, SLOTS, PACKED, FAST>(a, tab, (chunk + local) * 4,
+                                                     static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
+                                                     philox_act, acc, errs);
         }
 #endif
     }
@@ -868,17 +874,23 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     const int grid_used = small ? grid_v : grid_b;
     a.quads_per_cta = ((n >> 2) + grid_used - 1) / grid_used;  // full quads only; the ragged tail is handled separately
     a.rk = philox_round_keys(seed);
+    const bool packed = ep_len == nullptr;
+    const bool fast = action && obs && reward && terminated && truncated && !final_obs && autoreset != 0;
+#define EF_LAUNCH_VEC(SM, SL, PK, FS)                                                                                    \
+    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS>, a, SM, grid_v, st,        \
+                          EF_STEP_ASYNC ? size_t(EF_STEP_Q) * 4 * kThreads * 16 : 0)                                     \
+                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS, PK, FS>, a, SM, grid_b,    \
+                          st, EF_STEP_ASYNC ? size_t(EF_STEP_BIG_Q) * 4 * kThreads * 16 : 0)
 #define EF_DISPATCH(SM, SL)                                                                                              \
-    if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                      \
-    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS>, a, SM, grid_v, st,                  \
-                          EF_STEP_ASYNC ? size_t(EF_STEP_Q) * 4 * kThreads * 16 : 0)                                       \
-                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS>, a, SM, grid_b, st,          \
-                          EF_STEP_ASYNC ? size_t(EF_STEP_BIG_Q) * 4 * kThreads * 16 : 0)
+    if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                    \
+    if (SM && fast) { if (packed) { EF_LAUNCH_VEC(SM, SL, true, SM); } else { EF_LAUNCH_VEC(SM, SL, false, SM); } }      \
+    if (packed) { EF_LAUNCH_VEC(SM, SL, true, false); } else { EF_LAUNCH_VEC(SM, SL, false, false); }
     if (smem) {
         if (grid->n_slots == 1) { EF_DISPATCH(true, 1); } else { EF_DISPATCH(true, 4); }
     } else {
         if (grid->n_slots == 1) { EF_DISPATCH(false, 1); } else { EF_DISPATCH(false, 4); }
     }
+#undef EF_LAUNCH_VEC
 #undef EF_DISPATCH
 }
 
