@@ -339,6 +339,7 @@ class VecGridWorld(VecEnv):
         self._term = self._out[o_term:o_term + n]
         self._trunc = self._out[o_trunc:o_trunc + n]
         self._final_obs = None
+        self._fast_args = None   # cached pointer arguments of the lean step() path
         self._P = None
         self.rng = rng
         self._rng_state = self._rng_inc = None
@@ -416,6 +417,7 @@ class VecGridWorld(VecEnv):
             self._packed = False
             self._pos_split, self._ep_len_split = pos, ln
             del self._pl
+            self._fast_args = None
 
     # -- table ----------------------------------------------------------------------------------------------------
     def _start_cell(self):
@@ -436,6 +438,7 @@ class VecGridWorld(VecEnv):
         d.table_cells = self.spec.n_cells + 1
         d.table = self._table.data_ptr()
         self._desc = d
+        self._fast_args = None
         # an episode_length_limit <= 0 truncates on every step in the reference (counter >= limit); the kernel's
         # "<= 0 means None" encoding cannot express that, so refuse it loudly rather than diverge silently.
         if self.episode_length_limit is not None and self.episode_length_limit <= 0:
@@ -519,6 +522,25 @@ class VecGridWorld(VecEnv):
         draws    optional uint32-valued [N] injected outcome draws r (u = r * 2**-32); default: Philox.
         Returns (obs int32 [N,2], reward fp32 [N], terminated bool [N], truncated bool [N], info)."""
         torch = self._torch
+        if (draws is None and not return_final_obs and not self.strict and self.rng == "philox"
+                and torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+                and actions.dim() == 1 and actions.shape[0] == self.num_envs and actions.is_contiguous()):
+            # lean path of the usual call (CUDA int32 actions in, CUDA tensors out): the fixed pointer arguments are
+            # cached, so one step() costs one ctypes call -- a Python-driven loop then keeps pace with the ~10 us kernel
+            fixed = self._fast_args
+            if fixed is None:
+                fixed = self._fast_args = (
+                    (self._desc,) + self._state_ptrs() + (self.ep_ret.data_ptr(),),
+                    (self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(), self._trunc.data_ptr(), None,
+                     self._stats_raw.data_ptr(), self.err.data_ptr()),
+                    (self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)))
+            head, tail, outs = fixed
+            clock = self._clock
+            self._call_lean(self._lib.ef_gridworld_step, *head, actions.data_ptr(), None, self._seed,
+                            0 if clock is not None else self._t, self.env_offset, *tail,
+                            None if clock is None else clock.data_ptr(), self.num_envs, int(self._autoreset))
+            self._t += 1
+            return outs[0], outs[1], outs[2], outs[3], {}
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
         mode = self.host_transport if host_io else None
         if mode == "pipelined" and (self.rng == "pcg64" or draws is not None or self._clock is not None):

@@ -130,6 +130,16 @@ class VecEnv:
         with self._torch.cuda.device(self.device):
             _lib.check(fn(*args, self._stream()))
 
+    def _call_lean(self, fn, *args):
+        """_call without the device context manager when the env's device is already current (the usual case)."""
+        torch = self._torch
+        if torch.cuda.current_device() == self.device.index:
+            status = fn(*args, torch.cuda.current_stream().cuda_stream)
+            if status:
+                _lib.check(status)
+        else:
+            self._call(fn, *args)
+
     def _pipe(self):
         """Lazily created ef_host_pipe (two copy streams + events) of the pipelined host-buffer step."""
         if self._pipe_handle is None:
