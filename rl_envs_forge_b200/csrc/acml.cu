@@ -194,18 +194,20 @@ struct CarArgs {
     unsigned long long* clock;
     int64_t n;
     int32_t autoreset, reset_mode;  // reset_mode: 0 random (Philox), 1 equal (max_cars // 2 each)
+    PhiloxKeys rk;                  // round keys of `seed` (step kernel)
 };
 
 // numpy legacy next_double over the (env, step) Philox substream: ((a >> 5) * 2^26 + (b >> 6)) / 2^53 from two words.
 struct DoubleStream {
-    uint64_t seed, t;
+    const PhiloxKeys& rk;
+    uint64_t t;
     uint32_t g, consumed;
     uint4 blk;
-    __device__ __forceinline__ DoubleStream(uint64_t seed_, uint32_t g_, uint64_t t_) : seed(seed_), t(t_), g(g_), consumed(0) {
-        blk = draw_block(seed, g, t, kStreamAcml, 0);
+    __device__ __forceinline__ DoubleStream(const PhiloxKeys& rk_, uint32_t g_, uint64_t t_) : rk(rk_), t(t_), g(g_), consumed(0) {
+        blk = draw_block_rk(rk, g, t, kStreamAcml, 0);
     }
     __device__ __forceinline__ double next() {  // words are consumed in pairs, so a double never straddles two blocks
-        if ((consumed & 3u) == 0u && consumed != 0u) blk = draw_block(seed, g, t, kStreamAcml, consumed >> 2);
+        if ((consumed & 3u) == 0u && consumed != 0u) blk = draw_block_rk(rk, g, t, kStreamAcml, consumed >> 2);
         const bool second = (consumed & 2u) != 0u;
         const uint32_t wa = second ? blk.z : blk.x, wb = second ? blk.w : blk.y;
         consumed += 2u;
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs
         int32_t ca = max(s.x - moved * sign, 0), cb = max(s.y + moved * sign, 0);
         const int32_t cost = mag * a.move_cost;
         // _simulate_rentals_and_returns (:76-104): requests A, requests B, returns A, returns B -- in that order
-        DoubleStream ds(a.seed, g, t);
+        DoubleStream ds(a.rk, g, t);
         const int4 draws = poisson4(ds, a);
         const int32_t req_a = draws.x, req_b = draws.y, ret_a = draws.z, ret_b = draws.w;
         const int32_t rent_a = min(ca, req_a), rent_b = min(cb, req_b);
@@ -401,6 +403,7 @@ extern "C" int ef_car_rental_step(const ef_car_rental_params* p, int32_t* state,
     a.obs = reinterpret_cast<int2*>(obs); a.reward = reward; a.terminated = terminated; a.truncated = truncated;
     a.final_obs = reinterpret_cast<int2*>(final_obs);
     a.stats = stats; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = autoreset;
+    a.rk = philox_round_keys(seed);
     return launch_kernel(car_rental_step_kernel, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
 }
 

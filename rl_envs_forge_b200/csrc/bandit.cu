@@ -27,6 +27,7 @@ struct BanditArgs {
     double* stats;
     uint32_t* err;
     int64_t n;
+    PhiloxKeys rk;  // round keys of `seed`
 };
 
 // Primitive stream of one (env, step).  The first Philox block and the transcendental-heavy values every family starts
@@ -81,15 +82,16 @@ struct Primitives {
 // The same primitive stream, evaluated on demand.  Used by the family-sorted kernel, where the lanes of a warp hold the
 // same family and nothing needs hoisting; word for word and formula for formula identical to `Primitives`.
 struct LazyPrimitives {
-    uint64_t seed, t;
+    const PhiloxKeys& rk;
+    uint64_t t;
     uint32_t g, consumed;
     uint4 blk;
-    __device__ __forceinline__ LazyPrimitives(uint64_t seed_, uint32_t g_, uint64_t t_) : seed(seed_), t(t_), g(g_), consumed(0) {
-        blk = draw_block(seed, g, t, kStreamBandit, 0);
+    __device__ __forceinline__ LazyPrimitives(const PhiloxKeys& rk_, uint32_t g_, uint64_t t_) : rk(rk_), t(t_), g(g_), consumed(0) {
+        blk = draw_block_rk(rk, g, t, kStreamBandit, 0);
     }
     __device__ __forceinline__ uint32_t word() {
         const uint32_t lane = consumed & 3u;
-        if (lane == 0u && consumed != 0u) blk = draw_block(seed, g, t, kStreamBandit, consumed >> 2);
+        if (lane == 0u && consumed != 0u) blk = draw_block_rk(rk, g, t, kStreamBandit, consumed >> 2);
         ++consumed;
         return lane == 0u ? blk.x : lane == 1u ? blk.y : lane == 2u ? blk.z : blk.w;
     }
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, kSortedCtasPerSm) bandit_step_sorted
             const uint32_t rec = s_sorted[p];
             const uint32_t l = rec & 0xfffu, act = rec >> 12;
             const uint32_t g = static_cast<uint32_t>(a.env_offset + base_i + l);
-            LazyPrimitives pr(a.seed, g, t);
+            LazyPrimitives pr(a.rk, g, t);
             const float r = sample_arm(load_arm(arms, act), pr, a.seed, g, act);
             s_rew[l] = r;
             acc.steps += 1u;
@@ -385,6 +387,7 @@ extern "C" int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* acti
     BanditArgs a{};
     a.arms = arms; a.k = k; a.action = action; a.seed = seed; a.t0 = t0; a.env_offset = env_offset; a.K = K;
     a.obs = obs; a.reward = reward; a.stats = stats; a.err = err; a.n = n;
+    a.rk = philox_round_keys(seed);
     const bool unsorted = getenv("ENVFORGE_BANDIT_UNSORTED") != nullptr;  // A/B + parity switch: the plain kernel
     if (k <= kSortedMaxArms && !unsorted) {
         const int64_t units = (n + kTile - 1) / kTile * K;

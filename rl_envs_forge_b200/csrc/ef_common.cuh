@@ -135,6 +135,12 @@ __device__ __forceinline__ uint4 draw_block(uint64_t seed, uint32_t g, uint64_t 
                          stream | (block << 8), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
 }
 
+// draw_block with host-derived round keys (kernel-parameter constant bank).
+__device__ __forceinline__ uint4 draw_block_rk(const PhiloxKeys& rk, uint32_t g, uint64_t counter, uint32_t stream,
+                                               uint32_t block = 0) {
+    return philox4x32_10_rk(g, static_cast<uint32_t>(counter), static_cast<uint32_t>(counter >> 32), stream | (block << 8), rk);
+}
+
 // Grouped-stream words of the four consecutive envs g0 .. g0+3 at counter t.  g0 & 3 is the same for every thread of a
 // launch (it equals env_offset & 3), so the second call is a launch-uniform branch taken only for unaligned shards.
 // Unaligned shard (env_offset & 3 != 0): the quad straddles two Philox blocks.  Kept out of line: it is launch-uniformly

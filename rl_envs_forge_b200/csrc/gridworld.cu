@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
             const int64_t o = static_cast<int64_t>(k) * a.n + base;
             uint32_t wt[4] = {0u, 0u, 0u, 0u};
             int32_t act[4];
-            if constexpr (SLOTS == 4) group_words4(a.seed, g0, t, kStreamTransition, wt);
+            if constexpr (SLOTS == 4) group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, wt);
             if constexpr (EXT_ACTIONS) {
                 if (act_vec) {
                     const int4 a4 = __ldg(reinterpret_cast<const int4*>(a.action + o));
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
                 }
             } else {
                 uint32_t wp[4];
-                group_words4(a.seed, g0, t, kStreamPolicy, wp);
+                group_words4_rk(a.rk, a.seed, g0, t, kStreamPolicy, wp);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(wp[j] >> 30);
             }
@@ -983,6 +983,7 @@ extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int3
     a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K;
     a.reward = rewards; a.flags = flags; a.stats = stats; a.err = err; a.n = n; a.autoreset = 1;
+    a.rk = philox_round_keys(seed);
     a.clock = reinterpret_cast<unsigned long long*>(clock);
     const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
