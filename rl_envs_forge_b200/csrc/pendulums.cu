@@ -17,6 +17,7 @@ struct PendArgs {
     float* ep_ret;
     const float* action;
     uint64_t seed, t, env_offset;
+    PhiloxKeys rk;  // round keys of `seed` (rollout policy draws)
     float* obs;
     float* reward;
     uint8_t* terminated;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
                 }
             } else {
                 uint32_t w[4];
-                group_words4(a.seed, g0, t, kStreamPolicy, w);
+                group_words4_rk(a.rk, a.seed, g0, t, kStreamPolicy, w);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) act[j] = policy_action(w[j]);
             }
@@ -347,6 +348,7 @@ static int rollout_impl(const ef_pendulum_params* p, float* state, int32_t* ep_l
     PendArgs a{};
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
+    a.rk = philox_round_keys(seed);
     a.stats = stats; a.n = n; a.autoreset = 1; a.clock = reinterpret_cast<unsigned long long*>(clock);
     const int grid = grid_for((n + 3) / 4, EF_PEND_ROLLOUT_GRID_PER_SM);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
