@@ -18,6 +18,7 @@ struct PendArgs {
     const float* action;
     uint64_t seed, t, env_offset;
     PhiloxKeys rk;  // round keys of `seed` (rollout policy draws)
+    int64_t per_cta;  // step kernel: contiguous envs per CTA (a multiple of the CTA size), divided on the host
     float* obs;
     float* reward;
     uint8_t* terminated;
@@ -144,7 +145,9 @@ __device__ __forceinline__ float policy_action(uint32_t w) { return uniform_f32(
 // Step kernel (HBM-bound).  The batch is cut into one contiguous chunk per CTA; a thread issues the loads of EF_PEND_U
 // envs (stride = CTA size, so every access of a warp is contiguous) before stepping them, which keeps ~4x more bytes in
 // flight per SM than one env per thread.
-template <class Env>
+// FAST: the common call shape is known at compile time -- actions given, obs (distinct from state) / reward / terminated /
+// truncated all requested, no final_obs, no acc, auto-reset on -- so the launch-uniform null checks vanish.
+template <class Env, bool FAST>
 __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs a) {
     using Vec = typename Env::Vec;
     pdl_launch_dependents();
@@ -152,35 +155,38 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
     EpisodeAcc acc;
     const uint64_t t = a.t + clock_read(a.clock);
     const unsigned long long ticket = clock_ticket(a.clock);
-    int64_t per_cta = (a.n + gridDim.x - 1) / gridDim.x;
-    per_cta = (per_cta + kThreads - 1) / kThreads * kThreads;  // keeps every CTA's chunk 256-env aligned
+    const int64_t per_cta = a.per_cta;  // keeps every CTA's chunk 256-env aligned
     const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t end = min(begin + per_cta, a.n);
     for (int64_t chunk = begin; chunk < end; chunk += static_cast<int64_t>(EF_PEND_U) * kThreads) {
         Vec s[EF_PEND_U];
         int32_t len[EF_PEND_U];
         float ret[EF_PEND_U], act[EF_PEND_U];
+        // 32-bit bookkeeping inside the chunk; 64-bit only for the addresses
+        const uint32_t left = static_cast<uint32_t>(min(end - chunk, static_cast<int64_t>(EF_PEND_U) * kThreads));
 #pragma unroll
         for (int j = 0; j < EF_PEND_U; ++j) {
-            const int64_t i = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-            if (i < end) {
+            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+            if (local < left) {
+                const int64_t i = chunk + local;
                 s[j] = reinterpret_cast<const Vec*>(a.state)[i];
                 len[j] = a.ep_len[i];
                 ret[j] = a.ep_ret[i];
-                act[j] = a.action ? __ldg(a.action + i) : 0.0f;
+                act[j] = (FAST || a.action) ? __ldg(a.action + i) : 0.0f;
             }
         }
 #pragma unroll
         for (int j = 0; j < EF_PEND_U; ++j) {
-            const int64_t i = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-            if (i >= end) continue;
+            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+            if (local >= left) continue;
+            const int64_t i = chunk + local;
             const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-            if (!a.action) act[j] = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
+            if (!FAST && !a.action) act[j] = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
             float rew, a0, a1;
             const uint32_t f = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew, a0, a1);
             acc.steps += 1u;
-            if (a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s[j];
-            if (a.autoreset && f) {
+            if (!FAST && a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s[j];
+            if ((FAST || a.autoreset) && f) {
                 acc.finish(len[j], ret[j]);
                 s[j] = Env::init(a.p, a.seed, g, t, kStreamResetAuto);
                 len[j] = 0;
@@ -189,11 +195,11 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
             reinterpret_cast<Vec*>(a.state)[i] = s[j];
             a.ep_len[i] = len[j];
             a.ep_ret[i] = ret[j];
-            if (a.obs && a.obs != a.state) reinterpret_cast<Vec*>(a.obs)[i] = s[j];
-            if (a.reward) a.reward[i] = rew;
-            if (a.terminated) a.terminated[i] = f & 1u;
-            if (a.truncated) a.truncated[i] = (f >> 1) & 1u;
-            if (a.acc) Env::store_acc(a.acc, i, a0, a1);
+            if (FAST || (a.obs && a.obs != a.state)) reinterpret_cast<Vec*>(a.obs)[i] = s[j];
+            if (FAST || a.reward) a.reward[i] = rew;
+            if (FAST || a.terminated) a.terminated[i] = f & 1u;
+            if (FAST || a.truncated) a.truncated[i] = (f >> 1) & 1u;
+            if (!FAST && a.acc) Env::store_acc(a.acc, i, a0, a1);
         }
     }
     cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, 1ull);
@@ -334,8 +340,11 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
     a.seed = seed; a.t = t; a.env_offset = env_offset; a.obs = obs; a.reward = reward;
     a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs; a.acc = acc;
     a.stats = stats; a.n = n; a.autoreset = autoreset; a.clock = reinterpret_cast<unsigned long long*>(clock);
-    return launch_kernel(pendulum_step_kernel<Env>, a, grid_for((n + EF_PEND_U - 1) / EF_PEND_U, EF_PEND_GRID_PER_SM), 0,
-                         static_cast<cudaStream_t>(stream));
+    const int grid = grid_for((n + EF_PEND_U - 1) / EF_PEND_U, EF_PEND_GRID_PER_SM);
+    a.per_cta = ((n + grid - 1) / grid + kThreads - 1) / kThreads * kThreads;
+    const bool fast = action && obs && obs != state && reward && terminated && truncated && !final_obs && !acc && autoreset != 0;
+    if (fast) return launch_kernel(pendulum_step_kernel<Env, true>, a, grid, 0, static_cast<cudaStream_t>(stream));
+    return launch_kernel(pendulum_step_kernel<Env, false>, a, grid, 0, static_cast<cudaStream_t>(stream));
 }
 
 template <class Env>
