@@ -59,8 +59,14 @@ struct CartPole {
     using Vec = float4;
     static __device__ __forceinline__ Vec init(const ef_pendulum_params& p, uint64_t seed, uint32_t g, uint64_t ctr,
                                                uint32_t stream) {
-        if (p.fixed_init) return make_float4(p.init_state[0], p.init_state[1], p.init_state[2], p.init_state[3]);
-        const uint4 w = draw_block(seed, g, ctr, stream);
+        if (p.fixed_init) return fixed_state(p);
+        return from_words(p, draw_block(seed, g, ctr, stream));
+    }
+    static __device__ __forceinline__ Vec fixed_state(const ef_pendulum_params& p) {
+        return make_float4(p.init_state[0], p.init_state[1], p.init_state[2], p.init_state[3]);
+    }
+    // initial state from the four words of the env's reset block (_initialize_state: U(init_lo, init_hi) per component)
+    static __device__ __forceinline__ Vec from_words(const ef_pendulum_params& p, uint4 w) {
         const float span = p.init_hi - p.init_lo;
         return make_float4(uniform_f32(w.x, p.init_lo, span), uniform_f32(w.y, p.init_lo, span),
                            uniform_f32(w.z, p.init_lo, span), uniform_f32(w.w, p.init_lo, span));
@@ -95,8 +101,13 @@ struct PendulumDisk {
     using Vec = float2;
     static __device__ __forceinline__ Vec init(const ef_pendulum_params& p, uint64_t seed, uint32_t g, uint64_t ctr,
                                                uint32_t stream) {
-        if (p.fixed_init) return make_float2(p.init_state[0], p.init_state[1]);
-        const uint4 w = draw_block(seed, g, ctr, stream);
+        if (p.fixed_init) return fixed_state(p);
+        return from_words(p, draw_block(seed, g, ctr, stream));
+    }
+    static __device__ __forceinline__ Vec fixed_state(const ef_pendulum_params& p) {
+        return make_float2(p.init_state[0], p.init_state[1]);
+    }
+    static __device__ __forceinline__ Vec from_words(const ef_pendulum_params& p, uint4 w) {
         const float span = p.init_hi - p.init_lo;
         return make_float2(uniform_f32(w.x, p.init_lo, span), uniform_f32(w.y, p.init_lo, span));
     }
@@ -279,13 +290,38 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
                 }
             }
             if (__ballot_sync(0xffffffffu, any_fin)) {  // warp vote: reset path only where some lane finished
+                bool fin[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (valid[j] && f[j]) {
+                    fin[j] = valid[j] && f[j];
+                    if (fin[j]) {
                         acc.finish(len[j], ret[j]);
-                        s[j] = Env::init(a.p, a.seed, g0 + j, t, kStreamResetAuto);
                         len[j] = 0;
                         ret[j] = 0.0f;
+                    }
+                }
+                if (a.p.fixed_init) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (fin[j]) s[j] = Env::fixed_state(a.p);
+                } else {
+                    // Reset draws, one pass per finished slot OF A LANE rather than one pass per slot of the warp.  Each
+                    // finished env needs its own Philox block (stream RESET_AUTO of (env, t), ~100 instructions).  Written
+                    // as `for j: if (fin[j]) s[j] = init(...)` the warp executes the call once for every slot j in which
+                    // ANY lane finished -- with random actions a CartPole episode lasts ~20 steps, so that is 3-4 calls
+                    // per warp-step for a handful of active lanes (37 % of the executed instructions).  Here every lane
+                    // walks its OWN pending slots; a lane rarely has more than one, so the warp makes ~1.4 calls.
+                    uint32_t pending = (fin[0] ? 1u : 0u) | (fin[1] ? 2u : 0u) | (fin[2] ? 4u : 0u) | (fin[3] ? 8u : 0u);
+                    while (__any_sync(0xffffffffu, pending != 0u)) {
+                        if (pending != 0u) {
+                            const uint32_t j = static_cast<uint32_t>(__ffs(pending)) - 1u;
+                            const Vec fresh = Env::from_words(a.p, draw_block_rk(a.rk, g0 + j, t, kStreamResetAuto));
+                            if (j == 0u) s[0] = fresh;
+                            else if (j == 1u) s[1] = fresh;
+                            else if (j == 2u) s[2] = fresh;
+                            else s[3] = fresh;
+                            pending &= pending - 1u;
+                        }
                     }
                 }
             }
