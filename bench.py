@@ -411,12 +411,19 @@ def run_ours(args):
         details["gambler_step"] = {"env_steps_per_s": ng / sec, "envs": ng, "GBps": 42 * ng / sec / 1e9,
                                    "roofline_frac": 42 * ng / sec / 1e9 / peak}
         del gm, a_g
+        gm = VecGamblersProblem(1 << 22, goal_amount=100, win_probability=0.4, start_capital=10, seed=seed,
+                                env_offset=rank * (1 << 22))
+        sec = ev_time(lambda: gm.rollout(Kr), 10)
+        details["gambler_rollout_K64_random_policy"] = {"env_steps_per_s": (1 << 22) * Kr / sec, "envs": 1 << 22}
+        del gm
         ng = 1 << 22
         cr = VecJacksCarRental(ng, seed=seed, env_offset=rank * ng)
         a_c = torch.randint(0, 11, (ng,), dtype=torch.int32, device="cuda")
         sec = ev_time(lambda: cr.step(a_c), 20)
         details["car_rental_step"] = {"env_steps_per_s": ng / sec, "envs": ng, "GBps": 54 * ng / sec / 1e9,
                                       "note": "four FP64 legacy-numpy Poisson draws per env-step: issue-bound"}
+        sec = ev_time(lambda: cr.rollout(16), 5)
+        details["car_rental_rollout_K16_random_policy"] = {"env_steps_per_s": ng * 16 / sec, "envs": ng}
         del cr, a_c
         lrng = np.random.default_rng(5)
         nl, side, mz = 1 << 19, 32, 64
@@ -430,6 +437,9 @@ def run_ours(args):
             per_env = 4 + 12 + 12 + 4 + 2 + obytes          # action, state r/w, reward, flags, observation
             details[key] = {"env_steps_per_s": nl / sec, "envs": nl, "mazes": mz, "GBps": per_env * nl / sec / 1e9,
                             "roofline_frac": per_env * nl / sec / 1e9 / peak, "bytes_per_env_step": per_env}
+            if vis is None:
+                sec = ev_time(lambda: lb.rollout(Kr), 10)
+                details["labyrinth_rollout_K64_random_policy"] = {"env_steps_per_s": nl * Kr / sec, "envs": nl, "mazes": mz}
             del lb
         del a_l
         if world > 1:

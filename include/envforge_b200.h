@@ -270,6 +270,11 @@ int ef_gambler_step(const ef_gambler_params* p, int32_t* state, int32_t* ep_len,
                     const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, int32_t* obs, float* reward,
                     uint8_t* terminated, uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
                     uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
+/* K fused steps (t0 .. t0+K-1), capital in registers, auto-reset always on.  actions [K,n] int32 or NULL (uniform legal
+ * bet); rewards [K,n] float / flags [K,n] uint8 (bit0 terminated, bit1 truncated) or NULL. */
+int ef_gambler_rollout(const ef_gambler_params* p, int32_t* state, int32_t* ep_len, float* ep_ret, const int32_t* actions,
+                       uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K, float* rewards, uint8_t* flags,
+                       double* stats, uint32_t* err, uint64_t* clock, int64_t n, void* stream);
 int ef_gambler_reset(int32_t start_capital, int32_t* state, int32_t* ep_len, float* ep_ret, int32_t* obs,
                      const uint8_t* mask, int64_t n, void* stream);
 
@@ -291,6 +296,10 @@ int ef_car_rental_step(const ef_car_rental_params* p, int32_t* state, int32_t* e
                        const int32_t* action, uint64_t seed, uint64_t t, uint64_t env_offset, int32_t* obs, float* reward,
                        uint8_t* terminated, uint8_t* truncated, int32_t* final_obs, double* stats, uint64_t* clock,
                        int64_t n, int32_t autoreset, void* stream);
+/* K fused steps; actions [K,n] or NULL (uniform random action); rewards [K,n] / flags [K,n] (bit1 truncated) or NULL. */
+int ef_car_rental_rollout(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,
+                          const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K, float* rewards,
+                          uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
 int ef_car_rental_reset(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                         uint64_t epoch, uint64_t env_offset, int32_t* obs, const uint8_t* mask, int64_t n, void* stream);
 
@@ -325,6 +334,11 @@ int ef_labyrinth_step(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_l
                       uint64_t seed, uint64_t t, uint64_t env_offset, uint8_t* obs, float* reward, uint8_t* terminated,
                       uint8_t* truncated, uint8_t* final_obs, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
                       int32_t autoreset, void* stream);
+/* K fused steps without observation rendering (position in registers; render once afterwards with ef_labyrinth_observe).
+ * actions [K,n] or NULL (uniform random direction); rewards [K,n] / flags [K,n] (bit0 terminated, bit1 truncated) or NULL. */
+int ef_labyrinth_rollout(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_len, float* ep_ret, const int32_t* actions,
+                         uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K, float* rewards, uint8_t* flags,
+                         double* stats, uint32_t* err, uint64_t* clock, int64_t n, void* stream);
 /* Labyrinth.state (:195-208) for n players: renders `obs` from the current positions, touches nothing else. */
 int ef_labyrinth_observe(const ef_labyrinth_desc* maze, const int32_t* pos, uint64_t env_offset, uint8_t* obs, int64_t n,
                          void* stream);

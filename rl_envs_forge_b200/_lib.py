@@ -91,6 +91,12 @@ SIGNATURES = {
     "ef_episode_stat_reduce": (C.c_int, [_P, _P, _P, _I64, _P]),
     "ef_gambler_step": (C.c_int, [C.POINTER(GamblerParams), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _I64, _I32, _P]),
+    "ef_gambler_rollout": (C.c_int, [C.POINTER(GamblerParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _P,
+                                     _I64, _P]),
+    "ef_car_rental_rollout": (C.c_int, [C.POINTER(CarRentalParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P,
+                                        _I64, _P]),
+    "ef_labyrinth_rollout": (C.c_int, [C.POINTER(LabyrinthDesc), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _P,
+                                       _I64, _P]),
     "ef_gambler_reset": (C.c_int, [_I32, _P, _P, _P, _P, _P, _I64, _P]),
     "ef_car_rental_step": (C.c_int, [C.POINTER(CarRentalParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
                                      _P, _P, _I64, _I32, _P]),

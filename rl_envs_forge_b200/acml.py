@@ -93,6 +93,19 @@ class _AcmlBase(VecEnv):
     def _strict_check(self):
         pass
 
+    def _rollout_buffers(self, K, actions, return_rewards):
+        torch, n = self._torch, self.num_envs
+        if actions is not None:
+            if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+                    and tuple(actions.shape) == (K, n)):
+                raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
+            actions = actions.contiguous()
+        rew = flg = None
+        if return_rewards:
+            rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+            flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        return actions, rew, flg
+
     def get_state(self):
         return {"state": self._state.clone(), "ep_len": self.ep_len.clone(), "ep_ret": self.ep_ret.clone(), "t": self._t}
 
@@ -170,6 +183,17 @@ class VecGamblersProblem(_AcmlBase):
                        _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(term), _lib.ptr(trunc), _lib.ptr(fobs),
                        _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n, int(self.autoreset))
         return self._step_common(actions, launch, return_final_obs)
+
+    def rollout(self, K, actions=None, *, return_rewards=False):
+        """K fused steps in one kernel (capital in registers, auto-reset on).  actions: CUDA int32 [K,N] or None for the
+        in-kernel policy (a legal bet, uniform in 0..min(s, goal - s)).  Returns (rewards fp32 [K,N], flags uint8 [K,N]:
+        bit0 terminated, bit1 truncated) if return_rewards else None; episode statistics accumulate in `stats`."""
+        actions, rew, flg = self._rollout_buffers(K, actions, return_rewards)
+        self._call(self._lib.ef_gambler_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len),
+                   _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew),
+                   _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), self.num_envs)
+        self._t += int(K)
+        return (rew, flg) if return_rewards else None
 
     def _strict_check(self):
         try:
@@ -275,6 +299,16 @@ class VecJacksCarRental(_AcmlBase):
                        _lib.ptr(rew), _lib.ptr(term), _lib.ptr(trunc), _lib.ptr(fobs), _lib.ptr(self._stats_raw),
                        _lib.ptr(self._clock), n, int(self.autoreset))
         return self._step_common(actions, launch, return_final_obs)
+
+    def rollout(self, K, actions=None, *, return_rewards=False):
+        """K fused steps in one kernel (cars in registers).  actions: CUDA int32 [K,N] or None (uniform random action).
+        Returns (rewards fp32 [K,N], flags uint8 [K,N]: bit1 truncated) if return_rewards else None."""
+        actions, rew, flg = self._rollout_buffers(K, actions, return_rewards)
+        self._call(self._lib.ef_car_rental_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len),
+                   _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew),
+                   _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self._clock), self.num_envs)
+        self._t += int(K)
+        return (rew, flg) if return_rewards else None
 
     # -- host-side tables of the reference (dynamic-programming users read them) ------------------------------------------
     def _precompute_poisson_probabilities(self, max_value=12):

@@ -40,6 +40,10 @@ struct GamblerArgs {
     unsigned long long* clock;
     int64_t n;
     int32_t autoreset;
+    // rollout only
+    int32_t K;
+    uint8_t* flags;
+    PhiloxKeys rk;
 };
 
 // One env-step.  Returns bit0 terminated, bit1 truncated, bit2 rejected (state untouched: the reference asserts first).
@@ -176,6 +180,67 @@ __global__ void __launch_bounds__(kThreads) gambler_step_kernel(const GamblerArg
     cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
 }
 
+// Fused K-step rollout: a thread keeps four consecutive gamblers in registers for all K steps (one Philox call per step
+// for their four outcome draws, one more for their four random bets), auto-reset always on.  State is read and written
+// once per launch (24 B / K per env-step); `reward` [K, n] / `flags` [K, n] (bit0 terminated, bit1 truncated) are optional.
+__global__ void __launch_bounds__(kThreads) gambler_rollout_kernel(const GamblerArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint64_t t0 = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t quads = (a.n + 3) / 4;
+    for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < quads; v += stride) {
+        const int64_t base = v * 4;
+        const uint32_t g0 = static_cast<uint32_t>(a.env_offset + base);
+        int32_t s[4], len[4];
+        float ret[4];
+        bool valid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            valid[j] = base + j < a.n;
+            const int64_t i = valid[j] ? base + j : 0;
+            s[j] = a.state[i];
+            len[j] = a.ep_len[i];
+            ret[j] = a.ep_ret[i];
+        }
+        for (int k = 0; k < a.K; ++k) {
+            const uint64_t t = t0 + static_cast<uint64_t>(k);
+            const int64_t o = static_cast<int64_t>(k) * a.n + base;
+            uint32_t w[4], wp[4];
+            group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, w);
+            if (!a.action) group_words4_rk(a.rk, a.seed, g0, t, kStreamPolicy, wp);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!valid[j]) continue;
+                const int32_t bet = a.action ? __ldg(a.action + o + j) : gambler_policy(a, s[j], wp[j]);
+                float rew;
+                const uint32_t f = gambler_transition(a, g0 + j, s[j], len[j], ret[j], bet, w[j], rew, errs);
+                if (!(f & 4u)) acc.steps += 1u;
+                if (a.reward) a.reward[o + j] = rew;
+                if (a.flags) a.flags[o + j] = static_cast<uint8_t>(f & 3u);
+                if (f & 3u) {
+                    acc.finish(len[j], ret[j]);
+                    s[j] = a.start;
+                    len[j] = 0;
+                    ret[j] = 0.0f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (valid[j]) {
+                a.state[base + j] = s[j];
+                a.ep_len[base + j] = len[j];
+                a.ep_ret[base + j] = ret[j];
+            }
+        }
+    }
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, static_cast<unsigned long long>(a.K));
+}
+
 // ---- JacksCarRental -------------------------------------------------------------------------------------------------
 struct CarArgs {
     int32_t max_cars, max_move, credit, move_cost, limit;
@@ -194,7 +259,9 @@ struct CarArgs {
     unsigned long long* clock;
     int64_t n;
     int32_t autoreset, reset_mode;  // reset_mode: 0 random (Philox), 1 equal (max_cars // 2 each)
-    PhiloxKeys rk;                  // round keys of `seed` (step kernel)
+    PhiloxKeys rk;                  // round keys of `seed` (step / rollout kernels)
+    int32_t K;                      // rollout only
+    uint8_t* flags;                 // rollout only: [K, n] bit1 = truncated
 };
 
 // numpy legacy next_double over the (env, step) Philox substream: ((a >> 5) * 2^26 + (b >> 6)) / 2^53 from two words.
@@ -254,6 +321,64 @@ __device__ __forceinline__ int2 car_initial_state(const CarArgs& a, uint32_t g, 
                      static_cast<int32_t>(__umulhi(w.y, static_cast<uint32_t>(a.max_cars) + 1u)));
 }
 
+// One JacksCarRental transition of env g at step t from raw action `raw`; returns the reward.
+__device__ __forceinline__ float car_transition(const CarArgs& a, uint32_t g, uint64_t t, int2& s, int32_t raw) {
+    // _move_cars_and_calculate_cost (car_rental.py:54-74); the reference never validates the action
+    const int32_t act = raw - a.max_move;
+    const int32_t mag = abs(act), sign = (act > 0) - (act < 0);
+    const int32_t moved = min(min(act > 0 ? s.x : s.y, mag), a.max_move);
+    int32_t ca = max(s.x - moved * sign, 0), cb = max(s.y + moved * sign, 0);
+    const int32_t cost = mag * a.move_cost;
+    // _simulate_rentals_and_returns (:76-104): requests A, requests B, returns A, returns B -- in that order
+    DoubleStream ds(a.rk, g, t);
+    const int4 draws = poisson4(ds, a);
+    const int32_t rent_a = min(ca, draws.x), rent_b = min(cb, draws.y);
+    const float rew = static_cast<float>((rent_a + rent_b) * a.credit - cost);
+    s = make_int2(min(ca - rent_a + draws.z, a.max_cars), min(cb - rent_b + draws.w, a.max_cars));
+    return rew;
+}
+
+// Fused K-step rollout: one env per thread, state in registers for all K steps; `action` [K, n] or NULL (uniform random
+// action), `reward` [K, n] / `flags` [K, n] optional.  Episodes only end through the optional step limit.
+__global__ void __launch_bounds__(kThreads) car_rental_rollout_kernel(const CarArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    EpisodeAcc acc;
+    const uint64_t t0 = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        int2 s = a.state[i];
+        int32_t len = a.ep_len[i];
+        float ret = a.ep_ret[i];
+        for (int k = 0; k < a.K; ++k) {
+            const uint64_t t = t0 + static_cast<uint64_t>(k);
+            const int64_t o = static_cast<int64_t>(k) * a.n + i;
+            const int32_t raw = a.action ? __ldg(a.action + o)
+                                         : static_cast<int32_t>(__umulhi(group_word1(a.seed, g, t, kStreamPolicy),
+                                                                         2u * static_cast<uint32_t>(a.max_move) + 1u));
+            const float rew = car_transition(a, g, t, s, raw);
+            ret += rew;
+            len += 1;
+            const bool trunc = a.limit > 0 && len >= a.limit;
+            if (a.reward) a.reward[o] = rew;
+            if (a.flags) a.flags[o] = trunc ? 2 : 0;
+            if (trunc) {
+                acc.finish(len, ret);
+                s = car_initial_state(a, g, t, kStreamResetAuto);
+                len = 0;
+                ret = 0.0f;
+            }
+        }
+        acc.steps += static_cast<uint32_t>(a.K);
+        a.state[i] = s;
+        a.ep_len[i] = len;
+        a.ep_ret[i] = ret;
+    }
+    cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, static_cast<unsigned long long>(a.K));
+}
+
 __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs a) {
     pdl_launch_dependents();
     pdl_wait();
@@ -270,21 +395,7 @@ __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs
         const int32_t raw = a.action ? __ldg(a.action + i)
                                      : static_cast<int32_t>(__umulhi(group_word1(a.seed, g, t, kStreamPolicy),
                                                                      2u * static_cast<uint32_t>(a.max_move) + 1u));
-        // _move_cars_and_calculate_cost (car_rental.py:54-74); the reference never validates the action
-        const int32_t act = raw - a.max_move;
-        const int32_t mag = abs(act), sign = (act > 0) - (act < 0);
-        const int32_t moved = min(min(act > 0 ? s.x : s.y, mag), a.max_move);
-        int32_t ca = max(s.x - moved * sign, 0), cb = max(s.y + moved * sign, 0);
-        const int32_t cost = mag * a.move_cost;
-        // _simulate_rentals_and_returns (:76-104): requests A, requests B, returns A, returns B -- in that order
-        DoubleStream ds(a.rk, g, t);
-        const int4 draws = poisson4(ds, a);
-        const int32_t req_a = draws.x, req_b = draws.y, ret_a = draws.z, ret_b = draws.w;
-        const int32_t rent_a = min(ca, req_a), rent_b = min(cb, req_b);
-        const float rew = static_cast<float>((rent_a + rent_b) * a.credit - cost);
-        ca = min(ca - rent_a + ret_a, a.max_cars);
-        cb = min(cb - rent_b + ret_b, a.max_cars);
-        s = make_int2(ca, cb);
+        const float rew = car_transition(a, g, t, s, raw);
         ret += rew;
         len += 1;
         acc.steps += 1u;
@@ -379,6 +490,23 @@ extern "C" int ef_gambler_step(const ef_gambler_params* p, int32_t* state, int32
     return launch_kernel(gambler_step_kernel<false>, a, grid_for(n, 8), 0, st);
 }
 
+extern "C" int ef_gambler_rollout(const ef_gambler_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,
+                                  const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                  float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
+                                  void* stream) {
+    if (!p || p->goal_amount < 0 || p->goal_amount > (1 << 30) || p->win_threshold > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n < 0 || K < 0 || !state || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    GamblerArgs a{};
+    a.goal = p->goal_amount; a.start = p->start_capital; a.limit = p->episode_limit; a.win_thr = p->win_threshold;
+    a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
+    a.stats = stats; a.err = err; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = 1;
+    a.rk = philox_round_keys(seed);
+    return launch_kernel(gambler_rollout_kernel, a, grid_for((n + 3) / 4, 8), 0, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int ef_gambler_reset(int32_t start_capital, int32_t* state, int32_t* ep_len, float* ep_ret, int32_t* obs,
                                 const uint8_t* mask, int64_t n, void* stream) {
     if (n < 0 || !state || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
@@ -405,6 +533,22 @@ extern "C" int ef_car_rental_step(const ef_car_rental_params* p, int32_t* state,
     a.stats = stats; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = autoreset;
     a.rk = philox_round_keys(seed);
     return launch_kernel(car_rental_step_kernel, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ef_car_rental_rollout(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,
+                                     const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                     float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n,
+                                     void* stream) {
+    CarArgs a{};
+    if (int s = fill_car_args(p, a)) return s;
+    if (n < 0 || K < 0 || !state || !ep_len || !ep_ret || !aligned(state, 8)) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    a.state = reinterpret_cast<int2*>(state); a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
+    a.stats = stats; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = 1;
+    a.rk = philox_round_keys(seed);
+    return launch_kernel(car_rental_rollout_kernel, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ef_car_rental_reset(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,

@@ -44,6 +44,9 @@ struct LabArgs {
     int64_t n;
     int32_t autoreset;
     int32_t vision_smem;  // 1: vision windows are assembled per thread in shared memory (kLabEnvsPerCta * d * d bytes)
+    // rollout only
+    int32_t K;
+    uint8_t* flags;
 };
 
 __device__ __forceinline__ int32_t lab_maze_of(const LabArgs& a, int64_t i) {
@@ -265,6 +268,77 @@ __global__ void __launch_bounds__(kThreads) labyrinth_kernel(const LabArgs a) {
     if constexpr (STEP) cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
 }
 
+// One transition of one player (labyrinth.py:245-288).  Returns bit0 terminated, bit2 rejected (invalid Action).
+__device__ __forceinline__ uint32_t lab_transition(const LabArgs& a, const uint8_t* __restrict__ grid, int32_t tgt, uint32_t g,
+                                                   int32_t& pos, int32_t act, float& rew, ErrorAcc& errs) {
+    rew = 0.0f;
+    if (static_cast<uint32_t>(act) > 3u) {  // Action(action) raises ValueError (:261)
+        errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+        return 4u;
+    }
+    const int32_t pr = pos / a.cols, pc = pos - pr * a.cols;
+    const int32_t r = pr + (act == 2) - (act == 0), c = pc + (act == 1) - (act == 3);  // player.py:72-80
+    bool ok = r >= 0 && r < a.rows && c >= 0 && c < a.cols;                              // :300-305
+    const int32_t nxt = r * a.cols + c;
+    if (ok) ok = __ldg(grid + nxt) != kLabWall;                                           // :306-308
+    rew = a.r_wall;
+    if (!ok) return 0u;
+    pos = nxt;
+    rew = a.r_neutral;
+    if (pos == tgt) {  // :279-286
+        rew = a.r_target;
+        return 1u;
+    }
+    return 0u;
+}
+
+// Fused K-step rollout: one player per thread, position and counters in registers for all K steps, no observation
+// rendering (call ef_labyrinth_observe afterwards).  `action` [K, n] or NULL (uniform random direction), `reward` [K, n] /
+// `flags` [K, n] (bit0 terminated, bit1 truncated) optional; auto-reset to the maze's start cell always on.
+__global__ void __launch_bounds__(kThreads) labyrinth_rollout_kernel(const LabArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint64_t t0 = a.t + clock_read(a.clock);
+    const unsigned long long ticket = clock_ticket(a.clock);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+        const int32_t maze = lab_maze_of(a, i);
+        const int32_t tgt = __ldg(a.target_cell + maze), start = __ldg(a.start_cell + maze);
+        const uint8_t* __restrict__ grid = a.grids + static_cast<int64_t>(maze) * a.cells;
+        int32_t pos = a.pos[i], len = a.ep_len[i];
+        float ret = a.ep_ret[i];
+        for (int k = 0; k < a.K; ++k) {
+            const uint64_t t = t0 + static_cast<uint64_t>(k);
+            const int64_t o = static_cast<int64_t>(k) * a.n + i;
+            const int32_t act = a.action ? __ldg(a.action + o)
+                                         : static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30);
+            float rew;
+            uint32_t f = lab_transition(a, grid, tgt, g, pos, act, rew, errs);
+            if (!(f & 4u)) {
+                ret += rew;
+                len += 1;
+                acc.steps += 1u;
+                if (a.limit > 0 && len >= a.limit) f |= 2u;
+            }
+            if (a.reward) a.reward[o] = rew;
+            if (a.flags) a.flags[o] = static_cast<uint8_t>(f & 3u);
+            if (f & 3u) {
+                acc.finish(len, ret);
+                pos = start;
+                len = 0;
+                ret = 0.0f;
+            }
+        }
+        a.pos[i] = pos;
+        a.ep_len[i] = len;
+        a.ep_ret[i] = ret;
+    }
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, static_cast<unsigned long long>(a.K));
+}
+
 __global__ void __launch_bounds__(kThreads) labyrinth_reset_kernel(const LabArgs a, const uint8_t* mask) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -330,6 +404,21 @@ extern "C" int ef_labyrinth_step(const ef_labyrinth_desc* maze, int32_t* pos, in
     a.stats = stats; a.err = err; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = autoreset;
     const size_t smem = lab_vision_smem(a);
     return launch_kernel(labyrinth_kernel<true>, a, lab_grid(n), smem, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ef_labyrinth_rollout(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                    const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                    float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock,
+                                    int64_t n, void* stream) {
+    LabArgs a{};
+    if (int s = fill_lab_args(maze, a)) return s;
+    if (n < 0 || K < 0 || !pos || !ep_len || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
+    a.stats = stats; a.err = err; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = 1;
+    return launch_kernel(labyrinth_rollout_kernel, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ef_labyrinth_observe(const ef_labyrinth_desc* maze, const int32_t* pos, uint64_t env_offset, uint8_t* obs,

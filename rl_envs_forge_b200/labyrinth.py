@@ -208,5 +208,25 @@ class VecLabyrinth(VecEnv):
             info["final_observation"] = fobs
         return obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
 
+    def rollout(self, K, actions=None, *, return_rewards=False):
+        """K fused steps in one kernel (positions in registers, no observation rendering -- read `state` afterwards).
+        actions: CUDA int32 [K,N] or None (uniform random direction).  Returns (rewards fp32 [K,N], flags uint8 [K,N]:
+        bit0 terminated, bit1 truncated) if return_rewards else None; auto-reset to the maze's start cell is always on."""
+        torch, n = self._torch, self.num_envs
+        if actions is not None:
+            if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+                    and tuple(actions.shape) == (K, n)):
+                raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
+            actions = actions.contiguous()
+        rew = flg = None
+        if return_rewards:
+            rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+            flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        self._call(self._lib.ef_labyrinth_rollout, self._desc, _lib.ptr(self.pos), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
+                   _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
+                   _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
+        self._t += int(K)
+        return (rew, flg) if return_rewards else None
+
     def _describe_error(self, count, env, detail, kind_id, kind):
         return f"{detail} is not a valid Action (env {env}; {count} rejected env-step(s))"

@@ -194,3 +194,54 @@ def test_car_rental_reference_surface_and_mdp():
         got = mdp[((int(key[0]), int(key[1])), int(key[2]))]
         assert got[0] == tuple(int(x) for x in nxt) and got[2] is False
         assert abs(got[1] - rew) <= 1e-12 * max(1.0, abs(rew))
+
+
+# ---- fused rollouts ----------------------------------------------------------------------------------------------------
+def test_gambler_rollout_equals_step_sequence():
+    """K fused steps == K step() calls: with external actions (rewards / flags emitted) and with the in-kernel policy
+    (fed to step() through its host twin: bet = mulhi(policy word, min(s, goal - s) + 1))."""
+    import torch
+    from rl_envs_forge_b200 import VecGamblersProblem
+    n, K, seed = 100_003, 40, 8
+    kw = dict(goal_amount=60, win_probability=0.45, start_capital=9, episode_length_limit=25, seed=seed, env_offset=500)
+    a, b = VecGamblersProblem(n, **kw), VecGamblersProblem(n, **kw)
+    acts = torch.randint(0, 12, (K, n), dtype=torch.int32, device="cuda")
+    acts[3, ::101] = 77                                              # rejected bets
+    rew, flg = a.rollout(K, acts, return_rewards=True)
+    for k in range(K):
+        o = b.step(acts[k])
+        assert torch.equal(rew[k], o[1]) and torch.equal(flg[k], o[2].to(torch.uint8) | (o[3].to(torch.uint8) << 1)), k
+    assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    assert int(a.err[0]) == int(b.err[0]) == (n + 100) // 101
+    g = np.arange(n) + 500
+    a.rollout(K)                                                     # random policy, nothing emitted
+    for k in range(K):
+        wp = philox.group_word(seed, g, K + k, philox.STREAM_POLICY).astype(np.uint64)
+        s = b.state.cpu().numpy().astype(np.int64)
+        hi = np.maximum(np.minimum(s, 60 - s), 0).astype(np.uint64)
+        b.step(torch.from_numpy(((wp * (hi + 1)) >> np.uint64(32)).astype(np.int32)).cuda())
+    assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert sa["episodes"] == sb["episodes"] and sa["length_sum"] == sb["length_sum"] and sa["env_steps"] == sb["env_steps"]
+    assert sa["return_sum"] == sb["return_sum"]
+
+
+def test_car_rental_rollout_equals_step_sequence():
+    import torch
+    from rl_envs_forge_b200 import VecJacksCarRental
+    n, K, seed = 20_001, 12, 4
+    kw = dict(seed=seed, env_offset=64, episode_length_limit=5)
+    a, b = VecJacksCarRental(n, **kw), VecJacksCarRental(n, **kw)
+    acts = torch.randint(0, 11, (K, n), dtype=torch.int32, device="cuda")
+    rew, flg = a.rollout(K, acts, return_rewards=True)
+    for k in range(K):
+        o = b.step(acts[k])
+        assert torch.equal(rew[k], o[1]) and torch.equal(flg[k], o[3].to(torch.uint8) << 1), k
+    assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    g = np.arange(n) + 64
+    a.rollout(K)
+    for k in range(K):
+        wp = philox.group_word(seed, g, K + k, philox.STREAM_POLICY).astype(np.uint64)
+        b.step(torch.from_numpy(((wp * np.uint64(11)) >> np.uint64(32)).astype(np.int32)).cuda())
+    assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    assert a.episode_stats()["episodes"] == b.episode_stats()["episodes"] == n * (2 * K // 5)

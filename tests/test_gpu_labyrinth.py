@@ -153,3 +153,33 @@ def test_host_buffer_path_from_mazes_and_snapshots():
     assert torch.equal(b.state, before)
     obs, _ = b.reset(mask=torch.arange(n, device="cuda") < 10)
     assert torch.equal(b.pos[:10].cpu(), torch.from_numpy((starts[:, 0] * 20 + starts[:, 1]).astype(np.int32))[np.arange(10) % 6])
+
+
+def test_rollout_equals_step_sequence():
+    """K fused steps (no rendering) == K step() calls: external actions with emitted rewards / flags, then the in-kernel
+    random policy through its host twin (policy word >> 30)."""
+    import torch
+    from oracle import philox
+    from rl_envs_forge_b200 import VecLabyrinth
+    rng = np.random.default_rng(12)
+    grids, starts, targets = _random_mazes(rng, 9, 14, 11)
+    n, K, seed, off = 50_003, 48, 6, 300
+    kw = dict(episode_length_limit=20, seed=seed, env_offset=off)
+    a, b = VecLabyrinth(n, grids, starts, targets, **kw), VecLabyrinth(n, grids, starts, targets, **kw)
+    acts = torch.randint(0, 4, (K, n), dtype=torch.int32, device="cuda")
+    acts[5, ::77] = 6                                                # rejected actions
+    rew, flg = a.rollout(K, acts, return_rewards=True)
+    for k in range(K):
+        o = b.step(acts[k], return_obs=False)
+        assert torch.equal(rew[k], o[1]) and torch.equal(flg[k], o[2].to(torch.uint8) | (o[3].to(torch.uint8) << 1)), k
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    assert int(a.err[0]) == int(b.err[0]) > 0
+    g = np.arange(n) + off
+    a.rollout(K)
+    for k in range(K):
+        wp = philox.group_word(seed, g, K + k, philox.STREAM_POLICY)
+        b.step(torch.from_numpy((wp >> np.uint32(30)).astype(np.int32)).cuda(), return_obs=False)
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    assert torch.equal(a.state, b.state)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert sa["episodes"] == sb["episodes"] > 0 and sa["length_sum"] == sb["length_sum"] and sa["env_steps"] == sb["env_steps"]
