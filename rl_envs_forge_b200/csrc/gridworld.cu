@@ -58,22 +58,46 @@ struct GridArgs {
     unsigned long long* clock;
 };
 
+// Table staging by TMA bulk copy: thread 0 arms an mbarrier and issues ONE cp.async.bulk for the whole table; the copy
+// runs while the CTA goes on (griddepcontrol.wait, input loads), and stage_table_wait() is called right before the first
+// table lookup.  Replaces a 256-thread LDG/STS loop (5 % of the step kernel's instructions) that also had to finish
+// before anything else could start.  Falls back to the loop when the table is not 16-byte aligned.
 template <bool SMEM>
-__device__ __forceinline__ const uint2* stage_table(const GridArgs& a) {
+__device__ __forceinline__ const uint2* stage_table_begin(const GridArgs& a, uint64_t* bar, bool& pending) {
     extern __shared__ __align__(16) uint2 s_table[];
+    pending = false;
     if constexpr (SMEM) {
-        if (aligned(a.table, 16)) {  // table_len is a multiple of 4 entries: copy two 8-byte entries per access
-            const uint4* src = reinterpret_cast<const uint4*>(a.table);
-            uint4* dst = reinterpret_cast<uint4*>(s_table);
-            for (int i = threadIdx.x; i < (a.table_len >> 1); i += blockDim.x) dst[i] = __ldg(src + i);
+        if (aligned(a.table, 16)) {  // table_len is a multiple of 4 entries, i.e. of 32 bytes
+            if (threadIdx.x == 0) {
+                mbar_init(bar, 1u);
+                bulk_copy_g2s(s_table, a.table, static_cast<uint32_t>(a.table_len) * static_cast<uint32_t>(sizeof(uint2)), bar);
+            }
+            pending = true;
         } else {
             for (int i = threadIdx.x; i < a.table_len; i += blockDim.x) s_table[i] = __ldg(a.table + i);
         }
-        __syncthreads();
+        __syncthreads();  // the mbarrier (or the table itself) is visible to every thread from here on
         return s_table;
     } else {
         return a.table;
     }
+}
+
+__device__ __forceinline__ void stage_table_wait(uint64_t* bar, bool& pending) {
+    if (pending) {
+        mbar_wait(bar, 0u);
+        pending = false;
+    }
+}
+
+// Synchronous form for the kernels that need the table right away (scalar step, PCG64 step, rollouts).
+template <bool SMEM>
+__device__ __forceinline__ const uint2* stage_table(const GridArgs& a) {
+    __shared__ uint64_t bar;
+    bool pending;
+    const uint2* tab = stage_table_begin<SMEM>(a, &bar, pending);
+    stage_table_wait(&bar, pending);
+    return tab;
 }
 
 __device__ __forceinline__ int2 cell_to_obs(const GridArgs& a, int32_t cell) {
@@ -395,7 +419,9 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #if EF_EXPERIMENT & 4
     const uint2* __restrict__ tab = a.table;
 #else
-    const uint2* __restrict__ tab = stage_table<SMEM>(a);  // prologue: independent of the previous launch
+    __shared__ uint64_t table_bar;
+    bool table_pending;
+    const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
 #endif
     pdl_launch_dependents();
     pdl_wait();                                            // previous launch complete, its writes visible
@@ -453,6 +479,9 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
             if (local < left) in[j] = load_quad<PACKED, FAST>(a, (chunk + local) * 4, philox_act);
         }
+#if !(EF_EXPERIMENT & 4)
+        stage_table_wait(&table_bar, table_pending);  // the bulk copy had the whole load phase to land
+#endif
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
@@ -463,6 +492,9 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         }
 #endif
     }
+#if !(EF_EXPERIMENT & 4)
+    stage_table_wait(&table_bar, table_pending);  // CTAs that own no full quad (tiny batches) still need the table below
+#endif
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x < (a.n & 3)) {  // ragged tail: at most three envs
         const int64_t i = (quads << 2) + threadIdx.x;
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
