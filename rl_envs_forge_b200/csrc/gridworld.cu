@@ -26,7 +26,7 @@ struct GridArgs {
     int32_t table_len;   // entries
     int32_t cols;
     uint32_t cols_magic; // ceil(2^32 / cols): row = umulhi(cell, magic), exact for cell < 65536 (cols > 1)
-    uint32_t thr0, thr1, thr2;
+    uint64_t thr0, thr1, thr2;  // 64-bit: a threshold at or beyond the index cap is 2^32, which no draw reaches
     int32_t idx_cap;
     int32_t start_cell;
     int32_t limit;       // <= 0: none
@@ -141,7 +141,8 @@ __device__ __forceinline__ int4 pack4(const int32_t (&pos)[4], const int32_t (&l
                      static_cast<int32_t>(v[3]));
 }
 
-// Outcome index = number of thresholds <= r, i.e. (r >= thr0) + (r >= thr1) + (r >= thr2), computed without predicate
+// Outcome index = min(number of thresholds <= r, idx_cap).  The host stores the thresholds at or beyond idx_cap as 2^32
+// (unreachable for a 32-bit draw), which makes the min implicit; the count itself is computed without predicate
 // registers: the high word of the 64-bit difference r - thr is 0xffffffff exactly when r < thr.  (The comparison form
 // made ptxas spill predicates into a general register in the 16-envs-per-thread step kernel.)
 __device__ __forceinline__ uint32_t outcome_index(const GridArgs& a, uint32_t r) {
@@ -165,7 +166,7 @@ __device__ __forceinline__ uint32_t transition(const GridArgs& a, const uint2* _
     uint32_t slot = row;
     if constexpr (SLOTS == 4) {
         const uint32_t idx = outcome_index(a, r);
-        slot = row * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
+        slot = row * 4u + idx;
     }
     const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
     const uint32_t oflags = o.x >> 16;
@@ -203,7 +204,7 @@ __device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __re
         uint32_t slot = static_cast<uint32_t>(q.pos[j]) * 4u + static_cast<uint32_t>(act[j]);
         if constexpr (SLOTS == 4) {
             const uint32_t idx = outcome_index(a, r[j]);
-            slot = slot * 4u + min(idx, static_cast<uint32_t>(a.idx_cap));
+            slot = slot * 4u + idx;
         }
         const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
         const uint32_t ok = ((o.x >> 17) & 3u) == 0u ? 1u : 0u;  // 0 for a rejected (inert) row
@@ -845,9 +846,9 @@ static int fill_args(const ef_grid_desc* g, GridArgs& a) {
     a.table_len = static_cast<int32_t>(tcells * 4 * g->n_slots);
     a.cols = g->cols;
     a.cols_magic = g->cols > 1 ? static_cast<uint32_t>(((1ull << 32) + g->cols - 1) / static_cast<uint64_t>(g->cols)) : 0u;
-    a.thr0 = g->thr[0];
-    a.thr1 = g->thr[1];
-    a.thr2 = g->thr[2];
+    a.thr0 = g->idx_cap > 0 ? g->thr[0] : (1ull << 32);
+    a.thr1 = g->idx_cap > 1 ? g->thr[1] : (1ull << 32);
+    a.thr2 = g->idx_cap > 2 ? g->thr[2] : (1ull << 32);
     a.idx_cap = g->idx_cap;
     a.start_cell = g->start_cell;
     a.limit = g->episode_limit;
