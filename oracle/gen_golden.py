@@ -8,6 +8,7 @@ constructor kwargs as a JSON string under `config`, the injected inputs (actions
 outputs.  numpy version used is recorded in `numpy_version` (matters for PendulumDisk, see oracle/pendulums.py).
 """
 import json
+import math
 import os
 
 import numpy as np
@@ -256,6 +257,161 @@ def car_rental_case(R, name, kw, n_steps, seed):
     print("carrental", name, "mean reward", float(np.mean(out["reward"])))
 
 
+# ---- the reference driven by the ENGINE's Philox streams ("identical injected random draws and actions") -----------------
+# These files let the GPU box compare the device DIRECTLY with outputs of the unmodified reference: env i of the batch is
+# one reference instance whose random draws are replaced by the engine's Philox words of (seed, global env index, step) and
+# whose actions are the engine's in-kernel random policy, so `Vec*.rollout(K)` / `step()` must reproduce them.
+class _ChoiceFromEngine:
+    """np_random stand-in for GridWorld: choice(n, p=probs) consumes the engine's transition word of the current step with
+    numpy's own rule, searchsorted(cumsum(p) / cumsum(p)[-1], u, 'right') (Generator.choice), u = r * 2**-32."""
+
+    def __init__(self):
+        self.r = None
+
+    def choice(self, n, p=None):
+        # Generator.choice validates first: |sum(p) - 1| > sqrt(eps) raises before any draw (numpy _generator.pyx)
+        if abs(math.fsum(p) - 1.0) > math.sqrt(np.finfo(np.float64).eps):
+            raise ValueError("probabilities do not sum to 1")
+        u = float(self.r) * 2.0 ** -32
+        cdf = np.cumsum(np.asarray(p, np.float64))
+        cdf /= cdf[-1]
+        return int(np.searchsorted(cdf, u, side="right"))
+
+
+def engine_gridworld_case(R, name, cfg, n_envs, n_steps, seed, env_offset):
+    from oracle import philox
+    kw = dict(cfg)
+    kw["special_transitions"] = {(k[0], R.Action(k[1])): v for k, v in kw["special_transitions"].items()}
+    g = np.arange(n_envs) + env_offset
+    wt = np.stack([philox.group_word(seed, g, t, philox.STREAM_TRANSITION) for t in range(n_steps)])   # [T, N]
+    wp = np.stack([philox.group_word(seed, g, t, philox.STREAM_POLICY) for t in range(n_steps)])
+    act = (wp >> np.uint32(30)).astype(np.int64)
+    obs = np.zeros((n_steps, n_envs, 2), np.int8)
+    rew = np.zeros((n_steps, n_envs), np.float32)
+    flags = np.zeros((n_steps, n_envs), np.uint8)        # bit0 done, bit1 truncated, bit2 the reference raised
+    for i in range(n_envs):
+        env = R.GridWorld(seed=0, **kw)
+        shim = _ChoiceFromEngine()
+        env.np_random = shim
+        env.reset()
+        for t in range(n_steps):
+            shim.r = wt[t, i]
+            try:
+                o, r, d, tr, _ = env.step(int(act[t, i]))
+            except ValueError:
+                flags[t, i] = 4                              # state untouched, no reward
+                obs[t, i] = env.state
+                continue
+            rew[t, i] = r
+            flags[t, i] = (1 if d else 0) | (2 if tr else 0)
+            if d or tr:
+                o, _ = env.reset()                           # same-step auto-reset: next observation = start state
+            obs[t, i] = o
+    np.savez_compressed(os.path.join(OUT, f"engine_gridworld_{name}.npz"), obs=obs, reward=rew, flags=flags,
+                        seed=seed, env_offset=env_offset, config=_jsonable_grid_cfg(cfg))
+    print("engine gridworld", name, "episodes", int((flags & 3 > 0).sum()), "raised", int((flags & 4 > 0).sum()))
+
+
+def engine_gambler_case(R, name, kw, n_envs, n_steps, seed, env_offset):
+    from oracle import philox
+    g = np.arange(n_envs) + env_offset
+    goal = kw["goal_amount"]
+    state = np.zeros((n_steps, n_envs), np.int32)
+    rew = np.zeros((n_steps, n_envs), np.float32)
+    done = np.zeros((n_steps, n_envs), bool)
+    real_rand = np.random.rand
+    try:
+        for i in range(n_envs):
+            env = R.GamblersProblem(**kw)
+            for t in range(n_steps):
+                r32 = int(philox.group_word(seed, g[i:i + 1], t, philox.STREAM_TRANSITION)[0])
+                wp = int(philox.group_word(seed, g[i:i + 1], t, philox.STREAM_POLICY)[0])
+                hi = max(min(env.state, goal - env.state), 0)
+                bet = (wp * (hi + 1)) >> 32                  # the engine's random policy: uniform legal bet
+                np.random.rand = lambda r32=r32: r32 * 2.0 ** -32
+                s, r, d, _, _ = env.step(int(bet))
+                rew[t, i], done[t, i] = r, d
+                if d:
+                    s, _ = env.reset()
+                state[t, i] = s
+    finally:
+        np.random.rand = real_rand
+    np.savez_compressed(os.path.join(OUT, f"engine_gambler_{name}.npz"), state=state, reward=rew, done=done, seed=seed,
+                        env_offset=env_offset, config=json.dumps(kw))
+    print("engine gambler", name, "episodes", int(done.sum()), "wins", int(rew.sum()))
+
+
+def engine_car_rental_case(R, name, kw, n_envs, n_steps, seed, env_offset):
+    """scipy.stats.poisson.rvs is replaced by numpy's legacy Poisson algorithm (oracle.acml.legacy_poisson, bit-exact vs
+    RandomState.poisson) over the engine's Philox doubles of (env, step)."""
+    import scipy.stats
+    from oracle import acml, philox
+    cr_mod = __import__("rl_envs_forge.envs.acml.car_rental.car_rental", fromlist=["poisson"])
+    n_act = 2 * kw.get("max_move_cars", 5) + 1
+    g = np.arange(n_envs) + env_offset
+    state = np.zeros((n_steps, n_envs, 2), np.int32)
+    rew = np.zeros((n_steps, n_envs), np.float32)
+    real = cr_mod.poisson
+
+    class _Rvs:
+        src = None
+
+        def rvs(self, lam):
+            return acml.legacy_poisson(self.src, lam)
+
+        def pmf(self, k, lam):
+            return scipy.stats.poisson.pmf(k, lam)
+    fake = _Rvs()
+    try:
+        cr_mod.poisson = fake
+        for i in range(n_envs):
+            env = R.JacksCarRental(init_state_option="equal", **kw)
+            for t in range(n_steps):
+                wp = int(philox.group_word(seed, g[i:i + 1], t, philox.STREAM_POLICY)[0])
+                fake.src = acml.PhiloxDoubles(seed, int(g[i]), t)
+                s, r, _, _, _ = env.step(int((wp * n_act) >> 32))
+                state[t, i], rew[t, i] = s, r
+    finally:
+        cr_mod.poisson = real
+    np.savez_compressed(os.path.join(OUT, f"engine_carrental_{name}.npz"), state=state, reward=rew, seed=seed,
+                        env_offset=env_offset, config=json.dumps(kw))
+    print("engine carrental", name, "mean reward", float(rew.mean()))
+
+
+def engine_bandit_case(R, name, k, arm_params, n_envs, n_steps, seed, env_offset):
+    """Arm.sample draws from `np_random`; here that is oracle.bandit.LegacyDistributions (bit-exact vs RandomState) over the
+    engine's per-(bandit, timestep) Philox primitives, so the float64 rewards are what the reference returns for the
+    engine's draws.  Custom arms only (default arms draw their means in __init__ from the RandomState)."""
+    from oracle import bandit as OB, philox
+    g = np.arange(n_envs) + env_offset
+    rew = np.zeros((n_steps, n_envs), np.float64)
+    act = np.zeros((n_steps, n_envs), np.int32)
+    for i in range(n_envs):
+        env = R.KArmedBandit(k=k, arm_params={a: dict(p) for a, p in arm_params.items()}, seed=0)
+        for t in range(n_steps):
+            wp = int(philox.group_word(seed, g[i:i + 1], t, philox.STREAM_POLICY)[0])
+            a = (wp * k) >> 32
+            env.np_random = OB.LegacyDistributions(OB.PhiloxPrimitives(seed, int(g[i]), t))
+            for arm in env.arms:                             # arms sample through the env's generator
+                if hasattr(arm, "np_random"):
+                    arm.np_random = env.np_random
+            _, r, _, _, _ = env.step(int(a))
+            rew[t, i], act[t, i] = r, a
+    np.savez_compressed(os.path.join(OUT, f"engine_bandit_{name}.npz"), reward=rew, action=act, seed=seed,
+                        env_offset=env_offset, k=k)
+    print("engine bandit", name, "mean reward", float(rew.mean()))
+
+
+def engine_cases(R):
+    engine_gridworld_case(R, "config2_p08", dict(CONFIG2_LAYOUT, p_success=0.8), 384, 256, seed=41, env_offset=1 << 20)
+    engine_gridworld_case(R, "config2_p1", dict(CONFIG2_LAYOUT, p_success=1.0), 128, 256, seed=42, env_offset=7)
+    engine_gambler_case(R, "default", dict(goal_amount=100, win_probability=0.4, start_capital=10), 256, 200, seed=43,
+                        env_offset=1000)
+    engine_car_rental_case(R, "default", dict(), 128, 60, seed=44, env_offset=12345)
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items() if "distribution" in p}
+    engine_bandit_case(R, "config3_custom_arms", len(arms), arms, 128, 30, seed=45, env_offset=99)
+
+
 def labyrinth_case(R, name, kw, n_steps, action_seed):
     """Labyrinth trajectory on a maze generated by the reference: every step's pre/post position, reward, done and the
     full observation are recorded.  A finished episode continues from the start position on the SAME maze
@@ -312,6 +468,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
     import sys
+    if "engine" in sys.argv[1:]:
+        engine_cases(R)
+        return
     if "acml" in sys.argv[1:] or "labyrinth" in sys.argv[1:]:
         if "acml" in sys.argv[1:]:
             acml_cases(R)
@@ -351,6 +510,8 @@ def main():
     acml_cases(R)
     # -- Labyrinth stepping on reference-generated mazes ------------------------------
     labyrinth_cases(R)
+    # -- the reference driven by the engine's own Philox streams (direct device-vs-reference vectors) ---------------------
+    engine_cases(R)
 
 
 if __name__ == "__main__":
