@@ -449,6 +449,12 @@ def run_ours(args):
                 v["env_steps_per_s"] = float(t.item())
                 v["aggregate_over_gpus"] = world
     line["details"] = details
+    if "cartpole_step" in details:   # BASELINE.json's metric names two envs: GridWorld is `value`, CartPole rides along here
+        cp_d = details["cartpole_step"]
+        line["secondary"] = {"metric": "env-steps/sec (CartPole step, 2^22 envs per GPU, actions resident in HBM)",
+                             "value": cp_d["env_steps_per_s"], "unit": UNIT, "n_gpus": world,
+                             "roofline_frac_per_gpu": cp_d.get("roofline_frac"),
+                             "rollout_K64_value": details.get("cartpole_rollout_K64_ext_actions_emit", {}).get("env_steps_per_s")}
 
     if sampler is not None:
         time.sleep(0.06)
