@@ -31,6 +31,10 @@ class VecPendulumBase(VecEnv):
         self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
         n, dev = self.num_envs, self.device
         self._state = torch.zeros((n, self.DIM), dtype=torch.float32, device=dev)
+        # The observation of these envs IS the (post-reset) state (cart_pole.py:166, pendulum_disk.py:158).  alias_obs=True
+        # (default) returns the state tensor itself as the observation -- like every output of step(), valid until the next
+        # call, not to be modified in place -- and saves writing DIM*4 bytes per env-step a second time; alias_obs=False
+        # keeps a separate observation buffer.
         self._obs = self._state if alias_obs else torch.zeros((n, self.DIM), dtype=torch.float32, device=dev)
         self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self._term = torch.zeros(n, dtype=torch.uint8, device=dev)

@@ -21,7 +21,7 @@ class VecCartPole(VecPendulumBase):
     def __init__(self, num_envs=1, tau=0.02, continuous_reward=False, episode_length_limit=1000,
                  angle_termination=None, initial_state=None, nonlinear_reward=False, reward_decay_rate=3.0,
                  reward_angle_range=(-0.1, 0.1), *, device=None, seed=None, env_offset=0, autoreset=True, strict=False,
-                 alias_obs=False):
+                 alias_obs=True):
         # cart_pole.py:56-64
         self.gravity = 9.8
         self.mass_cart = 1.0

@@ -156,9 +156,11 @@ __device__ __forceinline__ float policy_action(uint32_t w) { return uniform_f32(
 // Step kernel (HBM-bound).  The batch is cut into one contiguous chunk per CTA; a thread issues the loads of EF_PEND_U
 // envs (stride = CTA size, so every access of a warp is contiguous) before stepping them, which keeps ~4x more bytes in
 // flight per SM than one env per thread.
-// FAST: the common call shape is known at compile time -- actions given, obs (distinct from state) / reward / terminated /
-// truncated all requested, no final_obs, no acc, auto-reset on -- so the launch-uniform null checks vanish.
-template <class Env, bool FAST>
+// FAST != 0: the common call shape is known at compile time -- actions given, obs / reward / terminated / truncated all
+// requested, no final_obs, no acc, auto-reset on -- so the launch-uniform null checks vanish.  FAST == 1: obs is a buffer
+// of its own; FAST == 2: obs aliases the state buffer (the observation IS the new state, cart_pole.py:166 /
+// pendulum_disk.py:158), so it is not written a second time: 16 (8) fewer bytes per env-step.
+template <class Env, int FAST>
 __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs a) {
     using Vec = typename Env::Vec;
     pdl_launch_dependents();
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
             reinterpret_cast<Vec*>(a.state)[i] = s[j];
             a.ep_len[i] = len[j];
             a.ep_ret[i] = ret[j];
-            if (FAST || (a.obs && a.obs != a.state)) reinterpret_cast<Vec*>(a.obs)[i] = s[j];
+            if (FAST == 1 || (FAST == 0 && a.obs && a.obs != a.state)) reinterpret_cast<Vec*>(a.obs)[i] = s[j];
             if (FAST || a.reward) a.reward[i] = rew;
             if (FAST || a.terminated) a.terminated[i] = f & 1u;
             if (FAST || a.truncated) a.truncated[i] = (f >> 1) & 1u;
@@ -378,9 +380,10 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
     a.stats = stats; a.n = n; a.autoreset = autoreset; a.clock = reinterpret_cast<unsigned long long*>(clock);
     const int grid = grid_for((n + EF_PEND_U - 1) / EF_PEND_U, EF_PEND_GRID_PER_SM);
     a.per_cta = ((n + grid - 1) / grid + kThreads - 1) / kThreads * kThreads;
-    const bool fast = action && obs && obs != state && reward && terminated && truncated && !final_obs && !acc && autoreset != 0;
-    if (fast) return launch_kernel(pendulum_step_kernel<Env, true>, a, grid, 0, static_cast<cudaStream_t>(stream));
-    return launch_kernel(pendulum_step_kernel<Env, false>, a, grid, 0, static_cast<cudaStream_t>(stream));
+    const bool fast = action && obs && reward && terminated && truncated && !final_obs && !acc && autoreset != 0;
+    if (fast && obs != state) return launch_kernel(pendulum_step_kernel<Env, 1>, a, grid, 0, static_cast<cudaStream_t>(stream));
+    if (fast) return launch_kernel(pendulum_step_kernel<Env, 2>, a, grid, 0, static_cast<cudaStream_t>(stream));
+    return launch_kernel(pendulum_step_kernel<Env, 0>, a, grid, 0, static_cast<cudaStream_t>(stream));
 }
 
 template <class Env>

@@ -19,7 +19,7 @@ class VecPendulumDisk(VecPendulumBase):
     def __init__(self, num_envs=1, tau=0.005, continuous_reward=False, episode_length_limit=1000,
                  angle_termination=None, initial_state=None, nonlinear_reward=False, reward_decay_rate=3.0,
                  reward_angle_range=(-0.2, 0.2), *, device=None, seed=None, env_offset=0, autoreset=True, strict=False,
-                 alias_obs=False):
+                 alias_obs=True):
         # pendulum_disk.py:58-64
         self.J = 1.91e-4
         self.m = 0.055

@@ -283,3 +283,21 @@ def test_host_buffer_path_equals_device_path(kind, transport):
             assert np.array_equal(x, y.cpu().numpy())
         assert np.array_equal(oa[4]["final_observation"], ob[4]["final_observation"].cpu().numpy())
     assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len)
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "pendulumdisk"])
+def test_aliased_observation_equals_separate_observation_buffer(kind):
+    """alias_obs=True (default): the state tensor doubles as the observation (the reference returns np.array(self.state));
+    alias_obs=False writes a separate buffer.  Same numbers either way, over auto-resets."""
+    import torch
+    Vec, _, _, dim = _cls(kind)
+    n = 8195
+    a, b = Vec(n, seed=2, episode_length_limit=9), Vec(n, seed=2, episode_length_limit=9, alias_obs=False)
+    assert a._obs is a._state and b._obs is not b._state
+    for t in range(25):
+        act = torch.empty(n, device="cuda").uniform_(-3, 3)
+        oa, ob = a.step(act), b.step(act)
+        for x, y in zip(oa[:4], ob[:4]):
+            assert torch.equal(x, y), t
+        assert oa[0].data_ptr() == a.state.data_ptr()
+    assert torch.equal(a.state, b.state) and a.episode_stats()["episodes"] == b.episode_stats()["episodes"] > 0
