@@ -199,7 +199,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from rl_envs_forge_b200 import VecGamblersProblem, VecJacksCarRental, VecLabyrinth
+    from rl_envs_forge_b200 import VecGamblersProblem, VecGridWorldLayouts, VecJacksCarRental, VecLabyrinth
     from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandit, VecPendulumDisk, all_reduce_stats
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -360,6 +360,23 @@ def run_ours(args):
         sec = ev_time(lambda: sets[0].rollout(Kr), 10)
         details["gridworld_rollout_K64_random_policy"] = {"env_steps_per_s": n * Kr / sec, "envs": n}
         del sets[1:]
+        # stream-exact mode (every env owns numpy's PCG64 generator: 42 B + 48 B of generator state per env-step) and a batch
+        # that mixes eight layouts (one env per thread, tables staged back to back in shared memory)
+        npc = 1 << 18           # seeding expands one numpy SeedSequence per env on the host (5 s per 2^20 envs)
+        pc = VecGridWorld(npc, seed=seed, special_transitions=spec, rng="pcg64", env_offset=rank * npc, **CONFIG2)
+        a_pc = acts[0][:npc].contiguous()
+        sec = ev_time(lambda: pc.step(a_pc), 50)
+        details["gridworld_step_pcg64_stream_exact"] = {"env_steps_per_s": npc / sec, "envs": npc, "us_per_launch": sec * 1e6,
+                                                        "GBps": (GRID_BYTES_PER_STEP + 48) * npc / sec / 1e9}
+        del pc, a_pc
+        lay = dict(start_state=CONFIG2["start_state"], walls=CONFIG2["walls"], terminal_states=CONFIG2["terminal_states"],
+                   special_transitions=spec)
+        ml = VecGridWorldLayouts(n, [lay] * 8, rows=8, cols=8, p_success=CONFIG2["p_success"],
+                                 episode_length_limit=CONFIG2["episode_length_limit"], seed=seed, env_offset=rank * n)
+        sec = ev_time(lambda: ml.step(acts[0]), 50)
+        details["gridworld_step_8_layouts"] = {"env_steps_per_s": n / sec, "envs": n, "us_per_launch": sec * 1e6,
+                                               "GBps": GRID_BYTES_PER_STEP * n / sec / 1e9}
+        del ml
         # the step kernel at a batch large enough to amortise launch ramp-up/drain (config 5 per-GPU share and beyond)
         nbig = 1 << 24
         gbig = [VecGridWorld(nbig, seed=seed, special_transitions=spec, env_offset=rank * 4 * nbig + i * nbig, **CONFIG2)
