@@ -38,7 +38,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
     nvcc = _nvcc()
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     lib = LIB[:-3] + tag + ".so"
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = s[:-3] + tag + ".o"
@@ -48,7 +48,13 @@ def build(force=False, verbose=False, defines=(), tag=""):
                    + ["-c", s, "-o", o])
             if verbose:
                 print(" ".join(cmd))
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
+    if jobs:  # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for r in pool.map(lambda c: subprocess.run(c, check=False), jobs):
+                if r.returncode != 0:
+                    raise subprocess.CalledProcessError(r.returncode, r.args)
     if force or _stale(lib, objs):
         cmd = [nvcc, "-shared", "-cudart", "static", "-o", lib] + objs
         if verbose:
