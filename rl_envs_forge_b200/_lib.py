@@ -32,6 +32,15 @@ class GridDesc(C.Structure):
                 ("table_cells", C.c_int32), ("table", C.c_void_p)]
 
 
+class GridStepArgs(C.Structure):
+    _fields_ = [("grid", C.POINTER(GridDesc)), ("pos", C.c_void_p), ("ep_len", C.c_void_p), ("ep_ret", C.c_void_p),
+                ("action", C.c_void_p), ("draw", C.c_void_p), ("seed", C.c_uint64), ("t", C.c_uint64),
+                ("env_offset", C.c_uint64), ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
+                ("truncated", C.c_void_p), ("final_obs", C.c_void_p), ("stats", C.c_void_p), ("err", C.c_void_p),
+                ("clock", C.c_void_p), ("n", C.c_int64), ("autoreset", C.c_int32), ("reserved", C.c_int32),
+                ("stream", C.c_void_p)]
+
+
 class PendulumParams(C.Structure):
     _fields_ = [("tau", C.c_float), ("c", C.c_float * 8), ("angle_threshold", C.c_float),
                 ("angle_termination", C.c_float), ("reward_mode", C.c_int32), ("reward_lo", C.c_float),
@@ -69,6 +78,7 @@ SIGNATURES = {
     "ef_device_info": (C.c_int, [_P, _P, _P]),
     "ef_gridworld_step": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _I64, _I32, _P]),
+    "ef_gridworld_step_v": (C.c_int, [C.POINTER(GridStepArgs)]),
     "ef_gridworld_step_layouts": (C.c_int, [C.POINTER(GridDesc), _I32, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P,
                                             _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "ef_gridworld_step_pcg64": (C.c_int, [C.POINTER(GridDesc), C.POINTER(C.c_uint64), _I32, _P, _P, _P, _P, _P, _P, _U64, _P,

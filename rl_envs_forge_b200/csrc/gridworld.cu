@@ -927,6 +927,13 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
 #undef EF_DISPATCH
 }
 
+extern "C" int ef_gridworld_step_v(const ef_gridworld_step_args* x) {
+    if (!x) return EF_ERR_INVALID_ARGUMENT;
+    return ef_gridworld_step(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset, x->obs,
+                             x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err, x->clock, x->n,
+                             x->autoreset, x->stream);
+}
+
 extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
                                          const int32_t* start_cells, int32_t* pos, int32_t* ep_len, float* ep_ret,
                                          const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t,

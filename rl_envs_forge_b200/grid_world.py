@@ -529,16 +529,34 @@ class VecGridWorld(VecEnv):
             # cached, so one step() costs one ctypes call -- a Python-driven loop then keeps pace with the ~10 us kernel
             fixed = self._fast_args
             if fixed is None:
-                fixed = self._fast_args = (
-                    (self._desc,) + self._state_ptrs() + (self.ep_ret.data_ptr(),),
-                    (self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(), self._trunc.data_ptr(), None,
-                     self._stats_raw.data_ptr(), self.err.data_ptr()),
-                    (self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)))
-            head, tail, outs = fixed
+                x = _lib.GridStepArgs()
+                x.grid = _lib.C.pointer(self._desc)
+                x.pos, x.ep_len = self._state_ptrs()
+                x.ep_ret = self.ep_ret.data_ptr()
+                x.seed, x.env_offset = self._seed, self.env_offset
+                x.obs, x.reward = self._obs.data_ptr(), self._reward.data_ptr()
+                x.terminated, x.truncated = self._term.data_ptr(), self._trunc.data_ptr()
+                x.stats, x.err = self._stats_raw.data_ptr(), self.err.data_ptr()
+                x.n = self.num_envs
+                fixed = self._fast_args = (x, _lib.C.byref(x), self._lib.ef_gridworld_step_v, self.device.index,
+                                           (self._obs, self._reward, self._term.view(torch.bool),
+                                            self._trunc.view(torch.bool)))
+            x, ref, fn, dev_index, outs = fixed
             clock = self._clock
-            self._call_lean(self._lib.ef_gridworld_step, *head, actions.data_ptr(), None, self._seed,
-                            0 if clock is not None else self._t, self.env_offset, *tail,
-                            None if clock is None else clock.data_ptr(), self.num_envs, int(self._autoreset))
+            x.action = actions.data_ptr()
+            x.t = 0 if clock is not None else self._t
+            x.clock = None if clock is None else clock.data_ptr()
+            x.seed = self._seed
+            x.autoreset = int(self._autoreset)
+            if torch.cuda.current_device() == dev_index:
+                x.stream = torch.cuda.current_stream().cuda_stream
+                status = fn(ref)
+            else:
+                with torch.cuda.device(self.device):
+                    x.stream = torch.cuda.current_stream().cuda_stream
+                    status = fn(ref)
+            if status:
+                _lib.check(status)
             self._t += 1
             return outs[0], outs[1], outs[2], outs[3], {}
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
