@@ -245,3 +245,41 @@ def test_car_rental_rollout_equals_step_sequence():
         b.step(torch.from_numpy(((wp * np.uint64(11)) >> np.uint64(32)).astype(np.int32)).cuda())
     assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
     assert a.episode_stats()["episodes"] == b.episode_stats()["episodes"] == n * (2 * K // 5)
+
+
+# ---- edge cases --------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 31, 33, 1023, 1025])
+def test_ragged_sizes(n):
+    """Tiny and ragged batches (vector body + scalar tail of the gambler kernel, partial CTAs elsewhere) == the same envs
+    cut out of a large batch (global env index keys every draw)."""
+    import torch
+    from rl_envs_forge_b200 import VecGamblersProblem, VecJacksCarRental
+    off = 4096
+    for cls, kw, hi in ((VecGamblersProblem, dict(goal_amount=40, win_probability=0.5, start_capital=5), 12),
+                        (VecJacksCarRental, dict(init_state_option="equal"), 11)):
+        big = cls(off + 2048, seed=9, **kw)
+        small = cls(n, seed=9, env_offset=off, **kw)
+        for t in range(6):
+            act = torch.randint(0, hi, (off + 2048,), dtype=torch.int32, device="cuda")
+            ob, os_ = big.step(act), small.step(act[off:off + n].clone())
+            for x, y in zip(ob[:4], os_[:4]):
+                assert torch.equal(x[off:off + n], y), (cls.__name__, n, t)
+        big.rollout(5)
+        small.rollout(5)
+        assert torch.equal(big.state[off:off + n], small.state)
+
+
+def test_empty_batches_are_noops_through_the_c_abi():
+    import ctypes
+    from rl_envs_forge_b200 import _lib
+    lib = _lib.load()
+    gp = _lib.GamblerParams()
+    gp.goal_amount, gp.win_threshold = 10, 1 << 31
+    fake = ctypes.c_void_p(0x1000)
+    assert lib.ef_gambler_step(ctypes.byref(gp), fake, fake, fake, None, None, 0, 0, 0, *([None] * 8), 0, 1, None) == 0
+    assert lib.ef_gambler_rollout(ctypes.byref(gp), fake, fake, fake, None, 0, 0, 0, 4, None, None, None, None, None, 0, None) == 0
+    cp = _lib.CarRentalParams()
+    cp.max_cars, cp.max_move_cars = 20, 5
+    assert lib.ef_car_rental_step(ctypes.byref(cp), fake, fake, fake, None, 0, 0, 0, *([None] * 7), 0, 1, None) == 0
+    cp.lam[1] = 12.0
+    assert lib.ef_car_rental_step(ctypes.byref(cp), fake, fake, fake, None, 0, 0, 0, *([None] * 7), 8, 1, None) == 3   # unsupported

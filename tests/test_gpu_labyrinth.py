@@ -183,3 +183,24 @@ def test_rollout_equals_step_sequence():
     assert torch.equal(a.state, b.state)
     sa, sb = a.episode_stats(), b.episode_stats()
     assert sa["episodes"] == sb["episodes"] > 0 and sa["length_sum"] == sb["length_sum"] and sa["env_steps"] == sb["env_steps"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 255, 257])
+def test_ragged_sizes_and_sharding(n):
+    """Partial CTAs of the 256-players-per-CTA kernel; a shard (env_offset) reproduces its slice of the whole batch."""
+    import torch
+    from rl_envs_forge_b200 import VecLabyrinth
+    rng = np.random.default_rng(n)
+    grids, starts, targets = _random_mazes(rng, 5, 10, 10)
+    off = 1000
+    for vision in (None, 2):
+        big = VecLabyrinth(off + 600, grids, starts, targets, state_vision_range=vision, seed=3)
+        small = VecLabyrinth(n, grids, starts, targets, state_vision_range=vision, seed=3, env_offset=off)
+        for t in range(8):
+            act = torch.randint(0, 4, (off + 600,), dtype=torch.int32, device="cuda")
+            ob, os_ = big.step(act), small.step(act[off:off + n].clone())
+            for x, y in zip(ob[:4], os_[:4]):
+                assert torch.equal(x[off:off + n], y), (n, vision, t)
+        big.rollout(7)
+        small.rollout(7)
+        assert torch.equal(big.pos[off:off + n], small.pos) and torch.equal(big.state[off:off + n], small.state)
