@@ -16,6 +16,7 @@
 // and the counter in bits 16-31.  Possible whenever the counter cannot exceed 65535 (auto-reset on, 0 < limit <= 65535;
 // cells are < 65536 by construction of the table), it removes 8 of the 42 bytes an env-step moves.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ef_common.cuh"
 
@@ -196,7 +197,7 @@ struct Quad {
 
 template <bool SMEM, int SLOTS>
 __device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __restrict__ tab, Quad& q,
-                                            const int32_t (&act)[4], const uint32_t (&r)[4]) {
+                                            const int32_t (&act)[4], const uint32_t (&r)[4], const uint32_t (&off)[4]) {
     q.term = q.trunc = q.bad = 0u;
     const int32_t limit = a.limit > 0 ? a.limit : 0x7fffffff;
 #pragma unroll
@@ -206,6 +207,7 @@ __device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __re
             const uint32_t idx = outcome_index(a, r[j]);
             slot = slot * 4u + idx;
         }
+        slot += off[j];  // table of this env's layout (all zero, and folded away, for single-layout batches)
         const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
         const uint32_t ok = ((o.x >> 17) & 3u) == 0u ? 1u : 0u;  // 0 for a rejected (inert) row
         q.rew[j] = __uint_as_float(o.y);
@@ -222,17 +224,19 @@ __device__ __forceinline__ void transition4(const GridArgs& a, const uint2* __re
 // Rare path: classify and record the rejected env-steps of a quad (a rejected env keeps its position, so the row can
 // be rebuilt from the post-step state).  Arguments by value: keeps the quad in registers.
 template <bool SMEM, int SLOTS>
-__device__ __noinline__ uint4 record_bad4(const uint2* __restrict__ tab, uint32_t bad, uint32_t g0, int4 pos, int4 act) {
+__device__ __noinline__ uint4 record_bad4(const uint2* __restrict__ tab, uint32_t bad, uint32_t g0, int4 pos, int4 act,
+                                          uint4 off = make_uint4(0u, 0u, 0u, 0u)) {
     uint32_t e_count = 0u, e_g = 0u, e_detail = 0u, e_kind = 0u;
     const int32_t ps[4] = {pos.x, pos.y, pos.z, pos.w};
     const int32_t ac[4] = {act.x, act.y, act.z, act.w};
+    const uint32_t of[4] = {off.x, off.y, off.z, off.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if (!((bad >> j) & 1u)) continue;
         ++e_count;
         e_g = g0 + j;
         const uint32_t row = static_cast<uint32_t>(ps[j]) * 4u + static_cast<uint32_t>(ac[j]);
-        const uint2 o = SMEM ? tab[row * SLOTS] : __ldg(tab + row * SLOTS);
+        const uint2 o = SMEM ? tab[of[j] + row * SLOTS] : __ldg(tab + of[j] + row * SLOTS);
         e_detail = row;
         e_kind = ((o.x >> 16) & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS;
     }
@@ -240,12 +244,14 @@ __device__ __noinline__ uint4 record_bad4(const uint2* __restrict__ tab, uint32_
 }
 
 // Auto-reset + statistics of the finished envs of a quad (fin = byte-wise finished bits).
-__device__ __forceinline__ void finish4(const GridArgs& a, Quad& q, uint32_t fin, EpisodeAcc& acc) {
+// `lay` = layout of each env in a mixed-layout batch (start cell fetched here, on the rare finishing path, rather than
+// up front for every env); null for single-layout batches, which reset to a.start_cell.
+__device__ __forceinline__ void finish4(const GridArgs& a, Quad& q, uint32_t fin, EpisodeAcc& acc, const int32_t* lay = nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         if ((fin >> (8 * j)) & 1u) {
             acc.finish(q.len[j], q.ret[j]);
-            q.pos[j] = a.start_cell;
+            q.pos[j] = lay ? __ldg(a.start_cells + lay[j]) : a.start_cell;
             q.len[j] = 0;
             q.ret[j] = 0.0f;
         }
@@ -256,14 +262,16 @@ __device__ __forceinline__ void finish4(const GridArgs& a, Quad& q, uint32_t fin
 struct QuadIn {
     int4 p4, l4, a4;
     float4 r4;
+    int4 y4;  // layout index of each env (mixed-layout batches with an explicit index only)
 };
 
 // PACKED: the state word layout is known at compile time (ep_len == NULL).  FAST: the common call shape is known at
 // compile time -- actions given, obs / reward / terminated / truncated all requested, no final_obs, auto-reset on -- so
 // the launch-uniform null checks and their branches disappear from the instruction stream.
-template <bool PACKED, bool FAST>
+template <bool PACKED, bool FAST, bool HET = false>
 __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, bool philox_act) {
     QuadIn in;
+    if constexpr (HET) in.y4 = a.layout ? __ldg(reinterpret_cast<const int4*>(a.layout + base)) : make_int4(0, 0, 0, 0);
 #if EF_STREAMING
     in.p4 = __ldcs(reinterpret_cast<const int4*>(a.pos + base));
     in.l4 = PACKED ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.ep_len + base));
@@ -280,7 +288,7 @@ __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, boo
 }
 
 // One step of a full quad: draws, branch-free transitions, auto-reset, 128-bit stores.
-template <bool SMEM, int SLOTS, bool PACKED, bool FAST>
+template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false>
 __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
                                           uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
                                           ErrorAcc& errs) {
@@ -311,7 +319,27 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) { q.pos[j] = (q.pos[j] + act[j]) & 63; q.len[j] += 1; q.rew[j] = __uint_as_float(r[j] >> 9); q.ret[j] += q.rew[j]; }
 #else
-    transition4<SMEM, SLOTS>(a, tab, q, act, r);
+    // HET: the batch mixes layouts -- every env walks its own table (offset into the staged tables) and resets to its own
+    // start cell.  Otherwise both arrays are compile-time constants and fold away.
+    uint32_t off[4] = {0u, 0u, 0u, 0u};
+    int32_t lay[4] = {in.y4.x, in.y4.y, in.y4.z, in.y4.w};
+    if constexpr (HET) {
+        if (!a.layout) {  // layout = global env index mod n_layouts: one division per quad, the rest by wrap-around
+            const uint32_t nl = static_cast<uint32_t>(a.n_layouts);
+            const uint32_t l0 = g0 % nl;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t x = l0 + j;
+                x -= x >= nl ? nl : 0u;
+                x -= x >= nl ? nl : 0u;
+                x -= x >= nl ? nl : 0u;
+                lay[j] = static_cast<int32_t>(x);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) off[j] = static_cast<uint32_t>(lay[j]) * static_cast<uint32_t>(a.layout_len);
+    }
+    transition4<SMEM, SLOTS>(a, tab, q, act, r, off);
 #endif
     uint32_t rejected = 0u;
     if (((act[0] | act[1] | act[2] | act[3]) & ~3) != 0) {
@@ -327,14 +355,16 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         q.term = q.trunc = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t f = transition<SMEM, SLOTS>(a, tab, g0 + j, q.pos[j], q.len[j], q.ret[j], act[j], r[j], q.rew[j], errs);
+            const uint32_t f = transition<SMEM, SLOTS>(a, tab + off[j], g0 + j, q.pos[j], q.len[j], q.ret[j], act[j], r[j],
+                                                       q.rew[j], errs);
             q.term |= (f & 1u) << (8 * j);
             q.trunc |= ((f >> 1) & 1u) << (8 * j);
             rejected += (f >> 2) & 1u;
         }
     } else if (q.bad) {
         const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]),
-                                                 make_int4(act[0], act[1], act[2], act[3]));
+                                                 make_int4(act[0], act[1], act[2], act[3]),
+                                                 make_uint4(off[0], off[1], off[2], off[3]));
         errs.count += e.x;
         errs.g = e.y;
         errs.detail = e.z;
@@ -350,7 +380,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
     }
     const uint32_t fin = (FAST || a.autoreset) ? (q.term | q.trunc) : 0u;
-    if (fin) finish4(a, q, fin, acc);
+    if (fin) finish4(a, q, fin, acc, HET ? lay : nullptr);
 #if EF_STREAMING
 #define EF_ST(ptr, val) __stcs(ptr, val)
 #else
@@ -415,7 +445,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 // quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
 // (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
 // load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
-template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST>
+template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false>
 __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
 #if EF_EXPERIMENT & 4
     const uint2* __restrict__ tab = a.table;
@@ -478,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left) in[j] = load_quad<PACKED, FAST>(a, (chunk + local) * 4, philox_act);
+            if (local < left) in[j] = load_quad<PACKED, FAST, HET>(a, (chunk + local) * 4, philox_act);
         }
 #if !(EF_EXPERIMENT & 4)
         stage_table_wait(&table_bar, table_pending);  // the bulk copy had the whole load phase to land
@@ -487,9 +517,9 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
             if (local < left)
-                step_quad<SMEM, SLOTS, PACKED, FAST>(a, tab, (chunk + local) * 4,
-                                                     static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
-                                                     philox_act, acc, errs);
+                step_quad<SMEM, SLOTS, PACKED, FAST, HET>(a, tab, (chunk + local) * 4,
+                                                          static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
+                                                          philox_act, acc, errs);
         }
 #endif
     }
@@ -506,7 +536,14 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
                                        : __ldg(a.action + i);
         uint32_t r = 0u;
         if constexpr (SLOTS == 4) r = group_word1(a.seed, g, t, kStreamTransition);
-        const uint32_t f = transition<SMEM, SLOTS>(a, tab, g, pos, len, ret, act, r, rew, errs);
+        const uint2* __restrict__ tab_i = tab;
+        int32_t start = a.start_cell;
+        if constexpr (HET) {
+            const int32_t lay = a.layout ? __ldg(a.layout + i) : static_cast<int32_t>(g % static_cast<uint32_t>(a.n_layouts));
+            tab_i = tab + static_cast<int64_t>(lay) * a.layout_len;
+            start = __ldg(a.start_cells + lay);
+        }
+        const uint32_t f = transition<SMEM, SLOTS>(a, tab_i, g, pos, len, ret, act, r, rew, errs);
         if (!(f & 4u)) acc.steps += 1u;
         if (a.final_obs) {
             const int2 fo = cell_to_obs(a, pos);
@@ -515,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         }
         if (a.autoreset && (f & 3u)) {
             acc.finish(len, ret);
-            pos = a.start_cell;
+            pos = start;
             len = 0;
             ret = 0.0f;
         }
@@ -768,7 +805,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
                     rejected += valid[j] ? ((f >> 2) & 1u) : 0u;
                 }
             } else {
-                transition4<SMEM, SLOTS>(a, tab, q, act, wt);
+                const uint32_t no_off[4] = {0u, 0u, 0u, 0u};
+                transition4<SMEM, SLOTS>(a, tab, q, act, wt, no_off);
                 q.bad &= valid_bits;
                 if (q.bad) {
                     const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]),
@@ -959,6 +997,29 @@ extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_lay
     a.table_len = static_cast<int32_t>(total);  // what stage_table copies
     const int grid_s = grid_for(n, 8);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // Vector kernel (four envs per thread, 128-bit accesses, dynamically scheduled CTAs) whenever the buffers allow it;
+    // injected draws and unaligned views take the one-env-per-thread kernel.
+    const bool vec = draw == nullptr && n >= 4 && aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) &&
+                     aligned(action, 16) && aligned(obs, 16) && aligned(reward, 16) && aligned(terminated, 4) &&
+                     aligned(truncated, 4) && aligned(final_obs, 16) && aligned(layout_index, 16);
+    if (vec) {
+        const int64_t quads = n >> 2;
+        // Q = 2 quads per thread like the single-layout large-batch variant, but compiled for 2 CTAs/SM: the per-env table
+        // offsets and layout indices push the 3-CTA (80-register) build into local-memory spills (156 B of spill stores).
+        const int grid_b = grid_for((quads + EF_STEP_BIG_Q - 1) / EF_STEP_BIG_Q, EF_STEP_BIG_GRID_PER_SM);
+        a.quads_per_cta = (quads + grid_b - 1) / grid_b;
+        a.rk = philox_round_keys(seed);
+        const bool packed = ep_len == nullptr;
+#define EF_HET(SM, SL)                                                                                                      \
+    return packed ? launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, 2, true, false, true>, a, SM, grid_b, st)           \
+                  : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, 2, false, false, true>, a, SM, grid_b, st)
+        if (smem) {
+            if (grid->n_slots == 1) { EF_HET(true, 1); } else { EF_HET(true, 4); }
+        } else {
+            if (grid->n_slots == 1) { EF_HET(false, 1); } else { EF_HET(false, 4); }
+        }
+#undef EF_HET
+    }
     if (smem) {
         if (grid->n_slots == 1) return launch(gridworld_step_scalar_kernel<true, 1>, a, true, grid_s, st);
         return launch(gridworld_step_scalar_kernel<true, 4>, a, true, grid_s, st);
