@@ -41,6 +41,7 @@ class VecPendulumBase(VecEnv):
         self._trunc = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._final_obs = None
         self._acc = None
+        self._fast_args = None   # cached pointer arguments of the lean step() path
         self._params = self._make_params()
         self._fn_step = getattr(self._lib, self._FN + "_step")
         self._fn_rollout = getattr(self._lib, self._FN + "_rollout")
@@ -143,6 +144,22 @@ class VecPendulumBase(VecEnv):
         """step (cart_pole.py:107-180 / pendulum_disk.py:108-172) for all envs.  actions: fp32 [N] or [N,1]."""
         torch = self._torch
         n = self.num_envs
+        if (not return_final_obs and not return_info and not self.strict and torch.is_tensor(actions) and actions.is_cuda
+                and actions.dtype == torch.float32 and actions.numel() == n and actions.is_contiguous()):
+            # lean path of the usual call (CUDA fp32 actions in, CUDA tensors out): pointer arguments cached
+            fixed = self._fast_args
+            if fixed is None:
+                fixed = self._fast_args = (
+                    (self._params, self._state.data_ptr(), self.ep_len.data_ptr(), self.ep_ret.data_ptr()),
+                    (self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(), self._trunc.data_ptr(), None, None,
+                     self._stats_raw.data_ptr()),
+                    (self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)))
+            head, tail, outs = fixed
+            clock = self._clock
+            self._call_lean(self._fn_step, *head, actions.data_ptr(), self._seed, 0 if clock is not None else self._t,
+                            self.env_offset, *tail, None if clock is None else clock.data_ptr(), n, int(self.autoreset))
+            self._t += 1
+            return outs[0], outs[1], outs[2], outs[3], {}
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
         mode = self.host_transport if host_io else None
         if mode == "pipelined" and self._clock is not None:
