@@ -209,6 +209,15 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: rl_envs_forge_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU: run on (and first-touch pinned host memory from) the CPUs closest to this GPU, so the
+        # host-buffer path does not cross sockets.  Best effort -- NVML may be unavailable in a container.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, R, K, W = args.envs_per_gpu, args.sets, args.steps, args.warmup
