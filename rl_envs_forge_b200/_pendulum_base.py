@@ -148,13 +148,16 @@ class VecPendulumBase(VecEnv):
                 and actions.dtype == torch.float32 and actions.numel() == n and actions.is_contiguous()):
             # lean path of the usual call (CUDA fp32 actions in, CUDA tensors out): pointer arguments cached
             fixed = self._fast_args
+            if fixed is not None and (fixed[3] is not self.ep_len or fixed[4] is not self.ep_ret):
+                fixed = None     # a counter tensor was replaced by assignment: rebuild the cached pointers
             if fixed is None:
                 fixed = self._fast_args = (
                     (self._params, self._state.data_ptr(), self.ep_len.data_ptr(), self.ep_ret.data_ptr()),
                     (self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(), self._trunc.data_ptr(), None, None,
                      self._stats_raw.data_ptr()),
-                    (self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)))
-            head, tail, outs = fixed
+                    (self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)),
+                    self.ep_len, self.ep_ret)
+            head, tail, outs = fixed[:3]
             clock = self._clock
             self._call_lean(self._fn_step, *head, actions.data_ptr(), self._seed, 0 if clock is not None else self._t,
                             self.env_offset, *tail, None if clock is None else clock.data_ptr(), n, int(self.autoreset))

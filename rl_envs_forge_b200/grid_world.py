@@ -528,6 +528,9 @@ class VecGridWorld(VecEnv):
             # lean path of the usual call (CUDA int32 actions in, CUDA tensors out): the fixed pointer arguments are
             # cached, so one step() costs one ctypes call -- a Python-driven loop then keeps pace with the ~10 us kernel
             fixed = self._fast_args
+            state_t = self._pl if self._packed else self._pos_split
+            if fixed is not None and (fixed[5] is not self.ep_ret or fixed[6] is not state_t):
+                fixed = None     # a state tensor was replaced by assignment: rebuild the cached pointers
             if fixed is None:
                 x = _lib.GridStepArgs()
                 x.grid = _lib.C.pointer(self._desc)
@@ -540,8 +543,8 @@ class VecGridWorld(VecEnv):
                 x.n = self.num_envs
                 fixed = self._fast_args = (x, _lib.C.byref(x), self._lib.ef_gridworld_step_v, self.device.index,
                                            (self._obs, self._reward, self._term.view(torch.bool),
-                                            self._trunc.view(torch.bool)))
-            x, ref, fn, dev_index, outs = fixed
+                                            self._trunc.view(torch.bool)), self.ep_ret, state_t)
+            x, ref, fn, dev_index, outs = fixed[:5]
             clock = self._clock
             x.action = actions.data_ptr()
             x.t = 0 if clock is not None else self._t

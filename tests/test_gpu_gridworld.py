@@ -553,3 +553,22 @@ def test_packed_state_layout_equals_split_layout():
         assert not a._packed and torch.equal(a.ep_len, st["ep_len"])
     with pytest.raises(ValueError):
         VecGridWorld(4, state_layout="packed")                 # no episode limit: the counter is unbounded
+
+
+def test_lean_step_path_survives_reassigned_state_tensors():
+    """The usual call shape caches its pointer arguments; replacing a state tensor by assignment must not leave a stale
+    pointer behind."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    cfg = _vec_kwargs(_config2(0.8))
+    a, b = VecGridWorld(4096, seed=3, **cfg), VecGridWorld(4096, seed=3, **cfg)
+    act = torch.randint(0, 4, (4096,), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        a.step(act)
+        b.step(act)
+    a.ep_ret = a.ep_ret.clone()                      # new tensor objects, same contents
+    a.pos = a.pos.clone()
+    for _ in range(5):
+        for x, y in zip(a.step(act)[:4], b.step(act)[:4]):
+            assert torch.equal(x, y)
+    assert torch.equal(a.ep_ret, b.ep_ret) and torch.equal(a.pos, b.pos)
