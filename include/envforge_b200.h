@@ -183,6 +183,13 @@ int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len
                          float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
                          void* stream);
 
+/* ef_gridworld_rollout that also materialises the trajectory of observations: obs [K,n,2] int32 (row, col) after each
+ * step's auto-reset (what K step() calls would have returned); rewards / flags as above, each nullable. */
+int ef_gridworld_rollout_traj(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                              const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                              int32_t* obs, float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock,
+                              int64_t n, void* stream);
+
 /* GridWorld.reset (:530-551) for all envs (mask == NULL) or those with mask[i] != 0. */
 int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos, int32_t* ep_len, float* ep_ret,
                        int32_t* obs, const uint8_t* mask, int64_t n, void* stream);

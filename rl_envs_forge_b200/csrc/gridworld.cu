@@ -832,6 +832,14 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
             if (__ballot_sync(0xffffffffu, fin != 0u)) {  // warp vote: skip the reset path where nobody finished
                 if (fin) finish4(a, q, fin, acc);
             }
+            if constexpr (EMIT) {
+                if (a.obs) {  // trajectory of observations [K, n, 2]: (row, col) after auto-reset, like step()
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (valid[j]) reinterpret_cast<int2*>(a.obs)[o + j] = cell_to_obs(a, q.pos[j]);
+                    }
+                }
+            }
         }
         if (full) {
             if (packed) {
@@ -1103,6 +1111,38 @@ extern "C" int ef_gridworld_rollout(const ef_grid_desc* grid, int32_t* pos, int3
         if (grid->n_slots == 1) EF_DISPATCH2(false, 1); else EF_DISPATCH2(false, 4);
     }
 #undef EF_DISPATCH2
+}
+
+extern "C" int ef_gridworld_rollout_traj(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                         const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                         int32_t* obs, float* rewards, uint8_t* flags, double* stats, uint32_t* err,
+                                         uint64_t* clock, int64_t n, void* stream) {
+    GridArgs a{};
+    if (int s = fill_args(grid, a)) return s;
+    if (n < 0 || K < 0 || !pos || !ep_ret || !aligned(obs, 8)) return EF_ERR_INVALID_ARGUMENT;
+    if (!ep_len && !packed_ok(a, 1)) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K;
+    a.obs = obs; a.reward = rewards; a.flags = flags; a.stats = stats; a.err = err; a.n = n; a.autoreset = 1;
+    a.rk = philox_round_keys(seed);
+    a.clock = reinterpret_cast<unsigned long long*>(clock);
+    const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
+    const bool ext = actions != nullptr;
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid_r = grid_for((n + 3) / 4, 8);
+#define EF_TRAJ(SM, SL)                                                                                       \
+    do {                                                                                                      \
+        if (ext) return launch(gridworld_rollout_kernel<SM, SL, true, true>, a, SM, grid_r, st);              \
+        return launch(gridworld_rollout_kernel<SM, SL, false, true>, a, SM, grid_r, st);                      \
+    } while (0)
+    if (smem) {
+        if (grid->n_slots == 1) EF_TRAJ(true, 1); else EF_TRAJ(true, 4);
+    } else {
+        if (grid->n_slots == 1) EF_TRAJ(false, 1); else EF_TRAJ(false, 4);
+    }
+#undef EF_TRAJ
 }
 
 extern "C" int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos, int32_t* ep_len, float* ep_ret,

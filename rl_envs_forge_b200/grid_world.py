@@ -656,9 +656,10 @@ class VecGridWorld(VecEnv):
             info["final_observation"] = fobs
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
 
-    def rollout(self, K, actions=None, *, return_rewards=False):
+    def rollout(self, K, actions=None, *, return_rewards=False, return_obs=False):
         """K fused steps in one kernel (state in registers, auto-reset on).  actions: CUDA int32 [K,N] or None for the
-        in-kernel uniform random policy.  Returns (rewards fp32 [K,N], flags uint8 [K,N]) if return_rewards else None;
+        in-kernel uniform random policy.  Returns None, (rewards fp32 [K,N], flags uint8 [K,N]) if return_rewards, or
+        (obs int32 [K,N,2], rewards, flags) if return_obs -- the observations K step() calls would have returned;
         episode statistics accumulate in `self.stats` either way."""
         torch = self._torch
         n = self.num_envs
@@ -669,14 +670,22 @@ class VecGridWorld(VecEnv):
                     and tuple(actions.shape) == (K, n)):
                 raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
             actions = actions.contiguous()
-        rew = flg = None
-        if return_rewards:
+        rew = flg = obs = None
+        if return_rewards or return_obs:
             rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
-        self._call(self._lib.ef_gridworld_rollout, self._desc, *self._state_ptrs(),
-                   _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K),
-                   _lib.ptr(rew), _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
+        if return_obs:
+            obs = torch.empty((K, n, 2), dtype=torch.int32, device=self.device)
+            self._call(self._lib.ef_gridworld_rollout_traj, self._desc, *self._state_ptrs(), _lib.ptr(self.ep_ret),
+                       _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew),
+                       _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
+        else:
+            self._call(self._lib.ef_gridworld_rollout, self._desc, *self._state_ptrs(), _lib.ptr(self.ep_ret),
+                       _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
+                       _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
         self._t += int(K)
+        if return_obs:
+            return obs, rew, flg
         return (rew, flg) if return_rewards else None
 
     def _describe_error(self, count, env, detail, kind_id, kind):

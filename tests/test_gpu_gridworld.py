@@ -572,3 +572,22 @@ def test_lean_step_path_survives_reassigned_state_tensors():
         for x, y in zip(a.step(act)[:4], b.step(act)[:4]):
             assert torch.equal(x, y)
     assert torch.equal(a.ep_ret, b.ep_ret) and torch.equal(a.pos, b.pos)
+
+
+@pytest.mark.parametrize("external", [False, True])
+def test_rollout_trajectory_of_observations_equals_step_sequence(external):
+    """rollout(K, return_obs=True) materialises what K step() calls would have returned: obs [K,N,2], rewards, flags."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, K, seed = 30_001, 70, 12
+    cfg = _vec_kwargs(_config2(0.8))
+    cfg["episode_length_limit"] = 25
+    a, b = VecGridWorld(n, seed=seed, **cfg), VecGridWorld(n, seed=seed, state_layout="split", **cfg)
+    acts = torch.randint(0, 4, (K, n), dtype=torch.int32, device="cuda") if external else None
+    obs, rew, flg = a.rollout(K, acts, return_obs=True)
+    assert obs.shape == (K, n, 2) and obs.dtype == torch.int32
+    for k in range(K):
+        o = b.step(acts[k] if external else None_actions(b, k))
+        assert torch.equal(obs[k], o[0]) and torch.equal(rew[k], o[1]), k
+        assert torch.equal(flg[k], o[2].to(torch.uint8) | (o[3].to(torch.uint8) << 1)), k
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len)
