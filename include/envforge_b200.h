@@ -228,6 +228,10 @@ int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len,
 int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
                         float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
+/* ..._rollout that also materialises the observation trajectory: obs [K,n,4] fp32, the state after each step's auto-reset. */
+int ef_cartpole_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                             const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K, float* obs,
+                             float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
 /* reset: initial state from params (fixed) or Philox STREAM_RESET_USER at counter `epoch`; mask nullable. */
 int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                       uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
@@ -241,6 +245,10 @@ int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep
 int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                              const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
                              float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
+int ef_pendulum_disk_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                  const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                  float* obs /* [K,n,2] */, float* rewards, uint8_t* flags, double* stats, uint64_t* clock,
+                                  int64_t n, void* stream);
 int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                            uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
 

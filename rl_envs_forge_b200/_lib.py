@@ -92,6 +92,10 @@ SIGNATURES = {
                                    _P, _P, _I64, _I32, _P]),
     "ef_cartpole_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,
                                       _P, _I64, _P]),
+    "ef_cartpole_rollout_traj": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,
+                                           _P, _P, _I64, _P]),
+    "ef_pendulum_disk_rollout_traj": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P,
+                                                _P, _P, _P, _I64, _P]),
     "ef_cartpole_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
     "ef_pendulum_disk_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
                                         _P, _P, _P, _I64, _I32, _P]),

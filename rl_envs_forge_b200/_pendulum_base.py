@@ -45,6 +45,7 @@ class VecPendulumBase(VecEnv):
         self._params = self._make_params()
         self._fn_step = getattr(self._lib, self._FN + "_step")
         self._fn_rollout = getattr(self._lib, self._FN + "_rollout")
+        self._fn_rollout_traj = getattr(self._lib, self._FN + "_rollout_traj")
         self._fn_reset = getattr(self._lib, self._FN + "_reset")
         self._fn_step_host = getattr(self._lib, self._FN + "_step_host")
         self.reset()
@@ -261,8 +262,10 @@ class VecPendulumBase(VecEnv):
             info["steps"] = self.ep_len
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
 
-    def rollout(self, K, actions=None, *, return_rewards=False):
-        """K fused steps (state in registers, auto-reset on).  actions: CUDA fp32 [K,N] or None (U(-3,3) Philox policy)."""
+    def rollout(self, K, actions=None, *, return_rewards=False, return_obs=False):
+        """K fused steps (state in registers, auto-reset on).  actions: CUDA fp32 [K,N] or None (U(-3,3) Philox policy).
+        Returns None, (rewards fp32 [K,N], flags uint8 [K,N]: bit0 terminated, bit1 truncated) if return_rewards, or
+        (obs fp32 [K,N,DIM], rewards, flags) if return_obs -- the observations K step() calls would have returned."""
         torch = self._torch
         n = self.num_envs
         if actions is not None:
@@ -270,14 +273,22 @@ class VecPendulumBase(VecEnv):
                     and tuple(actions.shape) == (K, n)):
                 raise ValueError(f"actions must be a CUDA float32 tensor of shape ({K}, {n})")
             actions = actions.contiguous()
-        rew = flg = None
-        if return_rewards:
+        rew = flg = obs = None
+        if return_rewards or return_obs:
             rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
             flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
-        self._call(self._fn_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
-                   _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
-                   _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n)
+        if return_obs:
+            obs = torch.empty((K, n, self.DIM), dtype=torch.float32, device=self.device)
+            self._call(self._fn_rollout_traj, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
+                       _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew),
+                       _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n)
+        else:
+            self._call(self._fn_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
+                       _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
+                       _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n)
         self._t += int(K)
         if self._obs is not self._state:
             self._obs.copy_(self._state)
+        if return_obs:
+            return obs, rew, flg
         return (rew, flg) if return_rewards else None

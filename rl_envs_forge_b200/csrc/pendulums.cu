@@ -327,6 +327,14 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
                     }
                 }
             }
+            if constexpr (EMIT) {
+                if (a.obs) {  // trajectory of observations [K, n, DIM]: the state after auto-reset, like step()
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (valid[j]) reinterpret_cast<Vec*>(a.obs)[o + j] = s[j];
+                    }
+                }
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -389,18 +397,19 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
 template <class Env>
 static int rollout_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                        float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream) {
+                        float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream,
+                        float* obs_traj = nullptr) {
     if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
-    if (K < 0) return EF_ERR_INVALID_ARGUMENT;
+    if (K < 0 || !aligned(obs_traj, sizeof(typename Env::Vec))) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0 || K == 0) return EF_OK;
     PendArgs a{};
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
-    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags; a.obs = obs_traj;
     a.rk = philox_round_keys(seed);
     a.stats = stats; a.n = n; a.autoreset = 1; a.clock = reinterpret_cast<unsigned long long*>(clock);
     const int grid = grid_for((n + 3) / 4, EF_PEND_ROLLOUT_GRID_PER_SM);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr;
+    const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr || obs_traj != nullptr;
     if (ext && emit) return launch_kernel(pendulum_rollout_kernel<Env, true, true>, a, grid, 0, st);
     if (ext) return launch_kernel(pendulum_rollout_kernel<Env, true, false>, a, grid, 0, st);
     if (emit) return launch_kernel(pendulum_rollout_kernel<Env, false, true>, a, grid, 0, st);
@@ -436,6 +445,14 @@ extern "C" int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, in
                                    void* stream) {
     return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n, stream);
 }
+extern "C" int ef_cartpole_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                        const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                        float* obs, float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n,
+                                        void* stream) {
+    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n,
+                                  stream, obs);
+}
+
 extern "C" int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                  uint64_t seed, uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n,
                                  void* stream) {
@@ -455,6 +472,14 @@ extern "C" int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* stat
                                         int64_t n, void* stream) {
     return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n, stream);
 }
+extern "C" int ef_pendulum_disk_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
+                                             const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                             float* obs, float* rewards, uint8_t* flags, double* stats, uint64_t* clock,
+                                             int64_t n, void* stream) {
+    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock,
+                                      n, stream, obs);
+}
+
 extern "C" int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                       uint64_t seed, uint64_t epoch, uint64_t env_offset, const uint8_t* mask,
                                       int64_t n, void* stream) {

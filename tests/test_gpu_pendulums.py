@@ -301,3 +301,20 @@ def test_aliased_observation_equals_separate_observation_buffer(kind):
             assert torch.equal(x, y), t
         assert oa[0].data_ptr() == a.state.data_ptr()
     assert torch.equal(a.state, b.state) and a.episode_stats()["episodes"] == b.episode_stats()["episodes"] > 0
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "pendulumdisk"])
+def test_rollout_trajectory_of_observations_equals_step_sequence(kind):
+    """rollout(K, return_obs=True): obs [K,N,DIM] / rewards / flags are bit for bit what K step() calls return."""
+    import torch
+    Vec, _, _, dim = _cls(kind)
+    n, K = 20_003, 40
+    a, b = Vec(n, seed=6, episode_length_limit=11), Vec(n, seed=6, episode_length_limit=11)
+    acts = torch.empty((K, n), device="cuda").uniform_(-3, 3)
+    obs, rew, flg = a.rollout(K, acts, return_obs=True)
+    assert obs.shape == (K, n, dim)
+    for k in range(K):
+        o = b.step(acts[k])
+        assert torch.equal(obs[k], o[0]) and torch.equal(rew[k], o[1]), k
+        assert torch.equal(flg[k], o[2].to(torch.uint8) | (o[3].to(torch.uint8) << 1)), k
+    assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len)
