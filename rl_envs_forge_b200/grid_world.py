@@ -275,91 +275,23 @@ class GridSpec:
         return np.ascontiguousarray(tab)
 
 
-class VecGridWorld(VecEnv):
-    """N GridWorld instances sharing one configuration.  See module docstring; kwargs as in the reference."""
-    _HOST_TRANSPORT = "staged"   # the one-pass persistent step kernel serialises its PCIe reads and writes: DMA wins
+class _GridStateLayout:
+    """State storage shared by VecGridWorld and VecGridWorldLayouts: `pos` / `ep_len` as two int32 arrays (split) or, when
+    the episode counter provably stays below 2^16 (auto-reset on, 0 < episode_length_limit <= 65535), packed into one
+    int32 word per env -- cell in bits 0-15, counter in bits 16-31: 8 fewer bytes through HBM per env-step.  Set
+    `self._packed` before VecEnv.__init__ runs, then call `_alloc_grid_state()`."""
 
-    def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
-                 special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
-                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox",
-                 state_layout="auto"):
-        """`rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
-        `rng="pcg64"`: every env owns the generator the reference would build for it,
-        Generator(PCG64(SeedSequence(seed_i))) with seed_i = seed + global env index (or `seed` given as a sequence of
-        N ints): `VecGridWorld(1, seed=s, rng="pcg64")` reproduces `GridWorld(seed=s)` draw for draw."""
-        if state_layout not in ("auto", "packed", "split"):
-            raise ValueError("state_layout must be 'auto', 'packed' or 'split'")
-        can_pack = (bool(autoreset) and isinstance(episode_length_limit, (int, np.integer))
-                    and 0 < episode_length_limit <= 65535)
-        if state_layout == "packed" and not can_pack:
-            raise ValueError("state_layout='packed' needs autoreset=True and 0 < episode_length_limit <= 65535")
-        # packed: cell (bits 0-15) and episode_length_counter (bits 16-31) share one int32 per env -- 8 fewer bytes per
-        # env-step through HBM; `pos` / `ep_len` stay available as (computed) properties
-        self._packed = can_pack and state_layout != "split"
-        seed_list = None
-        if rng not in ("philox", "pcg64"):
-            raise ValueError("rng must be 'philox' or 'pcg64'")
-        if rng == "pcg64" and seed is not None and not isinstance(seed, int):
-            seed_list = [int(x) for x in seed]
-            seed = seed_list[0] if seed_list else None
-        validate_args(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, seed,
-                      slip_distribution, p_success, episode_length_limit)
-        self.spec = GridSpec(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, p_success,
-                             episode_length_limit)
-        super().__init__(num_envs, device, seed, env_offset, autoreset)
+    @staticmethod
+    def _can_pack(autoreset, episode_length_limit):
+        return (bool(autoreset) and isinstance(episode_length_limit, (int, np.integer)) and 0 < episode_length_limit <= 65535)
+
+    def _alloc_grid_state(self):
         torch = self._torch
-        self.rows, self.cols = rows, cols
-        self.start_state = start_state
-        self.terminal_states = terminal_states
-        self.walls = self.spec.walls
-        self.special_transitions = self.spec.special_transitions
-        self.rewards = self.spec.rewards
-        self.p_success = p_success
-        self.slip_distribution = slip_distribution or {a: (1.0 - p_success) / (len(Action) - 1) for a in Action}
-        self.episode_length_limit = episode_length_limit
-        self.strict = bool(strict)
-        self.single_action_space = spaces.Discrete(4)
-        self.single_observation_space = spaces.Tuple((spaces.Discrete(rows), spaces.Discrete(cols)))
-        self.action_space = spaces.Batched(self.single_action_space, num_envs)
-        self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
-        n, dev = self.num_envs, self.device
         if self._packed:
-            self._pl = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._pl = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         else:
-            self._pos_split = torch.zeros(n, dtype=torch.int32, device=dev)
-        # the four per-step outputs live back to back in ONE allocation (16-byte aligned sections), so the host-buffer
-        # path brings them back with a single device->host copy
-        pad = lambda b: (b + 15) // 16 * 16  # noqa: E731
-        o_rew, o_term, o_trunc = pad(8 * n), pad(8 * n) + pad(4 * n), pad(8 * n) + pad(4 * n) + pad(n)
-        self._out_bytes = o_trunc + pad(n)
-        self._out = torch.zeros(self._out_bytes, dtype=torch.uint8, device=dev)
-        self._out_sections = (o_rew, o_term, o_trunc)
-        self._obs = self._out[:8 * n].view(torch.int32).view(n, 2)
-        self._reward = self._out[o_rew:o_rew + 4 * n].view(torch.float32)
-        self._term = self._out[o_term:o_term + n]
-        self._trunc = self._out[o_trunc:o_trunc + n]
-        self._final_obs = None
-        self._fast_args = None   # cached pointer arguments of the lean step() path
-        self._P = None
-        self.rng = rng
-        self._rng_state = self._rng_inc = None
-        if rng == "pcg64":
-            from . import pcg64
-            if seed_list is None:
-                base = self._seed if seed is None else int(seed)
-                seed_list = [base + self.env_offset + i for i in range(n)]
-            if len(seed_list) != n:
-                raise ValueError(f"seed sequence must hold {n} integers")
-            st, inc = pcg64.pcg64_initial_state(seed_list)
-            self._rng_state = torch.from_numpy(st.view(np.int64)).to(dev)
-            self._rng_inc = torch.from_numpy(inc.view(np.int64)).to(dev)
-            thr, cap = pcg64.thresholds53(p_success)
-            self._thr53 = (_lib.C.c_uint64 * 3)(*thr)
-            self._cap53 = cap
-        self._upload_table()
-        self.reset()
+            self._pos_split = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
 
-    # -- state layout ---------------------------------------------------------------------------------------------
     def _state_ptrs(self):
         """(pos, ep_len) arguments of the C ABI: the packed word and NULL, or the two split arrays."""
         if self._packed:
@@ -418,6 +350,87 @@ class VecGridWorld(VecEnv):
             self._pos_split, self._ep_len_split = pos, ln
             del self._pl
             self._fast_args = None
+
+
+class VecGridWorld(_GridStateLayout, VecEnv):
+    """N GridWorld instances sharing one configuration.  See module docstring; kwargs as in the reference."""
+    _HOST_TRANSPORT = "staged"   # the one-pass persistent step kernel serialises its PCIe reads and writes: DMA wins
+
+    def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
+                 special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
+                 episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox",
+                 state_layout="auto"):
+        """`rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
+        `rng="pcg64"`: every env owns the generator the reference would build for it,
+        Generator(PCG64(SeedSequence(seed_i))) with seed_i = seed + global env index (or `seed` given as a sequence of
+        N ints): `VecGridWorld(1, seed=s, rng="pcg64")` reproduces `GridWorld(seed=s)` draw for draw."""
+        if state_layout not in ("auto", "packed", "split"):
+            raise ValueError("state_layout must be 'auto', 'packed' or 'split'")
+        can_pack = self._can_pack(autoreset, episode_length_limit)
+        if state_layout == "packed" and not can_pack:
+            raise ValueError("state_layout='packed' needs autoreset=True and 0 < episode_length_limit <= 65535")
+        # packed: cell (bits 0-15) and episode_length_counter (bits 16-31) share one int32 per env -- 8 fewer bytes per
+        # env-step through HBM; `pos` / `ep_len` stay available as (computed) properties
+        self._packed = can_pack and state_layout != "split"
+        seed_list = None
+        if rng not in ("philox", "pcg64"):
+            raise ValueError("rng must be 'philox' or 'pcg64'")
+        if rng == "pcg64" and seed is not None and not isinstance(seed, int):
+            seed_list = [int(x) for x in seed]
+            seed = seed_list[0] if seed_list else None
+        validate_args(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, seed,
+                      slip_distribution, p_success, episode_length_limit)
+        self.spec = GridSpec(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, p_success,
+                             episode_length_limit)
+        super().__init__(num_envs, device, seed, env_offset, autoreset)
+        torch = self._torch
+        self.rows, self.cols = rows, cols
+        self.start_state = start_state
+        self.terminal_states = terminal_states
+        self.walls = self.spec.walls
+        self.special_transitions = self.spec.special_transitions
+        self.rewards = self.spec.rewards
+        self.p_success = p_success
+        self.slip_distribution = slip_distribution or {a: (1.0 - p_success) / (len(Action) - 1) for a in Action}
+        self.episode_length_limit = episode_length_limit
+        self.strict = bool(strict)
+        self.single_action_space = spaces.Discrete(4)
+        self.single_observation_space = spaces.Tuple((spaces.Discrete(rows), spaces.Discrete(cols)))
+        self.action_space = spaces.Batched(self.single_action_space, num_envs)
+        self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
+        n, dev = self.num_envs, self.device
+        self._alloc_grid_state()
+        # the four per-step outputs live back to back in ONE allocation (16-byte aligned sections), so the host-buffer
+        # path brings them back with a single device->host copy
+        pad = lambda b: (b + 15) // 16 * 16  # noqa: E731
+        o_rew, o_term, o_trunc = pad(8 * n), pad(8 * n) + pad(4 * n), pad(8 * n) + pad(4 * n) + pad(n)
+        self._out_bytes = o_trunc + pad(n)
+        self._out = torch.zeros(self._out_bytes, dtype=torch.uint8, device=dev)
+        self._out_sections = (o_rew, o_term, o_trunc)
+        self._obs = self._out[:8 * n].view(torch.int32).view(n, 2)
+        self._reward = self._out[o_rew:o_rew + 4 * n].view(torch.float32)
+        self._term = self._out[o_term:o_term + n]
+        self._trunc = self._out[o_trunc:o_trunc + n]
+        self._final_obs = None
+        self._fast_args = None   # cached pointer arguments of the lean step() path
+        self._P = None
+        self.rng = rng
+        self._rng_state = self._rng_inc = None
+        if rng == "pcg64":
+            from . import pcg64
+            if seed_list is None:
+                base = self._seed if seed is None else int(seed)
+                seed_list = [base + self.env_offset + i for i in range(n)]
+            if len(seed_list) != n:
+                raise ValueError(f"seed sequence must hold {n} integers")
+            st, inc = pcg64.pcg64_initial_state(seed_list)
+            self._rng_state = torch.from_numpy(st.view(np.int64)).to(dev)
+            self._rng_inc = torch.from_numpy(inc.view(np.int64)).to(dev)
+            thr, cap = pcg64.thresholds53(p_success)
+            self._thr53 = (_lib.C.c_uint64 * 3)(*thr)
+            self._cap53 = cap
+        self._upload_table()
+        self.reset()
 
     # -- table ----------------------------------------------------------------------------------------------------
     def _start_cell(self):
@@ -699,7 +712,7 @@ class VecGridWorld(VecEnv):
                 f"(env {env}; {count} rejected env-step(s))")
 
 
-class VecGridWorldLayouts(VecEnv):
+class VecGridWorldLayouts(_GridStateLayout, VecEnv):
     """N GridWorld instances spread over several LAYOUTS in one batch (per-env heterogeneous grids).
 
     `layouts` is a list of dicts with the per-layout reference kwargs `start_state`, `terminal_states`, `walls`,
@@ -712,7 +725,14 @@ class VecGridWorldLayouts(VecEnv):
     _HOST_TRANSPORT = "staged"
 
     def __init__(self, num_envs, layouts, rows=5, cols=5, rewards=None, p_success=1.0, episode_length_limit=None, *,
-                 layout_index=None, device=None, seed=None, env_offset=0, autoreset=True, strict=False):
+                 layout_index=None, device=None, seed=None, env_offset=0, autoreset=True, strict=False, state_layout="auto"):
+        if state_layout not in ("auto", "packed", "split"):
+            raise ValueError("state_layout must be 'auto', 'packed' or 'split'")
+        can_pack = self._can_pack(autoreset, episode_length_limit)
+        if state_layout == "packed" and not can_pack:
+            raise ValueError("state_layout='packed' needs autoreset=True and 0 < episode_length_limit <= 65535")
+        self._packed = can_pack and state_layout != "split"
+        self._fast_args = None
         if not layouts:
             raise ValueError("layouts must hold at least one layout dict")
         self.specs = []
@@ -744,7 +764,7 @@ class VecGridWorldLayouts(VecEnv):
             if li.shape[0] != n or (li < 0).any() or (li >= self.n_layouts).any():
                 raise ValueError(f"layout_index must hold {n} values in 0..{self.n_layouts - 1}")
             self._layout_index = torch.from_numpy(li.astype(np.int32)).to(dev)
-        self.pos = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._alloc_grid_state()
         self._obs = torch.zeros((n, 2), dtype=torch.int32, device=dev)
         self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self._term = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -802,8 +822,8 @@ class VecGridWorldLayouts(VecEnv):
         return {"pos": self.pos.clone(), "ep_len": self.ep_len.clone(), "ep_ret": self.ep_ret.clone(), "t": self._t}
 
     def set_state(self, state):
-        self.pos.copy_(state["pos"])
-        self.ep_len.copy_(state["ep_len"])
+        self.pos = state["pos"]
+        self.ep_len = state["ep_len"]
         self.ep_ret.copy_(state["ep_ret"])
         self._t = int(state.get("t", self._t))
 
@@ -815,13 +835,13 @@ class VecGridWorldLayouts(VecEnv):
         lay = torch.from_numpy(self.layout_of_env()).to(self.device)
         start = self._start_cells[lay]
         if mask is None:
-            self.pos.copy_(start)
-            self.ep_len.zero_()
+            self.pos = start
+            self.ep_len = torch.zeros_like(start)
             self.ep_ret.zero_()
         else:
             m = torch.as_tensor(mask, device=self.device).bool()
-            self.pos.copy_(torch.where(m, start, self.pos))
-            self.ep_len.masked_fill_(m, 0)
+            self.pos = torch.where(m, start, self.pos)
+            self.ep_len = torch.where(m, torch.zeros_like(start), self.ep_len)
             self.ep_ret.masked_fill_(m, 0.0)
         self._reset_epoch += 1
         return self.state, {}
@@ -850,7 +870,7 @@ class VecGridWorldLayouts(VecEnv):
                 self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
             fobs = self._final_obs
         self._call(self._lib.ef_gridworld_step_layouts, self._desc, self.n_layouts, _lib.ptr(self._layout_index),
-                   _lib.ptr(self._start_cells), _lib.ptr(self.pos), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(act),
+                   _lib.ptr(self._start_cells), *self._state_ptrs(), _lib.ptr(self.ep_ret), _lib.ptr(act),
                    _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward),
                    _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err),
                    _lib.ptr(self._clock), n, int(self.autoreset))
