@@ -190,7 +190,8 @@ class FlatTables:
             if abs(math.fsum(p) - 1.0) > _SQRT_EPS:
                 self.raises[row] = True
             c = np.cumsum(p)
-            c /= c[-1]
+            with np.errstate(invalid="ignore", divide="ignore"):   # a raising row (e.g. p_success = 0 special) may sum to 0
+                c /= c[-1]
             self.cdf[row, :len(outs)] = c
             for k, (to, rew, dn, _) in enumerate(outs):
                 self.nxt[row, k] = to[0] * port.cols + to[1]
