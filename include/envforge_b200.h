@@ -160,6 +160,11 @@ int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const
                               int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
                               double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 
+/* GridWorld.reset for a mixed-layout batch: env i returns to start_cells[layout of env i]; mask nullable. */
+int ef_gridworld_reset_layouts(int32_t n_layouts, const int32_t* layout_index, const int32_t* start_cells, int32_t cols,
+                               int32_t* pos, int32_t* ep_len, float* ep_ret, int32_t* obs, const uint8_t* mask,
+                               uint64_t env_offset, int64_t n, void* stream);
+
 /* Stream-exact variant of ef_gridworld_step: the outcome draw of env i comes from ITS OWN numpy-compatible generator,
  * Generator(PCG64(SeedSequence(seed_i))) as built by gym.utils.seeding.np_random (grid_world.py:69) and consumed by
  * Generator.choice (:515), so a batch seeded with the reference's seeds reproduces the reference's trajectories without

@@ -876,6 +876,24 @@ __global__ void __launch_bounds__(kThreads) gridworld_reset_kernel(int32_t start
     }
 }
 
+// Mixed-layout reset: env i goes back to the start cell of ITS layout (layout[i], or (env_offset + i) % n_layouts).
+__global__ void __launch_bounds__(kThreads) gridworld_reset_layouts_kernel(int32_t n_layouts, const int32_t* __restrict__ layout,
+                                                                           const int32_t* __restrict__ start_cells, int32_t cols,
+                                                                           int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                                                           int32_t* obs, const uint8_t* mask,
+                                                                           uint64_t env_offset, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        const int32_t lay = layout ? __ldg(layout + i) : static_cast<int32_t>((env_offset + i) % static_cast<uint64_t>(n_layouts));
+        const int32_t start = __ldg(start_cells + lay);
+        pos[i] = start;                   // packed layout (ep_len == NULL): counter bits are zero
+        if (ep_len) ep_len[i] = 0;
+        ep_ret[i] = 0.0f;
+        if (obs) { obs[2 * i] = start / cols; obs[2 * i + 1] = start % cols; }
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------
 constexpr size_t kMaxSmemTable = 96 * 1024;
 
@@ -1143,6 +1161,16 @@ extern "C" int ef_gridworld_rollout_traj(const ef_grid_desc* grid, int32_t* pos,
         if (grid->n_slots == 1) EF_TRAJ(false, 1); else EF_TRAJ(false, 4);
     }
 #undef EF_TRAJ
+}
+
+extern "C" int ef_gridworld_reset_layouts(int32_t n_layouts, const int32_t* layout_index, const int32_t* start_cells, int32_t cols,
+                                          int32_t* pos, int32_t* ep_len, float* ep_ret, int32_t* obs, const uint8_t* mask,
+                                          uint64_t env_offset, int64_t n, void* stream) {
+    if (n < 0 || cols <= 0 || n_layouts < 1 || !start_cells || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0) return EF_OK;
+    gridworld_reset_layouts_kernel<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_layouts, layout_index, start_cells, cols, pos, ep_len, ep_ret, obs, mask, env_offset, n);
+    return cuda_status(cudaGetLastError());
 }
 
 extern "C" int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos, int32_t* ep_len, float* ep_ret,

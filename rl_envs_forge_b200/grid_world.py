@@ -832,17 +832,10 @@ class VecGridWorldLayouts(_GridStateLayout, VecEnv):
         torch = self._torch
         if seed is not None:
             self.seed, self._seed = seed, resolve_seed(seed)
-        lay = torch.from_numpy(self.layout_of_env()).to(self.device)
-        start = self._start_cells[lay]
-        if mask is None:
-            self.pos = start
-            self.ep_len = torch.zeros_like(start)
-            self.ep_ret.zero_()
-        else:
-            m = torch.as_tensor(mask, device=self.device).bool()
-            self.pos = torch.where(m, start, self.pos)
-            self.ep_len = torch.where(m, torch.zeros_like(start), self.ep_len)
-            self.ep_ret.masked_fill_(m, 0.0)
+        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        self._call(self._lib.ef_gridworld_reset_layouts, self.n_layouts, _lib.ptr(self._layout_index),
+                   _lib.ptr(self._start_cells), self.cols, *self._state_ptrs(), _lib.ptr(self.ep_ret), _lib.ptr(self._obs),
+                   _lib.ptr(m), self.env_offset, self.num_envs)
         self._reset_epoch += 1
         return self.state, {}
 
