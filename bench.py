@@ -87,6 +87,31 @@ def _ref_worker(args):
     return done_steps, time.perf_counter() - t0
 
 
+def _ref_config1():
+    """BASELINE.json configs[0]: GridWorld() defaults (5x5, terminal (3,4) -> 1.0, p_success 1.0, no limit, seed 0), 10k
+    random-action steps with reset on done, one core, best of 3.  Returns env-steps/s."""
+    import numpy as np
+    from oracle.gridworld import GridWorldPort
+    best = 0.0
+    for _ in range(3):
+        port = GridWorldPort()
+        rng = np.random.default_rng(0)
+        actions = np.random.default_rng(0).integers(0, 4, 10_000)
+        mdp = port.mdp
+        port.reset()
+        t0 = time.perf_counter()
+        for a in actions:
+            outcomes = mdp[(port.state, int(a))]
+            idx = rng.choice(len(outcomes), p=[o[3] for o in outcomes])
+            nxt, reward, done, _ = outcomes[idx]
+            port.state = nxt
+            port.episode_length_counter += 1
+            if done:
+                port.reset()
+        best = max(best, 10_000 / (time.perf_counter() - t0))
+    return best
+
+
 def _ref_throughput(n_steps_per_worker, workers, pool):
     t0 = time.perf_counter()
     res = pool.map(_ref_worker, [(1000 + i, n_steps_per_worker) for i in range(workers)])
@@ -122,7 +147,10 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "envs": cores, "note": "one env per host process, reference-style step loop"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{cores} processes x {sample} transitions per step x {args.steps} steps "
-                                   f"(oracle/gridworld.py GridWorldPort + numpy Generator.choice, reset on done)"},
+                                   f"(oracle/gridworld.py GridWorldPort + numpy Generator.choice, reset on done)",
+                         "config1_single_core": {"value": _ref_config1(), "unit": UNIT,
+                                                 "what": "BASELINE configs[0]: default 5x5 grid, 10k random-action steps, "
+                                                         "one core, best of 3"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
