@@ -347,7 +347,8 @@ def run_ours(args):
     # The host path shares the box's PCIe root and host memory with whatever else runs there: on the pool's boxes the same
     # loop alternates between ~380 and ~550 us per step from one second to the next.  Time `e2e_windows` windows of k_e2e
     # steps each and report the best one (all of them are listed), the usual way to keep interference out of a host-side
-    # measurement; every window is a full timed region (H2D of the actions and D2H of the results inside, sync at the end).
+    # measurement (host CPU / PCIe power states also keep ramping for about a second: the windows climb before they settle);
+    # every window is a full timed region (H2D of the actions and D2H of the results inside, sync at the end).
     windows = []
     win_e2e = None
     for _ in range(max(1, args.e2e_windows)):
@@ -556,7 +557,7 @@ def main():
     ap.add_argument("--sets", type=int, default=8)
     ap.add_argument("--action-buffers", type=int, default=7)
     ap.add_argument("--e2e-steps", type=int, default=60)
-    ap.add_argument("--e2e-windows", type=int, default=8)
+    ap.add_argument("--e2e-windows", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-details", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
