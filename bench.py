@@ -509,6 +509,24 @@ def run_ours(args):
                 details["labyrinth_rollout_K64_random_policy"] = {"env_steps_per_s": nl * Kr / sec, "envs": nl, "mazes": mz}
             del lb
         del a_l
+        # ---- BASELINE configs[4]: 64M envs in total, sharded over the ranks, fused K=64 rollouts with the in-kernel policy and
+        # one all-reduce of the episode statistics per rollout (the engine's only collective) inside the timed region
+        n5 = (1 << 26) // world
+        tot5 = torch.zeros(8, dtype=torch.float64, device="cuda")
+        for key, make in (("config5_gridworld_rollout_K64_64M_envs_total",
+                           lambda: VecGridWorld(n5, seed=seed, special_transitions=spec, env_offset=rank * n5, **CONFIG2)),
+                          ("config5_cartpole_rollout_K64_64M_envs_total",
+                           lambda: VecCartPole(n5, seed=seed, env_offset=rank * n5))):
+            e5 = make()
+
+            def roll5():
+                e5.rollout(Kr)
+                tot5.copy_(e5.stats)
+                all_reduce_stats(tot5)
+            sec = ev_time(roll5, 3)
+            details[key] = {"env_steps_per_s": n5 * Kr / sec, "envs": n5, "envs_total": n5 * world, "ms_per_rollout": sec * 1e3,
+                            "collective": "all-reduce(sum) of 8 doubles per rollout" if world > 1 else "none (1 rank)"}
+            del e5
         if world > 1:
             for v in details.values():
                 t = torch.tensor([v["env_steps_per_s"]], dtype=torch.float64, device="cuda")
