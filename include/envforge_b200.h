@@ -148,6 +148,19 @@ typedef struct ef_gridworld_step_args {
 } ef_gridworld_step_args;
 int ef_gridworld_step_v(const ef_gridworld_step_args* args);
 
+/* ef_gridworld_step in the NARROW WIRE FORMAT of a host-side actor loop: actions are uint8 [n] (values > 3 are rejected
+ * like any other invalid Action), observations and final_obs are uint8 [n,2] -- needs rows <= 256 and cols <= 256
+ * (EF_ERR_UNSUPPORTED otherwise).  The reference's step() takes one Python int and returns a (row, col) tuple
+ * (grid_world.py:495-528); int32 is this engine's canonical widening of those, uint8 the narrowest dtype that still holds
+ * them.  An env-step then moves 9 bytes between host and device (1 in; 2 + 4 + 1 + 1 out) instead of 18, which is what a
+ * step() on HOST buffers is bound by (PCIe), and 25 instead of 34 through HBM.  State, randomness, statistics, error
+ * reporting and every other argument are those of ef_gridworld_step: the two calls produce the same trajectories.
+ * Vector path: action 4-byte aligned, obs / final_obs 8-byte aligned (else one env per thread). */
+int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret, const uint8_t* action,
+                         const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, uint8_t* obs,
+                         float* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* final_obs, double* stats,
+                         uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
+
 /* ef_gridworld_step for a batch that mixes several grid LAYOUTS (walls / terminal states / special transitions / start
  * state differ per layout; rows, cols, n_slots, thresholds and episode_limit are shared): `grid->table` holds n_layouts
  * consecutive tables of table_cells*4*n_slots entries each, env i walks table layout_index[i] (or

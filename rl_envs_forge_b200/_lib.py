@@ -79,6 +79,8 @@ SIGNATURES = {
     "ef_gridworld_step": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _I64, _I32, _P]),
     "ef_gridworld_step_v": (C.c_int, [C.POINTER(GridStepArgs)]),
+    "ef_gridworld_step_u8": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
+                                       _P, _P, _I64, _I32, _P]),
     "ef_gridworld_step_layouts": (C.c_int, [C.POINTER(GridDesc), _I32, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P,
                                             _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "ef_gridworld_reset_layouts": (C.c_int, [_I32, _P, _P, _I32, _P, _P, _P, _P, _P, _U64, _I64, _P]),

@@ -106,6 +106,51 @@ __device__ __forceinline__ int2 cell_to_obs(const GridArgs& a, int32_t cell) {
     return make_int2(row, cell - row * a.cols);
 }
 
+// Narrow wire format (W8): actions arrive as uint8 [n] and observations leave as uint8 [n,2] (rows, cols <= 256) -- the
+// format of a host-side actor loop, where PCIe rather than HBM carries every byte.  `action` / `obs` / `final_obs` of
+// GridArgs then point at bytes; everything between the load and the store is the same code.
+template <bool W8>
+__device__ __forceinline__ int32_t load_action1(const GridArgs& a, int64_t i) {
+    if constexpr (W8) return static_cast<int32_t>(__ldg(reinterpret_cast<const uint8_t*>(a.action) + i));
+    else return __ldg(a.action + i);
+}
+template <bool W8>
+__device__ __forceinline__ void store_obs1(int32_t* obs, int64_t i, int2 ob) {
+    if constexpr (W8) {
+        reinterpret_cast<uchar2*>(obs)[i] = make_uchar2(static_cast<uint8_t>(ob.x), static_cast<uint8_t>(ob.y));
+    } else {
+        obs[2 * i] = ob.x;
+        obs[2 * i + 1] = ob.y;
+    }
+}
+// Observations of a quad: two 128-bit stores of int32 pairs, or one 64-bit store of byte pairs.
+template <bool W8>
+__device__ __forceinline__ void store_obs4(const GridArgs& a, int32_t* obs, int64_t base, const int32_t (&pos)[4]) {
+    if constexpr (W8) {
+        const int2 o0 = cell_to_obs(a, pos[0]), o1 = cell_to_obs(a, pos[1]);
+        const int2 o2 = cell_to_obs(a, pos[2]), o3 = cell_to_obs(a, pos[3]);
+        const uint32_t lo = static_cast<uint32_t>(o0.x) | static_cast<uint32_t>(o0.y) << 8 |
+                            static_cast<uint32_t>(o1.x) << 16 | static_cast<uint32_t>(o1.y) << 24;
+        const uint32_t hi = static_cast<uint32_t>(o2.x) | static_cast<uint32_t>(o2.y) << 8 |
+                            static_cast<uint32_t>(o3.x) << 16 | static_cast<uint32_t>(o3.y) << 24;
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(obs) + 2 * base) = make_uint2(lo, hi);
+    } else {
+        int4* o = reinterpret_cast<int4*>(obs + 2 * base);
+        const int2 o0 = cell_to_obs(a, pos[0]), o1 = cell_to_obs(a, pos[1]);
+#if EF_STREAMING
+        __stcs(o, make_int4(o0.x, o0.y, o1.x, o1.y));
+#else
+        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
+#endif
+        const int2 o2 = cell_to_obs(a, pos[2]), o3 = cell_to_obs(a, pos[3]);
+#if EF_STREAMING
+        __stcs(o + 1, make_int4(o2.x, o2.y, o3.x, o3.y));
+#else
+        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
+#endif
+    }
+}
+
 // Scalar state access in either layout (see "Packed state" above).
 __device__ __forceinline__ void load_state1(const GridArgs& a, int64_t i, int32_t& pos, int32_t& len) {
     if (a.ep_len) {
@@ -268,7 +313,7 @@ struct QuadIn {
 // PACKED: the state word layout is known at compile time (ep_len == NULL).  FAST: the common call shape is known at
 // compile time -- actions given, obs / reward / terminated / truncated all requested, no final_obs, auto-reset on -- so
 // the launch-uniform null checks and their branches disappear from the instruction stream.
-template <bool PACKED, bool FAST, bool HET = false>
+template <bool PACKED, bool FAST, bool HET = false, bool W8 = false>
 __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, bool philox_act) {
     QuadIn in;
     if constexpr (HET) in.y4 = a.layout ? __ldg(reinterpret_cast<const int4*>(a.layout + base)) : make_int4(0, 0, 0, 0);
@@ -282,13 +327,19 @@ __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, boo
     if constexpr (PACKED) in.l4 = make_int4(0, 0, 0, 0);
     else in.l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
     in.r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
-    in.a4 = (!FAST && philox_act) ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
+    if constexpr (W8) {  // four action bytes in one 32-bit load
+        const uint32_t w = philox_act ? 0u : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.action) + base));
+        in.a4 = make_int4(static_cast<int32_t>(w & 0xffu), static_cast<int32_t>((w >> 8) & 0xffu),
+                          static_cast<int32_t>((w >> 16) & 0xffu), static_cast<int32_t>(w >> 24));
+    } else {
+        in.a4 = (!FAST && philox_act) ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
+    }
 #endif
     return in;
 }
 
 // One step of a full quad: draws, branch-free transitions, auto-reset, 128-bit stores.
-template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false>
+template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
 __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
                                           uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
                                           ErrorAcc& errs) {
@@ -339,20 +390,18 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) off[j] = static_cast<uint32_t>(lay[j]) * static_cast<uint32_t>(a.layout_len);
     }
-    transition4<SMEM, SLOTS>(a, tab, q, act, r, off);
+    // An action outside 0..3 (the reference raises ValueError in Action(action)) must never index the table: a wild
+    // value would read far outside it.  Such quads skip the branch-free walk and go one env at a time through the
+    // checking path below.
+    const bool wild = ((act[0] | act[1] | act[2] | act[3]) & ~3) != 0;
+    if (!wild) transition4<SMEM, SLOTS>(a, tab, q, act, r, off);
 #endif
     uint32_t rejected = 0u;
-    if (((act[0] | act[1] | act[2] | act[3]) & ~3) != 0) {
-        // some action is outside 0..3 (the reference raises ValueError in Action(action)): redo the quad one env at a
-        // time through the checking path, from the loaded state
-        if (packed) {
-            unpack4(in.p4, q.pos, q.len);
-        } else {
-            q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
-            q.len[0] = in.l4.x; q.len[1] = in.l4.y; q.len[2] = in.l4.z; q.len[3] = in.l4.w;
-        }
-        q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
-        q.term = q.trunc = 0u;
+#if EF_EXPERIMENT & 2
+    const bool wild = false;
+#endif
+    if (wild) {
+        q.term = q.trunc = q.bad = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t f = transition<SMEM, SLOTS>(a, tab + off[j], g0 + j, q.pos[j], q.len[j], q.ret[j], act[j], r[j],
@@ -372,13 +421,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         rejected = e.x;
     }
     acc.steps += 4u - rejected;
-    if (!FAST && a.final_obs) {  // pre-reset observation, only materialised on request
-        int4* o = reinterpret_cast<int4*>(a.final_obs + 2 * base);
-        const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
-        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
-        const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
-        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
-    }
+    if (!FAST && a.final_obs) store_obs4<W8>(a, a.final_obs, base, q.pos);  // pre-reset observation, only on request
     const uint32_t fin = (FAST || a.autoreset) ? (q.term | q.trunc) : 0u;
     if (fin) finish4(a, q, fin, acc, HET ? lay : nullptr);
 #if EF_STREAMING
@@ -393,13 +436,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
         EF_ST(reinterpret_cast<int4*>(a.ep_len + base), make_int4(q.len[0], q.len[1], q.len[2], q.len[3]));
     }
     EF_ST(reinterpret_cast<float4*>(a.ep_ret + base), make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]));
-    if (FAST || a.obs) {  // observation after auto-reset = (row, col) of the stored position
-        int4* o = reinterpret_cast<int4*>(a.obs + 2 * base);
-        const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
-        EF_ST(o, make_int4(o0.x, o0.y, o1.x, o1.y));
-        const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
-        EF_ST(o + 1, make_int4(o2.x, o2.y, o3.x, o3.y));
-    }
+    if (FAST || a.obs) store_obs4<W8>(a, a.obs, base, q.pos);  // observation after auto-reset = (row, col) of the stored position
     if (FAST || a.reward) EF_ST(reinterpret_cast<float4*>(a.reward + base), make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]));
     if (FAST || a.terminated) EF_ST(reinterpret_cast<uint32_t*>(a.terminated + base), q.term);
     if (FAST || a.truncated) EF_ST(reinterpret_cast<uint32_t*>(a.truncated + base), q.trunc);
@@ -445,7 +482,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 // quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
 // (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
 // load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
-template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false>
+template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
 __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
 #if EF_EXPERIMENT & 4
     const uint2* __restrict__ tab = a.table;
@@ -508,7 +545,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left) in[j] = load_quad<PACKED, FAST, HET>(a, (chunk + local) * 4, philox_act);
+            if (local < left) in[j] = load_quad<PACKED, FAST, HET, W8>(a, (chunk + local) * 4, philox_act);
         }
 #if !(EF_EXPERIMENT & 4)
         stage_table_wait(&table_bar, table_pending);  // the bulk copy had the whole load phase to land
@@ -517,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
             if (local < left)
-                step_quad<SMEM, SLOTS, PACKED, FAST, HET>(a, tab, (chunk + local) * 4,
+                step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
                                                           static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
                                                           philox_act, acc, errs);
         }
@@ -533,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         load_state1(a, i, pos, len);
         float ret = a.ep_ret[i], rew;
         const int32_t act = philox_act ? static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30)
-                                       : __ldg(a.action + i);
+                                       : load_action1<W8>(a, i);
         uint32_t r = 0u;
         if constexpr (SLOTS == 4) r = group_word1(a.seed, g, t, kStreamTransition);
         const uint2* __restrict__ tab_i = tab;
@@ -547,8 +584,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         if (!(f & 4u)) acc.steps += 1u;
         if (a.final_obs) {
             const int2 fo = cell_to_obs(a, pos);
-            a.final_obs[2 * i] = fo.x;
-            a.final_obs[2 * i + 1] = fo.y;
+            store_obs1<W8>(a.final_obs, i, fo);
         }
         if (a.autoreset && (f & 3u)) {
             acc.finish(len, ret);
@@ -560,8 +596,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         a.ep_ret[i] = ret;
         if (a.obs) {
             const int2 ob = cell_to_obs(a, pos);
-            a.obs[2 * i] = ob.x;
-            a.obs[2 * i + 1] = ob.y;
+            store_obs1<W8>(a.obs, i, ob);
         }
         if (a.reward) a.reward[i] = rew;
         if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
@@ -575,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 }
 
 // Scalar kernel: one env per thread, any alignment, optional injected outcome draws (parity tests, unaligned views).
-template <bool SMEM, int SLOTS>
+template <bool SMEM, int SLOTS, bool W8 = false>
 __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const GridArgs a) {
     const uint2* __restrict__ tab = stage_table<SMEM>(a);
     pdl_launch_dependents();
@@ -592,7 +627,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
         load_state1(a, i, pos, len);
         float ret = a.ep_ret[i], rew;
         const int32_t act = philox_act ? static_cast<int32_t>(group_word1(a.seed, g, t, kStreamPolicy) >> 30)
-                                       : __ldg(a.action + i);
+                                       : load_action1<W8>(a, i);
         uint32_t r = 0u;
         if constexpr (SLOTS == 4) r = a.draw ? __ldg(a.draw + i) : group_word1(a.seed, g, t, kStreamTransition);
         const uint2* __restrict__ tab_i = tab;
@@ -606,8 +641,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
         if (!(f & 4u)) acc.steps += 1u;
         if (a.final_obs) {
             const int2 fo = cell_to_obs(a, pos);
-            a.final_obs[2 * i] = fo.x;
-            a.final_obs[2 * i + 1] = fo.y;
+            store_obs1<W8>(a.final_obs, i, fo);
         }
         if (a.autoreset && (f & 3u)) {
             acc.finish(len, ret);
@@ -619,8 +653,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
         a.ep_ret[i] = ret;
         if (a.obs) {
             const int2 ob = cell_to_obs(a, pos);
-            a.obs[2 * i] = ob.x;
-            a.obs[2 * i + 1] = ob.y;
+            store_obs1<W8>(a.obs, i, ob);
         }
         if (a.reward) a.reward[i] = rew;
         if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
@@ -936,25 +969,29 @@ static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStr
 
 using namespace ef;
 
-extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
-                                 const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t,
-                                 uint64_t env_offset, int32_t* obs, float* reward, uint8_t* terminated,
-                                 uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
-                                 uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+// Shared body of ef_gridworld_step (W8 = false: int32 actions / observations) and ef_gridworld_step_u8 (W8 = true).
+template <bool W8>
+static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret, const void* action,
+                               const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, void* obs,
+                               float* reward, uint8_t* terminated, uint8_t* truncated, void* final_obs, double* stats,
+                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
     if (n < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
+    if (W8 && (grid->rows > 256 || grid->cols > 256)) return EF_ERR_UNSUPPORTED;  // (row, col) must fit a byte each
     if (!ep_len && !packed_ok(a, autoreset)) return EF_ERR_INVALID_ARGUMENT;
     if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0) return EF_OK;
-    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action; a.draw = draw;
+    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = static_cast<const int32_t*>(action); a.draw = draw;
     a.seed = seed; a.t = t; a.env_offset = env_offset;
-    a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs;
+    a.obs = static_cast<int32_t*>(obs); a.reward = reward; a.terminated = terminated; a.truncated = truncated;
+    a.final_obs = static_cast<int32_t*>(final_obs);
     a.stats = stats; a.err = err; a.n = n; a.autoreset = autoreset;
     a.clock = reinterpret_cast<unsigned long long*>(clock);
+    // a quad's accesses: 16 B of int32 actions / 2 x 16 B of int32 observations, or 4 B / 8 B in the narrow format
     const bool vec = draw == nullptr && aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) &&
-                     aligned(action, 16) && aligned(obs, 16) && aligned(reward, 16) && aligned(terminated, 4) &&
-                     aligned(truncated, 4) && aligned(final_obs, 16);
+                     aligned(action, W8 ? 4 : 16) && aligned(obs, W8 ? 8 : 16) && aligned(reward, 16) &&
+                     aligned(terminated, 4) && aligned(truncated, 4) && aligned(final_obs, W8 ? 8 : 16);
     const bool smem = !EF_FORCE_GLOBAL_TABLE && static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     // Small batches (one pass fits the resident grid): EF_STEP_Q quads per thread, all loads in flight, persistent grid.
@@ -974,12 +1011,15 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     const bool packed = ep_len == nullptr;
     const bool fast = action && obs && reward && terminated && truncated && !final_obs && autoreset != 0;
 #define EF_LAUNCH_VEC(SM, SL, PK, FS)                                                                                    \
-    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS>, a, SM, grid_v, st,        \
-                          EF_STEP_ASYNC ? size_t(EF_STEP_Q) * 4 * kThreads * 16 : 0)                                     \
-                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS, PK, FS>, a, SM, grid_b,    \
-                          st, EF_STEP_ASYNC ? size_t(EF_STEP_BIG_Q) * 4 * kThreads * 16 : 0)
+    return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS, false, W8>, a, SM, grid_v, \
+                          st, EF_STEP_ASYNC ? size_t(EF_STEP_Q) * 4 * kThreads * 16 : 0)                                 \
+                 : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS, PK, FS, false, W8>, a, SM, \
+                          grid_b, st, EF_STEP_ASYNC ? size_t(EF_STEP_BIG_Q) * 4 * kThreads * 16 : 0)
+    // The narrow format has the compile-time call-shape specialisation (FAST) only: its callers are actor loops that
+    // pass actions and take every output; other call shapes (and tables too large for shared memory) use the generic
+    // build, which for W8 is instantiated for the packed state only when the table is staged.
 #define EF_DISPATCH(SM, SL)                                                                                              \
-    if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL>, a, SM, grid_s, st);                                    \
+    if (!vec) return launch(gridworld_step_scalar_kernel<SM, SL, W8>, a, SM, grid_s, st);                                \
     if (SM && fast) { if (packed) { EF_LAUNCH_VEC(SM, SL, true, SM); } else { EF_LAUNCH_VEC(SM, SL, false, SM); } }      \
     if (packed) { EF_LAUNCH_VEC(SM, SL, true, false); } else { EF_LAUNCH_VEC(SM, SL, false, false); }
     if (smem) {
@@ -989,6 +1029,24 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
     }
 #undef EF_LAUNCH_VEC
 #undef EF_DISPATCH
+}
+
+extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                 const int32_t* action, const uint32_t* draw, uint64_t seed, uint64_t t,
+                                 uint64_t env_offset, int32_t* obs, float* reward, uint8_t* terminated,
+                                 uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
+                                 uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+    return gridworld_step_impl<false>(grid, pos, ep_len, ep_ret, action, draw, seed, t, env_offset, obs, reward, terminated,
+                                      truncated, final_obs, stats, err, clock, n, autoreset, stream);
+}
+
+extern "C" int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                    const uint8_t* action, const uint32_t* draw, uint64_t seed, uint64_t t,
+                                    uint64_t env_offset, uint8_t* obs, float* reward, uint8_t* terminated,
+                                    uint8_t* truncated, uint8_t* final_obs, double* stats, uint32_t* err,
+                                    uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+    return gridworld_step_impl<true>(grid, pos, ep_len, ep_ret, action, draw, seed, t, env_offset, obs, reward, terminated,
+                                     truncated, final_obs, stats, err, clock, n, autoreset, stream);
 }
 
 extern "C" int ef_gridworld_step_v(const ef_gridworld_step_args* x) {

@@ -9,6 +9,7 @@ episode return fp32), and the dict MDP is compiled into a flat outcome table tha
 Host-only pieces (`Action`, `validate_args`, `GridSpec`) import without CUDA; `VecGridWorld` needs a B200.
 """
 import math
+import os
 from enum import IntEnum
 
 import numpy as np
@@ -359,13 +360,20 @@ class VecGridWorld(_GridStateLayout, VecEnv):
     def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
                  special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
                  episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox",
-                 state_layout="auto"):
-        """`rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
+                 state_layout="auto", wire="canonical"):
+        """`wire="compact"`: step() takes uint8 actions and returns uint8 (row, col) observations (rows, cols <= 256)
+        through `ef_gridworld_step_u8` -- 9 instead of 18 bytes per env-step between host and device, same trajectories.
+
+        `rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
         `rng="pcg64"`: every env owns the generator the reference would build for it,
         Generator(PCG64(SeedSequence(seed_i))) with seed_i = seed + global env index (or `seed` given as a sequence of
         N ints): `VecGridWorld(1, seed=s, rng="pcg64")` reproduces `GridWorld(seed=s)` draw for draw."""
         if state_layout not in ("auto", "packed", "split"):
             raise ValueError("state_layout must be 'auto', 'packed' or 'split'")
+        if wire not in ("canonical", "compact"):
+            raise ValueError("wire must be 'canonical' or 'compact'")
+        self._w8 = wire == "compact"
+        self.wire = wire
         can_pack = self._can_pack(autoreset, episode_length_limit)
         if state_layout == "packed" and not can_pack:
             raise ValueError("state_layout='packed' needs autoreset=True and 0 < episode_length_limit <= 65535")
@@ -380,9 +388,17 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             seed = seed_list[0] if seed_list else None
         validate_args(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, seed,
                       slip_distribution, p_success, episode_length_limit)
+        if self._w8 and (rows > 256 or cols > 256):
+            raise ValueError("wire='compact' needs rows <= 256 and cols <= 256 (uint8 observations)")
+        if self._w8 and rng == "pcg64":
+            raise ValueError("wire='compact' is available with rng='philox' only")
         self.spec = GridSpec(rows, cols, start_state, terminal_states, walls, special_transitions, rewards, p_success,
                              episode_length_limit)
         super().__init__(num_envs, device, seed, env_offset, autoreset)
+        if self._w8 and "ENVFORGE_HOST_TRANSPORT" not in os.environ:
+            # 9 B/env: the kernel's own PCIe accesses (219 us per 2^20 envs) beat copy-engine staging (279 us) -- the
+            # opposite of the 18 B/env canonical format (profiles/r01_host_transport.md)
+            self.host_transport = "zerocopy"
         torch = self._torch
         self.rows, self.cols = rows, cols
         self.start_state = start_state
@@ -403,11 +419,13 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         # the four per-step outputs live back to back in ONE allocation (16-byte aligned sections), so the host-buffer
         # path brings them back with a single device->host copy
         pad = lambda b: (b + 15) // 16 * 16  # noqa: E731
-        o_rew, o_term, o_trunc = pad(8 * n), pad(8 * n) + pad(4 * n), pad(8 * n) + pad(4 * n) + pad(n)
+        ob = 2 * n if self._w8 else 8 * n    # bytes of the observation section: uint8 or int32 (row, col) pairs
+        o_rew, o_term, o_trunc = pad(ob), pad(ob) + pad(4 * n), pad(ob) + pad(4 * n) + pad(n)
         self._out_bytes = o_trunc + pad(n)
         self._out = torch.zeros(self._out_bytes, dtype=torch.uint8, device=dev)
         self._out_sections = (o_rew, o_term, o_trunc)
-        self._obs = self._out[:8 * n].view(torch.int32).view(n, 2)
+        self._obs_bytes = ob
+        self._obs = self._out[:ob].view(n, 2) if self._w8 else self._out[:ob].view(torch.int32).view(n, 2)
         self._reward = self._out[o_rew:o_rew + 4 * n].view(torch.float32)
         self._term = self._out[o_term:o_term + n]
         self._trunc = self._out[o_trunc:o_trunc + n]
@@ -520,8 +538,11 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         m = None
         if mask is not None:
             m = self._torch.as_tensor(mask, device=self.device).to(self._torch.uint8).contiguous()
-        self._call(self._lib.ef_gridworld_reset, self._desc.start_cell, self.cols, *self._state_ptrs(), _lib.ptr(self.ep_ret), _lib.ptr(self._obs), _lib.ptr(m), self.num_envs)
+        self._call(self._lib.ef_gridworld_reset, self._desc.start_cell, self.cols, *self._state_ptrs(), _lib.ptr(self.ep_ret),
+                   None if self._w8 else _lib.ptr(self._obs), _lib.ptr(m), self.num_envs)
         self._reset_epoch += 1
+        if self._w8:   # the reset kernel writes int32 pairs; the compact observation is derived from the state (cold path)
+            self._obs.copy_(self.state.clamp(0, 255).to(self._torch.uint8))
         obs = self._obs
         if not self.spec._in_grid(self.start_state):  # off-grid start: report it verbatim like the reference
             obs = self._torch.tensor(self.start_state, dtype=self._torch.int32, device=self.device).expand(self.num_envs, 2)
@@ -535,7 +556,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         draws    optional uint32-valued [N] injected outcome draws r (u = r * 2**-32); default: Philox.
         Returns (obs int32 [N,2], reward fp32 [N], terminated bool [N], truncated bool [N], info)."""
         torch = self._torch
-        if (draws is None and not return_final_obs and not self.strict and self.rng == "philox"
+        if (draws is None and not return_final_obs and not self.strict and self.rng == "philox" and not self._w8
                 and torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
                 and actions.dim() == 1 and actions.shape[0] == self.num_envs and actions.is_contiguous()):
             # lean path of the usual call (CUDA int32 actions in, CUDA tensors out): the fixed pointer arguments are
@@ -577,25 +598,37 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             return outs[0], outs[1], outs[2], outs[3], {}
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
         mode = self.host_transport if host_io else None
-        if mode == "pipelined" and (self.rng == "pcg64" or draws is not None or self._clock is not None):
+        if mode == "pipelined" and (self.rng == "pcg64" or draws is not None or self._clock is not None or self._w8):
             mode = "staged"     # the pipelined entry point covers the plain Philox step only
         zero_copy = mode == "zerocopy"
         n = self.num_envs
+        w8 = self._w8
+        act_dtype = torch.uint8 if w8 else torch.int32
+        obs_dtype, obs_np = (torch.uint8, np.uint8) if w8 else (torch.int32, np.int32)
         if host_io:
-            if torch.is_tensor(actions):      # CPU torch tensor (pinned int32 => used in place)
-                a = actions.reshape(-1).to(torch.int32)
+            if torch.is_tensor(actions):      # CPU torch tensor (pinned, of the wire dtype => used in place)
+                a = actions.reshape(-1)
+                if a.dtype != act_dtype:      # narrowing keeps invalid actions invalid: everything outside 0..255 -> 255
+                    a = a.clamp(-1, 255).to(torch.uint8) if w8 else a.to(torch.int32)
             else:
                 a = np.asarray(actions)
-                a = (a.reshape(1) if a.shape == () else a).astype(np.int32, copy=False)
-            h_act = self._host_in("action", a, torch.int32, (n,))
+                a = a.reshape(1) if a.shape == () else a
+                if w8 and a.dtype != np.uint8:
+                    a = np.where((a < 0) | (a > 255), 255, a).astype(np.uint8)
+                elif not w8:
+                    a = a.astype(np.int32, copy=False)
+            h_act = self._host_in("action", a, act_dtype, (n,))
             if mode == "staged":
-                p_act = _lib.ptr(self._to_device("action", h_act, torch.int32, (n,)))
+                p_act = _lib.ptr(self._to_device("action", h_act, act_dtype, (n,)))
             else:
                 p_act = h_act.data_ptr()
         else:
             if tuple(actions.shape) != (n,):
                 raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
-            act = actions if actions.dtype == torch.int32 else actions.to(torch.int32)
+            if actions.dtype == act_dtype:
+                act = actions
+            else:
+                act = actions.clamp(-1, 255).to(torch.uint8) if w8 else actions.to(torch.int32)
             act = act.contiguous()
             p_act = _lib.ptr(act)
         drw = None
@@ -608,10 +641,10 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         fobs = None
         if return_final_obs:
             if zero_copy:
-                fobs = self._pinned("o_final_obs", (n, 2), torch.int32)
+                fobs = self._pinned("o_final_obs", (n, 2), obs_dtype)
             else:
                 if self._final_obs is None:
-                    self._final_obs = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+                    self._final_obs = torch.zeros((n, 2), dtype=obs_dtype, device=self.device)
                 fobs = self._final_obs
         o_rew, o_term, o_trunc = self._out_sections
         if zero_copy:
@@ -641,7 +674,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
                        p_act, self.env_offset, p_obs, p_rew, p_term, p_trunc, _lib.ptr(fobs), _lib.ptr(self._stats_raw),
                        _lib.ptr(self.err), n, int(self.autoreset))
         else:
-            self._call(self._lib.ef_gridworld_step, self._desc, *self._state_ptrs(),
+            self._call(self._lib.ef_gridworld_step_u8 if w8 else self._lib.ef_gridworld_step, self._desc, *self._state_ptrs(),
                        _lib.ptr(self.ep_ret), p_act, _lib.ptr(drw), self._seed, self._t_arg(), self.env_offset,
                        p_obs, p_rew, p_term, p_trunc, _lib.ptr(fobs), _lib.ptr(self._stats_raw), _lib.ptr(self.err),
                        _lib.ptr(self._clock), n, int(self.autoreset))
@@ -663,7 +696,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
                 if return_final_obs:
                     info["final_observation"] = out[1]
                 buf = out[0]
-            return (buf[:8 * n].view(np.int32).reshape(n, 2), buf[o_rew:o_rew + 4 * n].view(np.float32),
+            return (buf[:self._obs_bytes].view(obs_np).reshape(n, 2), buf[o_rew:o_rew + 4 * n].view(np.float32),
                     buf[o_term:o_term + n].view(np.bool_), buf[o_trunc:o_trunc + n].view(np.bool_), info)
         if return_final_obs:
             info["final_observation"] = fobs

@@ -591,3 +591,32 @@ def test_rollout_trajectory_of_observations_equals_step_sequence(external):
         assert torch.equal(obs[k], o[0]) and torch.equal(rew[k], o[1]), k
         assert torch.equal(flg[k], o[2].to(torch.uint8) | (o[3].to(torch.uint8) << 1)), k
     assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len)
+
+
+def test_wild_action_values_are_rejected_without_touching_the_table():
+    """Actions far outside 0..3 (the reference raises ValueError in Action(action), grid_world.py:497) are counted and
+    leave the env untouched; they must not be used as a table index on the way (vector and scalar kernels)."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    cfg = _vec_kwargs(_config2(1.0))      # p_success = 1: no cell the reference raises on, every error is an action
+    for n in (1 << 16, 4099, 3):
+        env = VecGridWorld(n, seed=3, **cfg)
+        twin = VecGridWorld(n, seed=3, **cfg)
+        rng = np.random.default_rng(n)
+        bad_total = 0
+        for t in range(20):
+            act = rng.integers(0, 4, n).astype(np.int32)
+            ok = act.copy()
+            bad = rng.random(n) < 0.01
+            bad[0] = True
+            act[bad] = rng.choice(np.array([4, -1, 1 << 20, -(1 << 31), (1 << 31) - 1, 1 << 16], np.int64), int(bad.sum())).astype(np.int32)
+            bad_total += int(bad.sum())
+            pre = env.pos.clone()
+            obs, rew, term, trunc, _ = env.step(torch.from_numpy(act).cuda())
+            o2 = twin.step(torch.from_numpy(ok).cuda())
+            good = torch.from_numpy(~bad).cuda()
+            assert torch.equal(obs[good], o2[0][good]) and torch.equal(rew[good], o2[1][good])
+            assert torch.equal(env.pos[~good], pre[~good]) and float(rew[~good].abs().sum()) == 0.0
+            twin.pos, twin.ep_len = env.pos.clone(), env.ep_len.clone()
+            twin.ep_ret.copy_(env.ep_ret)
+        assert int(env.err.cpu().numpy()[0]) == bad_total

@@ -15,6 +15,7 @@ from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandi
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=40)
+ap.add_argument("--only", default="")
 a = ap.parse_args()
 n = a.n
 walls = {(1, 1), (1, 2), (2, 5), (3, 5), (4, 5), (6, 2), (6, 3), (5, 6)}
@@ -23,12 +24,20 @@ mk = {
                                        special_transitions={((3, 3), Action.UP): ((6, 6), 0.5)}, p_success=0.8,
                                        episode_length_limit=200, seed=1),
                   lambda r: r.integers(0, 4, n).astype(np.int32), 18),
+    "gridworld_u8": (lambda: VecGridWorld(n, rows=8, cols=8, walls=walls, terminal_states={(7, 7): 1.0, (0, 7): -1.0},
+                                          special_transitions={((3, 3), Action.UP): ((6, 6), 0.5)}, p_success=0.8,
+                                          episode_length_limit=200, seed=1, wire="compact"),
+                     lambda r: r.integers(0, 4, n).astype(np.uint8), 9),
     "cartpole": (lambda: VecCartPole(n, seed=1), lambda r: r.uniform(-3, 3, n).astype(np.float32), 26),
     "pendulum": (lambda: VecPendulumDisk(n, seed=1), lambda r: r.uniform(-3, 3, n).astype(np.float32), 18),
     "bandit": (lambda: VecKArmedBandit(n, k=10, seed=1), lambda r: r.integers(0, 10, n).astype(np.int32), 12),
 }
 for name, (make, gen, bytes_per_env) in mk.items():
+    if a.only and name not in a.only.split(","):
+        continue
     for transport in ("staged", "zerocopy", "pipelined:2", "pipelined:4", "pipelined:8", "pipelined+h2d:4", "pipelined+h2d:8"):
+        if name.endswith("_u8") and transport.startswith("pipelined"):
+            continue
         env = make()
         env.host_transport = transport.split(":")[0].split("+")[0]
         env.host_stage_actions = "+h2d" in transport
