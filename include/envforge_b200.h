@@ -438,6 +438,13 @@ int ef_gridworld_step_host(ef_host_pipe* pipe, const ef_grid_desc* grid, int32_t
                            int32_t* d_final_obs, int32_t* h_obs, float* h_reward, uint8_t* h_terminated,
                            uint8_t* h_truncated, int32_t* h_final_obs, double* stats, uint32_t* err, int64_t n,
                            int32_t autoreset, int32_t chunks, void* stream);
+/* The same pipeline over the narrow wire format (see ef_gridworld_step_u8): uint8 actions, uint8 [n,2] observations. */
+int ef_gridworld_step_u8_host(ef_host_pipe* pipe, const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                              const uint8_t* h_action, uint8_t* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,
+                              uint8_t* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+                              uint8_t* d_final_obs, uint8_t* h_obs, float* h_reward, uint8_t* h_terminated,
+                              uint8_t* h_truncated, uint8_t* h_final_obs, double* stats, uint32_t* err, int64_t n,
+                              int32_t autoreset, int32_t chunks, void* stream);
 int ef_cartpole_step_host(ef_host_pipe* pipe, const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                           const float* h_action, float* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,
                           float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated, float* d_final_obs,

@@ -128,6 +128,8 @@ SIGNATURES = {
     "ef_host_pipe_destroy": (C.c_int, [_P]),
     "ef_gridworld_step_host": (C.c_int, [_P, C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 10
                                + [_P, _P, _I64, _I32, _I32, _P]),
+    "ef_gridworld_step_u8_host": (C.c_int, [_P, C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 10
+                                  + [_P, _P, _I64, _I32, _I32, _P]),
     "ef_cartpole_step_host": (C.c_int, [_P, C.POINTER(PendulumParams), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 12
                               + [_P, _I64, _I32, _I32, _P]),
     "ef_pendulum_disk_step_host": (C.c_int, [_P, C.POINTER(PendulumParams), _P, _P, _P, _P, _P, _U64, _U64, _U64]

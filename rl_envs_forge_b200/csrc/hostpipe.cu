@@ -144,6 +144,25 @@ extern "C" int ef_gridworld_step_host(ef_host_pipe* pipe, const ef_grid_desc* gr
                          });
 }
 
+extern "C" int ef_gridworld_step_u8_host(ef_host_pipe* pipe, const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len,
+                                         float* ep_ret, const uint8_t* h_action, uint8_t* d_action, uint64_t seed,
+                                         uint64_t t, uint64_t env_offset, uint8_t* d_obs, float* d_reward,
+                                         uint8_t* d_terminated, uint8_t* d_truncated, uint8_t* d_final_obs, uint8_t* h_obs,
+                                         float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated, uint8_t* h_final_obs,
+                                         double* stats, uint32_t* err, int64_t n, int32_t autoreset, int32_t chunks,
+                                         void* stream) {
+    const HostOut outs[5] = {{d_obs, h_obs, 2}, {d_reward, h_reward, 4}, {d_terminated, h_terminated, 1},
+                             {d_truncated, h_truncated, 1}, {d_final_obs, h_final_obs, 2}};
+    return run_host_pipe(pipe, h_action, d_action, 1, outs, 5, n, chunks, static_cast<cudaStream_t>(stream),
+                         [&](int64_t off, int64_t cnt, const void* in) {
+                             return ef_gridworld_step_u8(grid, pos + off, at(ep_len, off), ep_ret + off,
+                                                         static_cast<const uint8_t*>(in), nullptr, seed, t, env_offset + off,
+                                                         at(d_obs, off, 2), at(d_reward, off), at(d_terminated, off),
+                                                         at(d_truncated, off), at(d_final_obs, off, 2), stats, err, nullptr,
+                                                         cnt, autoreset, stream);
+                         });
+}
+
 #define EF_PENDULUM_STEP_HOST(NAME, STEP, DIM, ACCW)                                                                    \
     extern "C" int NAME(ef_host_pipe* pipe, const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,    \
                         const float* h_action, float* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,          \

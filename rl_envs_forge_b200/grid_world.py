@@ -598,7 +598,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             return outs[0], outs[1], outs[2], outs[3], {}
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
         mode = self.host_transport if host_io else None
-        if mode == "pipelined" and (self.rng == "pcg64" or draws is not None or self._clock is not None or self._w8):
+        if mode == "pipelined" and (self.rng == "pcg64" or draws is not None or self._clock is not None):
             mode = "staged"     # the pipelined entry point covers the plain Philox step only
         zero_copy = mode == "zerocopy"
         n = self.num_envs
@@ -657,10 +657,10 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         if mode == "pipelined":
             h_out = self._pinned("o_out", (self._out_bytes,), torch.uint8)
             hb = h_out.data_ptr()
-            d_act = _lib.ptr(self._device_scratch("action", (n,), torch.int32)) if self.host_stage_actions else None
-            h_fobs = self._pinned("o_final_obs", (n, 2), torch.int32) if return_final_obs else None
+            d_act = _lib.ptr(self._device_scratch("action", (n,), act_dtype)) if self.host_stage_actions else None
+            h_fobs = self._pinned("o_final_obs", (n, 2), obs_dtype) if return_final_obs else None
             with torch.cuda.device(self.device):
-                _lib.check(self._lib.ef_gridworld_step_host(
+                _lib.check((self._lib.ef_gridworld_step_u8_host if w8 else self._lib.ef_gridworld_step_host)(
                     self._pipe(), self._desc, *self._state_ptrs(), _lib.ptr(self.ep_ret), p_act, d_act,
                     self._seed, self._t, self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._term),
                     _lib.ptr(self._trunc), _lib.ptr(fobs), hb, hb + o_rew, hb + o_term, hb + o_trunc, _lib.ptr(h_fobs),

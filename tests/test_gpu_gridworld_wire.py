@@ -120,7 +120,7 @@ def test_compact_equals_canonical(layout, autoreset):
         b.check_errors()
 
 
-@pytest.mark.parametrize("transport", ["zerocopy", "staged", "pipelined"])
+@pytest.mark.parametrize("transport", ["zerocopy", "staged", "pipelined", "pipelined+h2d"])
 def test_compact_host_buffer_path_equals_device_path(transport):
     """numpy / pinned uint8 actions in -> numpy out (uint8 observations); wider integer dtypes are narrowed on the host
     with out-of-range values kept invalid."""
@@ -129,7 +129,7 @@ def test_compact_host_buffer_path_equals_device_path(transport):
     cfg = _vec_kwargs(_config2(0.8))
     n = 10_001
     a = VecGridWorld(n, seed=4, wire="compact", **cfg)
-    a.host_transport = transport         # "pipelined" has no narrow entry point: it falls back to "staged"
+    a.host_transport, a.host_stage_actions, a.host_chunks = transport.split("+")[0], transport.endswith("+h2d"), 3
     b = VecGridWorld(n, seed=4, wire="compact", **cfg)
     rng = np.random.default_rng(0)
     for i in range(24):

@@ -35,9 +35,7 @@ mk = {
 for name, (make, gen, bytes_per_env) in mk.items():
     if a.only and name not in a.only.split(","):
         continue
-    for transport in ("staged", "zerocopy", "pipelined:2", "pipelined:4", "pipelined:8", "pipelined+h2d:4", "pipelined+h2d:8"):
-        if name.endswith("_u8") and transport.startswith("pipelined"):
-            continue
+    for transport in ("staged", "zerocopy", "pipelined:1", "pipelined:2", "pipelined:4", "pipelined:8", "pipelined+h2d:4", "pipelined+h2d:8"):
         env = make()
         env.host_transport = transport.split(":")[0].split("+")[0]
         env.host_stage_actions = "+h2d" in transport
