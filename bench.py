@@ -438,6 +438,8 @@ def run_ours(args):
         sec = ev_time(lambda: ml.step(acts[0]), 50)
         details["gridworld_step_8_layouts"] = {"env_steps_per_s": n / sec, "envs": n, "us_per_launch": sec * 1e6,
                                                "GBps": GRID_BYTES_PER_STEP * n / sec / 1e9}
+        sec = ev_time(lambda: ml.rollout(Kr), 10)
+        details["gridworld_rollout_K64_8_layouts_random_policy"] = {"env_steps_per_s": n * Kr / sec, "envs": n}
         del ml
         # the step kernel at a batch large enough to amortise launch ramp-up/drain (config 5 per-GPU share and beyond)
         nbig = 1 << 24

@@ -173,6 +173,15 @@ int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const
                               int32_t* obs, float* reward, uint8_t* terminated, uint8_t* truncated, int32_t* final_obs,
                               double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 
+/* K fused steps of a mixed-layout batch (ef_gridworld_rollout / ef_gridworld_rollout_traj for the batches of
+ * ef_gridworld_step_layouts): state in registers for all K steps, auto-reset to the env's own start cell, table offset
+ * and start cell fetched once per launch.  obs [K,n,2] int32 / rewards [K,n] / flags [K,n] each nullable. */
+int ef_gridworld_rollout_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
+                                 const int32_t* start_cells, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                 const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
+                                 int32_t* obs, float* rewards, uint8_t* flags, double* stats, uint32_t* err,
+                                 uint64_t* clock, int64_t n, void* stream);
+
 /* GridWorld.reset for a mixed-layout batch: env i returns to start_cells[layout of env i]; mask nullable. */
 int ef_gridworld_reset_layouts(int32_t n_layouts, const int32_t* layout_index, const int32_t* start_cells, int32_t cols,
                                int32_t* pos, int32_t* ep_len, float* ep_ret, int32_t* obs, const uint8_t* mask,

@@ -83,6 +83,8 @@ SIGNATURES = {
                                        _P, _P, _I64, _I32, _P]),
     "ef_gridworld_step_layouts": (C.c_int, [C.POINTER(GridDesc), _I32, _P, _P, _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P,
                                             _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "ef_gridworld_rollout_layouts": (C.c_int, [C.POINTER(GridDesc), _I32, _P, _P, _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P,
+                                               _P, _P, _P, _P, _I64, _P]),
     "ef_gridworld_reset_layouts": (C.c_int, [_I32, _P, _P, _I32, _P, _P, _P, _P, _P, _U64, _I64, _P]),
     "ef_gridworld_step_pcg64": (C.c_int, [C.POINTER(GridDesc), C.POINTER(C.c_uint64), _I32, _P, _P, _P, _P, _P, _P, _U64, _P,
                                           _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),

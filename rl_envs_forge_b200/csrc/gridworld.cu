@@ -757,7 +757,9 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_pcg64_kernel(const Gr
 // draws, one more their four random actions; the four table walks are independent, which gives the scheduler ILP).
 // A warp votes (ballot) on "any of my lanes finished an episode this step"; the reset / statistics path is skipped by
 // warps where nobody did.  State is read and written once per launch (24 B / K per env-step).
-template <bool SMEM, int SLOTS, bool EXT_ACTIONS, bool EMIT>
+// HET: the batch mixes layouts (ef_gridworld_rollout_layouts) -- each env walks its own table at a fixed offset into the
+// staged tables and resets to its own start cell; both are fetched once, before the K steps.
+template <bool SMEM, int SLOTS, bool EXT_ACTIONS, bool EMIT, bool HET = false>
 __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridArgs a) {
     const uint2* __restrict__ tab = stage_table<SMEM>(a);
     pdl_launch_dependents();
@@ -799,6 +801,17 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
                 q.ret[j] = valid[j] ? a.ep_ret[base + j] : 0.0f;
             }
         }
+        uint32_t off[4] = {0u, 0u, 0u, 0u};
+        int32_t lay[4] = {0, 0, 0, 0};
+        if constexpr (HET) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (a.layout) lay[j] = valid[j] ? __ldg(a.layout + base + j) : 0;
+                else lay[j] = static_cast<int32_t>((g0 + j) % static_cast<uint32_t>(a.n_layouts));
+                off[j] = static_cast<uint32_t>(lay[j]) * static_cast<uint32_t>(a.layout_len);
+                if (!valid[j]) q.pos[j] = __ldg(a.start_cells + lay[j]);   // dummy env: any cell of its own table
+            }
+        }
         // lanes past the end of the batch (only in the last, ragged quad) carry dummy envs: masks keep them out of
         // statistics, errors and stores
         const uint32_t valid_bytes = (valid[0] ? 0x1u : 0u) | (valid[1] ? 0x100u : 0u) | (valid[2] ? 0x10000u : 0u) |
@@ -831,19 +844,19 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     ErrorAcc scratch;
-                    const uint32_t f = transition<SMEM, SLOTS>(a, tab, g0 + j, q.pos[j], q.len[j], q.ret[j], act[j], wt[j],
-                                                               q.rew[j], valid[j] ? errs : scratch);
+                    const uint32_t f = transition<SMEM, SLOTS>(a, tab + off[j], g0 + j, q.pos[j], q.len[j], q.ret[j], act[j],
+                                                               wt[j], q.rew[j], valid[j] ? errs : scratch);
                     q.term |= (f & 1u) << (8 * j);
                     q.trunc |= ((f >> 1) & 1u) << (8 * j);
                     rejected += valid[j] ? ((f >> 2) & 1u) : 0u;
                 }
             } else {
-                const uint32_t no_off[4] = {0u, 0u, 0u, 0u};
-                transition4<SMEM, SLOTS>(a, tab, q, act, wt, no_off);
+                transition4<SMEM, SLOTS>(a, tab, q, act, wt, off);  // off: all zero, and folded away, unless HET
                 q.bad &= valid_bits;
                 if (q.bad) {
                     const uint4 e = record_bad4<SMEM, SLOTS>(tab, q.bad, g0, make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]),
-                                                             make_int4(act[0], act[1], act[2], act[3]));
+                                                             make_int4(act[0], act[1], act[2], act[3]),
+                                                             make_uint4(off[0], off[1], off[2], off[3]));
                     errs.count += e.x;
                     errs.g = e.y;
                     errs.detail = e.z;
@@ -863,7 +876,7 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
             }
             const uint32_t fin = (q.term | q.trunc) & valid_bytes;
             if (__ballot_sync(0xffffffffu, fin != 0u)) {  // warp vote: skip the reset path where nobody finished
-                if (fin) finish4(a, q, fin, acc);
+                if (fin) finish4(a, q, fin, acc, HET ? lay : nullptr);
             }
             if constexpr (EMIT) {
                 if (a.obs) {  // trajectory of observations [K, n, 2]: (row, col) after auto-reset, like step()
@@ -1219,6 +1232,45 @@ extern "C" int ef_gridworld_rollout_traj(const ef_grid_desc* grid, int32_t* pos,
         if (grid->n_slots == 1) EF_TRAJ(false, 1); else EF_TRAJ(false, 4);
     }
 #undef EF_TRAJ
+}
+
+extern "C" int ef_gridworld_rollout_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
+                                            const int32_t* start_cells, int32_t* pos, int32_t* ep_len, float* ep_ret,
+                                            const int32_t* actions, uint64_t seed, uint64_t t0, uint64_t env_offset,
+                                            int32_t K, int32_t* obs, float* rewards, uint8_t* flags, double* stats,
+                                            uint32_t* err, uint64_t* clock, int64_t n, void* stream) {
+    GridArgs a{};
+    if (int s = fill_args(grid, a)) return s;
+    if (n_layouts < 1 || !start_cells || n < 0 || K < 0 || !pos || !ep_ret || !aligned(obs, 8)) return EF_ERR_INVALID_ARGUMENT;
+    if (static_cast<int64_t>(a.table_len) * n_layouts > (1ll << 30)) return EF_ERR_UNSUPPORTED;
+    if (!ep_len && !packed_ok(a, 1)) return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return EF_OK;
+    a.layout = layout_index; a.start_cells = start_cells; a.n_layouts = n_layouts; a.layout_len = a.table_len;
+    a.pos = pos; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
+    a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K;
+    a.obs = obs; a.reward = rewards; a.flags = flags; a.stats = stats; a.err = err; a.n = n; a.autoreset = 1;
+    a.rk = philox_round_keys(seed);
+    a.clock = reinterpret_cast<unsigned long long*>(clock);
+    const int64_t total = static_cast<int64_t>(a.table_len) * n_layouts;
+    const bool smem = static_cast<size_t>(total) * sizeof(uint2) <= kMaxSmemTable;
+    a.table_len = static_cast<int32_t>(total);  // what stage_table copies: all layouts back to back
+    const bool ext = actions != nullptr, emit = obs != nullptr || rewards != nullptr || flags != nullptr;
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid_r = grid_for((n + 3) / 4, 8);
+#define EF_ROLL_HET(SM, SL)                                                                                         \
+    do {                                                                                                            \
+        if (ext && emit) return launch(gridworld_rollout_kernel<SM, SL, true, true, true>, a, SM, grid_r, st);     \
+        if (ext) return launch(gridworld_rollout_kernel<SM, SL, true, false, true>, a, SM, grid_r, st);            \
+        if (emit) return launch(gridworld_rollout_kernel<SM, SL, false, true, true>, a, SM, grid_r, st);           \
+        return launch(gridworld_rollout_kernel<SM, SL, false, false, true>, a, SM, grid_r, st);                    \
+    } while (0)
+    if (smem) {
+        if (grid->n_slots == 1) EF_ROLL_HET(true, 1); else EF_ROLL_HET(true, 4);
+    } else {
+        if (grid->n_slots == 1) EF_ROLL_HET(false, 1); else EF_ROLL_HET(false, 4);
+    }
+#undef EF_ROLL_HET
 }
 
 extern "C" int ef_gridworld_reset_layouts(int32_t n_layouts, const int32_t* layout_index, const int32_t* start_cells, int32_t cols,

@@ -753,8 +753,8 @@ class VecGridWorldLayouts(_GridStateLayout, VecEnv):
     `episode_length_limit` are shared, so one set of outcome thresholds serves every table.  Env i walks layout
     `layout_index[i]`, default `(env_offset + i) % len(layouts)`.  Each layout is compiled by the same table compiler as
     `VecGridWorld` (`GridSpec`, i.e. grid_world.py:245-274 and friends); `mdp_of(l)` / `P_of(l)` export them.
-    One launch steps the whole mixed batch (`ef_gridworld_step_layouts`); fused rollouts and the PCG64 stream mode are
-    per-layout features of `VecGridWorld`."""
+    One launch steps the whole mixed batch (`ef_gridworld_step_layouts`), one launch rolls it out for K fused steps
+    (`ef_gridworld_rollout_layouts`); the PCG64 stream mode is a per-layout feature of `VecGridWorld`."""
     _HOST_TRANSPORT = "staged"
 
     def __init__(self, num_envs, layouts, rows=5, cols=5, rewards=None, p_success=1.0, episode_length_limit=None, *,
@@ -913,6 +913,30 @@ class VecGridWorldLayouts(_GridStateLayout, VecEnv):
         if return_final_obs:
             info["final_observation"] = fobs
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
+
+    def rollout(self, K, actions=None, *, return_rewards=False, return_obs=False):
+        """K fused steps of the mixed batch in one kernel (state in registers, auto-reset to each env's own start cell);
+        arguments and returns as `VecGridWorld.rollout`."""
+        torch, n = self._torch, self.num_envs
+        if actions is not None:
+            if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+                    and tuple(actions.shape) == (K, n)):
+                raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
+            actions = actions.contiguous()
+        rew = flg = obs = None
+        if return_rewards or return_obs:
+            rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+            flg = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        if return_obs:
+            obs = torch.empty((K, n, 2), dtype=torch.int32, device=self.device)
+        self._call(self._lib.ef_gridworld_rollout_layouts, self._desc, self.n_layouts, _lib.ptr(self._layout_index),
+                   _lib.ptr(self._start_cells), *self._state_ptrs(), _lib.ptr(self.ep_ret), _lib.ptr(actions), self._seed,
+                   self._t_arg(), self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(flg),
+                   _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
+        self._t += int(K)
+        if return_obs:
+            return obs, rew, flg
+        return (rew, flg) if return_rewards else None
 
     def _describe_error(self, count, env, detail, kind_id, kind):
         if kind_id == 1:

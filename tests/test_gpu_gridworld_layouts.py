@@ -97,3 +97,52 @@ def test_layout_exports_reset_and_equivalence_with_single_layout_env():
     assert multi2.state.cpu().tolist() == [[0, 0], [2, 2]] + [[1, 0], [3, 2]] * 4
     with pytest.raises(ValueError):
         VecGridWorldLayouts(4, [dict(rows=3)], rows=8, cols=8)
+
+
+@pytest.mark.parametrize("rows,cols,p,m,explicit,n", [(8, 8, 0.8, 7, False, 30_011), (8, 8, 1.0, 3, True, 4096),
+                                                       (40, 40, 0.7, 5, True, 10_002), (8, 8, 0.8, 4, True, 3)])
+@pytest.mark.parametrize("external", [False, True])
+@pytest.mark.parametrize("layout", ["packed", "split"])
+def test_mixed_layout_rollout_equals_step_sequence(rows, cols, p, m, explicit, n, external, layout):
+    """ef_gridworld_rollout_layouts (K fused steps, state in registers) against K calls of the mixed-layout step, which the
+    test above pins to the oracle: same observations, rewards, flags, final state, statistics and error count -- with the
+    in-kernel random policy (its host twin feeds step()) and with external actions that include invalid ones."""
+    import torch
+    from rl_envs_forge_b200 import Action, VecGridWorldLayouts
+    rng = np.random.default_rng(rows * 7 + m)
+    layouts = _random_layouts(rng, m, rows, cols)
+    vec_layouts = [dict(l, special_transitions={(k[0], Action(k[1])): v for k, v in l["special_transitions"].items()})
+                   for l in layouts]
+    seed, off, limit, K = 5, (4096 + 8 if n % 2 == 0 else 777), 25, 37
+    li = rng.integers(0, m, n) if explicit else None
+    mk = lambda: VecGridWorldLayouts(n, vec_layouts, rows=rows, cols=cols, p_success=p, episode_length_limit=limit,  # noqa: E731
+                                     layout_index=li, seed=seed, env_offset=off, state_layout=layout)
+    a, b = mk(), mk()
+    # a few plain steps first so that the rollout starts from a mixed state and a non-zero step counter
+    for _ in range(3):
+        act = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).cuda()
+        a.step(act)
+        b.step(act)
+    g = np.arange(n) + off
+    if external:
+        acts = rng.integers(0, 4, (K, n)).astype(np.int32)
+        acts[rng.random((K, n)) < 0.003] = 11
+    else:
+        acts = np.stack([(philox.group_word(seed, g, 3 + k, philox.STREAM_POLICY) >> np.uint32(30)).astype(np.int32)
+                         for k in range(K)])
+    d_acts = torch.from_numpy(acts).cuda()
+    obs, rew, flg = a.rollout(K, d_acts if external else None, return_obs=True)
+    for k in range(K):
+        o, r, te, tr, _ = b.step(d_acts[k])
+        assert torch.equal(obs[k], o), k
+        assert torch.equal(rew[k], r), k
+        assert torch.equal(flg[k] & 1, te.to(torch.uint8)) and torch.equal(flg[k] >> 1, tr.to(torch.uint8)), k
+    assert torch.equal(a.pos, b.pos) and torch.equal(a.ep_len, b.ep_len) and torch.equal(a.ep_ret, b.ep_ret)
+    sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
+    assert sa[0] == sb[0] and sa[1] == sb[1] and sa[4] == sb[4] and np.allclose(sa[2:4], sb[2:4], rtol=1e-12)
+    assert int(a.err[0]) == int(b.err[0])
+    assert a.step_count == b.step_count == 3 + K
+    # statistics-only rollout (nothing materialised) continues the same trajectories
+    a.rollout(5, d_acts[:5] if external else None)
+    rw, fl = b.rollout(5, d_acts[:5] if external else None, return_rewards=True)
+    assert rw.shape == (5, n) and torch.equal(a.pos, b.pos) and torch.equal(a.ep_ret, b.ep_ret)
