@@ -303,6 +303,13 @@ typedef struct ef_arm {
     int32_t reserved;
 } ef_arm;
 
+/* Arm parameters in float64, for the stream-exact mode below (the float64 legacy samplers take them unrounded). */
+typedef struct ef_arm64 {
+    int32_t family;   /* ef_arm_family */
+    int32_t reserved;
+    double p0, p1;
+} ef_arm64;
+
 /* KArmedBandit.step (:175-200) for n bandits over K consecutive timesteps (K = 1 is the plain step).
  *   arms     device [K,k] ef_arm: parameters in force when the reward of timestep index t0+j is drawn.
  *   action   [K,n] int32 or NULL (uniform random arm from the Philox policy word).
@@ -314,6 +321,19 @@ typedef struct ef_arm {
 int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_t seed,
                    uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
                    uint32_t* err, int64_t n, void* stream);
+/* STREAM-EXACT KArmedBandit.step: every bandit owns the generator the reference builds for it -- numpy's legacy
+ * RandomState(seed_i), MT19937 (k_armed_bandit.py:145, :215) -- and Arm.sample (:66-122) runs numpy's legacy float64
+ * algorithms on it, so the reward stream of env i is that of KArmedBandit(seed=seed_i) without injected draws.
+ *   arms       device [k] ef_arm64, parameters in force for this step (EF_ARM_DEFAULT_NORMAL: mean = means[i,arm] + p0).
+ *   key        [624, n] uint32, word-major MT19937 state;  pos / has_gauss [n] int32;  gauss [n] double -- the fields of
+ *              RandomState.get_state(), updated in place.  The host seeds them with numpy itself.
+ *   means      [n, k] double: randn(k) of each env's generator (_create_default_arms :160-165), nullable.
+ *   reward     [n] fp32 (the engine's public reward dtype), reward64 [n] double (the unrounded sample); each nullable.
+ * 2.5 KB of state per env: meant for small n; the Philox kernels above are the throughput path. */
+int ef_bandit_step_mt19937(const ef_arm64* arms, int32_t k, const int32_t* action, uint32_t* key, int32_t* pos,
+                           int32_t* has_gauss, double* gauss, const double* means, uint64_t env_offset, int32_t* obs,
+                           float* reward, double* reward64, double* stats, uint32_t* err, int64_t n, void* stream);
+
 /* Per-env default-arm means (fp32 [n,k], the values the kernel re-derives); for KArmedBandit.arms / state. */
 int ef_bandit_default_means(int32_t k, uint64_t seed, uint64_t env_offset, float* means, int64_t n, void* stream);
 

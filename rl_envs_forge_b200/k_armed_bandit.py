@@ -9,6 +9,12 @@ arms with randn means (:160-165), custom arms with index check (:167-173), `step
 The arm set is shared by all N bandits (default arms have a per-bandit mean re-derived in-kernel from Philox).  User
 `param_functions` are arbitrary Python callables: they are evaluated on the host, per timestep, into the small arm
 table the kernel reads; sampling itself (8 families) runs on the device in fp32.
+
+`rng="mt19937"` is the stream-exact mode: every bandit owns numpy's legacy `RandomState(seed_i)` (what the reference
+builds at :145 / :215) with `seed_i = seed + global env index` (or `seed` given as a sequence of N ints), default means are
+that generator's `randn(k)`, and `Arm.sample` runs numpy's legacy float64 algorithms on the device
+(`ef_bandit_step_mt19937`): `VecKArmedBandit(1, seed=s, rng="mt19937")` replays `KArmedBandit(seed=s)`.  2.5 KB of
+generator state per bandit, so it is capped at 2**18 bandits; the Philox mode is the throughput path.
 """
 import numpy as np
 
@@ -93,7 +99,22 @@ class Arm:
 
 
 class VecKArmedBandit(VecEnv):
-    def __init__(self, num_envs=1, k=10, arm_params=None, seed=None, *, device=None, env_offset=0, strict=False):
+    MT19937_MAX_ENVS = 1 << 18
+
+    def __init__(self, num_envs=1, k=10, arm_params=None, seed=None, *, device=None, env_offset=0, strict=False,
+                 rng="philox"):
+        if rng not in ("philox", "mt19937"):
+            raise ValueError("rng must be 'philox' or 'mt19937'")
+        self.rng = rng
+        self._seed_list = None
+        if rng == "mt19937":
+            if num_envs > self.MT19937_MAX_ENVS:
+                raise ValueError(f"rng='mt19937' keeps 2.5 KB of generator state per bandit: at most {self.MT19937_MAX_ENVS} envs")
+            if seed is not None and not isinstance(seed, (int, np.integer)):
+                self._seed_list = [int(x) for x in seed]
+                if len(self._seed_list) != num_envs:
+                    raise ValueError(f"seed sequence must hold {num_envs} integers")
+                seed = self._seed_list[0]
         super().__init__(num_envs, device, seed, env_offset, autoreset=True)
         torch = self._torch
         self.k = k
@@ -115,6 +136,85 @@ class VecKArmedBandit(VecEnv):
         self._arm_key = None
         self.arms = None
         self._init_arms()
+        if rng == "mt19937":
+            self._reward64 = torch.zeros(n, dtype=torch.float64, device=dev)
+            self._init_mt19937()
+
+    # -- stream-exact mode: per-env numpy RandomState ---------------------------------------------------------------------
+    def _mt_seeds(self):
+        if self._seed_list is not None:
+            seeds = self._seed_list
+        else:
+            base = (self._seed & 0xFFFFFFFF) if self.seed is None else int(self.seed)
+            seeds = [base + self.env_offset + i for i in range(self.num_envs)]
+        for s in seeds:
+            if s < 0 or s > 0xFFFFFFFF:
+                raise ValueError("Seed must be between 0 and 2**32 - 1")     # numpy's own message (RandomState(seed))
+        return seeds
+
+    def _init_mt19937(self):
+        """Seed every env's generator with numpy itself and draw its default means (`randn(k)`, :162) -- what
+        `KArmedBandit.__init__` / `reset` do (:145, :215) -- then move the generator state to the device."""
+        torch, n, k = self._torch, self.num_envs, self.k
+        key = np.empty((624, n), np.uint32)
+        pos, has_gauss = np.empty(n, np.int32), np.empty(n, np.int32)
+        gauss, means = np.empty(n, np.float64), np.empty((n, k), np.float64)
+        for i, s in enumerate(self._mt_seeds()):
+            rs = np.random.RandomState(s)
+            means[i] = rs.randn(k)
+            st = rs.get_state()
+            key[:, i], pos[i], has_gauss[i], gauss[i] = st[1], st[2], st[3], st[4]
+        dev = self.device
+        self._mt_key = torch.from_numpy(key.view(np.int32)).to(dev)
+        self._mt_pos = torch.from_numpy(pos).to(dev)
+        self._mt_has_gauss = torch.from_numpy(has_gauss).to(dev)
+        self._mt_gauss = torch.from_numpy(gauss).to(dev)
+        self._mt_means = torch.from_numpy(means).to(dev)
+
+    def _arm_table64(self):
+        """Device [k] ef_arm64 table of the parameters in force now (float64, unrounded)."""
+        torch = self._torch
+        tab = np.zeros(self.k, dtype=[("family", "<i4"), ("reserved", "<i4"), ("p0", "<f8"), ("p1", "<f8")])
+        for i, a in enumerate(self.arms):
+            tab[i]["family"], tab[i]["p0"], tab[i]["p1"] = a.packed()
+        raw = torch.from_numpy(tab.view(np.uint8).copy())
+        stage = self._pinned("h_arms64", tuple(raw.shape), torch.uint8)
+        stage.copy_(raw)
+        return self._device_scratch("arms64", tuple(raw.shape), torch.uint8).copy_(stage, non_blocking=True)
+
+    @property
+    def reward64(self):
+        """float64 [N] unrounded samples of the last step (rng='mt19937' only)."""
+        return self._reward64
+
+    def _step_mt19937(self, actions):
+        torch, n = self._torch, self.num_envs
+        host_io = not (torch.is_tensor(actions) and actions.is_cuda)
+        if host_io:
+            a = (actions.numpy() if torch.is_tensor(actions) else np.asarray(actions)).reshape(-1)
+            if self.strict:
+                assert ((0 <= a) & (a < self.k)).all(), "Invalid action, must be between 0 and k-1."
+            act = self._to_device("action", self._host_in("action", a.astype(np.int32, copy=False), torch.int32, (n,)),
+                                  torch.int32, (n,))
+        else:
+            if tuple(actions.shape) != (n,):
+                raise ValueError(f"actions must have shape ({n},), got {tuple(actions.shape)}")
+            act = (actions if actions.dtype == torch.int32 else actions.to(torch.int32)).contiguous()
+        arms = self._arm_table64()
+        self._call(self._lib.ef_bandit_step_mt19937, _lib.ptr(arms), self.k, _lib.ptr(act), _lib.ptr(self._mt_key),
+                   _lib.ptr(self._mt_pos), _lib.ptr(self._mt_has_gauss), _lib.ptr(self._mt_gauss), _lib.ptr(self._mt_means),
+                   self.env_offset, _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._reward64),
+                   _lib.ptr(self._stats_raw), _lib.ptr(self.err), n)
+        self._advance(1)
+        if self.strict:
+            try:
+                self.check_errors()
+            except ValueError as e:
+                raise AssertionError("Invalid action, must be between 0 and k-1.") from e
+        if host_io:
+            obs, rew = self._to_host([("obs", self._obs), ("reward", self._reward)])
+            return obs, rew, np.ones(n, bool), np.zeros(n, bool), {}
+        return self._obs, self._reward, self._done, self._trunc, {}
 
     # -- arms (:155-173) ----------------------------------------------------------------------------------------------
     def _init_arms(self):
@@ -132,7 +232,10 @@ class VecKArmedBandit(VecEnv):
 
     @property
     def default_means(self):
-        """fp32 [N,k] default-arm means (what `np_random.randn(k)` is to one reference instance)."""
+        """fp32 [N,k] default-arm means (what `np_random.randn(k)` is to one reference instance); float64 and drawn by
+        numpy's own generator with rng='mt19937'."""
+        if self.rng == "mt19937":
+            return self._mt_means
         out = self._torch.empty((self.num_envs, self.k), dtype=self._torch.float32, device=self.device)
         self._call(self._lib.ef_bandit_default_means, self.k, self._seed, self.env_offset, _lib.ptr(out), self.num_envs)
         return out
@@ -174,6 +277,8 @@ class VecKArmedBandit(VecEnv):
     # -- hot path ---------------------------------------------------------------------------------------------------
     def step(self, actions):
         """KArmedBandit.step (:175-200) for all bandits: (obs = actions, reward fp32 [N], done = True, truncated = False, {})."""
+        if self.rng == "mt19937":
+            return self._step_mt19937(actions)
         torch = self._torch
         n = self.num_envs
         host_io = not (torch.is_tensor(actions) and actions.is_cuda)
@@ -234,6 +339,16 @@ class VecKArmedBandit(VecEnv):
                     and tuple(actions.shape) == (K, n)):
                 raise ValueError(f"actions must be a CUDA int32 tensor of shape ({K}, {n})")
             actions = actions.contiguous()
+        if self.rng == "mt19937":      # one launch per step (the generators advance step by step); small-N mode
+            if actions is None:
+                raise ValueError("rng='mt19937' needs explicit actions (the in-kernel random policy is a Philox stream)")
+            obs = torch.empty((K, n), dtype=torch.int32, device=self.device)
+            rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+            for j in range(K):
+                o, r = self._step_mt19937(actions[j])[:2]
+                obs[j].copy_(o)
+                rew[j].copy_(r)
+            return obs, rew
         arms = self._arm_table(K)
         obs = torch.empty((K, n), dtype=torch.int32, device=self.device)
         rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
@@ -257,10 +372,19 @@ class VecKArmedBandit(VecEnv):
             self.seed = seed
         # the reference builds RandomState(self.seed): a fixed seed replays the same means and reward stream,
         # seed=None draws fresh entropy
+        if self.rng == "mt19937" and seed is not None and not isinstance(seed, (int, np.integer)):
+            self._seed_list = [int(x) for x in seed]
+            if len(self._seed_list) != self.num_envs:
+                raise ValueError(f"seed sequence must hold {self.num_envs} integers")
+            self.seed = self._seed_list[0]
+        elif seed is not None:
+            self._seed_list = None
         self._seed = resolve_seed(self.seed)
         self._steps_since_reset = 0
         self._reset_epoch += 1
         self._init_arms()
+        if self.rng == "mt19937":
+            self._init_mt19937()
         return self._zero_obs, {}
 
     def _describe_error(self, count, env, detail, kind_id, kind):
