@@ -1103,7 +1103,15 @@ extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_lay
         const int64_t quads = n >> 2;
         // Q = 2 quads per thread like the single-layout large-batch variant, but compiled for 2 CTAs/SM: the per-env table
         // offsets and layout indices push the 3-CTA (80-register) build into local-memory spills (156 B of spill stores).
-        const int grid_b = grid_for((quads + EF_STEP_BIG_Q - 1) / EF_STEP_BIG_Q, EF_STEP_BIG_GRID_PER_SM);
+        // Persistent grid (2 resident CTAs per SM, each looping over its contiguous share) when the tables are staged:
+        // every CTA copies ALL layouts into its shared memory (64 KB for eight 8x8 layouts), so 64 dynamically scheduled
+        // CTAs per SM would move more table bytes out of L2 than the batch moves through HBM.
+        static const int het_per_sm = [] {
+            const char* e = getenv("ENVFORGE_HET_GRID_PER_SM");  // A/B switch; 0 = the dynamic grid for staged tables too
+            return e ? atoi(e) : 2;
+        }();
+        const int per_sm = (smem && het_per_sm > 0) ? het_per_sm : EF_STEP_BIG_GRID_PER_SM;
+        const int grid_b = grid_for((quads + EF_STEP_BIG_Q - 1) / EF_STEP_BIG_Q, per_sm);
         a.quads_per_cta = (quads + grid_b - 1) / grid_b;
         a.rk = philox_round_keys(seed);
         const bool packed = ep_len == nullptr;
