@@ -143,9 +143,10 @@ typedef struct ef_gridworld_step_args {
     uint64_t* clock;
     int64_t n;
     int32_t autoreset;
-    int32_t reserved;
+    int32_t wire;     /* 0: int32 action / obs / final_obs;  EF_WIRE_U8: they point at uint8 data (ef_gridworld_step_u8) */
     void* stream;
 } ef_gridworld_step_args;
+#define EF_WIRE_U8 0x1
 int ef_gridworld_step_v(const ef_gridworld_step_args* args);
 
 /* ef_gridworld_step in the NARROW WIRE FORMAT of a host-side actor loop: actions are uint8 [n] (values > 3 are rejected

@@ -15,6 +15,7 @@ EF_STATS_REPLICAS = 32
 EF_STATS_STRIDE = 16
 EF_ERR_LEN = 4
 EF_ABI_VERSION = 1
+EF_WIRE_U8 = 0x1
 
 EF_GRID_DONE = 0x1
 EF_GRID_NO_OUTCOMES = 0x2
@@ -37,7 +38,7 @@ class GridStepArgs(C.Structure):
                 ("action", C.c_void_p), ("draw", C.c_void_p), ("seed", C.c_uint64), ("t", C.c_uint64),
                 ("env_offset", C.c_uint64), ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
                 ("truncated", C.c_void_p), ("final_obs", C.c_void_p), ("stats", C.c_void_p), ("err", C.c_void_p),
-                ("clock", C.c_void_p), ("n", C.c_int64), ("autoreset", C.c_int32), ("reserved", C.c_int32),
+                ("clock", C.c_void_p), ("n", C.c_int64), ("autoreset", C.c_int32), ("wire", C.c_int32),
                 ("stream", C.c_void_p)]
 
 

@@ -1064,6 +1064,10 @@ extern "C" int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int3
 
 extern "C" int ef_gridworld_step_v(const ef_gridworld_step_args* x) {
     if (!x) return EF_ERR_INVALID_ARGUMENT;
+    if (x->wire & EF_WIRE_U8)  // action / obs / final_obs point at bytes (see ef_gridworld_step_u8)
+        return gridworld_step_impl<true>(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset,
+                                         x->obs, x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err,
+                                         x->clock, x->n, x->autoreset, x->stream);
     return ef_gridworld_step(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset, x->obs,
                              x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err, x->clock, x->n,
                              x->autoreset, x->stream);

@@ -556,8 +556,9 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         draws    optional uint32-valued [N] injected outcome draws r (u = r * 2**-32); default: Philox.
         Returns (obs int32 [N,2], reward fp32 [N], terminated bool [N], truncated bool [N], info)."""
         torch = self._torch
-        if (draws is None and not return_final_obs and not self.strict and self.rng == "philox" and not self._w8
-                and torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32
+        if (draws is None and not return_final_obs and not self.strict and self.rng == "philox"
+                and torch.is_tensor(actions) and actions.is_cuda
+                and actions.dtype == (torch.uint8 if self._w8 else torch.int32)
                 and actions.dim() == 1 and actions.shape[0] == self.num_envs and actions.is_contiguous()):
             # lean path of the usual call (CUDA int32 actions in, CUDA tensors out): the fixed pointer arguments are
             # cached, so one step() costs one ctypes call -- a Python-driven loop then keeps pace with the ~10 us kernel
@@ -575,6 +576,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
                 x.terminated, x.truncated = self._term.data_ptr(), self._trunc.data_ptr()
                 x.stats, x.err = self._stats_raw.data_ptr(), self.err.data_ptr()
                 x.n = self.num_envs
+                x.wire = _lib.EF_WIRE_U8 if self._w8 else 0
                 fixed = self._fast_args = (x, _lib.C.byref(x), self._lib.ef_gridworld_step_v, self.device.index,
                                            (self._obs, self._reward, self._term.view(torch.bool),
                                             self._trunc.view(torch.bool)), self.ep_ret, state_t)
