@@ -247,6 +247,8 @@ def run_ours(args):
             pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) on stdout: keep stdout to the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, R, K, W = args.envs_per_gpu, args.sets, args.steps, args.warmup
     seed = 20261019
