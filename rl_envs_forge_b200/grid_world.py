@@ -455,6 +455,8 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         s = self.start_state
         if self.spec._in_grid(s):
             return self.spec._cell_index(s)
+        if self._w8:   # an off-grid start is reported verbatim by the reference; it need not fit the uint8 observation
+            raise ValueError("wire='compact' needs a start_state inside the grid")
         return self.spec.n_cells  # pseudo-cell without outcomes: the reference accepts the start and raises on step
 
     def _upload_table(self):
@@ -529,6 +531,8 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         if new_start_state is not None:
             if not _is_cell(new_start_state):
                 raise ValueError("new_start_state must be a tuple of two integers")
+            if self._w8 and not self.spec._in_grid(new_start_state):
+                raise ValueError("wire='compact' needs a start_state inside the grid")
             self.start_state = new_start_state
             self.spec.start_state = new_start_state
             self._desc.start_cell = self._start_cell()

@@ -217,3 +217,49 @@ def test_compact_wire_limits():
         ob = b.step(torch.from_numpy(act).cuda())
         assert torch.equal(oa[0], ob[0].to(torch.int32)) and torch.equal(oa[1], ob[1]) and torch.equal(oa[2], ob[2])
     assert int(b.state.max()) >= 250
+
+
+def test_compact_cuda_graph_replay_equals_canonical_eager_steps():
+    """The lean step() path of the narrow format (one struct argument, `wire` flag) captured in a CUDA graph with the
+    device step clock: replays equal the eager canonical run."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, seed, per_graph, replays = 70_001, 31, 5, 6
+    cfg = _vec_kwargs(_config2(0.8))
+    eager = VecGridWorld(n, seed=seed, **cfg)
+    graphed = VecGridWorld(n, seed=seed, wire="compact", **cfg)
+    acts = [torch.randint(0, 4, (n,), dtype=torch.uint8, device="cuda") for _ in range(per_graph)]
+    acts32 = [a.to(torch.int32) for a in acts]
+    graphed.step(acts[0])
+    eager.step(acts32[0])
+    graphed.enable_device_clock()
+    stream = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(g, stream=stream):
+            for a in acts:
+                graphed.step(a)
+    torch.cuda.synchronize()
+    for _ in range(replays):
+        g.replay()
+        for a in acts32:
+            out_e = eager.step(a)
+    torch.cuda.synchronize()
+    assert graphed.step_count == 1 + per_graph * replays == eager.step_count
+    assert torch.equal(graphed.pos, eager.pos) and torch.equal(graphed.ep_len, eager.ep_len)
+    assert torch.equal(graphed.ep_ret, eager.ep_ret)
+    assert graphed._obs.dtype == torch.uint8 and torch.equal(graphed._obs.to(torch.int32), out_e[0])
+    assert torch.equal(graphed._reward, out_e[1])
+    sg, se = graphed.episode_stats(), eager.episode_stats()
+    assert sg["episodes"] == se["episodes"] > 0 and sg["env_steps"] == se["env_steps"]
+
+
+def test_compact_refuses_off_grid_start_states():
+    from rl_envs_forge_b200 import VecGridWorld
+    with pytest.raises(ValueError, match="inside the grid"):
+        VecGridWorld(4, start_state=(9, 9), wire="compact")
+    env = VecGridWorld(4, wire="compact")
+    with pytest.raises(ValueError, match="inside the grid"):
+        env.reset(new_start_state=(7, 0))
+    obs, _ = env.reset(new_start_state=(2, 3))
+    assert obs.cpu().tolist() == [[2, 3]] * 4 and env.start_state == (2, 3)
