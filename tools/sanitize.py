@@ -33,6 +33,24 @@ for n in (5, 4099):
             e.rollout(3, torch.randint(0, 4, (3, n), dtype=torch.int32, device="cuda"), return_rewards=True)
         e.reset(mask=ai > 1)
         e.running_episode_stats()
+    # narrow wire format (vector + scalar kernels, zero-copy / staged / pipelined host paths) with wild action bytes
+    a8 = torch.randint(0, 4, (n,), dtype=torch.uint8, device="cuda")
+    a8[::7] = 251
+    for kw in (dict(p_success=0.8, episode_length_limit=20), dict(p_success=1.0, autoreset=False)):
+        e = VecGridWorld(n, rows=8, cols=8, seed=1, wire="compact", **lay, **kw)
+        for _ in range(3):
+            e.step(a8, return_final_obs=True)
+            e.step(a8)
+        e.step(a8, draws=torch.randint(0, 2 ** 31, (n,), dtype=torch.int32, device="cuda"))
+        for tr in ("zerocopy", "staged", "pipelined"):
+            e.host_transport = tr
+            e.step(a8.cpu().numpy(), return_final_obs=True)
+    wild = ai.clone()
+    wild[::5] = torch.tensor([1 << 20, -7, (1 << 31) - 1, 4], dtype=torch.int32, device="cuda").repeat(n)[: wild[::5].numel()]
+    e = VecGridWorld(n, rows=8, cols=8, seed=1, p_success=0.8, **lay)
+    e.step(wild)
+    e.step(wild, return_final_obs=True)
+    e.rollout(3, wild.repeat(3, 1), return_rewards=True)
     big = VecGridWorld(n, rows=120, cols=120, seed=1, p_success=0.9, terminal_states={(119, 119): 1.0})  # global-memory table
     big.step(ai)
     big.rollout(2)
@@ -41,6 +59,12 @@ for n in (5, 4099):
     for _ in range(3):
         m.step(ai)
     m.step(ai, draws=torch.randint(0, 2 ** 31, (n,), dtype=torch.int32, device="cuda"))
+    m.step(wild)
+    m.rollout(4)
+    m.rollout(3, wild.repeat(3, 1), return_obs=True)
+    m2 = VecGridWorldLayouts(n, [lay] * 3, rows=8, cols=8, p_success=1.0, episode_length_limit=9, seed=2,
+                             layout_index=rng.integers(0, 3, n), state_layout="split")
+    m2.rollout(4, return_rewards=True)
     for cls in (VecCartPole, VecPendulumDisk):
         e = cls(n, seed=3, episode_length_limit=6)
         for _ in range(3):
@@ -58,6 +82,9 @@ for n in (5, 4099):
     b.step(ab)
     b.rollout(3)
     b.step(ab.clamp(max=7).cpu().numpy())
+    bm = VecKArmedBandit(min(n, 700), k=8, arm_params=arms, seed=4, rng="mt19937")     # stream-exact mode (MT19937 per env)
+    for _ in range(120):                                                              # past one 624-word regeneration
+        bm.step(ab[:bm.num_envs])
     os.environ["ENVFORGE_BANDIT_UNSORTED"] = "1"
     b.step(ab)
     del os.environ["ENVFORGE_BANDIT_UNSORTED"]
