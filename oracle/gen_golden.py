@@ -468,6 +468,12 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
     import sys
+    if "engine_big" in sys.argv[1:]:
+        # a 1M-step subsample of BASELINE config 2 (reference under the shim on a subsample of the population):
+        # 4096 envs x 256 steps of the unmodified reference under the engine's streams, limit 200 so that truncation occurs
+        engine_gridworld_case(R, "config2_p08_4096", dict(CONFIG2_LAYOUT, p_success=0.8, episode_length_limit=200), 4096, 256,
+                              seed=20261019, env_offset=3 << 18)
+        return
     if "engine" in sys.argv[1:]:
         engine_cases(R)
         return

@@ -19,7 +19,7 @@ def _g(name):
     return load(f"{GOLDEN}/engine_{name}.npz")
 
 
-@pytest.mark.parametrize("name", ["gridworld_config2_p08", "gridworld_config2_p1"])
+@pytest.mark.parametrize("name", ["gridworld_config2_p08", "gridworld_config2_p1", "gridworld_config2_p08_4096"])
 def test_gridworld_device_reproduces_engine_driven_reference(name):
     import torch
     from rl_envs_forge_b200 import Action, VecGridWorld

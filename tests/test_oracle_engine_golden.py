@@ -20,7 +20,7 @@ def _g(name):
 
 
 def test_gridworld_vectorised_oracle_reproduces_engine_driven_reference():
-    for name in ("gridworld_config2_p08", "gridworld_config2_p1"):
+    for name in ("gridworld_config2_p08", "gridworld_config2_p1", "gridworld_config2_p08_4096"):
         g = _g(name)
         cfg = grid_kwargs(g)
         seed, off = int(g["seed"]), int(g["env_offset"])
