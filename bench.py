@@ -247,9 +247,19 @@ def run_ours(args):
             pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) on stdout: keep stdout to the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner ("NCCL version ...") on stdout when the communicator is created: point fd 1 at
+        # stderr while that happens, so that stdout carries the ONE JSON line and nothing else
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()                     # forces communicator creation (and the banner) now
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     n, R, K, W = args.envs_per_gpu, args.sets, args.steps, args.warmup
     seed = 20261019
 
