@@ -70,6 +70,24 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ef_bandit_step_host(None, None, 10, None, None, 0, 0, 0, None, None, None, None, None, None, 8, 4, None) == 1
     assert lib.ef_gridworld_step_host(None, ctypes.byref(d), *([None] * 5), 0, 0, 0, *([None] * 12), 8, 1, 4, None) == 1
     assert lib.ef_host_pipe_create(None) == 1 and lib.ef_host_pipe_destroy(None) == 0
+    # narrow wire format: same descriptor checks, grids wider than a byte are refused before any launch
+    d.episode_limit = 10
+    assert lib.ef_gridworld_step_u8(None, *([None] * 5), 0, 0, 0, *([None] * 8), 8, 1, None) == 1
+    assert lib.ef_gridworld_step_u8(ctypes.byref(d), fake, None, fake, None, None, 0, 0, 0, *([None] * 8), 0, 1, None) == 0
+    d.rows, d.cols = 300, 2
+    assert lib.ef_gridworld_step_u8(ctypes.byref(d), fake, None, fake, None, None, 0, 0, 0, *([None] * 8), 8, 1, None) == 3
+    d.rows = d.cols = 2
+    assert lib.ef_gridworld_step_u8_host(None, ctypes.byref(d), *([None] * 5), 0, 0, 0, *([None] * 12), 8, 1, 4, None) == 1
+    x = _lib.GridStepArgs()
+    x.grid, x.pos, x.ep_ret, x.n, x.autoreset, x.wire = ctypes.pointer(d), 0x2000, 0x2000, 0, 1, _lib.EF_WIRE_U8
+    assert lib.ef_gridworld_step_v(ctypes.byref(x)) == 0 and lib.ef_gridworld_step_v(None) == 1
+    # mixed-layout rollout and the stream-exact bandit step: null state / generator buffers are rejected
+    assert lib.ef_gridworld_rollout_layouts(ctypes.byref(d), 2, None, None, *([None] * 4), 0, 0, 0, 4, *([None] * 6), 8, None) == 1
+    assert lib.ef_gridworld_rollout_layouts(ctypes.byref(d), 0, None, fake, fake, None, fake, None, 0, 0, 0, 4, *([None] * 6), 8,
+                                            None) == 1
+    assert lib.ef_bandit_step_mt19937(None, 10, *([None] * 6), 0, *([None] * 5), 8, None) == 1
+    assert lib.ef_bandit_step_mt19937(fake, 10, fake, fake, fake, fake, fake, None, 0, *([None] * 5), 0, None) == 0   # n == 0
+    assert lib.ef_bandit_step_mt19937(fake, 10, fake, fake, fake, fake, fake, None, 2 ** 32, *([None] * 5), 8, None) == 1
 
 
 def test_no_fallback_without_cuda():
