@@ -371,16 +371,21 @@ typedef struct ef_car_rental_params {
     int32_t max_cars, max_move_cars, rental_credit, move_car_cost;   /* car_rental.py:12-19 */
     int32_t episode_limit;    /* <= 0: none (the reference never ends an episode) */
     int32_t init_equal;       /* reset option: 0 "random" (uniform 0..max_cars per location), 1 "equal" (:134-142) */
-    double lam[4];            /* request_lambda[0], request_lambda[1], return_lambda[0], return_lambda[1]; each < 10 */
+    double lam[4];            /* request_lambda[0], request_lambda[1], return_lambda[0], return_lambda[1] */
     double exp_neg_lam[4];    /* exp(-lam[j]) as the host's libm computes it (numpy's random_poisson_mult does the same) */
+    /* rates >= 10 draw by numpy's random_poisson_ptrs; its per-rate constants, from the host's libm like numpy's own:
+     *   slam = sqrt(lam); b = 0.931 + 2.53*slam; a = -0.059 + 0.02483*b; invalpha = 1.1239 + 1.1328/(b - 3.4);
+     *   vr = 0.9277 - 3.6224/(b - 2).   Ignored (may be 0) for rates < 10. */
+    double log_lam[4], ptrs_a[4], ptrs_b[4], ptrs_log_invalpha[4], ptrs_vr[4];
 } ef_car_rental_params;
 
 /* JacksCarRental.step (:106-121) for n envs: move cars (:54-74), then four legacy-numpy Poisson draws (scipy.stats.
- * poisson.rvs, :89-92) by the multiplication method in FP64 over the Philox stream STREAM_ACML of (env, t).
+ * poisson.rvs, :89-92) in FP64 over the Philox stream STREAM_ACML of (env, t): the multiplication method for rates < 10,
+ * PTRS (transformed rejection with numpy's random_loggam) for rates >= 10, exactly where numpy switches.
  *   state  [n,2] int32 (cars at A, cars at B), 8-byte aligned.   action [n] int32 raw action (0 .. 2*max_move_cars; the
  *   reference does not validate it and neither does the kernel), or NULL: uniform random.
  *   obs / final_obs [n,2]; reward = rentals * credit - |action - max_move| * cost; terminated == 0 always.
- * EF_ERR_UNSUPPORTED for a lam >= 10 (numpy switches to the PTRS sampler there). */
+ * EF_ERR_UNSUPPORTED for a lam > 1e6. */
 int ef_car_rental_step(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,
                        const int32_t* action, uint64_t seed, uint64_t t, uint64_t env_offset, int32_t* obs, float* reward,
                        uint8_t* terminated, uint8_t* truncated, int32_t* final_obs, double* stats, uint64_t* clock,

@@ -10,7 +10,8 @@ Randomness that lives in third-party code NOT under /root/reference:
   * `np.random.rand()` (gambler_problem.py:51): one double from numpy's global legacy RandomState (MT19937).
   * `scipy.stats.poisson.rvs(lam)` (car_rental.py:89-92) -> the global RandomState's `poisson`, i.e. numpy's legacy
     `random_poisson`: lam == 0 -> 0 without a draw; lam < 10 -> multiplication method (X = number of uniforms whose
-    running product stays above exp(-lam)); lam >= 10 -> PTRS (not restated: the device path supports lam < 10 only).
+    running product stays above exp(-lam)); lam >= 10 -> PTRS, Hoermann's transformed rejection with numpy's own
+    `random_loggam` (two doubles per trial).
     numpy pinned 1.26.4 (poetry.lock:786-787), scipy from the same lock; the container has numpy 2.3 / scipy 1.18,
     whose legacy stream is frozen by numpy's compatibility policy.
   * `np.random.randint(0, max_cars + 1)` (car_rental.py:136-139): initial state; parity tests inject initial states.
@@ -64,10 +65,59 @@ class PhiloxDoubles:
         return (a * 67108864.0 + b) / 9007199254740992.0
 
 
+_LOGGAM_A = (8.333333333333333e-02, -2.777777777777778e-03, 7.936507936507937e-04, -5.952380952380952e-04,
+             8.417508417508418e-04, -1.917526917526918e-03, 6.410256410256410e-03, -2.955065359477124e-02,
+             1.796443723688307e-01, -1.39243221690590e+00)
+
+
+def random_loggam(x):
+    """numpy's random_loggam (distributions.c): log-gamma by an asymptotic series after shifting x to >= 7."""
+    if x == 1.0 or x == 2.0:
+        return 0.0
+    n = int(7 - x) if x < 7.0 else 0
+    x0 = x + n
+    x2 = (1.0 / x0) * (1.0 / x0)
+    gl0 = _LOGGAM_A[9]
+    for k in range(8, -1, -1):
+        gl0 *= x2
+        gl0 += _LOGGAM_A[k]
+    gl = gl0 / x0 + 0.5 * 1.8378770664093453e+00 + (x0 - 0.5) * math.log(x0) - x0
+    if x < 7.0:
+        for _ in range(n):
+            gl -= math.log(x0 - 1.0)
+            x0 -= 1.0
+    return gl
+
+
+def ptrs_constants(lam):
+    """Per-rate constants of numpy's random_poisson_ptrs (Hoermann's transformed rejection), float64 like the C code."""
+    slam = math.sqrt(lam)
+    b = 0.931 + 2.53 * slam
+    a = -0.059 + 0.02483 * b
+    invalpha = 1.1239 + 1.1328 / (b - 3.4)
+    vr = 0.9277 - 3.6224 / (b - 2)
+    return dict(loglam=math.log(lam), a=a, b=b, log_invalpha=math.log(invalpha), vr=vr)
+
+
 def legacy_poisson(src, lam):
-    """numpy legacy random_poisson for lam < 10 (multiplication method), float64 like the C code."""
+    """numpy legacy random_poisson, float64 like the C code: lam == 0 -> 0 without a draw; lam < 10 -> multiplication
+    method; lam >= 10 -> PTRS (two doubles per trial)."""
     if lam >= 10:
-        raise NotImplementedError("PTRS branch (lam >= 10) is not restated")
+        c = ptrs_constants(lam)
+        while True:
+            u = src.double() - 0.5
+            v = src.double()
+            us = 0.5 - abs(u)
+            if us == 0.0:             # u == -0.5: 2a/us is +inf in C, k = floor(-inf) < 0 -> next trial
+                continue
+            k = math.floor((2 * c["a"] / us + c["b"]) * u + lam + 0.43)
+            if us >= 0.07 and v <= c["vr"]:
+                return k
+            if k < 0 or (us < 0.013 and v > us):
+                continue
+            lv = math.log(v) if v > 0.0 else -math.inf
+            if lv + c["log_invalpha"] - math.log(c["a"] / (us * us) + c["b"]) <= -lam + k * c["loglam"] - random_loggam(k + 1):
+                return k
     if lam == 0:
         return 0
     enlam = math.exp(-lam)
@@ -198,9 +248,29 @@ def car_rental_engine_step_vec(p, seed, g, t, state, action):
         cursor = cursor + active
         return ((wa >> np.uint64(5)).astype(np.float64) * 67108864.0 + (wb >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
 
+    def poisson_ptrs(lam):
+        c = ptrs_constants(lam)
+        out = np.zeros(n, np.int64)
+        active = np.ones(n, bool)
+        while active.any():
+            u = doubles(active.astype(np.int64)) - 0.5
+            v = doubles(active.astype(np.int64))
+            us = 0.5 - np.abs(u)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                k = np.floor((2 * c["a"] / us + c["b"]) * u + lam + 0.43)
+                quick = (us >= 0.07) & (v <= c["vr"])
+                skip = (k < 0) | ((us < 0.013) & (v > us)) | ~np.isfinite(k)
+                kk = np.where(skip | quick, 1.0, k)
+                lg = np.array([random_loggam(float(x) + 1.0) for x in kk])
+                slow = (np.log(v) + c["log_invalpha"] - np.log(c["a"] / (us * us) + c["b"])) <= (-lam + kk * c["loglam"] - lg)
+            acc = active & (quick | (~skip & slow))
+            out[acc] = k[acc].astype(np.int64)
+            active = active & ~acc
+        return out
+
     def poisson(lam):
         if lam >= 10:
-            raise NotImplementedError
+            return poisson_ptrs(lam)
         x = np.zeros(n, np.int64)
         if lam == 0:
             return x

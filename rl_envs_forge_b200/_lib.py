@@ -58,7 +58,9 @@ class GamblerParams(C.Structure):
 class CarRentalParams(C.Structure):
     _fields_ = [("max_cars", C.c_int32), ("max_move_cars", C.c_int32), ("rental_credit", C.c_int32),
                 ("move_car_cost", C.c_int32), ("episode_limit", C.c_int32), ("init_equal", C.c_int32),
-                ("lam", C.c_double * 4), ("exp_neg_lam", C.c_double * 4)]
+                ("lam", C.c_double * 4), ("exp_neg_lam", C.c_double * 4), ("log_lam", C.c_double * 4),
+                ("ptrs_a", C.c_double * 4), ("ptrs_b", C.c_double * 4), ("ptrs_log_invalpha", C.c_double * 4),
+                ("ptrs_vr", C.c_double * 4)]
 
 
 class LabyrinthDesc(C.Structure):

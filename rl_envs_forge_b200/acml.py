@@ -233,8 +233,8 @@ class VecJacksCarRental(_AcmlBase):
         lams = [float(x) for x in list(request_lambda) + list(return_lambda)]
         if len(lams) != 4 or any(not (x >= 0) for x in lams):
             raise ValueError("request_lambda and return_lambda must each hold two non-negative rates")
-        if any(x >= 10 for x in lams):
-            raise NotImplementedError("rates >= 10 use numpy's PTRS Poisson sampler, which the device path does not implement")
+        if any(x > 1e6 for x in lams):
+            raise NotImplementedError("Poisson rates above 1e6 are not supported by the device path")
         for v in (max_cars, max_move_cars, rental_credit, move_car_cost):
             if not isinstance(v, (int, np.integer)):
                 raise TypeError("max_cars, max_move_cars, rental_credit and move_car_cost must be integers")
@@ -257,6 +257,13 @@ class VecJacksCarRental(_AcmlBase):
         for j, lam in enumerate(lams):
             p.lam[j] = lam
             p.exp_neg_lam[j] = math.exp(-lam)       # what numpy's random_poisson_mult computes (libm exp)
+            if lam >= 10:                           # numpy's random_poisson_ptrs constants (float64, libm sqrt / log)
+                slam = math.sqrt(lam)
+                b = 0.931 + 2.53 * slam
+                a = -0.059 + 0.02483 * b
+                p.log_lam[j], p.ptrs_a[j], p.ptrs_b[j] = math.log(lam), a, b
+                p.ptrs_log_invalpha[j] = math.log(1.1239 + 1.1328 / (b - 3.4))
+                p.ptrs_vr[j] = 0.9277 - 3.6224 / (b - 2)
         self._params = p
         self._precompute_poisson_probabilities(poisson_max_value)
         self._state = torch.zeros((self.num_envs, 2), dtype=torch.int32, device=self.device)

@@ -10,7 +10,7 @@
 // (42 B per env-step: action 4, capital/ep_len/ep_ret 12 read + 12 written, obs 4, reward 4, flags 2).
 //
 // JacksCarRental draws four Poisson variates per step through scipy.stats.poisson.rvs, i.e. numpy's legacy
-// random_poisson.  For lam < 10 that is the multiplication method on doubles; it is restated here in FP64 over doubles
+// random_poisson.  For lam < 10 that is the multiplication method on doubles (lam >= 10: PTRS, see poisson4_general); it is restated here in FP64 over doubles
 // built from two Philox words exactly as numpy builds one from two MT19937 outputs, so the integer results are
 // bit-exact against the oracle fed the same words (no accept/reject flips).  Issue-bound (about eight Philox calls and
 // sixteen FP64 multiplies per env-step), not HBM-bound.
@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(kThreads) gambler_rollout_kernel(const Gambler
 struct CarArgs {
     int32_t max_cars, max_move, credit, move_cost, limit;
     double lam[4], enlam[4];  // requests A, requests B, returns A, returns B; enlam = exp(-lam) from the host's libm
+    // rates >= 10 (numpy's PTRS branch): per-rate constants from the host's libm -- log(lam), a, b, log(invalpha), vr
+    double loglam[4], ptrs_a[4], ptrs_b[4], ptrs_log_invalpha[4], ptrs_vr[4];
     int2* state;
     int32_t* ep_len;
     float* ep_ret;
@@ -314,6 +316,73 @@ __device__ __forceinline__ int4 poisson4(DoubleStream& ds, const CarArgs& a) {
     return make_int4(x0, x1, x2, x3);
 }
 
+// numpy's random_loggam (distributions.c): log-gamma by an asymptotic series after shifting x up to >= 7.
+__device__ double loggam(double x) {
+    if (x == 1.0 || x == 2.0) return 0.0;
+    const int n = x < 7.0 ? static_cast<int>(7.0 - x) : 0;
+    double x0 = x + n;
+    const double x2 = (1.0 / x0) * (1.0 / x0);
+    const double c[10] = {8.333333333333333e-02, -2.777777777777778e-03, 7.936507936507937e-04, -5.952380952380952e-04,
+                          8.417508417508418e-04, -1.917526917526918e-03, 6.410256410256410e-03, -2.955065359477124e-02,
+                          1.796443723688307e-01, -1.39243221690590e+00};
+    double gl0 = c[9];
+#pragma unroll
+    for (int k = 8; k >= 0; --k) {
+        gl0 = __dmul_rn(gl0, x2);
+        gl0 = __dadd_rn(gl0, c[k]);
+    }
+    double gl = gl0 / x0 + 0.5 * 1.8378770664093453e+00 + (x0 - 0.5) * log(x0) - x0;
+    for (int k = 1; k <= n; ++k) {
+        gl -= log(x0 - 1.0);
+        x0 -= 1.0;
+    }
+    return gl;
+}
+
+// The general form of poisson4: any stage whose rate is >= 10 draws by numpy's random_poisson_ptrs (Hoermann's
+// transformed rejection: two doubles per trial, a quick-accept region, a quick-reject region, else a log-space test
+// against loggam(k + 1)); the other stages run the multiplication method as above, in the same single loop and the same
+// order of consumption.  Only instantiated into the kernels launched for such rates (template PTRS), so the default
+// configuration (rates 3, 4, 3, 2) keeps the shorter loop.
+__device__ int4 poisson4_general(DoubleStream& ds, const CarArgs& a) {
+    int32_t x[4] = {0, 0, 0, 0};
+    int stage = 0;
+    while (stage < 4 && a.lam[stage] == 0.0) ++stage;
+    double prod = 1.0;
+    for (int it = 0; it < kMaxPoissonTrips && stage < 4; ++it) {
+        const double lam = a.lam[stage];
+        bool done_stage;
+        if (lam >= 10.0) {
+            const double pa = a.ptrs_a[stage], pb = a.ptrs_b[stage];
+            const double U = ds.next() - 0.5;
+            const double V = ds.next();
+            const double us = 0.5 - fabs(U);
+            const double kf = floor((2.0 * pa / us + pb) * U + lam + 0.43);  // us == 0: -inf, rejected by kf < 0 below
+            bool accept;
+            if (us >= 0.07 && V <= a.ptrs_vr[stage]) {
+                accept = true;
+            } else if (kf < 0.0 || (us < 0.013 && V > us)) {
+                accept = false;
+            } else {
+                accept = (log(V) + a.ptrs_log_invalpha[stage] - log(pa / (us * us) + pb)) <=
+                         (-lam + kf * a.loglam[stage] - loggam(kf + 1.0));
+            }
+            if (accept) x[stage] = static_cast<int32_t>(kf);
+            done_stage = accept;
+        } else {
+            prod *= ds.next();
+            done_stage = !(prod > a.enlam[stage]);
+            if (!done_stage) x[stage] += 1;
+        }
+        if (done_stage) {
+            prod = 1.0;
+            ++stage;
+            while (stage < 4 && a.lam[stage] == 0.0) ++stage;
+        }
+    }
+    return make_int4(x[0], x[1], x[2], x[3]);
+}
+
 __device__ __forceinline__ int2 car_initial_state(const CarArgs& a, uint32_t g, uint64_t counter, uint32_t stream) {
     if (a.reset_mode == 1) return make_int2(a.max_cars / 2, a.max_cars / 2);
     const uint4 w = draw_block(a.seed, g, counter, stream);
@@ -322,6 +391,7 @@ __device__ __forceinline__ int2 car_initial_state(const CarArgs& a, uint32_t g, 
 }
 
 // One JacksCarRental transition of env g at step t from raw action `raw`; returns the reward.
+template <bool PTRS>
 __device__ __forceinline__ float car_transition(const CarArgs& a, uint32_t g, uint64_t t, int2& s, int32_t raw) {
     // _move_cars_and_calculate_cost (car_rental.py:54-74); the reference never validates the action
     const int32_t act = raw - a.max_move;
@@ -331,7 +401,7 @@ __device__ __forceinline__ float car_transition(const CarArgs& a, uint32_t g, ui
     const int32_t cost = mag * a.move_cost;
     // _simulate_rentals_and_returns (:76-104): requests A, requests B, returns A, returns B -- in that order
     DoubleStream ds(a.rk, g, t);
-    const int4 draws = poisson4(ds, a);
+    const int4 draws = PTRS ? poisson4_general(ds, a) : poisson4(ds, a);
     const int32_t rent_a = min(ca, draws.x), rent_b = min(cb, draws.y);
     const float rew = static_cast<float>((rent_a + rent_b) * a.credit - cost);
     s = make_int2(min(ca - rent_a + draws.z, a.max_cars), min(cb - rent_b + draws.w, a.max_cars));
@@ -340,6 +410,7 @@ __device__ __forceinline__ float car_transition(const CarArgs& a, uint32_t g, ui
 
 // Fused K-step rollout: one env per thread, state in registers for all K steps; `action` [K, n] or NULL (uniform random
 // action), `reward` [K, n] / `flags` [K, n] optional.  Episodes only end through the optional step limit.
+template <bool PTRS>
 __global__ void __launch_bounds__(kThreads) car_rental_rollout_kernel(const CarArgs a) {
     pdl_launch_dependents();
     pdl_wait();
@@ -358,7 +429,7 @@ __global__ void __launch_bounds__(kThreads) car_rental_rollout_kernel(const CarA
             const int32_t raw = a.action ? __ldg(a.action + o)
                                          : static_cast<int32_t>(__umulhi(group_word1(a.seed, g, t, kStreamPolicy),
                                                                          2u * static_cast<uint32_t>(a.max_move) + 1u));
-            const float rew = car_transition(a, g, t, s, raw);
+            const float rew = car_transition<PTRS>(a, g, t, s, raw);
             ret += rew;
             len += 1;
             const bool trunc = a.limit > 0 && len >= a.limit;
@@ -379,6 +450,7 @@ __global__ void __launch_bounds__(kThreads) car_rental_rollout_kernel(const CarA
     cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, static_cast<unsigned long long>(a.K));
 }
 
+template <bool PTRS>
 __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs a) {
     pdl_launch_dependents();
     pdl_wait();
@@ -395,7 +467,7 @@ __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs
         const int32_t raw = a.action ? __ldg(a.action + i)
                                      : static_cast<int32_t>(__umulhi(group_word1(a.seed, g, t, kStreamPolicy),
                                                                      2u * static_cast<uint32_t>(a.max_move) + 1u));
-        const float rew = car_transition(a, g, t, s, raw);
+        const float rew = car_transition<PTRS>(a, g, t, s, raw);
         ret += rew;
         len += 1;
         acc.steps += 1u;
@@ -442,14 +514,24 @@ __global__ void __launch_bounds__(kThreads) gambler_reset_kernel(int32_t start, 
     }
 }
 
+static bool uses_ptrs(const CarArgs& a) {
+    return a.lam[0] >= 10.0 || a.lam[1] >= 10.0 || a.lam[2] >= 10.0 || a.lam[3] >= 10.0;
+}
+
 static int fill_car_args(const ef_car_rental_params* p, CarArgs& a) {
     if (!p || p->max_cars < 0 || p->max_cars > (1 << 20) || p->max_move_cars < 0 || p->max_move_cars > (1 << 20))
         return EF_ERR_INVALID_ARGUMENT;
     for (int j = 0; j < 4; ++j) {
         if (!(p->lam[j] >= 0.0)) return EF_ERR_INVALID_ARGUMENT;
-        if (p->lam[j] >= 10.0) return EF_ERR_UNSUPPORTED;  // numpy switches to PTRS there; not implemented
+        if (p->lam[j] > 1.0e6) return EF_ERR_UNSUPPORTED;  // the draw must fit an int32 with room to spare
         a.lam[j] = p->lam[j];
         a.enlam[j] = p->exp_neg_lam[j];
+        a.loglam[j] = p->log_lam[j];
+        a.ptrs_a[j] = p->ptrs_a[j];
+        a.ptrs_b[j] = p->ptrs_b[j];
+        a.ptrs_log_invalpha[j] = p->ptrs_log_invalpha[j];
+        a.ptrs_vr[j] = p->ptrs_vr[j];
+        if (p->lam[j] >= 10.0 && !(p->ptrs_b[j] > 3.4 && p->ptrs_a[j] > 0.0)) return EF_ERR_INVALID_ARGUMENT;  // constants missing
     }
     a.max_cars = p->max_cars;
     a.max_move = p->max_move_cars;
@@ -532,7 +614,8 @@ extern "C" int ef_car_rental_step(const ef_car_rental_params* p, int32_t* state,
     a.final_obs = reinterpret_cast<int2*>(final_obs);
     a.stats = stats; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = autoreset;
     a.rk = philox_round_keys(seed);
-    return launch_kernel(car_rental_step_kernel, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
+    if (uses_ptrs(a)) return launch_kernel(car_rental_step_kernel<true>, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
+    return launch_kernel(car_rental_step_kernel<false>, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ef_car_rental_rollout(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,
@@ -548,7 +631,8 @@ extern "C" int ef_car_rental_rollout(const ef_car_rental_params* p, int32_t* sta
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags;
     a.stats = stats; a.clock = reinterpret_cast<unsigned long long*>(clock); a.n = n; a.autoreset = 1;
     a.rk = philox_round_keys(seed);
-    return launch_kernel(car_rental_rollout_kernel, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
+    if (uses_ptrs(a)) return launch_kernel(car_rental_rollout_kernel<true>, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
+    return launch_kernel(car_rental_rollout_kernel<false>, a, grid_for(n, 8), 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ef_car_rental_reset(const ef_car_rental_params* p, int32_t* state, int32_t* ep_len, float* ep_ret,

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header():
     assert _lib.GridDesc.table.offset == 40
     assert ctypes.sizeof(_lib.LabyrinthDesc) == 64 and _lib.LabyrinthDesc.grids.offset == 32
     assert ctypes.sizeof(_lib.GamblerParams) == 24 and _lib.GamblerParams.win_threshold.offset == 16
-    assert ctypes.sizeof(_lib.CarRentalParams) == 88 and _lib.CarRentalParams.lam.offset == 24
+    assert ctypes.sizeof(_lib.CarRentalParams) == 248 and _lib.CarRentalParams.lam.offset == 24
     assert ctypes.sizeof(_lib.PendulumParams) == 4 + 32 + 4 * 4 + 4 * 4 + 4 * 4 + 16  # 100 bytes
 
 

@@ -119,7 +119,10 @@ def test_gambler_reference_surface():
 # ---- JacksCarRental ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kw", [dict(), dict(max_cars=4, max_move_cars=2, request_lambda=[2, 2], return_lambda=[2, 2]),
                                 dict(max_cars=10, max_move_cars=3, request_lambda=[0, 9.5], return_lambda=[1, 0],
-                                     rental_credit=7, move_car_cost=3)], ids=["default", "small", "zero_lambda"])
+                                     rental_credit=7, move_car_cost=3),
+                                dict(max_cars=40, max_move_cars=5, request_lambda=[12, 4], return_lambda=[15.5, 0]),
+                                dict(max_cars=200, max_move_cars=20, request_lambda=[60, 10], return_lambda=[25, 133.3])],
+                         ids=["default", "small", "zero_lambda", "ptrs_mixed", "ptrs_all"])
 def test_car_rental_steps_match_oracle(kw):
     """Device step == reference step fed by the same Philox doubles (oracle pinned against the reference's own golden
     trajectories in tests/test_oracle_acml.py).  Exact: cars, rewards, counters."""
@@ -172,7 +175,7 @@ def test_car_rental_limit_reset_modes_and_host_path():
     before = b.state.clone()
     assert torch.equal(b.reset("bogus")[0], before)                                         # unknown option: untouched
     with pytest.raises(NotImplementedError):
-        VecJacksCarRental(4, request_lambda=[12, 3])
+        VecJacksCarRental(4, request_lambda=[2e6, 3])
 
 
 def test_car_rental_reference_surface_and_mdp():
@@ -226,11 +229,13 @@ def test_gambler_rollout_equals_step_sequence():
     assert sa["return_sum"] == sb["return_sum"]
 
 
-def test_car_rental_rollout_equals_step_sequence():
+@pytest.mark.parametrize("rates", [dict(), dict(request_lambda=[12, 4], return_lambda=[15.5, 0], max_cars=40)],
+                         ids=["default", "ptrs"])
+def test_car_rental_rollout_equals_step_sequence(rates):
     import torch
     from rl_envs_forge_b200 import VecJacksCarRental
     n, K, seed = 20_001, 12, 4
-    kw = dict(seed=seed, env_offset=64, episode_length_limit=5)
+    kw = dict(seed=seed, env_offset=64, episode_length_limit=5, **rates)
     a, b = VecJacksCarRental(n, **kw), VecJacksCarRental(n, **kw)
     acts = torch.randint(0, 11, (K, n), dtype=torch.int32, device="cuda")
     rew, flg = a.rollout(K, acts, return_rewards=True)
@@ -281,5 +286,7 @@ def test_empty_batches_are_noops_through_the_c_abi():
     cp = _lib.CarRentalParams()
     cp.max_cars, cp.max_move_cars = 20, 5
     assert lib.ef_car_rental_step(ctypes.byref(cp), fake, fake, fake, None, 0, 0, 0, *([None] * 7), 0, 1, None) == 0
-    cp.lam[1] = 12.0
+    cp.lam[1] = 12.0          # a rate in numpy's PTRS range needs its PTRS constants in the descriptor
+    assert lib.ef_car_rental_step(ctypes.byref(cp), fake, fake, fake, None, 0, 0, 0, *([None] * 7), 8, 1, None) == 1
+    cp.lam[1] = 2.0e6
     assert lib.ef_car_rental_step(ctypes.byref(cp), fake, fake, fake, None, 0, 0, 0, *([None] * 7), 8, 1, None) == 3   # unsupported

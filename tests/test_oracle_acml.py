@@ -9,7 +9,7 @@ from oracle import acml as OA
 from tests._golden import golden_files, load
 
 
-@pytest.mark.parametrize("lam", [0.0, 0.3, 1.0, 2.0, 3.0, 4.0, 9.5, 9.999])
+@pytest.mark.parametrize("lam", [0.0, 0.3, 1.0, 2.0, 3.0, 4.0, 9.5, 9.999, 10.0, 10.5, 12.5, 37.0, 100.0, 999.0, 1e5])
 def test_legacy_poisson_bit_exact_vs_numpy(lam):
     ref = np.random.RandomState(99)
     src = OA.MTDoubles(np.random.RandomState(99))
@@ -18,13 +18,26 @@ def test_legacy_poisson_bit_exact_vs_numpy(lam):
     assert ref.random_sample() == src.double()          # both streams consumed the same number of doubles
 
 
+def test_legacy_poisson_mixed_rates_share_one_stream():
+    """Multiplication-method and PTRS draws interleaved on one generator, the way one JacksCarRental step mixes them."""
+    ref = np.random.RandomState(4)
+    src = OA.MTDoubles(np.random.RandomState(4))
+    for _ in range(1500):
+        for lam in (12.0, 4.0, 15.5, 0.0, 3.0, 250.0):
+            assert int(ref.poisson(lam)) == OA.legacy_poisson(src, lam)
+    assert ref.random_sample() == src.double()
+    for x in (1.0, 2.0, 3.0, 6.5, 7.0, 12.0, 400.0):
+        import math
+        assert OA.random_loggam(x) == pytest.approx(math.lgamma(x), rel=1e-10, abs=1e-12)
+
+
 def test_scipy_poisson_rvs_is_the_global_legacy_stream():
     """car_rental.py:89-92 calls scipy.stats.poisson.rvs: it must draw from np.random's global RandomState."""
     from scipy.stats import poisson
     np.random.seed(5)
-    got = [int(poisson.rvs(lam)) for lam in (3, 4, 3, 2) * 50]
+    got = [int(poisson.rvs(lam)) for lam in (3, 4, 3, 2, 14, 30.5) * 50]
     src = OA.MTDoubles(np.random.RandomState(5))
-    assert got == [OA.legacy_poisson(src, lam) for lam in (3, 4, 3, 2) * 50]
+    assert got == [OA.legacy_poisson(src, lam) for lam in (3, 4, 3, 2, 14, 30.5) * 50]
 
 
 @pytest.mark.parametrize("path", golden_files("gambler"), ids=lambda p: p.split("gambler_")[-1][:-4])
@@ -65,8 +78,9 @@ def test_car_rental_golden(path):
         assert state == tuple(int(x) for x in post) and reward == int(r)
 
 
-def test_car_rental_engine_vec_equals_scalar():
-    p = OA.CarRentalParams(max_cars=20, max_move_cars=5, request_lambda=(3, 4), return_lambda=(3, 2))
+@pytest.mark.parametrize("lams", [((3, 4), (3, 2)), ((12, 4), (15.5, 0)), ((40, 10), (25, 33.3))])
+def test_car_rental_engine_vec_equals_scalar(lams):
+    p = OA.CarRentalParams(max_cars=20, max_move_cars=5, request_lambda=lams[0], return_lambda=lams[1])
     rng = np.random.default_rng(1)
     n = 400
     g = np.arange(1000, 1000 + n)
