@@ -108,3 +108,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_header_is_plain_c_and_the_c_host_links(lib, tmp_path):
+    """include/envforge_b200.h must compile as C11 (no C++ / torch types in the signatures), and the plain-C host of the ABI
+    (tests/c/abi_host.c, run on the GPU box by tests/test_gpu_c_abi_host.py) must build and link against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "envforge_b200.h"\nint main(void) { return sizeof(ef_grid_desc) == 48 && sizeof(ef_arm64) == 24 '
+                   '&& sizeof(ef_gridworld_step_args) == 160 && sizeof(ef_car_rental_params) == 248 ? 0 : 1; }\n')
+    exe = tmp_path / "hdr"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o",
+                    str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+    assert ctypes.sizeof(_lib.GridStepArgs) == 160
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert os.path.exists(os.path.join(ROOT, "tests", "c", "abi_host"))
