@@ -141,30 +141,14 @@ class VecKArmedBandit(VecEnv):
             self._init_mt19937()
 
     # -- stream-exact mode: per-env numpy RandomState ---------------------------------------------------------------------
-    def _mt_seeds(self):
-        if self._seed_list is not None:
-            seeds = self._seed_list
-        else:
-            base = (self._seed & 0xFFFFFFFF) if self.seed is None else int(self.seed)
-            seeds = [base + self.env_offset + i for i in range(self.num_envs)]
-        for s in seeds:
-            if s < 0 or s > 0xFFFFFFFF:
-                raise ValueError("Seed must be between 0 and 2**32 - 1")     # numpy's own message (RandomState(seed))
-        return seeds
-
     def _init_mt19937(self):
         """Seed every env's generator with numpy itself and draw its default means (`randn(k)`, :162) -- what
         `KArmedBandit.__init__` / `reset` do (:145, :215) -- then move the generator state to the device."""
-        torch, n, k = self._torch, self.num_envs, self.k
-        key = np.empty((624, n), np.uint32)
-        pos, has_gauss = np.empty(n, np.int32), np.empty(n, np.int32)
-        gauss, means = np.empty(n, np.float64), np.empty((n, k), np.float64)
-        for i, s in enumerate(self._mt_seeds()):
-            rs = np.random.RandomState(s)
-            means[i] = rs.randn(k)
-            st = rs.get_state()
-            key[:, i], pos[i], has_gauss[i], gauss[i] = st[1], st[2], st[3], st[4]
-        dev = self.device
+        from . import mt19937
+        torch, dev = self._torch, self.device
+        base = (self._seed & 0xFFFFFFFF) if self.seed is None else int(self.seed)
+        seeds = mt19937.env_seeds(base, self._seed_list, self.env_offset, self.num_envs)
+        key, pos, has_gauss, gauss, means = mt19937.initial_state(seeds, self.k)
         self._mt_key = torch.from_numpy(key.view(np.int32)).to(dev)
         self._mt_pos = torch.from_numpy(pos).to(dev)
         self._mt_has_gauss = torch.from_numpy(has_gauss).to(dev)
