@@ -195,7 +195,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -230,32 +230,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------ our arm
-def _time_region(torch, dist, world, fn):
-    """barrier + synchronize on both sides, CUDA events on the launching stream; returns (max-over-ranks ms, (t0, t1))."""
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    start.record()
-    fn()
-    end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    w1 = time.perf_counter()
-    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return float(ms.item()), (w0, w1)
-
-
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from rl_envs_forge_b200 import VecGamblersProblem, VecGridWorldLayouts, VecJacksCarRental, VecLabyrinth
-    from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandit, VecPendulumDisk, all_reduce_stats
+    from rl_envs_forge_b200 import Action, VecCartPole, VecGridWorld, VecKArmedBandit, VecPendulumDisk
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -289,6 +269,13 @@ def run_ours(args):
             os.close(saved_stdout)
     n, R, K, W = args.envs_per_gpu, args.sets, args.steps, args.warmup
     seed = 20261019
+    from rl_envs_forge_b200 import StatsReducer, _lib as ef_lib
+    if os.environ.get("ENVFORGE_LIB") and not args.allow_variant:
+        raise SystemExit("bench.py: ENVFORGE_LIB selects a tuning variant of the library; pass --allow-variant to time it "
+                         "(the line records the library path and hash either way)")
+    import hashlib
+    with open(ef_lib.LIB_PATH, "rb") as f:
+        lib_sha = hashlib.sha256(f.read()).hexdigest()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     spec = {(SPECIAL[0], Action(SPECIAL[1])): (SPECIAL[2], SPECIAL[3])}
@@ -301,7 +288,7 @@ def run_ours(args):
     # fresh action every step (a fixed action per env would pin agents against walls / on the rejected cell)
     A = args.action_buffers
     acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda") for _ in range(A)]
-    G = R * A  # launches per captured graph: every (set, action buffer) pairing once
+    G = R * A  # launches per "round" graph: every (set, action buffer) pairing once
 
     def direct(i):
         sets[i % R].step(acts[i % A])
@@ -309,11 +296,12 @@ def run_ours(args):
     for i in range(G):   # un-timed: module load, allocator
         direct(i)
     torch.cuda.synchronize()
-    # one CUDA graph = one round over the R env sets; the tail graph covers K % R launches
+    # The K launches of a timed window = (K // G) replays of the "round" graph + ONE replay of the "tail" graph (K % G
+    # launches).  Warm-up replays exactly these graphs, so no first-replay (instantiation upload) cost can land in a window.
     stream = torch.cuda.Stream()
     graphs = {}
     with torch.cuda.stream(stream):
-        for name, count in (("round", G), ("tail", K % G)):
+        for name, count in (("round", G if K >= G else 0), ("tail", K % G)):
             if count == 0:
                 continue
             g = torch.cuda.CUDAGraph()
@@ -323,51 +311,150 @@ def run_ours(args):
             graphs[name] = g
     torch.cuda.synchronize()
 
-    def launch_k(k):
-        for _ in range(k // G):
+    def launch_window():
+        for _ in range(K // G):
             graphs["round"].replay()
-        if k % G:
-            if k % G == K % G and "tail" in graphs:
-                graphs["tail"].replay()
-            else:
-                for i in range(k % G):
-                    direct(i)
+        if K % G:
+            graphs["tail"].replay()
 
-    launch_k(max(W, 3))  # W warm-up steps (>= 3)
+    # Episode statistics: one fold kernel per window on the stepping stream; for N > 1 the cross-GPU sum of the folded
+    # vector (the engine's only collective) runs on a side stream, overlapped with the window's launches: a window starts
+    # the exchange of the vector folded at the end of the previous window and waits for it (stream-side) at its own end.
+    red = StatsReducer(sets, transport=args.stats_transport)
+    red.fold()
+    red.exchange_async()        # pre-warm the exchange path (NCCL communicator / peer mailboxes) before anything is timed
+    red.wait()
     torch.cuda.synchronize()
-    before = sum(e.stats[4] for e in sets).clone()
-    tot = torch.zeros(8, dtype=torch.float64, device="cuda")
 
-    def timed():
-        launch_k(K)
-        if world > 1:  # the engine's only collective: sum of the episode statistics (64 B) over NVLink
-            tot.copy_(sum(e.stats for e in sets))
-            all_reduce_stats(tot)
+    def window_body():
+        if world > 1:
+            red.exchange_async()
+        launch_window()
+        red.fold()
+        if world > 1:
+            red.wait()
 
-    ms, win_main = _time_region(torch, dist, world, timed)
-    after = sum(e.stats[4] for e in sets).clone()
-    steps_done = after - before
+    warm_windows = max(2, -(-max(W, 3) // K))     # >= W warm-up steps, and every graph replayed at least twice
+    for _ in range(warm_windows):
+        window_body()
+    torch.cuda.synchronize()
+
+    def steps_so_far():
+        return float(red.fold()[4].item())
+
+    # n_windows timed windows of EXACTLY K launches each, every one bracketed by barrier + synchronize on both sides and
+    # timed with CUDA events on the launching stream; the MEDIAN window is reported (all are listed).  A short spin kernel
+    # ahead of the start event lets the host enqueue the window while the GPU is still busy, so a 20-launch window measures
+    # the device's steady-state pace (what a --steps 100000 run measures) rather than the host's enqueue latency.
+    n_windows = max(1, args.windows if K * 1e-5 * args.windows < 30.0 else 3)
+    preroll_cycles = int(args.preroll_us * 1e-6 * 1.9e9)
+    win_ms, win_steps, spans = [], [], []
+    for _ in range(n_windows):
+        s0 = steps_so_far()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        if preroll_cycles > 0:
+            torch.cuda._sleep(preroll_cycles)
+        ev0.record()
+        window_body()
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        spans.append((w0, time.perf_counter()))
+        win_ms.append(ev0.elapsed_time(ev1))
+        win_steps.append(steps_so_far() - s0)
+    t_ms = torch.tensor(win_ms, dtype=torch.float64, device="cuda")
+    t_steps = torch.tensor(win_steps, dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(steps_done)
-    env_steps = float(steps_done.item())
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)      # per window: the slowest rank
+        dist.all_reduce(t_steps)                         # per window: env-steps of all ranks
+    win_ms, win_steps = t_ms.tolist(), t_steps.tolist()
+    order = sorted(range(n_windows), key=lambda i: win_ms[i])
+    mid = order[n_windows // 2]
+    ms = win_ms[mid]
+    env_steps = win_steps[mid]
     value = env_steps / (ms * 1e-3)
     launch_us = ms * 1e3 / K
+    win_main = (spans[0][0], spans[-1][1])
+
+    # the collective alone (not overlapped), for the record: fold + exchange + wait, CUDA events, after warm-up
+    collective_us = None
+    if world > 1:
+        for _ in range(5):
+            red.reduce()
+        dist.barrier()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(50):
+            red.fold()
+            red.exchange_async()
+            red.wait()
+        c1.record()
+        torch.cuda.synchronize()
+        cu = torch.tensor([c0.elapsed_time(c1) * 1e3 / 50], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cu, op=dist.ReduceOp.MAX)
+        collective_us = float(cu.item())
+        red.check()
+    # sharding invariance on hardware: a FRESH env set per rank, global env indices [rank * n_inv, (rank + 1) * n_inv) of a
+    # 2^23-env population, the same seed and step count whatever the number of ranks -> the all-reduced INTEGER statistics
+    # must be identical in the N = 1 / 2 / 4 / 8 lines (instances are independent, grid_world.py:495-528)
+    n_inv = (1 << 23) // world
+    inv_env = VecGridWorld(n_inv, seed=seed + 7, special_transitions=spec, env_offset=rank * n_inv, **CONFIG2)
+    inv_env.rollout(64)
+    inv_red = StatsReducer([inv_env], transport=args.stats_transport)
+    inv_tot = inv_red.reduce().tolist()
+    torch.cuda.synchronize()
+    inv_red.check()
+    sharding_invariant = {"envs_total": n_inv * world, "steps": 64, "seed": seed + 7, "episodes": int(inv_tot[0]),
+                          "length_sum": int(inv_tot[1]), "env_steps": int(inv_tot[4]), "return_sum": inv_tot[2],
+                          "note": "integer entries must not depend on n_gpus"}
+    inv_red.close()
+    del inv_env, inv_red
+
+    # clocks under the same load: the timed windows are far shorter than any sampling period, so the same graphs are
+    # replayed back to back for ~0.4 s right after them while nvidia-smi keeps sampling
+    probe0 = time.perf_counter()
+    reps = max(1, int(0.4 / max(ms * 1e-3, 1e-6)))
+    for _ in range(min(reps, 4000)):
+        launch_window()
+    torch.cuda.synchronize()
+    win_probe = (probe0, time.perf_counter())
+
     peak, peak_src = _peaks()
     achieved = GRID_BYTES_PER_STEP * n / (launch_us * 1e-6) / 1e9
     err_count = int(sum(int(e.err[0].item()) & 0xFFFFFFFF for e in sets))
+    stats_total = red.reduce().tolist()
+    torch.cuda.synchronize()
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warm_windows * K,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": n * world, "env_sets": R, "action_buffers": A,
                    "l2": f"inputs larger than L2: {R} rotating env sets x {(34 if sets[0]._packed else 42) * n / 1e6:.0f} MB",
-                   "launch": "CUDA graph replay of VecGridWorld.step (device step clock)", "actions": "resident in HBM",
-                   "rejected_env_steps": err_count, "parallelism": f"env-sharded x{world}"},
-        "gpu_launches": K,
+                   "launch": "CUDA graph replay of VecGridWorld.step (device step clock); warm-up replays the same graphs",
+                   "actions": "resident in HBM", "rejected_env_steps": err_count, "parallelism": f"env-sharded x{world}",
+                   "timed": f"{n_windows} windows of exactly {K} launches, median window reported",
+                   "preroll_us": args.preroll_us,
+                   "preroll": "a spin kernel AHEAD of the start event; the host enqueues the window while it runs"},
+        "windows_ms": win_ms, "windows_us_per_step": [w * 1e3 / K for w in win_ms],
+        "gpu_launches": K + 1 + (1 if world > 1 and red.transport == "peer" else 0),
+        "lib": {"path": os.path.relpath(ef_lib.LIB_PATH, ROOT), "sha256": lib_sha,
+                "variant": bool(os.environ.get("ENVFORGE_LIB"))},
+        "collective": {"what": "sum over ranks of the 64-byte episode-statistics vector, once per window, inside the timed "
+                               "region on a side stream (overlapped with the window's launches)",
+                       "transport": red.transport, "collective_us": collective_us,
+                       "collective_us_note": "fold + exchange + wait timed alone (not overlapped), max over ranks"},
+        "episode_stats_total": {"episodes": int(stats_total[0]), "env_steps": int(stats_total[4])},
+        "sharding_invariant": sharding_invariant,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic("gridworld_step_kernel"), "peak_source": peak_src,
-                     "kernel": "ef::gridworld_step_kernel<SMEM=true,SLOTS=4,Q=4,MINBLOCKS=2,PACKED=true,FAST=true>",
+                     "kernel": _traffic("_kernel") or "ef::gridworld_step_kernel",
                      "traffic_note": _traffic("_note"), "algorithmic_bytes_per_launch": GRID_BYTES_PER_STEP * n,
                      "moved_bytes_per_launch": (34 if sets[0]._packed else 42) * n,
                      "moved_note": "bytes the kernel's own layout moves: the packed state word (cell | episode counter << 16) "
@@ -604,21 +691,29 @@ def run_ours(args):
         # ---- BASELINE configs[4]: 64M envs in total, sharded over the ranks, fused K=64 rollouts with the in-kernel policy and
         # one all-reduce of the episode statistics per rollout (the engine's only collective) inside the timed region
         n5 = (1 << 26) // world
-        tot5 = torch.zeros(8, dtype=torch.float64, device="cuda")
         for key, make in (("config5_gridworld_rollout_K64_64M_envs_total",
                            lambda: VecGridWorld(n5, seed=seed, special_transitions=spec, env_offset=rank * n5, **CONFIG2)),
                           ("config5_cartpole_rollout_K64_64M_envs_total",
                            lambda: VecCartPole(n5, seed=seed, env_offset=rank * n5))):
             e5 = make()
+            r5 = StatsReducer([e5], transport=args.stats_transport)
 
             def roll5():
                 e5.rollout(Kr)
-                tot5.copy_(e5.stats)
-                all_reduce_stats(tot5)
+                r5.fold()
+                r5.exchange_async()     # side stream: overlaps the next rollout
+                r5.wait()
             sec = ev_time(roll5, 3)
+            tot5 = r5.reduce().tolist()  # 4 rollouts x 64 steps of the same 2^26 global envs whatever the number of ranks
+            torch.cuda.synchronize()
+            r5.check()
             details[key] = {"env_steps_per_s": n5 * Kr / sec, "envs": n5, "envs_total": n5 * world, "ms_per_rollout": sec * 1e3,
-                            "collective": "all-reduce(sum) of 8 doubles per rollout" if world > 1 else "none (1 rank)"}
-            del e5
+                            "collective": f"sum of 8 doubles per rollout ({r5.transport})" if world > 1 else "none (1 rank)",
+                            "stats_after_4_rollouts": {"episodes": int(tot5[0]), "length_sum": int(tot5[1]),
+                                                       "env_steps": int(tot5[4]),
+                                                       "note": "integer entries must not depend on n_gpus"}}
+            r5.close()
+            del e5, r5
         if world > 1:
             for v in details.values():
                 t = torch.tensor([v["env_steps_per_s"]], dtype=torch.float64, device="cuda")
@@ -636,8 +731,11 @@ def run_ours(args):
     if sampler is not None:
         time.sleep(0.06)
         sampler.stop()
-        line["clocks"] = sampler.summary([win_main, win_e2e])
-        line["clocks"]["in_timed_region"] = sum(1 for ts, _ in sampler.samples if win_main[0] <= ts <= win_main[1])
+        line["clocks"] = sampler.summary([win_main, win_probe, win_e2e])
+        line["clocks"]["in_timed_windows"] = sum(1 for ts, _ in sampler.samples if win_main[0] <= ts <= win_main[1])
+        line["clocks"]["in_load_probe"] = sum(1 for ts, _ in sampler.samples if win_probe[0] <= ts <= win_probe[1])
+        line["clocks"]["note"] = ("nvidia-smi every 20 ms over the timed windows, a ~0.4 s back-to-back replay of the same "
+                                  "graphs right after them (load probe) and the e2e windows")
 
     # ---- CPU baseline (rank 0, N = 1 only): the reference-style per-instance loop on the host cores, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -669,6 +767,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=60)
     ap.add_argument("--e2e-windows", type=int, default=30)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--windows", type=int, default=7, help="timed windows of --steps launches each (median reported)")
+    ap.add_argument("--preroll-us", type=float, default=300.0,
+                    help="spin kernel ahead of each window's start event (0 = none): host enqueue overlaps it")
+    ap.add_argument("--stats-transport", choices=["auto", "peer", "nccl"], default="auto")
+    ap.add_argument("--allow-variant", action="store_true", help="accept a library selected with ENVFORGE_LIB")
     ap.add_argument("--no-details", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

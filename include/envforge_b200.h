@@ -9,7 +9,8 @@
  * Conventions
  *   - Plain C types only.  Every buffer is DEVICE memory (pinned host memory for the h_ arguments of the *_step_host
  *     entry points) owned by the caller (PyTorch in the shipped host code);
- *     the library never allocates, frees or retains device memory and keeps no global state.  Descriptor structs
+ *     the library never allocates, frees or retains device memory and keeps no global state (one exception, stated
+ *     where it is declared: the 1 KB peer mailbox of ef_peer_comm).  Descriptor structs
  *     (ef_grid_desc, ef_pendulum_params, ef_bandit_desc) are small HOST structs passed by pointer and copied into
  *     kernel parameters; pointers inside them are device pointers.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous and
@@ -17,7 +18,7 @@
  *     call (the caller's current device).
  *   - Return value: EF_OK (0) or an ef_status code; never throws, never exits.  `ef_status_string` names a code.
  *   - Global env index g = env_offset + i (must stay < 2^32).  All in-kernel randomness is Philox4x32-10 with
- *     key = seed and counter = (g, 64-bit counter, stream id | block << 8); see csrc/philox.cuh.  Results therefore
+ *     key = seed and counter = (g, 64-bit counter, stream id | block << 8); see csrc/ef_common.cuh (twin: oracle/philox.py).  Results therefore
  *     do not depend on how envs are sharded over launches, ranks or GPUs.
  *   - `stats` (nullable) points at EF_STATS_REPLICAS x EF_STATS_STRIDE doubles that the kernels ADD to (atomically).
  *     Replica r lives at stats + r * EF_STATS_STRIDE; a CTA adds into replica (blockIdx.x % EF_STATS_REPLICAS) so that
@@ -445,6 +446,36 @@ int ef_labyrinth_reset(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_
  * (count, sum len, sum ret, sum ret^2) -- complements `stats`, which only sees finished episodes.
  * ------------------------------------------------------------------------------------------------------------ */
 int ef_episode_stat_reduce(const int32_t* ep_len, const float* ep_ret, double* out, int64_t n, void* stream);
+
+/* Fold the replicated `stats` accumulators of up to EF_STATS_MAX_SETS env sets into ONE vector:
+ *     out[f] = sum over sets s, replicas r of raw_sets[s][r * EF_STATS_STRIDE + f],   f < EF_STATS_LEN,
+ * in a fixed order (bit-reproducible).  `raw_sets` is a HOST array of n_sets DEVICE pointers (copied into the kernel
+ * parameters); `out` is EF_STATS_LEN device doubles.  One tiny CTA, stream-ordered, capturable in a CUDA graph -- this is
+ * what feeds the cross-GPU sum of the episode statistics (the engine's only collective). */
+#define EF_STATS_MAX_SETS 32
+int ef_stats_fold(const double* const* raw_sets, int32_t n_sets, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Cross-GPU sum of the statistics vector over NVLink peer memory, fused with the fold above (one kernel: fold the
+ * local replicas, store the 64-byte result into every peer's mailbox, wait for the peers' vectors, add them in rank
+ * order).  One process per GPU; every rank creates a comm, the 64-byte IPC handles are exchanged by the caller
+ * (torch.distributed all_gather in the shipped host code), then every rank connects.  The mailbox (world * 2 slots of
+ * 128 bytes) is the ONE piece of device memory this library allocates itself: it must be a cudaMalloc allocation of
+ * its own to be exportable with cudaIpcGetMemHandle.
+ *   ef_stats_fold_allreduce  out_local (nullable) receives this rank's folded vector, out_global the sum over ranks --
+ *                            bit-identical on every rank (same order of additions).  n_sets == 0 (raw_sets ignored): the
+ *                            vector was folded earlier by ef_stats_fold and out_local is the INPUT; this is how the
+ *                            exchange runs on a side stream while the stepping stream goes on.  Collective: every rank must launch it
+ *                            the same number of times.  A peer that does not show up within ~2 s makes the kernel give up
+ *                            and set status[0] (device uint32, nullable) to 1 instead of hanging the GPU.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define EF_PEER_HANDLE_BYTES 64
+typedef struct ef_peer_comm ef_peer_comm;
+int ef_peer_comm_create(int32_t rank, int32_t world, ef_peer_comm** comm, uint8_t* handle_out);
+int ef_peer_comm_connect(ef_peer_comm* comm, const uint8_t* all_handles);   /* world * EF_PEER_HANDLE_BYTES, rank-major */
+int ef_peer_comm_destroy(ef_peer_comm* comm);
+int ef_stats_fold_allreduce(ef_peer_comm* comm, const double* const* raw_sets, int32_t n_sets, double* out_local,
+                            double* out_global, uint32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Host-buffer step: the call a host-side actor makes once per step (the reference's `env.step(action)` with the

@@ -14,5 +14,6 @@ from .pendulum_disk import VecPendulumDisk  # noqa: F401
 from .acml import VecGamblersProblem, VecJacksCarRental  # noqa: F401
 from .labyrinth import VecLabyrinth  # noqa: F401
 from .vec_env import all_reduce_stats, shard_range, stats_to_dict  # noqa: F401
+from .stats import StatsReducer, fold_stats  # noqa: F401
 
 __version__ = "0.1.0"

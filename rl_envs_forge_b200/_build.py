@@ -12,7 +12,7 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libenvforge_b200.so")
-SOURCES = ["capi.cu", "gridworld.cu", "pendulums.cu", "bandit.cu", "bandit_mt19937.cu", "acml.cu", "labyrinth.cu", "hostpipe.cu"]
+SOURCES = ["capi.cu", "stats.cu", "gridworld.cu", "pendulums.cu", "bandit.cu", "bandit_mt19937.cu", "acml.cu", "labyrinth.cu", "hostpipe.cu"]
 HEADERS = ["ef_common.cuh", os.path.join("..", "..", "include", "envforge_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-Xcompiler", "-fPIC", "-cudart", "static"]

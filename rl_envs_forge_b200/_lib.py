@@ -14,6 +14,8 @@ EF_STATS_LEN = 8
 EF_STATS_REPLICAS = 32
 EF_STATS_STRIDE = 16
 EF_ERR_LEN = 4
+EF_STATS_MAX_SETS = 32
+EF_PEER_HANDLE_BYTES = 64
 EF_ABI_VERSION = 1
 EF_WIRE_U8 = 0x1
 
@@ -114,6 +116,11 @@ SIGNATURES = {
     "ef_bandit_step_mt19937": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _U64, _P, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_default_means": (C.c_int, [_I32, _U64, _U64, _P, _I64, _P]),
     "ef_episode_stat_reduce": (C.c_int, [_P, _P, _P, _I64, _P]),
+    "ef_stats_fold": (C.c_int, [C.POINTER(C.c_void_p), _I32, _P, _P]),
+    "ef_peer_comm_create": (C.c_int, [_I32, _I32, C.POINTER(C.c_void_p), _P]),
+    "ef_peer_comm_connect": (C.c_int, [_P, _P]),
+    "ef_peer_comm_destroy": (C.c_int, [_P]),
+    "ef_stats_fold_allreduce": (C.c_int, [_P, C.POINTER(C.c_void_p), _I32, _P, _P, _P, _P]),
     "ef_gambler_step": (C.c_int, [C.POINTER(GamblerParams), _P, _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
                                   _P, _P, _I64, _I32, _P]),
     "ef_gambler_rollout": (C.c_int, [C.POINTER(GamblerParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _P,

@@ -204,8 +204,10 @@ class VecEnv:
     # -- statistics / errors ---------------------------------------------------------------------------------------
     @property
     def stats(self):
-        """float64 [EF_STATS_LEN] device tensor: the statistics vector (sum over the replicas the kernels add into)."""
-        return self._stats_raw.view(_lib.EF_STATS_REPLICAS, _lib.EF_STATS_STRIDE)[:, :_lib.EF_STATS_LEN].sum(dim=0)
+        """float64 [EF_STATS_LEN] device tensor: the statistics vector (sum over the replicas the kernels add into),
+        folded by one `ef_stats_fold` launch on the current stream (fixed order of additions: bit-reproducible)."""
+        from .stats import fold_stats
+        return fold_stats([self])
 
     def episode_stats(self, all_reduce=False, reset=False):
         """Finished-episode statistics accumulated on device since construction (or the last reset=True call).
@@ -213,7 +215,7 @@ class VecEnv:
         all_reduce=True sums them over the ranks of the default process group first (one NCCL all-reduce of 64 B)."""
         vec = self.stats
         if all_reduce:
-            all_reduce_stats(vec)
+            all_reduce_stats(vec)   # blocking convenience form; StatsReducer keeps the exchange off the stepping stream
         if reset:
             self._stats_raw.zero_()
         return stats_to_dict(vec.cpu().tolist())
@@ -221,8 +223,9 @@ class VecEnv:
     def running_episode_stats(self):
         """(count, mean length, mean return) over the episodes currently in flight (device reduction)."""
         out = self._torch.zeros(_lib.EF_STATS_REPLICAS * _lib.EF_STATS_STRIDE, dtype=self._torch.float64, device=self.device)
-        self._call(self._lib.ef_episode_stat_reduce, _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), _lib.ptr(out),
-                   self.num_envs)
+        ln = self.ep_len   # a computed temporary in the packed GridWorld layout: keep it alive across the launch
+        self._call(self._lib.ef_episode_stat_reduce, _lib.ptr(ln), _lib.ptr(self.ep_ret), _lib.ptr(out), self.num_envs)
+        del ln
         out = out.view(_lib.EF_STATS_REPLICAS, _lib.EF_STATS_STRIDE)[:, :_lib.EF_STATS_LEN].sum(dim=0)
         return stats_to_dict(out.cpu().tolist())
 
