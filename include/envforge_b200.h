@@ -144,10 +144,13 @@ typedef struct ef_gridworld_step_args {
     uint64_t* clock;
     int64_t n;
     int32_t autoreset;
-    int32_t wire;     /* 0: int32 action / obs / final_obs;  EF_WIRE_U8: they point at uint8 data (ef_gridworld_step_u8) */
+    int32_t wire;     /* bit set: EF_WIRE_U8 = action / obs / final_obs point at uint8 data (ef_gridworld_step_u8);
+                         EF_WIRE_HOST_IO = some input / output buffer is PINNED HOST memory (the plain entry points find
+                         that out with cudaPointerGetAttributes; this struct call trusts the flag) */
     void* stream;
 } ef_gridworld_step_args;
 #define EF_WIRE_U8 0x1
+#define EF_WIRE_HOST_IO 0x2
 int ef_gridworld_step_v(const ef_gridworld_step_args* args);
 
 /* ef_gridworld_step in the NARROW WIRE FORMAT of a host-side actor loop: actions are uint8 [n] (values > 3 are rejected

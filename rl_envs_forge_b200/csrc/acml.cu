@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(kThreads) gambler_step_kernel(const GamblerArg
     pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
-    const uint64_t t = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t = a.t + clock_begin(a.clock, ticket);
     const bool policy = a.action == nullptr;
     if constexpr (VEC) {
         const int64_t quads = a.n >> 2;
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(kThreads) gambler_rollout_kernel(const Gambler
     pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
-    const uint64_t t0 = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t0 = a.t + clock_begin(a.clock, ticket);
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t quads = (a.n + 3) / 4;
     for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < quads; v += stride) {
@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(kThreads) car_rental_rollout_kernel(const CarA
     pdl_launch_dependents();
     pdl_wait();
     EpisodeAcc acc;
-    const uint64_t t0 = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t0 = a.t + clock_begin(a.clock, ticket);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(kThreads) car_rental_step_kernel(const CarArgs
     pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
-    const uint64_t t = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t = a.t + clock_begin(a.clock, ticket);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);

@@ -83,6 +83,27 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
+// The same in two steps, for several copies completing on one barrier: arm it with the total, then issue the copies.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Shared -> global bulk store (bulk-group completion).  The shared-memory bytes were written through the generic proxy:
+// the writers fence (fence_proxy_async) and synchronise with the issuing thread before it calls bulk_s2g.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     do {
@@ -252,12 +273,27 @@ struct ErrorAcc {
 // clock[0] = steps already taken, clock[1] = CTA ticket.  Every CTA reads clock[0] when it starts and then takes a
 // ticket; the CTA holding the last ticket knows every CTA has read the clock and advances it (in the epilogue).  The
 // ticket atomic is issued early so its round trip overlaps the CTA's loads; no fence is needed because a completed load
-// cannot be affected by the later write.
+// cannot be affected by the later write.  Within a CTA only thread 0 touches the clock (clock_begin below).
 __device__ __forceinline__ uint64_t clock_read(const unsigned long long* clock) {
     return clock ? *reinterpret_cast<const volatile unsigned long long*>(clock) : 0ull;
 }
 __device__ __forceinline__ unsigned long long clock_ticket(unsigned long long* clock) {
     return (clock != nullptr && threadIdx.x == 0) ? atomicAdd(&clock[1], 1ull) : 0ull;
+}
+// What the kernels call (every thread of the CTA, `clock` is launch-uniform): thread 0 reads the clock and THEN takes the
+// CTA's ticket; the value reaches the other threads through shared memory behind one barrier.  No other warp reads the
+// clock itself, so none can observe it after the last ticket holder has advanced it (a warp delayed past its own CTA's
+// ticket could otherwise draw with t + 1).  `ticket` is meaningful in thread 0 only, which is the thread cta_epilogue uses.
+__device__ __forceinline__ uint64_t clock_begin(unsigned long long* clock, unsigned long long& ticket, bool take_ticket = true) {
+    __shared__ unsigned long long s_clock_value;
+    ticket = 0ull;
+    if (clock == nullptr) return 0ull;
+    if (threadIdx.x == 0) {
+        s_clock_value = clock_read(clock);
+        if (take_ticket) ticket = clock_ticket(clock);
+    }
+    __syncthreads();
+    return s_clock_value;
 }
 
 constexpr int kWarpsPerCta = kThreads / 32;

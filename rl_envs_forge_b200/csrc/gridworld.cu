@@ -137,17 +137,9 @@ __device__ __forceinline__ void store_obs4(const GridArgs& a, int32_t* obs, int6
     } else {
         int4* o = reinterpret_cast<int4*>(obs + 2 * base);
         const int2 o0 = cell_to_obs(a, pos[0]), o1 = cell_to_obs(a, pos[1]);
-#if EF_STREAMING
-        __stcs(o, make_int4(o0.x, o0.y, o1.x, o1.y));
-#else
         o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
-#endif
         const int2 o2 = cell_to_obs(a, pos[2]), o3 = cell_to_obs(a, pos[3]);
-#if EF_STREAMING
-        __stcs(o + 1, make_int4(o2.x, o2.y, o3.x, o3.y));
-#else
         o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
-#endif
     }
 }
 
@@ -317,12 +309,6 @@ template <bool PACKED, bool FAST, bool HET = false, bool W8 = false>
 __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, bool philox_act) {
     QuadIn in;
     if constexpr (HET) in.y4 = a.layout ? __ldg(reinterpret_cast<const int4*>(a.layout + base)) : make_int4(0, 0, 0, 0);
-#if EF_STREAMING
-    in.p4 = __ldcs(reinterpret_cast<const int4*>(a.pos + base));
-    in.l4 = PACKED ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.ep_len + base));
-    in.r4 = __ldcs(reinterpret_cast<const float4*>(a.ep_ret + base));
-    in.a4 = philox_act ? make_int4(0, 0, 0, 0) : __ldcs(reinterpret_cast<const int4*>(a.action + base));
-#else
     in.p4 = *reinterpret_cast<const int4*>(a.pos + base);
     if constexpr (PACKED) in.l4 = make_int4(0, 0, 0, 0);
     else in.l4 = *reinterpret_cast<const int4*>(a.ep_len + base);
@@ -334,20 +320,19 @@ __device__ __forceinline__ QuadIn load_quad(const GridArgs& a, int64_t base, boo
     } else {
         in.a4 = (!FAST && philox_act) ? make_int4(0, 0, 0, 0) : __ldg(reinterpret_cast<const int4*>(a.action + base));
     }
-#endif
     return in;
 }
 
-// One step of a full quad: draws, branch-free transitions, auto-reset, 128-bit stores.
+// One step of a full quad, in registers: draws, branch-free transitions, rejected-step bookkeeping, auto-reset.  Leaves
+// the post-step quad in `q` (position / counter / return AFTER auto-reset; reward and flags of the step).  `base` is only
+// used for the optional pre-reset observation (final_obs), which is stored here because the reset overwrites it.
 template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
-__device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
-                                          uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
-                                          ErrorAcc& errs) {
-    Quad q;
+__device__ __forceinline__ void step_quad_compute(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
+                                                  uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
+                                                  ErrorAcc& errs, Quad& q) {
     int32_t act[4] = {in.a4.x, in.a4.y, in.a4.z, in.a4.w};
     uint32_t r[4] = {0u, 0u, 0u, 0u};
-    constexpr bool packed = PACKED;
-    if (packed) {
+    if constexpr (PACKED) {
         unpack4(in.p4, q.pos, q.len);
     } else {
         q.pos[0] = in.p4.x; q.pos[1] = in.p4.y; q.pos[2] = in.p4.z; q.pos[3] = in.p4.w;
@@ -360,16 +345,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(w[j] >> 30);
     }
-#if EF_EXPERIMENT & 1  // timing experiments only: no Philox
-    r[0] = g0 * 2654435761u; r[1] = r[0] + 0x9E3779B9u; r[2] = r[1] + 0x9E3779B9u; r[3] = r[2] + 0x9E3779B9u;
-#else
     if constexpr (SLOTS == 4) group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, r);
-#endif
-#if EF_EXPERIMENT & 2  // timing experiments only: no table walk
-    q.term = q.trunc = q.bad = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { q.pos[j] = (q.pos[j] + act[j]) & 63; q.len[j] += 1; q.rew[j] = __uint_as_float(r[j] >> 9); q.ret[j] += q.rew[j]; }
-#else
     // HET: the batch mixes layouts -- every env walks its own table (offset into the staged tables) and resets to its own
     // start cell.  Otherwise both arrays are compile-time constants and fold away.
     uint32_t off[4] = {0u, 0u, 0u, 0u};
@@ -395,11 +371,7 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
     // checking path below.
     const bool wild = ((act[0] | act[1] | act[2] | act[3]) & ~3) != 0;
     if (!wild) transition4<SMEM, SLOTS>(a, tab, q, act, r, off);
-#endif
     uint32_t rejected = 0u;
-#if EF_EXPERIMENT & 2
-    const bool wild = false;
-#endif
     if (wild) {
         q.term = q.trunc = q.bad = 0u;
 #pragma unroll
@@ -424,146 +396,40 @@ __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __rest
     if (!FAST && a.final_obs) store_obs4<W8>(a, a.final_obs, base, q.pos);  // pre-reset observation, only on request
     const uint32_t fin = (FAST || a.autoreset) ? (q.term | q.trunc) : 0u;
     if (fin) finish4(a, q, fin, acc, HET ? lay : nullptr);
-#if EF_STREAMING
-#define EF_ST(ptr, val) __stcs(ptr, val)
-#else
-#define EF_ST(ptr, val) (*(ptr) = (val))
-#endif
-    if (packed) {
-        EF_ST(reinterpret_cast<int4*>(a.pos + base), pack4(q.pos, q.len));
-    } else {
-        EF_ST(reinterpret_cast<int4*>(a.pos + base), make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]));
-        EF_ST(reinterpret_cast<int4*>(a.ep_len + base), make_int4(q.len[0], q.len[1], q.len[2], q.len[3]));
-    }
-    EF_ST(reinterpret_cast<float4*>(a.ep_ret + base), make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]));
-    if (FAST || a.obs) store_obs4<W8>(a, a.obs, base, q.pos);  // observation after auto-reset = (row, col) of the stored position
-    if (FAST || a.reward) EF_ST(reinterpret_cast<float4*>(a.reward + base), make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]));
-    if (FAST || a.terminated) EF_ST(reinterpret_cast<uint32_t*>(a.terminated + base), q.term);
-    if (FAST || a.truncated) EF_ST(reinterpret_cast<uint32_t*>(a.truncated + base), q.trunc);
-#undef EF_ST
 }
 
-#ifndef EF_STEP_MINBLOCKS
-#define EF_STEP_MINBLOCKS 2  // resident CTAs per SM the step kernel is compiled for (register cap 65536 / (256 * this))
-#endif
-#ifndef EF_EXPERIMENT
-#define EF_EXPERIMENT 0
-#endif
-#ifndef EF_STEP_ASYNC
-#define EF_STEP_ASYNC 0  // 1: stage inputs with cp.async into shared memory instead of registers
-#endif
-#ifndef EF_STREAMING
-#define EF_STREAMING 0  // 1: evict-first cache hints on the state/outputs streams
-#endif
-// Large batches, dynamic CTA scheduling.  Measured on B200 with the packed state layout (34 B moved per env-step), us per
-// launch at 4M / 16M envs: Q=2 x 3 CTAs/SM 28.9 / 105.1 (adopted), Q=4 x 2 32.8 / 110.4, Q=3 x 2 32.5 / 115.3,
-// Q=1 x 4 31.4 / 116.6, Q=2 x 4 36.5 / 125.9, Q=4 x 3 40.5 / 135.2 (the last two spill registers).
-#ifndef EF_STEP_BIG_Q
-#define EF_STEP_BIG_Q 2
-#endif
-#ifndef EF_STEP_BIG_MINBLOCKS
-#define EF_STEP_BIG_MINBLOCKS 3
-#endif
-#ifndef EF_STEP_BIG_GRID_PER_SM
-#define EF_STEP_BIG_GRID_PER_SM 64
-#endif
-#ifndef EF_STEP_GRID_PER_SM
-#define EF_STEP_GRID_PER_SM EF_STEP_MINBLOCKS  // grid cap in CTAs per SM
-#endif
-#ifndef EF_FORCE_GLOBAL_TABLE
-#define EF_FORCE_GLOBAL_TABLE 0  // experiment: read the table through L1 instead of staging it in shared memory
-#endif
-#ifndef EF_STEP_Q
-#define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
-#endif
-
-// ---- step -------------------------------------------------------------------------------------------------------------
-// Vector kernel (all pointers 16-byte aligned, Philox or no outcome draws).  The batch is cut into one contiguous chunk of
-// quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
-// (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
-// load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
-template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
-__global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
-#if EF_EXPERIMENT & 4
-    const uint2* __restrict__ tab = a.table;
-#else
-    __shared__ uint64_t table_bar;
-    bool table_pending;
-    const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
-#endif
-    pdl_launch_dependents();
-    pdl_wait();                                            // previous launch complete, its writes visible
-    EpisodeAcc acc;
-    ErrorAcc errs;
-    const uint64_t t = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
-    const bool philox_act = FAST ? false : a.action == nullptr;
-    const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
-    const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
-    const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
-    const int64_t q_end = min(q_begin + per_cta, quads);
-#if EF_STEP_ASYNC
-    // Inputs are staged with cp.async (LDGSTS) into per-thread shared-memory slots instead of registers: the loads of all Q
-    // quads are in flight without holding 16 registers each, which lets more CTAs be resident during the compute phase.
-    // A thread only reads back its own slots, so cp.async.wait_all suffices (no CTA barrier).
-    uint4* stage = reinterpret_cast<uint4*>(const_cast<uint2*>(tab) + (SMEM ? a.table_len : 0));
-#endif
-    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
-#if EF_STEP_ASYNC
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-            if (v < q_end) {
-                uint4* slot = stage + (j * 4) * kThreads + threadIdx.x;
-                cp_async16(slot, a.pos + v * 4);
-                if (a.ep_len) cp_async16(slot + kThreads, a.ep_len + v * 4);
-                cp_async16(slot + 2 * kThreads, a.ep_ret + v * 4);
-                if (!philox_act) cp_async16(slot + 3 * kThreads, a.action + v * 4);
-            }
-        }
-        cp_async_wait_all();
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const int64_t v = chunk + static_cast<int64_t>(j) * kThreads + threadIdx.x;
-            if (v < q_end) {
-                const uint4* slot = stage + (j * 4) * kThreads + threadIdx.x;
-                QuadIn in;
-                const uint4 p = slot[0], l = slot[kThreads], r = slot[2 * kThreads];
-                const uint4 c = philox_act ? make_uint4(0, 0, 0, 0) : slot[3 * kThreads];
-                in.p4 = make_int4(p.x, p.y, p.z, p.w);
-                in.l4 = make_int4(l.x, l.y, l.z, l.w);
-                in.r4 = make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
-                in.a4 = make_int4(c.x, c.y, c.z, c.w);
-                step_quad<SMEM, SLOTS, PACKED, FAST>(a, tab, v * 4, static_cast<uint32_t>(a.env_offset + v * 4), t, in,
-                                                     philox_act, acc, errs);
-            }
-        }
-#else
-        // 32-bit bookkeeping inside the chunk (a CTA's share is far below 2^31 quads); 64-bit only for the addresses
-        QuadIn in[Q];
-        const uint32_t left = static_cast<uint32_t>(min(q_end - chunk, static_cast<int64_t>(Q) * kThreads));
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left) in[j] = load_quad<PACKED, FAST, HET, W8>(a, (chunk + local) * 4, philox_act);
-        }
-#if !(EF_EXPERIMENT & 4)
-        stage_table_wait(&table_bar, table_pending);  // the bulk copy had the whole load phase to land
-#endif
-#pragma unroll
-        for (int j = 0; j < Q; ++j) {
-            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left)
-                step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
-                                                          static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
-                                                          philox_act, acc, errs);
-        }
-#endif
+// 128-bit stores of a stepped quad straight to global memory.
+template <bool PACKED, bool FAST, bool W8 = false>
+__device__ __forceinline__ void store_quad_global(const GridArgs& a, int64_t base, const Quad& q) {
+    if constexpr (PACKED) {
+        *reinterpret_cast<int4*>(a.pos + base) = pack4(q.pos, q.len);
+    } else {
+        *reinterpret_cast<int4*>(a.pos + base) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
+        *reinterpret_cast<int4*>(a.ep_len + base) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
     }
-#if !(EF_EXPERIMENT & 4)
-    stage_table_wait(&table_bar, table_pending);  // CTAs that own no full quad (tiny batches) still need the table below
-#endif
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < (a.n & 3)) {  // ragged tail: at most three envs
+    *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
+    if (FAST || a.obs) store_obs4<W8>(a, a.obs, base, q.pos);  // observation after auto-reset = (row, col) of the stored position
+    if (FAST || a.reward) *reinterpret_cast<float4*>(a.reward + base) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
+    if (FAST || a.terminated) *reinterpret_cast<uint32_t*>(a.terminated + base) = q.term;
+    if (FAST || a.truncated) *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
+}
+
+template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
+__device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
+                                          uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
+                                          ErrorAcc& errs) {
+    Quad q;
+    step_quad_compute<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, base, g0, t, in, philox_act, acc, errs, q);
+    store_quad_global<PACKED, FAST, W8>(a, base, q);
+}
+
+// Ragged tail of the vector kernels: the at most three envs past the last full quad, stepped by the last CTA through the
+// generic one-env code.
+template <bool SMEM, int SLOTS, bool HET, bool W8>
+__device__ __forceinline__ void step_tail(const GridArgs& a, const uint2* __restrict__ tab, uint64_t t, bool philox_act,
+                                          EpisodeAcc& acc, ErrorAcc& errs) {
+    const int64_t quads = a.n >> 2;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < (a.n & 3)) {
         const int64_t i = (quads << 2) + threadIdx.x;
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
         int32_t pos, len;
@@ -602,11 +468,255 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         if (a.terminated) a.terminated[i] = static_cast<uint8_t>(f & 1u);
         if (a.truncated) a.truncated[i] = static_cast<uint8_t>((f >> 1) & 1u);
     }
-#if EF_EXPERIMENT & 32  // keep the accumulation alive, skip the CTA epilogue
-    if (acc.episodes == 0xFFFFFFFFu && a.stats) { a.stats[0] = acc.ret + acc.ret_sq + static_cast<double>(acc.length + acc.steps + errs.count + ticket); }
-#elif !(EF_EXPERIMENT & 8)
-    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
+}
+
+#ifndef EF_STEP_MINBLOCKS
+#define EF_STEP_MINBLOCKS 2  // resident CTAs per SM the step kernel is compiled for (register cap 65536 / (256 * this))
 #endif
+// Large batches, dynamic CTA scheduling.  Measured on B200 with the packed state layout (34 B moved per env-step), us per
+// launch at 4M / 16M envs: Q=2 x 3 CTAs/SM 28.9 / 105.1 (adopted), Q=4 x 2 32.8 / 110.4, Q=3 x 2 32.5 / 115.3,
+// Q=1 x 4 31.4 / 116.6, Q=2 x 4 36.5 / 125.9, Q=4 x 3 40.5 / 135.2 (the last two spill registers).
+#ifndef EF_STEP_BIG_Q
+#define EF_STEP_BIG_Q 2
+#endif
+#ifndef EF_STEP_BIG_MINBLOCKS
+#define EF_STEP_BIG_MINBLOCKS 3
+#endif
+#ifndef EF_STEP_BIG_GRID_PER_SM
+#define EF_STEP_BIG_GRID_PER_SM 64
+#endif
+#ifndef EF_STEP_GRID_PER_SM
+#define EF_STEP_GRID_PER_SM EF_STEP_MINBLOCKS  // grid cap in CTAs per SM
+#endif
+#ifndef EF_STEP_Q
+#define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
+#endif
+// Pipelined step kernel (TMA in): used when the call has the FAST shape, the table is staged and a CTA's share fits its
+// shared memory.  EF_PIPE_CTAS = resident CTAs per SM it is compiled and sized for; EF_PIPE_TMA_OUT = outputs leave as
+// per-warp cp.async.bulk stores instead of 128-bit global stores.
+#ifndef EF_PIPE
+#define EF_PIPE 1
+#endif
+#ifndef EF_PIPE_CTAS
+#define EF_PIPE_CTAS 2
+#endif
+#ifndef EF_PIPE_TMA_OUT
+#define EF_PIPE_TMA_OUT 0
+#endif
+
+// ---- step -------------------------------------------------------------------------------------------------------------
+// Vector kernel (all pointers 16-byte aligned, Philox or no outcome draws).  The batch is cut into one contiguous chunk of
+// quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
+// (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
+// load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
+template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
+__global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
+    __shared__ uint64_t table_bar;
+    bool table_pending;
+    const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
+    pdl_launch_dependents();
+    pdl_wait();                                            // previous launch complete, its writes visible
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    unsigned long long ticket;
+    const uint64_t t = a.t + clock_begin(a.clock, ticket);  // thread 0 reads the device clock and takes the ticket
+    const bool philox_act = FAST ? false : a.action == nullptr;
+    const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
+    const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
+    const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
+    const int64_t q_end = min(q_begin + per_cta, quads);
+    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
+        // 32-bit bookkeeping inside the chunk (a CTA's share is far below 2^31 quads); 64-bit only for the addresses
+        QuadIn in[Q];
+        const uint32_t left = static_cast<uint32_t>(min(q_end - chunk, static_cast<int64_t>(Q) * kThreads));
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+            if (local < left) in[j] = load_quad<PACKED, FAST, HET, W8>(a, (chunk + local) * 4, philox_act);
+        }
+        stage_table_wait(&table_bar, table_pending);  // the bulk copy had the whole load phase to land
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+            if (local < left)
+                step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
+                                                          static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
+                                                          philox_act, acc, errs);
+        }
+    }
+    stage_table_wait(&table_bar, table_pending);  // CTAs that own no full quad (tiny batches) still need the table below
+    step_tail<SMEM, SLOTS, HET, W8>(a, tab, t, philox_act, acc, errs);
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
+}
+
+// ---- pipelined step (TMA in, optional TMA out) ------------------------------------------------------------------------
+// The same step for batches whose per-CTA share fits shared memory.  One elected thread moves the CTA's WHOLE input -- the
+// contiguous pos / ep_ret / action ranges of its quads -- into shared memory with cp.async.bulk, one mbarrier per stage of
+// 256 quads, the moment the previous launch is complete: every input byte of the launch is in flight at once, no thread
+// holds a register for it, and no thread spends issue slots on global loads or their 64-bit addresses.  A warp then steps
+// stage s as soon as its barrier flips, while the later stages are still landing; its outputs leave either as 128-bit
+// global stores (TMA_OUT = false) or -- written to the stage buffer in place -- as cp.async.bulk stores issued per warp
+// (TMA_OUT = true), so the writes of stage s stream out under the compute of stage s + 1.  Shapes: FAST only (actions
+// given, every output requested, auto-reset on), table staged in shared memory.
+constexpr int kPipeMaxStages = 8;
+
+template <bool PACKED, bool W8, bool TMA_OUT>
+struct PipeLayout {  // byte offsets inside one stage buffer (256 quads)
+    static constexpr uint32_t kQuad = 16u * kThreads;                 // one 16-byte vector per quad
+    static constexpr uint32_t kPos = 0u;
+    static constexpr uint32_t kLen = kQuad;                           // split state layout only
+    static constexpr uint32_t kRet = PACKED ? kQuad : 2u * kQuad;
+    static constexpr uint32_t kAct = kRet + kQuad;
+    static constexpr uint32_t kActBytes = W8 ? 4u * kThreads : kQuad;
+    static constexpr uint32_t kIn = kAct + kActBytes;                 // end of the inputs
+    // outputs (TMA_OUT): pos / ep_len / ep_ret in place; the reward takes over the int32 action vector
+    static constexpr uint32_t kRew = W8 ? kIn : kAct;
+    static constexpr uint32_t kObs = W8 ? kIn + kQuad : kIn;
+    static constexpr uint32_t kObsBytes = W8 ? 8u * kThreads : 2u * kQuad;
+    static constexpr uint32_t kTerm = kObs + kObsBytes;
+    static constexpr uint32_t kTrunc = kTerm + 4u * kThreads;
+    static constexpr uint32_t kStage = TMA_OUT ? kTrunc + 4u * kThreads : kIn;
+};
+
+template <int SLOTS, bool PACKED, bool W8, bool TMA_OUT, int MINBLOCKS>
+__global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_pipe_kernel(const GridArgs a) {
+    using L = PipeLayout<PACKED, W8, TMA_OUT>;
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    __shared__ uint64_t bars[1 + kPipeMaxStages];   // [0] table, [1 + s] inputs of stage s
+    __shared__ unsigned long long s_clock;
+    const uint32_t table_bytes = static_cast<uint32_t>(a.table_len) * static_cast<uint32_t>(sizeof(uint2));
+    const uint2* __restrict__ tab = reinterpret_cast<const uint2*>(pipe_smem);
+    unsigned char* const stages = pipe_smem + ((table_bytes + 127u) & ~127u);
+    const int64_t quads = a.n >> 2;
+    const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * a.quads_per_cta;   // multiple of 4 quads (host)
+    const int32_t count = static_cast<int32_t>(max(static_cast<int64_t>(0), min(a.quads_per_cta, quads - q_begin)));
+    const int32_t nstages = (count + kThreads - 1) / kThreads;
+    unsigned long long ticket = 0ull;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s <= nstages; ++s) mbar_init(&bars[s], 1u);
+        mbar_expect_tx(&bars[0], table_bytes);
+        bulk_g2s(pipe_smem, a.table, table_bytes, &bars[0]);   // the table does not depend on the previous launch
+    }
+    pdl_launch_dependents();
+    pdl_wait();                                                // previous launch complete, its writes visible
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstages; ++s) {
+            const uint32_t cnt = static_cast<uint32_t>(min(kThreads, count - s * kThreads));
+            const uint32_t vec = cnt * 16u;
+            const uint32_t act = W8 ? (cnt & ~3u) * 4u : vec;  // bulk copies move multiples of 16 bytes
+            unsigned char* st = stages + static_cast<size_t>(s) * L::kStage;
+            const int64_t q0 = q_begin + static_cast<int64_t>(s) * kThreads;
+            mbar_expect_tx(&bars[1 + s], vec * (PACKED ? 2u : 3u) + act);
+            bulk_g2s(st + L::kPos, a.pos + q0 * 4, vec, &bars[1 + s]);
+            if constexpr (!PACKED) bulk_g2s(st + L::kLen, a.ep_len + q0 * 4, vec, &bars[1 + s]);
+            bulk_g2s(st + L::kRet, a.ep_ret + q0 * 4, vec, &bars[1 + s]);
+            if (act) {
+                if constexpr (W8) bulk_g2s(st + L::kAct, reinterpret_cast<const uint8_t*>(a.action) + q0 * 4, act, &bars[1 + s]);
+                else bulk_g2s(st + L::kAct, a.action + q0 * 4, act, &bars[1 + s]);
+            }
+        }
+        if (a.clock != nullptr) {  // thread 0 alone touches the device clock: read, then take the CTA's ticket
+            s_clock = clock_read(a.clock);
+            ticket = clock_ticket(a.clock);
+        }
+    }
+    __syncthreads();   // barriers initialised, clock value published
+    const uint64_t t = a.t + (a.clock != nullptr ? s_clock : 0ull);
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    bool table_ready = false;
+    for (int s = 0; s < nstages; ++s) {
+        const int32_t cnt = min(kThreads, count - s * kThreads);
+        unsigned char* st = stages + static_cast<size_t>(s) * L::kStage;
+        const int64_t base = (q_begin + static_cast<int64_t>(s) * kThreads + threadIdx.x) * 4;
+        const bool live = static_cast<int32_t>(threadIdx.x) < cnt;
+        Quad q;
+        if (live) {
+            mbar_wait(&bars[1 + s], 0u);
+            QuadIn in;
+            in.p4 = *reinterpret_cast<const int4*>(st + L::kPos + threadIdx.x * 16u);
+            if constexpr (!PACKED) in.l4 = *reinterpret_cast<const int4*>(st + L::kLen + threadIdx.x * 16u);
+            in.r4 = *reinterpret_cast<const float4*>(st + L::kRet + threadIdx.x * 16u);
+            if constexpr (W8) {
+                // the up to three quads past the last 16-byte multiple of the action bytes were not bulk-copied
+                const uint32_t w = static_cast<int32_t>(threadIdx.x) < (cnt & ~3)
+                                       ? *reinterpret_cast<const uint32_t*>(st + L::kAct + threadIdx.x * 4u)
+                                       : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.action) + base));
+                in.a4 = make_int4(static_cast<int32_t>(w & 0xffu), static_cast<int32_t>((w >> 8) & 0xffu),
+                                  static_cast<int32_t>((w >> 16) & 0xffu), static_cast<int32_t>(w >> 24));
+            } else {
+                in.a4 = *reinterpret_cast<const int4*>(st + L::kAct + threadIdx.x * 16u);
+            }
+            if (!table_ready) {
+                mbar_wait(&bars[0], 0u);
+                table_ready = true;
+            }
+            step_quad_compute<true, SLOTS, PACKED, true, false, W8>(a, tab, base, static_cast<uint32_t>(a.env_offset + base), t,
+                                                                    in, false, acc, errs, q);
+        }
+        if constexpr (!TMA_OUT) {
+            if (live) store_quad_global<PACKED, true, W8>(a, base, q);
+        } else {
+            // outputs of this warp's 32 quads: contiguous in every array, so one bulk store per array.  Bulk stores move
+            // multiples of 16 bytes (4 quads of flag bytes): the at most three quads beyond go out as plain stores.
+            const int32_t wcnt = max(0, min(32, cnt - static_cast<int32_t>(warp) * 32));
+            const int32_t wbulk = wcnt & ~3;
+            if (live) {
+                if (static_cast<int32_t>(lane) < wbulk) {
+                    if constexpr (PACKED) {
+                        *reinterpret_cast<int4*>(st + L::kPos + threadIdx.x * 16u) = pack4(q.pos, q.len);
+                    } else {
+                        *reinterpret_cast<int4*>(st + L::kPos + threadIdx.x * 16u) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
+                        *reinterpret_cast<int4*>(st + L::kLen + threadIdx.x * 16u) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
+                    }
+                    *reinterpret_cast<float4*>(st + L::kRet + threadIdx.x * 16u) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
+                    *reinterpret_cast<float4*>(st + L::kRew + threadIdx.x * 16u) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
+                    const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
+                    const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
+                    if constexpr (W8) {
+                        const uint32_t lo = static_cast<uint32_t>(o0.x) | static_cast<uint32_t>(o0.y) << 8 |
+                                            static_cast<uint32_t>(o1.x) << 16 | static_cast<uint32_t>(o1.y) << 24;
+                        const uint32_t hi = static_cast<uint32_t>(o2.x) | static_cast<uint32_t>(o2.y) << 8 |
+                                            static_cast<uint32_t>(o3.x) << 16 | static_cast<uint32_t>(o3.y) << 24;
+                        *reinterpret_cast<uint2*>(st + L::kObs + threadIdx.x * 8u) = make_uint2(lo, hi);
+                    } else {
+                        int4* o = reinterpret_cast<int4*>(st + L::kObs + threadIdx.x * 32u);
+                        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
+                        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
+                    }
+                    *reinterpret_cast<uint32_t*>(st + L::kTerm + threadIdx.x * 4u) = q.term;
+                    *reinterpret_cast<uint32_t*>(st + L::kTrunc + threadIdx.x * 4u) = q.trunc;
+                } else {
+                    store_quad_global<PACKED, true, W8>(a, base, q);
+                }
+            }
+            if (wbulk > 0) {                 // warp-uniform
+                fence_proxy_async();         // my generic-proxy writes -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0u) {
+                    const uint32_t w0 = warp * 32u;   // first quad of the warp inside the stage
+                    const int64_t e0 = (q_begin + static_cast<int64_t>(s) * kThreads + w0) * 4;   // its first env
+                    const uint32_t nb = static_cast<uint32_t>(wbulk);
+                    bulk_s2g(a.pos + e0, st + L::kPos + w0 * 16u, nb * 16u);
+                    if constexpr (!PACKED) bulk_s2g(a.ep_len + e0, st + L::kLen + w0 * 16u, nb * 16u);
+                    bulk_s2g(a.ep_ret + e0, st + L::kRet + w0 * 16u, nb * 16u);
+                    bulk_s2g(a.reward + e0, st + L::kRew + w0 * 16u, nb * 16u);
+                    if constexpr (W8) bulk_s2g(reinterpret_cast<uint8_t*>(a.obs) + 2 * e0, st + L::kObs + w0 * 8u, nb * 8u);
+                    else bulk_s2g(a.obs + 2 * e0, st + L::kObs + w0 * 32u, nb * 32u);
+                    bulk_s2g(a.terminated + e0, st + L::kTerm + w0 * 4u, nb * 4u);
+                    bulk_s2g(a.truncated + e0, st + L::kTrunc + w0 * 4u, nb * 4u);
+                    bulk_commit();
+                }
+            }
+        }
+    }
+    if (!table_ready) mbar_wait(&bars[0], 0u);  // CTAs without a quad still drain the table copy (and the tail needs it)
+    if constexpr (TMA_OUT) {
+        if (lane == 0u) bulk_wait_read_all();   // the stage buffers must outlive the bulk stores' reads
+    }
+    step_tail<true, SLOTS, false, W8>(a, tab, t, false, acc, errs);
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
 }
 
 // Scalar kernel: one env per thread, any alignment, optional injected outcome draws (parity tests, unaligned views).
@@ -617,8 +727,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_step_scalar_kernel(const G
     pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
-    const uint64_t t = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t = a.t + clock_begin(a.clock, ticket);
     const bool philox_act = a.action == nullptr;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -769,8 +879,8 @@ __global__ void __launch_bounds__(kThreads) gridworld_rollout_kernel(const GridA
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t groups = (a.n + 3) / 4;
     const int64_t groups_round = (groups + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
-    const uint64_t t0 = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t0 = a.t + clock_begin(a.clock, ticket);
     const bool packed = a.ep_len == nullptr;
     const bool vec_ok = aligned(a.pos, 16) && aligned(a.ep_len, 16) && aligned(a.ep_ret, 16);
     for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < groups_round; v += stride) {
@@ -978,6 +1088,18 @@ static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStr
     return launch_kernel(kernel, a, grid, bytes, stream);
 }
 
+// Pinned host memory handed in as a UVA pointer (the zero-copy host-buffer step)?  Such buffers keep plain loads / stores:
+// the pipelined kernel's bulk copies are reserved for device memory.
+static bool is_host_memory(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;   // unknown memory: take the conservative path
+    }
+    return at.type != cudaMemoryTypeDevice;
+}
+
 }  // namespace ef
 
 using namespace ef;
@@ -987,7 +1109,8 @@ template <bool W8>
 static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret, const void* action,
                                const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, void* obs,
                                float* reward, uint8_t* terminated, uint8_t* truncated, void* final_obs, double* stats,
-                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream,
+                               bool host_io) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
     if (n < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
@@ -1005,7 +1128,7 @@ static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* 
     const bool vec = draw == nullptr && aligned(pos, 16) && aligned(ep_len, 16) && aligned(ep_ret, 16) &&
                      aligned(action, W8 ? 4 : 16) && aligned(obs, W8 ? 8 : 16) && aligned(reward, 16) &&
                      aligned(terminated, 4) && aligned(truncated, 4) && aligned(final_obs, W8 ? 8 : 16);
-    const bool smem = !EF_FORCE_GLOBAL_TABLE && static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
+    const bool smem = static_cast<size_t>(a.table_len) * sizeof(uint2) <= kMaxSmemTable;
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     // Small batches (one pass fits the resident grid): EF_STEP_Q quads per thread, all loads in flight, persistent grid.
     // Large batches: fewer quads per thread, more resident warps, CTAs scheduled dynamically over many passes.
@@ -1023,11 +1146,41 @@ static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* 
     a.rk = philox_round_keys(seed);
     const bool packed = ep_len == nullptr;
     const bool fast = action && obs && reward && terminated && truncated && !final_obs && autoreset != 0;
+    if (EF_PIPE && smem && fast && vec && !host_io && (n >> 2) > 0) {
+        // pipelined kernel: spread the full quads over the resident CTA slots, shares rounded up to 4 quads (16 bytes of
+        // flag / uint8-action bytes, the granularity of a bulk copy); taken when the share fits a CTA's shared memory
+        const int64_t fq = n >> 2;
+        const int grid_p = static_cast<int>(std::max<int64_t>(
+            1, std::min<int64_t>(static_cast<int64_t>(sm_count()) * EF_PIPE_CTAS, (fq + 31) / 32)));
+        const int64_t per_cta = ((fq + grid_p - 1) / grid_p + 3) & ~static_cast<int64_t>(3);
+        const int64_t nstages = (per_cta + kThreads - 1) / kThreads;
+        const size_t table_bytes = (static_cast<size_t>(a.table_len) * sizeof(uint2) + 127) & ~static_cast<size_t>(127);
+        const size_t stage_bytes = packed ? PipeLayout<true, W8, EF_PIPE_TMA_OUT != 0>::kStage
+                                          : PipeLayout<false, W8, EF_PIPE_TMA_OUT != 0>::kStage;
+        const size_t bytes = table_bytes + static_cast<size_t>(nstages) * stage_bytes;
+        const size_t cap = 232448 / EF_PIPE_CTAS - 2048;  // 227 KB per SM, minus the per-CTA reserve and the static arrays
+        if (nstages <= kPipeMaxStages && bytes <= cap) {
+            a.quads_per_cta = per_cta;
+#define EF_LAUNCH_PIPE(SL, PK)                                                                                            \
+    do {                                                                                                                  \
+        auto kernel = gridworld_step_pipe_kernel<SL, PK, W8, EF_PIPE_TMA_OUT != 0, EF_PIPE_CTAS>;                         \
+        if (bytes > 48 * 1024) {                                                                                          \
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                                       static_cast<int>(bytes));                                          \
+            if (e != cudaSuccess) return cuda_status(e);                                                                  \
+        }                                                                                                                 \
+        return launch_kernel(kernel, a, grid_p, bytes, st);                                                               \
+    } while (0)
+            if (grid->n_slots == 1) { if (packed) EF_LAUNCH_PIPE(1, true); else EF_LAUNCH_PIPE(1, false); }
+            else { if (packed) EF_LAUNCH_PIPE(4, true); else EF_LAUNCH_PIPE(4, false); }
+#undef EF_LAUNCH_PIPE
+        }
+    }
 #define EF_LAUNCH_VEC(SM, SL, PK, FS)                                                                                    \
     return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS, false, W8>, a, SM, grid_v, \
-                          st, EF_STEP_ASYNC ? size_t(EF_STEP_Q) * 4 * kThreads * 16 : 0)                                 \
+                          st)                                                                                            \
                  : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS, PK, FS, false, W8>, a, SM, \
-                          grid_b, st, EF_STEP_ASYNC ? size_t(EF_STEP_BIG_Q) * 4 * kThreads * 16 : 0)
+                          grid_b, st)
     // The narrow format has the compile-time call-shape specialisation (FAST) only: its callers are actor loops that
     // pass actions and take every output; other call shapes (and tables too large for shared memory) use the generic
     // build, which for W8 is instantiated for the packed state only when the table is staged.
@@ -1050,7 +1203,8 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
                                  uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
                                  uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     return gridworld_step_impl<false>(grid, pos, ep_len, ep_ret, action, draw, seed, t, env_offset, obs, reward, terminated,
-                                      truncated, final_obs, stats, err, clock, n, autoreset, stream);
+                                      truncated, final_obs, stats, err, clock, n, autoreset, stream,
+                                      is_host_memory(action) || is_host_memory(obs));
 }
 
 extern "C" int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
@@ -1059,18 +1213,20 @@ extern "C" int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int3
                                     uint8_t* truncated, uint8_t* final_obs, double* stats, uint32_t* err,
                                     uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     return gridworld_step_impl<true>(grid, pos, ep_len, ep_ret, action, draw, seed, t, env_offset, obs, reward, terminated,
-                                     truncated, final_obs, stats, err, clock, n, autoreset, stream);
+                                     truncated, final_obs, stats, err, clock, n, autoreset, stream,
+                                     is_host_memory(action) || is_host_memory(obs));
 }
 
 extern "C" int ef_gridworld_step_v(const ef_gridworld_step_args* x) {
     if (!x) return EF_ERR_INVALID_ARGUMENT;
+    const bool host_io = (x->wire & EF_WIRE_HOST_IO) != 0;  // the caller says so: no pointer query on this lean path
     if (x->wire & EF_WIRE_U8)  // action / obs / final_obs point at bytes (see ef_gridworld_step_u8)
         return gridworld_step_impl<true>(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset,
                                          x->obs, x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err,
-                                         x->clock, x->n, x->autoreset, x->stream);
-    return ef_gridworld_step(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset, x->obs,
-                             x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err, x->clock, x->n,
-                             x->autoreset, x->stream);
+                                         x->clock, x->n, x->autoreset, x->stream, host_io);
+    return gridworld_step_impl<false>(x->grid, x->pos, x->ep_len, x->ep_ret, static_cast<const int32_t*>(x->action), x->draw,
+                                      x->seed, x->t, x->env_offset, x->obs, x->reward, x->terminated, x->truncated,
+                                      x->final_obs, x->stats, x->err, x->clock, x->n, x->autoreset, x->stream, host_io);
 }
 
 extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,

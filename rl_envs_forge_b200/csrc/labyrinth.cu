@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(kThreads) labyrinth_kernel(const LabArgs a) {
     pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
-    const uint64_t t = a.t + clock_read(a.clock);
-    const unsigned long long ticket = STEP ? clock_ticket(a.clock) : 0ull;
+    unsigned long long ticket;
+    const uint64_t t = a.t + clock_begin(a.clock, ticket, STEP);
     for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * kLabEnvsPerCta; e0 < a.n;
          e0 += static_cast<int64_t>(gridDim.x) * kLabEnvsPerCta) {
         const int count = static_cast<int>(min(static_cast<int64_t>(kLabEnvsPerCta), a.n - e0));
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(kThreads) labyrinth_rollout_kernel(const LabAr
     pdl_wait();
     EpisodeAcc acc;
     ErrorAcc errs;
-    const uint64_t t0 = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t0 = a.t + clock_begin(a.clock, ticket);
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint32_t g = static_cast<uint32_t>(a.env_offset + i);

@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
     pdl_launch_dependents();
     pdl_wait();
     EpisodeAcc acc;
-    const uint64_t t = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t = a.t + clock_begin(a.clock, ticket);
     const int64_t per_cta = a.per_cta;  // keeps every CTA's chunk 256-env aligned
     const int64_t begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t end = min(begin + per_cta, a.n);
@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t quads = (a.n + 3) / 4;
     const int64_t quads_round = (quads + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
-    const uint64_t t0 = a.t + clock_read(a.clock);
-    const unsigned long long ticket = clock_ticket(a.clock);
+    unsigned long long ticket;
+    const uint64_t t0 = a.t + clock_begin(a.clock, ticket);
     const bool io_vec = ((a.n & 3) == 0) && aligned(a.action, 16) && aligned(a.reward, 16) && aligned(a.flags, 4);
     for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < quads_round; v += stride) {
         const int64_t base = v * 4;
