@@ -30,10 +30,11 @@
  *     raised on (atomic add); [1] reserved; [2..3] one 64-bit word describing the offender with the largest global index
  *     (atomic max): (1 + global env index) << 32 | ef_step_error kind << 24 | detail (24 bits: table row cell*4+action,
  *     or the action value).  Offending envs are left untouched (the reference raises before mutating state).
- *   - `clock` (nullable) points at 2 uint64 in device memory: clock[0] is ADDED to the `t` / `t0` argument to form
- *     the Philox time coordinate and is advanced by the kernel itself (by 1 per step call, K per rollout) once all
- *     its CTAs have read it; clock[1] is scratch (must start at 0).  It exists so a captured CUDA graph can be
- *     replayed without the host re-baking `t` into the kernel parameters.
+ *   - `clock` (nullable) points at 2 uint64 in device memory.  clock[0] counts steps in units of 2^-EF_CLOCK_SHIFT:
+ *     (clock[0] >> EF_CLOCK_SHIFT) is ADDED to the `t` / `t0` argument to form the Philox time coordinate, and a launch
+ *     that advances the envs by k steps (1 per step call, K per rollout) adds k << EF_CLOCK_SHIFT in total, every CTA its
+ *     share as it retires; clock[1] is reserved.  It exists so a captured CUDA graph can be replayed without the host
+ *     re-baking `t` into the kernel parameters.  Initialise it to (steps already taken) << EF_CLOCK_SHIFT.
  */
 #ifndef ENVFORGE_B200_H
 #define ENVFORGE_B200_H
@@ -49,6 +50,7 @@ extern "C" {
 #define EF_STATS_REPLICAS 32
 #define EF_STATS_STRIDE 16
 #define EF_ERR_LEN 4
+#define EF_CLOCK_SHIFT 20
 
 typedef enum ef_status {
     EF_OK = 0,
@@ -144,13 +146,10 @@ typedef struct ef_gridworld_step_args {
     uint64_t* clock;
     int64_t n;
     int32_t autoreset;
-    int32_t wire;     /* bit set: EF_WIRE_U8 = action / obs / final_obs point at uint8 data (ef_gridworld_step_u8);
-                         EF_WIRE_HOST_IO = some input / output buffer is PINNED HOST memory (the plain entry points find
-                         that out with cudaPointerGetAttributes; this struct call trusts the flag) */
+    int32_t wire;     /* 0: int32 action / obs / final_obs;  EF_WIRE_U8: they point at uint8 data (ef_gridworld_step_u8) */
     void* stream;
 } ef_gridworld_step_args;
 #define EF_WIRE_U8 0x1
-#define EF_WIRE_HOST_IO 0x2
 int ef_gridworld_step_v(const ef_gridworld_step_args* args);
 
 /* ef_gridworld_step in the NARROW WIRE FORMAT of a host-side actor loop: actions are uint8 [n] (values > 3 are rejected

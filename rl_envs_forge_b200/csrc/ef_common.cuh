@@ -269,37 +269,33 @@ struct ErrorAcc {
     }
 };
 
-// Device-resident step clock (optional, for CUDA-graph capture where the host cannot bump `t` between replays):
-// clock[0] = steps already taken, clock[1] = CTA ticket.  Every CTA reads clock[0] when it starts and then takes a
-// ticket; the CTA holding the last ticket knows every CTA has read the clock and advances it (in the epilogue).  The
-// ticket atomic is issued early so its round trip overlaps the CTA's loads; no fence is needed because a completed load
-// cannot be affected by the later write.  Within a CTA only thread 0 touches the clock (clock_begin below).
-__device__ __forceinline__ uint64_t clock_read(const unsigned long long* clock) {
-    return clock ? *reinterpret_cast<const volatile unsigned long long*>(clock) : 0ull;
+// Device-resident step clock (optional, for CUDA-graph capture where the host cannot bump `t` between replays).
+// clock[0] is a counter in units of 2^-20 steps: a launch that advances the envs by `inc` steps adds inc * 2^20 to it in
+// total -- every CTA adds its share (total / gridDim.x, CTA 0 also the remainder) with ONE fire-and-forget reduction when
+// it retires -- and any thread reads the step index as clock[0] >> 20.  While a launch is running the counter lies in
+// [t * 2^20, (t + inc) * 2^20) as long as at least one CTA (the reader itself) has not retired, so every thread of the
+// launch reads the same t whenever it looks: no ticket, no "last CTA" hand-over, no barrier, and the read is a plain
+// L2 hit that is issued ahead of the input loads.  (The previous scheme -- a ticket atomic next to the clock word, the
+// last ticket holder bumping it -- put a contended atomic round trip on every CTA's critical path: profiles/r02_*.)
+constexpr unsigned kClockShift = 20;
+__device__ __forceinline__ unsigned long long clock_fetch(const unsigned long long* clock) {
+    unsigned long long v = 0ull;
+    if (clock != nullptr) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(clock) : "memory");
+    return v;
 }
-__device__ __forceinline__ unsigned long long clock_ticket(unsigned long long* clock) {
-    return (clock != nullptr && threadIdx.x == 0) ? atomicAdd(&clock[1], 1ull) : 0ull;
-}
-// What the kernels call (every thread of the CTA, `clock` is launch-uniform): thread 0 reads the clock and THEN takes the
-// CTA's ticket; the value reaches the other threads through shared memory behind one barrier.  No other warp reads the
-// clock itself, so none can observe it after the last ticket holder has advanced it (a warp delayed past its own CTA's
-// ticket could otherwise draw with t + 1).  `ticket` is meaningful in thread 0 only, which is the thread cta_epilogue uses.
-__device__ __forceinline__ uint64_t clock_begin(unsigned long long* clock, unsigned long long& ticket, bool take_ticket = true) {
-    __shared__ unsigned long long s_clock_value;
+// Step index for every calling thread (`clock` is launch-uniform; null = the host passes `t` itself).
+__device__ __forceinline__ uint64_t clock_steps(unsigned long long fetched) { return fetched >> kClockShift; }
+// fetch + convert in one go for the kernels that have nothing to overlap the fetch with.  `ticket` is kept for the
+// call sites' sake (cta_epilogue ignores it).
+__device__ __forceinline__ uint64_t clock_begin(unsigned long long* clock, unsigned long long& ticket, bool = true) {
     ticket = 0ull;
-    if (clock == nullptr) return 0ull;
-    if (threadIdx.x == 0) {
-        s_clock_value = clock_read(clock);
-        if (take_ticket) ticket = clock_ticket(clock);
-    }
-    __syncthreads();
-    return s_clock_value;
+    return clock_steps(clock_fetch(clock));
 }
 
 constexpr int kWarpsPerCta = kThreads / 32;
 
 // CTA epilogue: fold the per-thread statistics / error accumulators into global memory with ONE barrier and at most
-// a handful of global reductions per CTA, then advance the device clock if this CTA holds the last ticket.
+// a handful of global reductions per CTA, then add this CTA's share to the device clock.
 // All threads of the CTA must call it.  `stats`, `err`, `clock` may each be null.
 __device__ __forceinline__ void cta_epilogue(const EpisodeAcc& acc, const ErrorAcc& errs, double* __restrict__ stats,
                                              uint32_t* __restrict__ err, unsigned long long* clock,
@@ -371,10 +367,12 @@ __device__ __forceinline__ void cta_epilogue(const EpisodeAcc& acc, const ErrorA
                                               static_cast<unsigned long long>(s_e[first][1] & 0xffffffu);
             atomicMax(reinterpret_cast<unsigned long long*>(err + 2), packed);
         }
-        if (clock != nullptr && ticket == static_cast<unsigned long long>(gridDim.x) - 1ull) {
-            clock[1] = 0ull;
-            clock[0] += clock_inc;
+        if (clock != nullptr && clock_inc != 0ull) {   // this CTA's share of clock_inc * 2^20 (see "step clock" above)
+            const unsigned long long total = clock_inc << kClockShift;
+            const unsigned long long share = total / gridDim.x;
+            atomicAdd(clock, blockIdx.x == 0 ? share + (total - share * gridDim.x) : share);
         }
+        (void)ticket;
     }
 }
 

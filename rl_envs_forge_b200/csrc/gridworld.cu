@@ -20,6 +20,10 @@
 
 #include "ef_common.cuh"
 
+#ifndef EF_STEP_LEAN
+#define EF_STEP_LEAN 1       // packed-word arithmetic of step_quad_packed (0: the generic step_quad_compute; same results)
+#endif
+
 namespace ef {
 
 struct GridArgs {
@@ -58,6 +62,35 @@ struct GridArgs {
     uint8_t* flags;
     unsigned long long* clock;
 };
+
+// Timeline hooks of the step kernels: compiled to nothing in the product build.  `python -m rl_envs_forge_b200._build
+// -DEF_TRACE=1 --tag=_trace` builds a tools-only variant (tools/step_trace.py) in which thread 0 of every CTA stores
+// %globaltimer / clock64 at the marked points; the results of a step are the same either way.
+#ifdef EF_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;   // [8 sets][4 steps][1024 CTAs][16 points][2]
+#define EF_TRACE_DECL unsigned long long tr_[32] = {0ull};
+#define EF_TRACE_POINT(i)                                                   \
+    do {                                                                    \
+        if (threadIdx.x == 0) {                                             \
+            unsigned long long gt_;                                         \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt_));          \
+            tr_[2 * (i)] = gt_;                                             \
+            tr_[2 * (i) + 1] = static_cast<unsigned long long>(clock64());  \
+        }                                                                   \
+    } while (0)
+#define EF_TRACE_FLUSH(t_)                                                                                               \
+    do {                                                                                                                 \
+        if (threadIdx.x == 0 && g_trace_buf != nullptr && blockIdx.x < 1024) {                                           \
+            const unsigned long long set_ = (a.env_offset / static_cast<unsigned long long>(a.n)) & 7ull;                \
+            unsigned long long* e_ = g_trace_buf + ((set_ * 4ull + ((t_) & 3ull)) * 1024ull + blockIdx.x) * 32ull;       \
+            for (int i_ = 0; i_ < 32; ++i_) e_[i_] = tr_[i_];                                                            \
+        }                                                                                                                \
+    } while (0)
+#else
+#define EF_TRACE_DECL
+#define EF_TRACE_POINT(i)
+#define EF_TRACE_FLUSH(t_)
+#endif
 
 // Table staging by TMA bulk copy: thread 0 arms an mbarrier and issues ONE cp.async.bulk for the whole table; the copy
 // runs while the CTA goes on (griddepcontrol.wait, input loads), and stage_table_wait() is called right before the first
@@ -414,13 +447,184 @@ __device__ __forceinline__ void store_quad_global(const GridArgs& a, int64_t bas
     if (FAST || a.truncated) *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
 }
 
+// base3 - [r < t0] - [r < t1] - [r < t2]  ==  base3 - 3 + #(thresholds <= r): three borrow-chained subtractions
+// (IADD3 with carry-out + IADD3.X) instead of three 64-bit differences.
+__device__ __forceinline__ uint32_t slot_minus_borrows(uint32_t base3, uint32_t r, uint32_t t0, uint32_t t1, uint32_t t2) {
+    asm("{\n\t"
+        ".reg .u32 t;\n\t"
+        "sub.cc.u32 t, %1, %2;\n\t"
+        "subc.u32 %0, %0, 0;\n\t"
+        "sub.cc.u32 t, %1, %3;\n\t"
+        "subc.u32 %0, %0, 0;\n\t"
+        "sub.cc.u32 t, %1, %4;\n\t"
+        "subc.u32 %0, %0, 0;\n\t"
+        "}"
+        : "+r"(base3)
+        : "r"(r), "r"(t0), "r"(t1), "r"(t2));
+    return base3;
+}
+
+// A stepped quad in the packed state layout: w = destination cell | episode counter << 16 (after auto-reset).
+struct PackedQuad {
+    uint32_t w[4];
+    float ret[4], rew[4];
+    uint32_t term, trunc;   // byte j = flag of env j
+};
+
+// One env of a packed quad through the checking path (an action outside 0..3, or a row the reference raises on), by
+// value so that the caller's quad stays in registers.  Returns {packed word, return bits, reward bits, f}: f bit0
+// terminated, bit1 truncated, bit2 rejected (state untouched), bits 8-15 the ef_step_error kind, bits 16-.. the detail.
+template <bool SMEM, int SLOTS>
+__device__ __noinline__ uint4 packed_slow_env(const uint2* __restrict__ tab, uint32_t thr0, uint32_t thr1, uint32_t thr2,
+                                              uint32_t idx_cap, uint32_t lim_hi, int32_t act, uint32_t r, uint32_t w, float ret) {
+    const uint32_t pos = w & 0xffffu;
+    if (static_cast<uint32_t>(act) > 3u)
+        return make_uint4(w, __float_as_uint(ret), 0u, 4u | (EF_STEP_BAD_ACTION << 8) | (static_cast<uint32_t>(act) << 16));
+    const uint32_t row = pos * 4u + static_cast<uint32_t>(act);
+    uint32_t slot = row * SLOTS;
+    if (SLOTS == 4) slot += min(slot_minus_borrows(3u, r, thr0, thr1, thr2), idx_cap);
+    const uint2 o = SMEM ? tab[slot] : __ldg(tab + slot);
+    const uint32_t fl = o.x >> 16;
+    if (fl & (EF_GRID_NO_OUTCOMES | EF_GRID_BAD_PROBS))
+        return make_uint4(w, __float_as_uint(ret), 0u,
+                          4u | (((fl & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS) << 8) | (row << 16));
+    w = __byte_perm(o.x, w, 0x7610) + 0x10000u;
+    return make_uint4(w, __float_as_uint(ret + __uint_as_float(o.y)), o.y, (fl & EF_GRID_DONE) | (w >= lim_hi ? 2u : 0u));
+}
+
+// One step of a full quad in the PACKED state layout with auto-reset on (what the packed layout implies), single-layout
+// batch.  Same Philox words, same table walk and same results as step_quad_compute, fewer instructions: the episode
+// counter is stepped inside the packed word (one PRMT + one add per env), the four flag bytes are gathered with three
+// PRMTs, the outcome index is a borrow chain, and rejected rows / out-of-range actions (rare) leave the straight-line code.
+template <bool SMEM, int SLOTS, bool FAST, bool W8>
+__device__ __forceinline__ void step_quad_packed(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
+                                                 uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
+                                                 ErrorAcc& errs, PackedQuad& q) {
+    int32_t act[4] = {in.a4.x, in.a4.y, in.a4.z, in.a4.w};
+    q.w[0] = static_cast<uint32_t>(in.p4.x); q.w[1] = static_cast<uint32_t>(in.p4.y);
+    q.w[2] = static_cast<uint32_t>(in.p4.z); q.w[3] = static_cast<uint32_t>(in.p4.w);
+    q.ret[0] = in.r4.x; q.ret[1] = in.r4.y; q.ret[2] = in.r4.z; q.ret[3] = in.r4.w;
+    if (!FAST && philox_act) {
+        uint32_t wp[4];
+        group_words4_rk(a.rk, a.seed, g0, t, kStreamPolicy, wp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(wp[j] >> 30);
+    }
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    if constexpr (SLOTS == 4) group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, r);
+    // thresholds at or beyond idx_cap are 2^32 (unreachable): clipped to 2^32 - 1 here, the index cap does the rest
+    const uint32_t thr0 = a.thr0 > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(a.thr0);
+    const uint32_t thr1 = a.thr1 > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(a.thr1);
+    const uint32_t thr2 = a.thr2 > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(a.thr2);
+    const uint32_t lim_hi = static_cast<uint32_t>(a.limit) << 16;   // packed layout: 0 < limit <= 65535
+    const bool wild = ((act[0] | act[1] | act[2] | act[3]) & ~3) != 0;
+    uint32_t gathered = 0u;
+    uint2 o[4];
+    if (!wild) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t slot = ((q.w[j] & 0xffffu) * 4u + static_cast<uint32_t>(act[j])) * SLOTS;
+            if constexpr (SLOTS == 4) {
+                if (a.idx_cap == 3) slot = slot_minus_borrows(slot + 3u, r[j], thr0, thr1, thr2);   // launch-uniform
+                else slot += min(slot_minus_borrows(3u, r[j], thr0, thr1, thr2), static_cast<uint32_t>(a.idx_cap));
+            }
+            o[j] = SMEM ? tab[slot] : __ldg(tab + slot);
+        }
+        // byte j of `gathered` = flag byte of env j's outcome (bit0 done, bit1 no outcomes, bit2 bad probabilities)
+        gathered = __byte_perm(__byte_perm(o[0].x, o[1].x, 0x0062), __byte_perm(o[2].x, o[3].x, 0x0062), 0x5410);
+    }
+    q.term = q.trunc = 0u;
+    if (!wild) {
+        // Rows the reference raises on are compiled INERT (next = own cell, reward 0, not done): applying one changes
+        // nothing but the episode counter, which the fix-up below takes back -- so the straight-line code never branches
+        // on them (they are ~0.1 % of the env-steps of BASELINE config 2, i.e. some lane of every eighth warp).
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            q.w[j] = __byte_perm(o[j].x, q.w[j], 0x7610) + 0x10000u;   // destination cell | (counter + 1) << 16
+            q.rew[j] = __uint_as_float(o[j].y);
+            q.ret[j] += q.rew[j];
+        }
+        uint32_t rejected = 0u;
+        const uint32_t badmask = gathered & 0x06060606u;
+        if (badmask) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t fl = (badmask >> (8 * j)) & 0xffu;
+                if (fl) {
+                    q.w[j] -= 0x10000u;
+                    ++rejected;
+                    errs.record(g0 + j, (q.w[j] & 0xffffu) * 4u + static_cast<uint32_t>(act[j]),
+                                (fl & EF_GRID_NO_OUTCOMES) ? EF_STEP_NO_OUTCOMES : EF_STEP_BAD_PROBS);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q.trunc |= (q.w[j] >= lim_hi ? 1u : 0u) << (8 * j);
+        q.term = gathered & 0x01010101u;
+        acc.steps += 4u - rejected;
+    } else {   // an action outside 0..3 somewhere in the quad: one env at a time through the checking path
+        uint32_t rejected = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 x = packed_slow_env<SMEM, SLOTS>(tab, thr0, thr1, thr2, static_cast<uint32_t>(a.idx_cap), lim_hi, act[j],
+                                                         r[j], q.w[j], q.ret[j]);
+            q.w[j] = x.x;
+            q.ret[j] = __uint_as_float(x.y);
+            q.rew[j] = __uint_as_float(x.z);
+            q.term |= (x.w & 1u) << (8 * j);
+            q.trunc |= ((x.w >> 1) & 1u) << (8 * j);
+            if (x.w & 4u) {
+                ++rejected;
+                errs.record(g0 + j, x.w >> 16, (x.w >> 8) & 0xffu);
+            }
+        }
+        acc.steps += 4u - rejected;
+    }
+    if (!FAST && a.final_obs) {  // pre-reset observation, only on request
+        const int32_t fp[4] = {static_cast<int32_t>(q.w[0] & 0xffffu), static_cast<int32_t>(q.w[1] & 0xffffu),
+                               static_cast<int32_t>(q.w[2] & 0xffffu), static_cast<int32_t>(q.w[3] & 0xffffu)};
+        store_obs4<W8>(a, a.final_obs, base, fp);
+    }
+    const uint32_t fin = q.term | q.trunc;   // auto-reset is on whenever the state is packed
+    if (fin) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if ((fin >> (8 * j)) & 1u) {
+                acc.finish(static_cast<int>(q.w[j] >> 16), q.ret[j]);
+                q.w[j] = static_cast<uint32_t>(a.start_cell);
+                q.ret[j] = 0.0f;
+            }
+        }
+    }
+}
+
+template <bool FAST, bool W8>
+__device__ __forceinline__ void store_quad_packed(const GridArgs& a, int64_t base, const PackedQuad& q) {
+    *reinterpret_cast<uint4*>(a.pos + base) = make_uint4(q.w[0], q.w[1], q.w[2], q.w[3]);
+    *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
+    if (FAST || a.obs) {  // observation after auto-reset = (row, col) of the stored position
+        const int32_t p[4] = {static_cast<int32_t>(q.w[0] & 0xffffu), static_cast<int32_t>(q.w[1] & 0xffffu),
+                              static_cast<int32_t>(q.w[2] & 0xffffu), static_cast<int32_t>(q.w[3] & 0xffffu)};
+        store_obs4<W8>(a, a.obs, base, p);
+    }
+    if (FAST || a.reward) *reinterpret_cast<float4*>(a.reward + base) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
+    if (FAST || a.terminated) *reinterpret_cast<uint32_t*>(a.terminated + base) = q.term;
+    if (FAST || a.truncated) *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
+}
+
 template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
 __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
                                           uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
                                           ErrorAcc& errs) {
-    Quad q;
-    step_quad_compute<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, base, g0, t, in, philox_act, acc, errs, q);
-    store_quad_global<PACKED, FAST, W8>(a, base, q);
+    if constexpr (EF_STEP_LEAN && PACKED && !HET) {
+        PackedQuad q;
+        step_quad_packed<SMEM, SLOTS, FAST, W8>(a, tab, base, g0, t, in, philox_act, acc, errs, q);
+        store_quad_packed<FAST, W8>(a, base, q);
+    } else {
+        Quad q;
+        step_quad_compute<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, base, g0, t, in, philox_act, acc, errs, q);
+        store_quad_global<PACKED, FAST, W8>(a, base, q);
+    }
 }
 
 // Ragged tail of the vector kernels: the at most three envs past the last full quad, stepped by the last CTA through the
@@ -491,19 +695,6 @@ __device__ __forceinline__ void step_tail(const GridArgs& a, const uint2* __rest
 #ifndef EF_STEP_Q
 #define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
 #endif
-// Pipelined step kernel (TMA in): used when the call has the FAST shape, the table is staged and a CTA's share fits its
-// shared memory.  EF_PIPE_CTAS = resident CTAs per SM it is compiled and sized for; EF_PIPE_TMA_OUT = outputs leave as
-// per-warp cp.async.bulk stores instead of 128-bit global stores.
-#ifndef EF_PIPE
-#define EF_PIPE 1
-#endif
-#ifndef EF_PIPE_CTAS
-#define EF_PIPE_CTAS 2
-#endif
-#ifndef EF_PIPE_TMA_OUT
-#define EF_PIPE_TMA_OUT 0
-#endif
-
 // ---- step -------------------------------------------------------------------------------------------------------------
 // Vector kernel (all pointers 16-byte aligned, Philox or no outcome draws).  The batch is cut into one contiguous chunk of
 // quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
@@ -513,28 +704,38 @@ template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bo
 __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
     __shared__ uint64_t table_bar;
     bool table_pending;
+    EF_TRACE_DECL
+    EF_TRACE_POINT(0);   // kernel entry
     const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
     pdl_launch_dependents();
     pdl_wait();                                            // previous launch complete, its writes visible
+    EF_TRACE_POINT(1);   // released by the previous launch
     EpisodeAcc acc;
     ErrorAcc errs;
-    unsigned long long ticket;
-    const uint64_t t = a.t + clock_begin(a.clock, ticket);  // thread 0 reads the device clock and takes the ticket
     const bool philox_act = FAST ? false : a.action == nullptr;
     const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
     const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
     const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t q_end = min(q_begin + per_cta, quads);
-    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
+    QuadIn in[Q];
+    auto issue_loads = [&](int64_t chunk) {
         // 32-bit bookkeeping inside the chunk (a CTA's share is far below 2^31 quads); 64-bit only for the addresses
-        QuadIn in[Q];
         const uint32_t left = static_cast<uint32_t>(min(q_end - chunk, static_cast<int64_t>(Q) * kThreads));
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
             if (local < left) in[j] = load_quad<PACKED, FAST, HET, W8>(a, (chunk + local) * 4, philox_act);
         }
+    };
+    const unsigned long long clk = clock_fetch(a.clock);   // in flight ahead of the input loads, consumed by Philox
+    if (q_begin < q_end) issue_loads(q_begin);
+    const uint64_t t = a.t + clock_steps(clk);
+    EF_TRACE_POINT(2);
+    for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
+        if (chunk != q_begin) issue_loads(chunk);
+        const uint32_t left = static_cast<uint32_t>(min(q_end - chunk, static_cast<int64_t>(Q) * kThreads));
         stage_table_wait(&table_bar, table_pending);  // the bulk copy had the whole load phase to land
+        EF_TRACE_POINT(3);   // loads issued, table staged
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
@@ -542,181 +743,15 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
                 step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
                                                           static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
                                                           philox_act, acc, errs);
+            if (j == 0) EF_TRACE_POINT(4);   // first quad stepped (its loads had to land)
         }
     }
     stage_table_wait(&table_bar, table_pending);  // CTAs that own no full quad (tiny batches) still need the table below
     step_tail<SMEM, SLOTS, HET, W8>(a, tab, t, philox_act, acc, errs);
-    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
-}
-
-// ---- pipelined step (TMA in, optional TMA out) ------------------------------------------------------------------------
-// The same step for batches whose per-CTA share fits shared memory.  One elected thread moves the CTA's WHOLE input -- the
-// contiguous pos / ep_ret / action ranges of its quads -- into shared memory with cp.async.bulk, one mbarrier per stage of
-// 256 quads, the moment the previous launch is complete: every input byte of the launch is in flight at once, no thread
-// holds a register for it, and no thread spends issue slots on global loads or their 64-bit addresses.  A warp then steps
-// stage s as soon as its barrier flips, while the later stages are still landing; its outputs leave either as 128-bit
-// global stores (TMA_OUT = false) or -- written to the stage buffer in place -- as cp.async.bulk stores issued per warp
-// (TMA_OUT = true), so the writes of stage s stream out under the compute of stage s + 1.  Shapes: FAST only (actions
-// given, every output requested, auto-reset on), table staged in shared memory.
-constexpr int kPipeMaxStages = 8;
-
-template <bool PACKED, bool W8, bool TMA_OUT>
-struct PipeLayout {  // byte offsets inside one stage buffer (256 quads)
-    static constexpr uint32_t kQuad = 16u * kThreads;                 // one 16-byte vector per quad
-    static constexpr uint32_t kPos = 0u;
-    static constexpr uint32_t kLen = kQuad;                           // split state layout only
-    static constexpr uint32_t kRet = PACKED ? kQuad : 2u * kQuad;
-    static constexpr uint32_t kAct = kRet + kQuad;
-    static constexpr uint32_t kActBytes = W8 ? 4u * kThreads : kQuad;
-    static constexpr uint32_t kIn = kAct + kActBytes;                 // end of the inputs
-    // outputs (TMA_OUT): pos / ep_len / ep_ret in place; the reward takes over the int32 action vector
-    static constexpr uint32_t kRew = W8 ? kIn : kAct;
-    static constexpr uint32_t kObs = W8 ? kIn + kQuad : kIn;
-    static constexpr uint32_t kObsBytes = W8 ? 8u * kThreads : 2u * kQuad;
-    static constexpr uint32_t kTerm = kObs + kObsBytes;
-    static constexpr uint32_t kTrunc = kTerm + 4u * kThreads;
-    static constexpr uint32_t kStage = TMA_OUT ? kTrunc + 4u * kThreads : kIn;
-};
-
-template <int SLOTS, bool PACKED, bool W8, bool TMA_OUT, int MINBLOCKS>
-__global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_pipe_kernel(const GridArgs a) {
-    using L = PipeLayout<PACKED, W8, TMA_OUT>;
-    extern __shared__ __align__(128) unsigned char pipe_smem[];
-    __shared__ uint64_t bars[1 + kPipeMaxStages];   // [0] table, [1 + s] inputs of stage s
-    __shared__ unsigned long long s_clock;
-    const uint32_t table_bytes = static_cast<uint32_t>(a.table_len) * static_cast<uint32_t>(sizeof(uint2));
-    const uint2* __restrict__ tab = reinterpret_cast<const uint2*>(pipe_smem);
-    unsigned char* const stages = pipe_smem + ((table_bytes + 127u) & ~127u);
-    const int64_t quads = a.n >> 2;
-    const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * a.quads_per_cta;   // multiple of 4 quads (host)
-    const int32_t count = static_cast<int32_t>(max(static_cast<int64_t>(0), min(a.quads_per_cta, quads - q_begin)));
-    const int32_t nstages = (count + kThreads - 1) / kThreads;
-    unsigned long long ticket = 0ull;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s <= nstages; ++s) mbar_init(&bars[s], 1u);
-        mbar_expect_tx(&bars[0], table_bytes);
-        bulk_g2s(pipe_smem, a.table, table_bytes, &bars[0]);   // the table does not depend on the previous launch
-    }
-    pdl_launch_dependents();
-    pdl_wait();                                                // previous launch complete, its writes visible
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < nstages; ++s) {
-            const uint32_t cnt = static_cast<uint32_t>(min(kThreads, count - s * kThreads));
-            const uint32_t vec = cnt * 16u;
-            const uint32_t act = W8 ? (cnt & ~3u) * 4u : vec;  // bulk copies move multiples of 16 bytes
-            unsigned char* st = stages + static_cast<size_t>(s) * L::kStage;
-            const int64_t q0 = q_begin + static_cast<int64_t>(s) * kThreads;
-            mbar_expect_tx(&bars[1 + s], vec * (PACKED ? 2u : 3u) + act);
-            bulk_g2s(st + L::kPos, a.pos + q0 * 4, vec, &bars[1 + s]);
-            if constexpr (!PACKED) bulk_g2s(st + L::kLen, a.ep_len + q0 * 4, vec, &bars[1 + s]);
-            bulk_g2s(st + L::kRet, a.ep_ret + q0 * 4, vec, &bars[1 + s]);
-            if (act) {
-                if constexpr (W8) bulk_g2s(st + L::kAct, reinterpret_cast<const uint8_t*>(a.action) + q0 * 4, act, &bars[1 + s]);
-                else bulk_g2s(st + L::kAct, a.action + q0 * 4, act, &bars[1 + s]);
-            }
-        }
-        if (a.clock != nullptr) {  // thread 0 alone touches the device clock: read, then take the CTA's ticket
-            s_clock = clock_read(a.clock);
-            ticket = clock_ticket(a.clock);
-        }
-    }
-    __syncthreads();   // barriers initialised, clock value published
-    const uint64_t t = a.t + (a.clock != nullptr ? s_clock : 0ull);
-    EpisodeAcc acc;
-    ErrorAcc errs;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    bool table_ready = false;
-    for (int s = 0; s < nstages; ++s) {
-        const int32_t cnt = min(kThreads, count - s * kThreads);
-        unsigned char* st = stages + static_cast<size_t>(s) * L::kStage;
-        const int64_t base = (q_begin + static_cast<int64_t>(s) * kThreads + threadIdx.x) * 4;
-        const bool live = static_cast<int32_t>(threadIdx.x) < cnt;
-        Quad q;
-        if (live) {
-            mbar_wait(&bars[1 + s], 0u);
-            QuadIn in;
-            in.p4 = *reinterpret_cast<const int4*>(st + L::kPos + threadIdx.x * 16u);
-            if constexpr (!PACKED) in.l4 = *reinterpret_cast<const int4*>(st + L::kLen + threadIdx.x * 16u);
-            in.r4 = *reinterpret_cast<const float4*>(st + L::kRet + threadIdx.x * 16u);
-            if constexpr (W8) {
-                // the up to three quads past the last 16-byte multiple of the action bytes were not bulk-copied
-                const uint32_t w = static_cast<int32_t>(threadIdx.x) < (cnt & ~3)
-                                       ? *reinterpret_cast<const uint32_t*>(st + L::kAct + threadIdx.x * 4u)
-                                       : __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(a.action) + base));
-                in.a4 = make_int4(static_cast<int32_t>(w & 0xffu), static_cast<int32_t>((w >> 8) & 0xffu),
-                                  static_cast<int32_t>((w >> 16) & 0xffu), static_cast<int32_t>(w >> 24));
-            } else {
-                in.a4 = *reinterpret_cast<const int4*>(st + L::kAct + threadIdx.x * 16u);
-            }
-            if (!table_ready) {
-                mbar_wait(&bars[0], 0u);
-                table_ready = true;
-            }
-            step_quad_compute<true, SLOTS, PACKED, true, false, W8>(a, tab, base, static_cast<uint32_t>(a.env_offset + base), t,
-                                                                    in, false, acc, errs, q);
-        }
-        if constexpr (!TMA_OUT) {
-            if (live) store_quad_global<PACKED, true, W8>(a, base, q);
-        } else {
-            // outputs of this warp's 32 quads: contiguous in every array, so one bulk store per array.  Bulk stores move
-            // multiples of 16 bytes (4 quads of flag bytes): the at most three quads beyond go out as plain stores.
-            const int32_t wcnt = max(0, min(32, cnt - static_cast<int32_t>(warp) * 32));
-            const int32_t wbulk = wcnt & ~3;
-            if (live) {
-                if (static_cast<int32_t>(lane) < wbulk) {
-                    if constexpr (PACKED) {
-                        *reinterpret_cast<int4*>(st + L::kPos + threadIdx.x * 16u) = pack4(q.pos, q.len);
-                    } else {
-                        *reinterpret_cast<int4*>(st + L::kPos + threadIdx.x * 16u) = make_int4(q.pos[0], q.pos[1], q.pos[2], q.pos[3]);
-                        *reinterpret_cast<int4*>(st + L::kLen + threadIdx.x * 16u) = make_int4(q.len[0], q.len[1], q.len[2], q.len[3]);
-                    }
-                    *reinterpret_cast<float4*>(st + L::kRet + threadIdx.x * 16u) = make_float4(q.ret[0], q.ret[1], q.ret[2], q.ret[3]);
-                    *reinterpret_cast<float4*>(st + L::kRew + threadIdx.x * 16u) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
-                    const int2 o0 = cell_to_obs(a, q.pos[0]), o1 = cell_to_obs(a, q.pos[1]);
-                    const int2 o2 = cell_to_obs(a, q.pos[2]), o3 = cell_to_obs(a, q.pos[3]);
-                    if constexpr (W8) {
-                        const uint32_t lo = static_cast<uint32_t>(o0.x) | static_cast<uint32_t>(o0.y) << 8 |
-                                            static_cast<uint32_t>(o1.x) << 16 | static_cast<uint32_t>(o1.y) << 24;
-                        const uint32_t hi = static_cast<uint32_t>(o2.x) | static_cast<uint32_t>(o2.y) << 8 |
-                                            static_cast<uint32_t>(o3.x) << 16 | static_cast<uint32_t>(o3.y) << 24;
-                        *reinterpret_cast<uint2*>(st + L::kObs + threadIdx.x * 8u) = make_uint2(lo, hi);
-                    } else {
-                        int4* o = reinterpret_cast<int4*>(st + L::kObs + threadIdx.x * 32u);
-                        o[0] = make_int4(o0.x, o0.y, o1.x, o1.y);
-                        o[1] = make_int4(o2.x, o2.y, o3.x, o3.y);
-                    }
-                    *reinterpret_cast<uint32_t*>(st + L::kTerm + threadIdx.x * 4u) = q.term;
-                    *reinterpret_cast<uint32_t*>(st + L::kTrunc + threadIdx.x * 4u) = q.trunc;
-                } else {
-                    store_quad_global<PACKED, true, W8>(a, base, q);
-                }
-            }
-            if (wbulk > 0) {                 // warp-uniform
-                fence_proxy_async();         // my generic-proxy writes -> visible to the async proxy
-                __syncwarp();
-                if (lane == 0u) {
-                    const uint32_t w0 = warp * 32u;   // first quad of the warp inside the stage
-                    const int64_t e0 = (q_begin + static_cast<int64_t>(s) * kThreads + w0) * 4;   // its first env
-                    const uint32_t nb = static_cast<uint32_t>(wbulk);
-                    bulk_s2g(a.pos + e0, st + L::kPos + w0 * 16u, nb * 16u);
-                    if constexpr (!PACKED) bulk_s2g(a.ep_len + e0, st + L::kLen + w0 * 16u, nb * 16u);
-                    bulk_s2g(a.ep_ret + e0, st + L::kRet + w0 * 16u, nb * 16u);
-                    bulk_s2g(a.reward + e0, st + L::kRew + w0 * 16u, nb * 16u);
-                    if constexpr (W8) bulk_s2g(reinterpret_cast<uint8_t*>(a.obs) + 2 * e0, st + L::kObs + w0 * 8u, nb * 8u);
-                    else bulk_s2g(a.obs + 2 * e0, st + L::kObs + w0 * 32u, nb * 32u);
-                    bulk_s2g(a.terminated + e0, st + L::kTerm + w0 * 4u, nb * 4u);
-                    bulk_s2g(a.truncated + e0, st + L::kTrunc + w0 * 4u, nb * 4u);
-                    bulk_commit();
-                }
-            }
-        }
-    }
-    if (!table_ready) mbar_wait(&bars[0], 0u);  // CTAs without a quad still drain the table copy (and the tail needs it)
-    if constexpr (TMA_OUT) {
-        if (lane == 0u) bulk_wait_read_all();   // the stage buffers must outlive the bulk stores' reads
-    }
-    step_tail<true, SLOTS, false, W8>(a, tab, t, false, acc, errs);
-    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
+    EF_TRACE_POINT(13);  // before the CTA epilogue
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, 0ull, 1ull);
+    EF_TRACE_POINT(14);  // done
+    EF_TRACE_FLUSH(t);
 }
 
 // Scalar kernel: one env per thread, any alignment, optional injected outcome draws (parity tests, unaligned views).
@@ -1088,18 +1123,6 @@ static int launch(Kernel kernel, const GridArgs& a, bool smem, int grid, cudaStr
     return launch_kernel(kernel, a, grid, bytes, stream);
 }
 
-// Pinned host memory handed in as a UVA pointer (the zero-copy host-buffer step)?  Such buffers keep plain loads / stores:
-// the pipelined kernel's bulk copies are reserved for device memory.
-static bool is_host_memory(const void* p) {
-    if (!p) return false;
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return true;   // unknown memory: take the conservative path
-    }
-    return at.type != cudaMemoryTypeDevice;
-}
-
 }  // namespace ef
 
 using namespace ef;
@@ -1109,8 +1132,7 @@ template <bool W8>
 static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret, const void* action,
                                const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, void* obs,
                                float* reward, uint8_t* terminated, uint8_t* truncated, void* final_obs, double* stats,
-                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream,
-                               bool host_io) {
+                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     GridArgs a{};
     if (int s = fill_args(grid, a)) return s;
     if (n < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
@@ -1146,36 +1168,6 @@ static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* 
     a.rk = philox_round_keys(seed);
     const bool packed = ep_len == nullptr;
     const bool fast = action && obs && reward && terminated && truncated && !final_obs && autoreset != 0;
-    if (EF_PIPE && smem && fast && vec && !host_io && (n >> 2) > 0) {
-        // pipelined kernel: spread the full quads over the resident CTA slots, shares rounded up to 4 quads (16 bytes of
-        // flag / uint8-action bytes, the granularity of a bulk copy); taken when the share fits a CTA's shared memory
-        const int64_t fq = n >> 2;
-        const int grid_p = static_cast<int>(std::max<int64_t>(
-            1, std::min<int64_t>(static_cast<int64_t>(sm_count()) * EF_PIPE_CTAS, (fq + 31) / 32)));
-        const int64_t per_cta = ((fq + grid_p - 1) / grid_p + 3) & ~static_cast<int64_t>(3);
-        const int64_t nstages = (per_cta + kThreads - 1) / kThreads;
-        const size_t table_bytes = (static_cast<size_t>(a.table_len) * sizeof(uint2) + 127) & ~static_cast<size_t>(127);
-        const size_t stage_bytes = packed ? PipeLayout<true, W8, EF_PIPE_TMA_OUT != 0>::kStage
-                                          : PipeLayout<false, W8, EF_PIPE_TMA_OUT != 0>::kStage;
-        const size_t bytes = table_bytes + static_cast<size_t>(nstages) * stage_bytes;
-        const size_t cap = 232448 / EF_PIPE_CTAS - 2048;  // 227 KB per SM, minus the per-CTA reserve and the static arrays
-        if (nstages <= kPipeMaxStages && bytes <= cap) {
-            a.quads_per_cta = per_cta;
-#define EF_LAUNCH_PIPE(SL, PK)                                                                                            \
-    do {                                                                                                                  \
-        auto kernel = gridworld_step_pipe_kernel<SL, PK, W8, EF_PIPE_TMA_OUT != 0, EF_PIPE_CTAS>;                         \
-        if (bytes > 48 * 1024) {                                                                                          \
-            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
-                                                       static_cast<int>(bytes));                                          \
-            if (e != cudaSuccess) return cuda_status(e);                                                                  \
-        }                                                                                                                 \
-        return launch_kernel(kernel, a, grid_p, bytes, st);                                                               \
-    } while (0)
-            if (grid->n_slots == 1) { if (packed) EF_LAUNCH_PIPE(1, true); else EF_LAUNCH_PIPE(1, false); }
-            else { if (packed) EF_LAUNCH_PIPE(4, true); else EF_LAUNCH_PIPE(4, false); }
-#undef EF_LAUNCH_PIPE
-        }
-    }
 #define EF_LAUNCH_VEC(SM, SL, PK, FS)                                                                                    \
     return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS, false, W8>, a, SM, grid_v, \
                           st)                                                                                            \
@@ -1203,8 +1195,7 @@ extern "C" int ef_gridworld_step(const ef_grid_desc* grid, int32_t* pos, int32_t
                                  uint8_t* truncated, int32_t* final_obs, double* stats, uint32_t* err,
                                  uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     return gridworld_step_impl<false>(grid, pos, ep_len, ep_ret, action, draw, seed, t, env_offset, obs, reward, terminated,
-                                      truncated, final_obs, stats, err, clock, n, autoreset, stream,
-                                      is_host_memory(action) || is_host_memory(obs));
+                                      truncated, final_obs, stats, err, clock, n, autoreset, stream);
 }
 
 extern "C" int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret,
@@ -1213,20 +1204,18 @@ extern "C" int ef_gridworld_step_u8(const ef_grid_desc* grid, int32_t* pos, int3
                                     uint8_t* truncated, uint8_t* final_obs, double* stats, uint32_t* err,
                                     uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     return gridworld_step_impl<true>(grid, pos, ep_len, ep_ret, action, draw, seed, t, env_offset, obs, reward, terminated,
-                                     truncated, final_obs, stats, err, clock, n, autoreset, stream,
-                                     is_host_memory(action) || is_host_memory(obs));
+                                     truncated, final_obs, stats, err, clock, n, autoreset, stream);
 }
 
 extern "C" int ef_gridworld_step_v(const ef_gridworld_step_args* x) {
     if (!x) return EF_ERR_INVALID_ARGUMENT;
-    const bool host_io = (x->wire & EF_WIRE_HOST_IO) != 0;  // the caller says so: no pointer query on this lean path
     if (x->wire & EF_WIRE_U8)  // action / obs / final_obs point at bytes (see ef_gridworld_step_u8)
         return gridworld_step_impl<true>(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset,
                                          x->obs, x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err,
-                                         x->clock, x->n, x->autoreset, x->stream, host_io);
+                                         x->clock, x->n, x->autoreset, x->stream);
     return gridworld_step_impl<false>(x->grid, x->pos, x->ep_len, x->ep_ret, static_cast<const int32_t*>(x->action), x->draw,
                                       x->seed, x->t, x->env_offset, x->obs, x->reward, x->terminated, x->truncated,
-                                      x->final_obs, x->stats, x->err, x->clock, x->n, x->autoreset, x->stream, host_io);
+                                      x->final_obs, x->stats, x->err, x->clock, x->n, x->autoreset, x->stream);
 }
 
 extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
@@ -1459,3 +1448,10 @@ extern "C" int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos
         start_cell, cols, pos, ep_len, ep_ret, obs, mask, n);
     return cuda_status(cudaGetLastError());
 }
+
+#ifdef EF_TRACE
+// tools-only build: where the step kernels store their timeline (device buffer of 8 * 4 * 1024 * 32 uint64, or NULL)
+extern "C" int ef_debug_set_trace(unsigned long long* buf) {
+    return cuda_status(cudaMemcpyToSymbol(ef::g_trace_buf, &buf, sizeof(buf)));
+}
+#endif

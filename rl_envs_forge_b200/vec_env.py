@@ -108,15 +108,16 @@ class VecEnv:
     # -- device clock ---------------------------------------------------------------------------------------------
     def enable_device_clock(self):
         """Keep the Philox time coordinate in device memory so that step()/rollout() can be captured in a CUDA graph and
-        replayed: the kernels read and advance the clock themselves instead of receiving `t` as a baked-in argument."""
+        replayed: the kernels read and advance the clock themselves instead of receiving `t` as a baked-in argument.
+        The device word counts in units of 2**-CLOCK_SHIFT steps (every CTA adds its share when it retires)."""
         if self._clock is None:
             torch = self._torch
-            self._clock = torch.tensor([self._t, 0], dtype=torch.int64, device=self.device)
+            self._clock = torch.tensor([self._t << _lib.EF_CLOCK_SHIFT, 0], dtype=torch.int64, device=self.device)
         return self._clock
 
     def disable_device_clock(self):
         if self._clock is not None:
-            self._t = int(self._clock[0].item())
+            self._t = int(self._clock[0].item()) >> _lib.EF_CLOCK_SHIFT
             self._clock = None
 
     def _t_arg(self):
@@ -247,7 +248,7 @@ class VecEnv:
 
     @property
     def step_count(self):
-        return self._t if self._clock is None else int(self._clock[0].item())
+        return self._t if self._clock is None else int(self._clock[0].item()) >> _lib.EF_CLOCK_SHIFT
 
     def close(self):
         if getattr(self, "_pipe_handle", None) is not None:
