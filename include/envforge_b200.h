@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define EF_ABI_VERSION 1
+#define EF_ABI_VERSION 2
 #define EF_STATS_LEN 8
 #define EF_STATS_REPLICAS 32
 #define EF_STATS_STRIDE 16
@@ -61,7 +61,9 @@ typedef enum ef_status {
 
 typedef enum ef_step_error {
     EF_STEP_OK = 0,
-    EF_STEP_BAD_ACTION = 1,        /* GridWorld: Action(a) ValueError (grid_world.py:505); bandit: assert (k_armed_bandit.py:186) */
+    EF_STEP_BAD_ACTION = 1,        /* GridWorld: Action(a) ValueError (grid_world.py:505); bandit: assert (k_armed_bandit.py:186);
+                                      CartPole / PendulumDisk: assert action_space.contains(action) (cart_pole.py:108,
+                                      pendulum_disk.py:109) -- |a| > 3 or NaN; detail = bits 8-31 of the fp32 action */
     EF_STEP_NO_OUTCOMES = 2,       /* GridWorld: "No outcomes defined" ValueError (grid_world.py:508-511), e.g. agent on a wall */
     EF_STEP_BAD_PROBS = 3          /* GridWorld: numpy choice "probabilities do not sum to 1" (grid_world.py:515) */
 } ef_step_error;
@@ -251,18 +253,20 @@ typedef struct ef_pendulum_params {
 /* CartPole.step (cart_pole.py:107-180) + reset (:91-105) as same-step auto-reset.
  *   state   [n,4] fp32 (x, x_dot, theta, theta_dot), 16-byte aligned.   action [n] fp32 force, or NULL: U(-3,3) policy.
  *   obs     [n,4] post-reset observation (nullable; may equal `state`).  final_obs [n,4] pre-reset (nullable).
- *   acc     [n,2] (x_acc, theta_acc) info values (nullable). */
+ *   acc     [n,2] (x_acc, theta_acc) info values (nullable).
+ *   err     (nullable) the reference asserts action_space.contains(action) (:108): an env-step whose action is NaN or
+ *           outside [-3, 3] is counted there (EF_STEP_BAD_ACTION) and leaves the env untouched -- reward 0, flags 0. */
 int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, const float* action,
                      uint64_t seed, uint64_t t, uint64_t env_offset, float* obs, float* reward, uint8_t* terminated,
-                     uint8_t* truncated, float* final_obs, float* acc, double* stats, uint64_t* clock, int64_t n,
+                     uint8_t* truncated, float* final_obs, float* acc, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
                      int32_t autoreset, void* stream);
 int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                        float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
+                        float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n, void* stream);
 /* ..._rollout that also materialises the observation trajectory: obs [K,n,4] fp32, the state after each step's auto-reset. */
 int ef_cartpole_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                              const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K, float* obs,
-                             float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
+                             float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n, void* stream);
 /* reset: initial state from params (fixed) or Philox STREAM_RESET_USER at counter `epoch`; mask nullable. */
 int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                       uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
@@ -272,13 +276,13 @@ int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len
 int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                           const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
                           float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs, float* acc,
-                          double* stats, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
+                          double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream);
 int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                              const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                             float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream);
+                             float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n, void* stream);
 int ef_pendulum_disk_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                   const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                                  float* obs /* [K,n,2] */, float* rewards, uint8_t* flags, double* stats, uint64_t* clock,
+                                  float* obs /* [K,n,2] */, float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock,
                                   int64_t n, void* stream);
 int ef_pendulum_disk_reset(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, uint64_t seed,
                            uint64_t epoch, uint64_t env_offset, const uint8_t* mask, int64_t n, void* stream);
@@ -517,14 +521,14 @@ int ef_cartpole_step_host(ef_host_pipe* pipe, const ef_pendulum_params* p, float
                           const float* h_action, float* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,
                           float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated, float* d_final_obs,
                           float* d_acc, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
-                          float* h_final_obs, float* h_acc, double* stats, int64_t n, int32_t autoreset, int32_t chunks,
+                          float* h_final_obs, float* h_acc, double* stats, uint32_t* err, int64_t n, int32_t autoreset, int32_t chunks,
                           void* stream);
 int ef_pendulum_disk_step_host(ef_host_pipe* pipe, const ef_pendulum_params* p, float* state, int32_t* ep_len,
                                float* ep_ret, const float* h_action, float* d_action, uint64_t seed, uint64_t t,
                                uint64_t env_offset, float* d_obs, float* d_reward, uint8_t* d_terminated,
                                uint8_t* d_truncated, float* d_final_obs, float* d_acc, float* h_obs, float* h_reward,
                                uint8_t* h_terminated, uint8_t* h_truncated, float* h_final_obs, float* h_acc,
-                               double* stats, int64_t n, int32_t autoreset, int32_t chunks, void* stream);
+                               double* stats, uint32_t* err, int64_t n, int32_t autoreset, int32_t chunks, void* stream);
 int ef_bandit_step_host(ef_host_pipe* pipe, const ef_arm* arms, int32_t k, const int32_t* h_action, int32_t* d_action,
                         uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t* d_obs, float* d_reward, int32_t* h_obs,
                         float* h_reward, double* stats, uint32_t* err, int64_t n, int32_t chunks, void* stream);

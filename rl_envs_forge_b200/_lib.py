@@ -16,7 +16,7 @@ EF_STATS_STRIDE = 16
 EF_ERR_LEN = 4
 EF_STATS_MAX_SETS = 32
 EF_PEER_HANDLE_BYTES = 64
-EF_ABI_VERSION = 1
+EF_ABI_VERSION = 2
 EF_WIRE_U8 = 0x1
 EF_CLOCK_SHIFT = 20
 
@@ -100,18 +100,18 @@ SIGNATURES = {
                                             _P, _I64, _P]),
     "ef_gridworld_reset": (C.c_int, [_I32, _I32, _P, _P, _P, _P, _P, _I64, _P]),
     "ef_cartpole_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
-                                   _P, _P, _I64, _I32, _P]),
+                                   _P, _P, _P, _I64, _I32, _P]),
     "ef_cartpole_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,
-                                      _P, _I64, _P]),
+                                      _P, _P, _I64, _P]),
     "ef_cartpole_rollout_traj": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,
-                                           _P, _P, _I64, _P]),
+                                           _P, _P, _P, _I64, _P]),
     "ef_pendulum_disk_rollout_traj": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P,
-                                                _P, _P, _P, _I64, _P]),
+                                                _P, _P, _P, _P, _I64, _P]),
     "ef_cartpole_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
     "ef_pendulum_disk_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P,
-                                        _P, _P, _P, _I64, _I32, _P]),
+                                        _P, _P, _P, _P, _I64, _I32, _P]),
     "ef_pendulum_disk_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P,
-                                           _P, _P, _I64, _P]),
+                                           _P, _P, _P, _I64, _P]),
     "ef_pendulum_disk_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
     "ef_bandit_step": (C.c_int, [_P, _I32, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_step_mt19937": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _U64, _P, _P, _P, _P, _P, _I64, _P]),
@@ -145,9 +145,9 @@ SIGNATURES = {
     "ef_gridworld_step_u8_host": (C.c_int, [_P, C.POINTER(GridDesc), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 10
                                   + [_P, _P, _I64, _I32, _I32, _P]),
     "ef_cartpole_step_host": (C.c_int, [_P, C.POINTER(PendulumParams), _P, _P, _P, _P, _P, _U64, _U64, _U64] + [_P] * 12
-                              + [_P, _I64, _I32, _I32, _P]),
+                              + [_P, _P, _I64, _I32, _I32, _P]),
     "ef_pendulum_disk_step_host": (C.c_int, [_P, C.POINTER(PendulumParams), _P, _P, _P, _P, _P, _U64, _U64, _U64]
-                                   + [_P] * 12 + [_P, _I64, _I32, _I32, _P]),
+                                   + [_P] * 12 + [_P, _P, _I64, _I32, _I32, _P]),
     "ef_bandit_step_host": (C.c_int, [_P, _P, _I32, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
 }
 

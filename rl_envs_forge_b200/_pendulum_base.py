@@ -133,6 +133,20 @@ class VecPendulumBase(VecEnv):
             self._obs.copy_(self._state)
         return self._obs, {}
 
+    def check_errors(self, clear=True):
+        """Raise AssertionError if any env-step since the last check carried an action the reference asserts on
+        (`assert self.action_space.contains(action)`, cart_pole.py:108 / pendulum_disk.py:109): NaN or outside [-3, 3].
+        Such env-steps were rejected on the device: env untouched, reward 0, flags 0, counted in `err`."""
+        e = [int(x) & 0xFFFFFFFF for x in self.err.cpu().tolist()]
+        if clear and e[0]:
+            self.err.zero_()
+        if e[0]:
+            packed = e[2] | (e[3] << 32)      # (1 + global env index) << 32 | kind << 24 | bits 8-31 of the fp32 action
+            env, detail = (packed >> 32) - 1, packed & 0xFFFFFF
+            approx = float(np.array([detail << 8], dtype=np.uint32).view(np.float32)[0])
+            raise AssertionError(f"{e[0]} env-step(s) rejected: action outside [-3, 3] invalid; first offender env {env}, "
+                                 f"action ~ {approx!r}")
+
     def _check_actions_strict(self, a):
         # Box(-3, 3, (1,), float32).contains (cart_pole.py:108): float32-castable dtype and |a| <= 3
         torch = self._torch
@@ -155,7 +169,7 @@ class VecPendulumBase(VecEnv):
                 fixed = self._fast_args = (
                     (self._params, self._state.data_ptr(), self.ep_len.data_ptr(), self.ep_ret.data_ptr()),
                     (self._obs.data_ptr(), self._reward.data_ptr(), self._term.data_ptr(), self._trunc.data_ptr(), None, None,
-                     self._stats_raw.data_ptr()),
+                     self._stats_raw.data_ptr(), self.err.data_ptr()),
                     (self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)),
                     self.ep_len, self.ep_ret)
             head, tail, outs = fixed[:3]
@@ -226,13 +240,13 @@ class VecPendulumBase(VecEnv):
                     self._pipe(), self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret), p_act,
                     d_act, self._seed, self._t, self.env_offset, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(term),
                     _lib.ptr(trunc), _lib.ptr(fobs), _lib.ptr(acc), *[_lib.ptr(h) for h in hosts],
-                    _lib.ptr(self._stats_raw), n, int(self.autoreset), self.host_chunks, self._stream()))
+                    _lib.ptr(self._stats_raw), _lib.ptr(self.err), n, int(self.autoreset), self.host_chunks, self._stream()))
             obs, rew, term, trunc, fobs, acc = hosts
         else:
             self._call(self._fn_step, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
                        p_act, self._seed, self._t_arg(), self.env_offset, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(term),
-                       _lib.ptr(trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n,
-                       int(self.autoreset))
+                       _lib.ptr(trunc), _lib.ptr(fobs), _lib.ptr(acc), _lib.ptr(self._stats_raw), _lib.ptr(self.err),
+                       _lib.ptr(self._clock), n, int(self.autoreset))
         self._t += 1
         info = {}
         if host_io:
@@ -281,11 +295,11 @@ class VecPendulumBase(VecEnv):
             obs = torch.empty((K, n, self.DIM), dtype=torch.float32, device=self.device)
             self._call(self._fn_rollout_traj, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
                        _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew),
-                       _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n)
+                       _lib.ptr(flg), _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
         else:
             self._call(self._fn_rollout, self._params, _lib.ptr(self._state), _lib.ptr(self.ep_len), _lib.ptr(self.ep_ret),
                        _lib.ptr(actions), self._seed, self._t_arg(), self.env_offset, int(K), _lib.ptr(rew), _lib.ptr(flg),
-                       _lib.ptr(self._stats_raw), _lib.ptr(self._clock), n)
+                       _lib.ptr(self._stats_raw), _lib.ptr(self.err), _lib.ptr(self._clock), n)
         self._t += int(K)
         if self._obs is not self._state:
             self._obs.copy_(self._state)

@@ -168,8 +168,8 @@ extern "C" int ef_gridworld_step_u8_host(ef_host_pipe* pipe, const ef_grid_desc*
                         const float* h_action, float* d_action, uint64_t seed, uint64_t t, uint64_t env_offset,          \
                         float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated, float* d_final_obs,  \
                         float* d_acc, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,        \
-                        float* h_final_obs, float* h_acc, double* stats, int64_t n, int32_t autoreset, int32_t chunks,   \
-                        void* stream) {                                                                                  \
+                        float* h_final_obs, float* h_acc, double* stats, uint32_t* err, int64_t n, int32_t autoreset,    \
+                        int32_t chunks, void* stream) {                                                                  \
         const HostOut outs[6] = {{d_obs, h_obs, 4 * DIM},       {d_reward, h_reward, 4},                                 \
                                  {d_terminated, h_terminated, 1}, {d_truncated, h_truncated, 1},                         \
                                  {d_final_obs, h_final_obs, 4 * DIM}, {d_acc, h_acc, 4 * ACCW}};                         \
@@ -179,7 +179,7 @@ extern "C" int ef_gridworld_step_u8_host(ef_host_pipe* pipe, const ef_grid_desc*
                                              static_cast<const float*>(in), seed, t, env_offset + off,                   \
                                              at(d_obs, off, DIM), at(d_reward, off), at(d_terminated, off),              \
                                              at(d_truncated, off), at(d_final_obs, off, DIM), at(d_acc, off, ACCW),      \
-                                             stats, nullptr, cnt, autoreset, stream);                                    \
+                                             stats, err, nullptr, cnt, autoreset, stream);                               \
                              });                                                                                         \
     }
 

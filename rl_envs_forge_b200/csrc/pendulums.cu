@@ -26,6 +26,7 @@ struct PendArgs {
     float* final_obs;
     float* acc;
     double* stats;
+    uint32_t* err;  // rejected env-steps: an action outside [-3, 3] or NaN (the reference asserts, cart_pole.py:108)
     int64_t n;
     int32_t autoreset;
     int32_t K;
@@ -143,6 +144,10 @@ __device__ __forceinline__ uint32_t env_step(const ef_pendulum_params& p, typena
 
 __device__ __forceinline__ float policy_action(uint32_t w) { return uniform_f32(w, -3.0f, 6.0f); }
 
+// `assert self.action_space.contains(action)` (cart_pole.py:108, pendulum_disk.py:109): Box(-3, 3) rejects |a| > 3 and NaN.
+// A rejected env-step leaves the env untouched and is counted in `err` (detail = the top 24 bits of the fp32 action).
+__device__ __forceinline__ bool action_rejected(float a) { return !(fabsf(a) <= 3.0f); }
+
 #ifndef EF_PEND_GRID_PER_SM
 #define EF_PEND_GRID_PER_SM 64  // measured on B200 at 4M envs: 64 (one pass, dynamic CTA scheduling) beats a persistent 3/SM grid by 20-25 %
 #endif
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
     pdl_launch_dependents();
     pdl_wait();
     EpisodeAcc acc;
+    ErrorAcc errs;
     unsigned long long ticket;
     const uint64_t t = a.t + clock_begin(a.clock, ticket);
     const int64_t per_cta = a.per_cta;  // keeps every CTA's chunk 256-env aligned
@@ -195,9 +201,14 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
             const int64_t i = chunk + local;
             const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
             if (!FAST && !a.action) act[j] = policy_action(group_word1(a.seed, g, t, kStreamPolicy));
-            float rew, a0, a1;
-            const uint32_t f = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew, a0, a1);
-            acc.steps += 1u;
+            float rew = 0.0f, a0 = 0.0f, a1 = 0.0f;
+            uint32_t f = 0u;
+            if ((FAST || a.action) && action_rejected(act[j])) {
+                errs.record(g, __float_as_uint(act[j]) >> 8, EF_STEP_BAD_ACTION);   // env untouched, outputs zero
+            } else {
+                f = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew, a0, a1);
+                acc.steps += 1u;
+            }
             if (!FAST && a.final_obs) reinterpret_cast<Vec*>(a.final_obs)[i] = s[j];
             if ((FAST || a.autoreset) && f) {
                 acc.finish(len[j], ret[j]);
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_step_kernel(const PendArgs 
             if (!FAST && a.acc) Env::store_acc(a.acc, i, a0, a1);
         }
     }
-    cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, 1ull);
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, 1ull);
 }
 
 // Fused K-step rollout.  A thread keeps FOUR consecutive envs in registers for all K steps: one Philox call per step
@@ -228,6 +239,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
     pdl_launch_dependents();
     pdl_wait();
     EpisodeAcc acc;
+    ErrorAcc errs;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     const int64_t quads = (a.n + 3) / 4;
     const int64_t quads_round = (quads + 31) & ~static_cast<int64_t>(31);  // warp-uniform trip count
@@ -241,6 +253,7 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
         int32_t len[4];
         float ret[4];
         bool valid[4];
+        uint32_t rejected = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             valid[j] = base + j < a.n;
@@ -274,7 +287,16 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float a0, a1;
-                f[j] = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew[j], a0, a1);
+                if (EXT_ACTIONS && action_rejected(act[j])) {   // the reference asserts: env untouched, outputs zero
+                    if (valid[j]) {
+                        errs.record(g0 + j, __float_as_uint(act[j]) >> 8, EF_STEP_BAD_ACTION);
+                        ++rejected;
+                    }
+                    rew[j] = 0.0f;
+                    f[j] = 0u;
+                } else {
+                    f[j] = env_step<Env>(a.p, s[j], len[j], ret[j], act[j], rew[j], a0, a1);
+                }
                 any_fin |= valid[j] && f[j];
             }
             if constexpr (EMIT) {
@@ -345,8 +367,9 @@ __global__ void __launch_bounds__(kThreads) pendulum_rollout_kernel(const PendAr
                 a.ep_ret[base + j] = ret[j];
             }
         }
+        acc.steps -= rejected;
     }
-    cta_epilogue(acc, ErrorAcc(), a.stats, nullptr, a.clock, ticket, static_cast<unsigned long long>(a.K));
+    cta_epilogue(acc, errs, a.stats, a.err, a.clock, ticket, static_cast<unsigned long long>(a.K));
 }
 
 template <class Env>
@@ -374,9 +397,10 @@ static int check_common(const ef_pendulum_params* p, const float* state, const i
 template <class Env>
 static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret, const float* action,
                      uint64_t seed, uint64_t t, uint64_t env_offset, float* obs, float* reward, uint8_t* terminated,
-                     uint8_t* truncated, float* final_obs, float* acc, double* stats, uint64_t* clock, int64_t n,
+                     uint8_t* truncated, float* final_obs, float* acc, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
                      int32_t autoreset, void* stream) {
     if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
+    if (!aligned(err, 8)) return EF_ERR_INVALID_ARGUMENT;
     if (!aligned(obs, sizeof(typename Env::Vec)) || !aligned(final_obs, sizeof(typename Env::Vec)) ||
         !aligned(acc, Env::DIM == 4 ? 8 : 4))
         return EF_ERR_INVALID_ARGUMENT;
@@ -385,7 +409,7 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = action;
     a.seed = seed; a.t = t; a.env_offset = env_offset; a.obs = obs; a.reward = reward;
     a.terminated = terminated; a.truncated = truncated; a.final_obs = final_obs; a.acc = acc;
-    a.stats = stats; a.n = n; a.autoreset = autoreset; a.clock = reinterpret_cast<unsigned long long*>(clock);
+    a.stats = stats; a.err = err; a.n = n; a.autoreset = autoreset; a.clock = reinterpret_cast<unsigned long long*>(clock);
     const int grid = grid_for((n + EF_PEND_U - 1) / EF_PEND_U, EF_PEND_GRID_PER_SM);
     a.per_cta = ((n + grid - 1) / grid + kThreads - 1) / kThreads * kThreads;
     const bool fast = action && obs && reward && terminated && truncated && !final_obs && !acc && autoreset != 0;
@@ -397,16 +421,17 @@ static int step_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len,
 template <class Env>
 static int rollout_impl(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                        float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n, void* stream,
-                        float* obs_traj = nullptr) {
+                        float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
+                        void* stream, float* obs_traj = nullptr) {
     if (int s = check_common<Env>(p, state, ep_len, ep_ret, env_offset, n)) return s;
+    if (!aligned(err, 8)) return EF_ERR_INVALID_ARGUMENT;
     if (K < 0 || !aligned(obs_traj, sizeof(typename Env::Vec))) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0 || K == 0) return EF_OK;
     PendArgs a{};
     a.p = *p; a.state = state; a.ep_len = ep_len; a.ep_ret = ep_ret; a.action = actions;
     a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K; a.reward = rewards; a.flags = flags; a.obs = obs_traj;
     a.rk = philox_round_keys(seed);
-    a.stats = stats; a.n = n; a.autoreset = 1; a.clock = reinterpret_cast<unsigned long long*>(clock);
+    a.stats = stats; a.err = err; a.n = n; a.autoreset = 1; a.clock = reinterpret_cast<unsigned long long*>(clock);
     const int grid = grid_for((n + 3) / 4, EF_PEND_ROLLOUT_GRID_PER_SM);
     const cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool ext = actions != nullptr, emit = rewards != nullptr || flags != nullptr || obs_traj != nullptr;
@@ -435,21 +460,21 @@ using namespace ef;
 extern "C" int ef_cartpole_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                 const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
                                 float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs, float* acc,
-                                double* stats, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+                                double* stats, uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
     return step_impl<CartPole>(p, state, ep_len, ep_ret, action, seed, t, env_offset, obs, reward, terminated, truncated,
-                               final_obs, acc, stats, clock, n, autoreset, stream);
+                               final_obs, acc, stats, err, clock, n, autoreset, stream);
 }
 extern "C" int ef_cartpole_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                    const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                                   float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n,
+                                   float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
                                    void* stream) {
-    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n, stream);
+    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, err, clock, n, stream);
 }
 extern "C" int ef_cartpole_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                                        float* obs, float* rewards, uint8_t* flags, double* stats, uint64_t* clock, int64_t n,
-                                        void* stream) {
-    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n,
+                                        float* obs, float* rewards, uint8_t* flags, double* stats, uint32_t* err, uint64_t* clock,
+                                        int64_t n, void* stream) {
+    return rollout_impl<CartPole>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, err, clock, n,
                                   stream, obs);
 }
 
@@ -461,22 +486,22 @@ extern "C" int ef_cartpole_reset(const ef_pendulum_params* p, float* state, int3
 extern "C" int ef_pendulum_disk_step(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                      const float* action, uint64_t seed, uint64_t t, uint64_t env_offset, float* obs,
                                      float* reward, uint8_t* terminated, uint8_t* truncated, float* final_obs,
-                                     float* acc, double* stats, uint64_t* clock, int64_t n, int32_t autoreset,
-                                     void* stream) {
+                                     float* acc, double* stats, uint32_t* err, uint64_t* clock, int64_t n,
+                                     int32_t autoreset, void* stream) {
     return step_impl<PendulumDisk>(p, state, ep_len, ep_ret, action, seed, t, env_offset, obs, reward, terminated,
-                                   truncated, final_obs, acc, stats, clock, n, autoreset, stream);
+                                   truncated, final_obs, acc, stats, err, clock, n, autoreset, stream);
 }
 extern "C" int ef_pendulum_disk_rollout(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                         const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset,
-                                        int32_t K, float* rewards, uint8_t* flags, double* stats, uint64_t* clock,
-                                        int64_t n, void* stream) {
-    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock, n, stream);
+                                        int32_t K, float* rewards, uint8_t* flags, double* stats, uint32_t* err,
+                                        uint64_t* clock, int64_t n, void* stream) {
+    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, err, clock, n, stream);
 }
 extern "C" int ef_pendulum_disk_rollout_traj(const ef_pendulum_params* p, float* state, int32_t* ep_len, float* ep_ret,
                                              const float* actions, uint64_t seed, uint64_t t0, uint64_t env_offset, int32_t K,
-                                             float* obs, float* rewards, uint8_t* flags, double* stats, uint64_t* clock,
-                                             int64_t n, void* stream) {
-    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, clock,
+                                             float* obs, float* rewards, uint8_t* flags, double* stats, uint32_t* err,
+                                             uint64_t* clock, int64_t n, void* stream) {
+    return rollout_impl<PendulumDisk>(p, state, ep_len, ep_ret, actions, seed, t0, env_offset, K, rewards, flags, stats, err, clock,
                                       n, stream, obs);
 }
 

@@ -55,7 +55,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ef_gridworld_rollout(ctypes.byref(d), None, None, None, None, 0, 0, 0, 4, None, None, None, None, None,
                                     8, None) == 1
     assert lib.ef_cartpole_step(None, None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, None,
-                                8, 1, None) == 1
+                                None, 8, 1, None) == 1
     assert lib.ef_bandit_step(None, 10, None, 0, 0, 0, 1, None, None, None, None, 8, None) == 1
     # packed GridWorld state (ep_len == NULL) is only accepted with auto-reset on and 0 < episode_limit <= 65535
     d.rows = d.cols = 2

@@ -4,6 +4,7 @@ Tolerance (BASELINE.json north_star): per step |device - ref| <=
 re-seeded to the device's (fp32) state each step.  Flags and the discrete reward are threshold comparisons; they may only
 differ where the compared quantity lies within the fp32 error band of the threshold -- those cases are counted."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -14,6 +15,8 @@ from tests._golden import golden_files, load
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-6
+# accelerations are differences of terms ~100x larger than the result (divided by J = 1.91e-4 for the disk): absolute floor
+ACC_ATOL = 2e-4
 
 
 def _within(dev, ref, angle_col=None):
@@ -75,7 +78,10 @@ def test_golden_steps_as_batch(kind):
         else:
             assert not ((rew != g["reward"]) & ~near).any()
         acc = info["x_acc"].cpu().numpy() if kind == "cartpole" else info["alpha_dot_dot"].cpu().numpy()
-        assert np.all(np.abs(acc - g["acc"][:, 0]) <= 1e-5 * np.abs(g["acc"][:, 0]) + 2e-4), path
+        excess = np.abs(acc - g["acc"][:, 0]) - 1e-5 * np.abs(g["acc"][:, 0])
+        print(f"{os.path.basename(path)}: acceleration error beyond 1e-5 relative: max {excess.max():.3e} (|acc| up to "
+              f"{np.abs(g['acc'][:, 0]).max():.1f})")
+        assert np.all(excess <= ACC_ATOL), path
 
 
 @pytest.mark.parametrize("kind,n", [("cartpole", 1 << 22), ("pendulumdisk", 1 << 22)])
@@ -318,3 +324,57 @@ def test_rollout_trajectory_of_observations_equals_step_sequence(kind):
         assert torch.equal(obs[k], o[0]) and torch.equal(rew[k], o[1]), k
         assert torch.equal(flg[k], o[2].to(torch.uint8) | (o[3].to(torch.uint8) << 1)), k
     assert torch.equal(a.state, b.state) and torch.equal(a.ep_len, b.ep_len)
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "pendulumdisk"])
+def test_invalid_actions_are_flagged_and_leave_the_env_untouched(kind):
+    """The reference asserts `action_space.contains(action)` (cart_pole.py:108, pendulum_disk.py:109): 5.0, NaN and
+    -3.0001 are rejected.  On the device such env-steps are counted in `err` (EF_STEP_BAD_ACTION), the env keeps its state
+    and counters, reward and flags are zero; check_errors() raises the reference's AssertionError with the offender.
+    The other envs of the batch step exactly as they do without the bad actions."""
+    import torch
+    cls = _cls(kind)[0]
+    n = 4096
+    env, ref = cls(n, seed=3), cls(n, seed=3)
+    a = torch.empty(n, device="cuda").uniform_(-3, 3)
+    for _ in range(5):                       # move away from the initial state, identical in both
+        env.step(a)
+        ref.step(a)
+    bad = {17: 5.0, 1000: float("nan"), 4095: -3.0001}
+    a_bad = a.clone()
+    for i, v in bad.items():
+        a_bad[i] = v
+    before = {k: v.clone() for k, v in env.get_state().items() if torch.is_tensor(v)}
+    steps0 = float(env.stats[4].item())
+    obs, rew, term, trunc, _ = env.step(a_bad)
+    robs, rrew, rterm, rtrunc, _ = ref.step(a)
+    idx = torch.tensor(sorted(bad), device="cuda")
+    keep = torch.ones(n, dtype=torch.bool, device="cuda")
+    keep[idx] = False
+    assert torch.equal(obs[keep], robs[keep]) and torch.equal(rew[keep], rrew[keep])
+    assert torch.equal(term[keep], rterm[keep]) and torch.equal(trunc[keep], rtrunc[keep])
+    assert torch.equal(env.state[idx], before["state"][idx])                 # untouched
+    assert torch.equal(env.ep_len[idx], before["ep_len"][idx]) and torch.equal(env.ep_ret[idx], before["ep_ret"][idx])
+    assert torch.all(rew[idx] == 0) and not bool(term[idx].any()) and not bool(trunc[idx].any())
+    assert float(env.stats[4].item()) - steps0 == n - len(bad)               # rejected env-steps are not counted
+    assert int(env.err[0].item()) == len(bad)
+    with pytest.raises(AssertionError, match="first offender env 4095"):     # largest global index wins the offender word
+        env.check_errors()
+    assert int(env.err[0].item()) == 0
+    env.check_errors()                                                       # cleared
+    # the fused rollout with external actions applies the same rule, step by step
+    K = 4
+    acts = torch.empty((K, n), device="cuda").uniform_(-3, 3)
+    acts_bad = acts.clone()
+    acts_bad[2, 7] = 3.5
+    acts_bad[0, 7] = float("inf")
+    s0 = float(env.stats[4].item())
+    r_bad, f_bad = env.rollout(K, acts_bad, return_rewards=True)
+    assert int(env.err[0].item()) == 2 and float(env.stats[4].item()) - s0 == K * n - 2
+    assert float(r_bad[2, 7]) == 0.0 and int(f_bad[2, 7]) == 0 and float(r_bad[0, 7]) == 0.0
+    with pytest.raises(AssertionError):
+        env.check_errors()
+    # the boundary itself is valid, like Box(-3, 3).contains
+    env.step(torch.full((n,), 3.0, device="cuda"))
+    env.step(torch.full((n,), -3.0, device="cuda"))
+    env.check_errors()
