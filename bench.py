@@ -58,15 +58,44 @@ def _traffic(kernel):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def _reference_gridworld():
+    """(GridWorld, Action, root) of the UNMODIFIED reference -- /root/reference in the build container, the git-ignored copy
+    oracle/_ref (made by oracle/build_ref.py, shipped with the snapshot) on the GPU box -- or None."""
+    try:
+        from oracle.ref_shim import load_reference_gridworld
+        return load_reference_gridworld()
+    except Exception:
+        return None
+
+
 def _ref_worker(args):
-    """One host process: a per-instance GridWorld stepped the way the reference steps it (dict MDP lookup +
-    numpy Generator.choice per step, reset on done/truncated).  Returns (env_steps, seconds)."""
+    """One host process: ONE GridWorld instance stepped the way a user of the reference steps it -- `env.step(action)` per
+    transition, `env.reset()` on done / truncated (grid_world.py:495-551) -- through the reference's own class when its
+    source is available (kind "reference"), else through the oracle's restatement of it (kind "port").
+    Returns (env_steps, seconds, kind)."""
     seed, n_steps = args
     import numpy as np
+    actions = np.random.default_rng(seed + 1).integers(0, 4, n_steps)
+    ref = _reference_gridworld()
+    if ref is not None:
+        GridWorld, RefAction, _ = ref
+        env = GridWorld(special_transitions={(SPECIAL[0], RefAction(SPECIAL[1])): (SPECIAL[2], SPECIAL[3])}, seed=seed,
+                        **CONFIG2)
+        env.reset()
+        done_steps = 0
+        t0 = time.perf_counter()
+        for a in actions:
+            try:
+                _, _, done, truncated, _ = env.step(int(a))
+            except ValueError:                                # the cell the reference raises on ((3,3), UP at p < 1)
+                continue
+            done_steps += 1
+            if done or truncated:
+                env.reset()
+        return done_steps, time.perf_counter() - t0, "reference"
     from oracle.gridworld import GridWorldPort
     port = GridWorldPort(special_transitions={(SPECIAL[0], SPECIAL[1]): (SPECIAL[2], SPECIAL[3])}, **CONFIG2)
     rng = np.random.default_rng(seed)   # Generator(PCG64), what gym.utils.seeding.np_random builds (grid_world.py:69)
-    actions = np.random.default_rng(seed + 1).integers(0, 4, n_steps)
     mdp = port.mdp
     port.reset()
     done_steps = 0
@@ -84,30 +113,40 @@ def _ref_worker(args):
         done_steps += 1
         if done or port.episode_length_counter >= port.episode_length_limit:
             port.reset()
-    return done_steps, time.perf_counter() - t0
+    return done_steps, time.perf_counter() - t0, "port"
 
 
 def _ref_config1():
     """BASELINE.json configs[0]: GridWorld() defaults (5x5, terminal (3,4) -> 1.0, p_success 1.0, no limit, seed 0), 10k
     random-action steps with reset on done, one core, best of 3.  Returns env-steps/s."""
     import numpy as np
-    from oracle.gridworld import GridWorldPort
+    ref = _reference_gridworld()
     best = 0.0
     for _ in range(3):
-        port = GridWorldPort()
-        rng = np.random.default_rng(0)
         actions = np.random.default_rng(0).integers(0, 4, 10_000)
-        mdp = port.mdp
-        port.reset()
-        t0 = time.perf_counter()
-        for a in actions:
-            outcomes = mdp[(port.state, int(a))]
-            idx = rng.choice(len(outcomes), p=[o[3] for o in outcomes])
-            nxt, reward, done, _ = outcomes[idx]
-            port.state = nxt
-            port.episode_length_counter += 1
-            if done:
-                port.reset()
+        if ref is not None:
+            env = ref[0](seed=0)
+            env.reset()
+            t0 = time.perf_counter()
+            for a in actions:
+                _, _, done, _, _ = env.step(int(a))
+                if done:
+                    env.reset()
+        else:
+            from oracle.gridworld import GridWorldPort
+            port = GridWorldPort()
+            rng = np.random.default_rng(0)
+            mdp = port.mdp
+            port.reset()
+            t0 = time.perf_counter()
+            for a in actions:
+                outcomes = mdp[(port.state, int(a))]
+                idx = rng.choice(len(outcomes), p=[o[3] for o in outcomes])
+                nxt, reward, done, _ = outcomes[idx]
+                port.state = nxt
+                port.episode_length_counter += 1
+                if done:
+                    port.reset()
         best = max(best, 10_000 / (time.perf_counter() - t0))
     return best
 
@@ -135,11 +174,23 @@ def _ref_vectorised(n=1 << 18, steps=6):
     return best
 
 
+def _cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    import platform
+    return platform.processor() or platform.machine()
+
+
 def _ref_throughput(n_steps_per_worker, workers, pool):
     t0 = time.perf_counter()
     res = pool.map(_ref_worker, [(1000 + i, n_steps_per_worker) for i in range(workers)])
     wall = time.perf_counter() - t0
-    return sum(r[0] for r in res), wall
+    return sum(r[0] for r in res), wall, res[0][2]
 
 
 def run_reference(args):
@@ -158,19 +209,21 @@ def run_reference(args):
         # warm-up also calibrates the per-step sample so that the timed K steps take ~args.cpu_seconds in total
         probe = 4000
         for _ in range(max(2, min(args.warmup, 3))):
-            n, wall = _ref_throughput(probe, cores, pool)
+            n, wall, kind = _ref_throughput(probe, cores, pool)
         rate_per_worker = max(n / cores / wall, 1.0)
         sample = int(max(50, min(200_000, args.cpu_seconds * rate_per_worker / max(args.steps, 1))))
-        n, wall = _ref_throughput(sample * args.steps, cores, pool)
+        n, wall, kind = _ref_throughput(sample * args.steps, cores, pool)
     value = n / wall
+    what = ("the reference's own GridWorld.step / reset (unmodified source, oracle/_ref or /root/reference, under the "
+            "gymnasium stub of oracle/ref_shim)" if kind == "reference"
+            else "oracle/gridworld.py GridWorldPort + numpy Generator.choice, reset on done (reference source not available)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs": cores, "note": "one env per host process, reference-style step loop"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} processes x {sample} transitions per step x {args.steps} steps "
-                                   f"(oracle/gridworld.py GridWorldPort + numpy Generator.choice, reset on done)",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "cpu_model": _cpu_model(),
+                         "sample": f"{cores} processes x {sample} transitions per step x {args.steps} steps ({what})",
                          "config1_single_core": {"value": _ref_config1(), "unit": UNIT,
                                                  "what": "BASELINE configs[0]: default 5x5 grid, 10k random-action steps, "
                                                          "one core, best of 3"},
@@ -746,7 +799,7 @@ def run_ours(args):
             ref = json.loads(out.stdout.strip().splitlines()[-1])
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:  # keep the GPU numbers even if the host arm fails
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e}"}
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "reference", "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

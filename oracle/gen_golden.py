@@ -464,10 +464,47 @@ def acml_cases(R):
                                            rental_credit=7, move_car_cost=3), 2000, seed=33)
 
 
+def transition_probs_cases(R):
+    """`GridWorld.transition_probs` (grid_world.py:82, :401-430) of the unmodified reference, densified: one file, per case
+    the constructor config, the slip distribution, the rows present and tp[row = cell * 4 + action, next cell]."""
+    crng = np.random.default_rng(77)
+    cases = [("default", dict(), None), ("slip_half", dict(p_success=0.5), None),
+             ("config2_p08", dict(CONFIG2_LAYOUT, p_success=0.8), None),
+             ("config2_custom_slip", dict(CONFIG2_LAYOUT, p_success=0.7), {0: 0.5, 1: 0.25, 2: 0.25, 3: 0.0}),
+             ("p0", dict(rows=4, cols=6, terminal_states={(3, 5): 2.0}, p_success=0.0), None)]
+    cases += [(f"random{i:02d}", random_grid_cfg(crng), None) for i in range(8)]
+    out = {"names": json.dumps([c[0] for c in cases])}
+    for name, cfg, slip in cases:
+        kw = dict(cfg)
+        if kw.get("special_transitions"):
+            kw["special_transitions"] = {(k[0], R.Action(k[1])): v for k, v in kw["special_transitions"].items()}
+        if slip is not None:
+            kw["slip_distribution"] = {R.Action(a): w for a, w in slip.items()}
+        env = R.GridWorld(seed=0, **kw)
+        S = env.rows * env.cols
+        present = np.zeros(S * 4, bool)
+        tp = np.zeros((S * 4, S), np.float64)
+        for (st, a), outs in env.transition_probs.items():
+            row = (st[0] * env.cols + st[1]) * 4 + int(a)
+            present[row] = True
+            for to, pr in outs.items():
+                tp[row, to[0] * env.cols + to[1]] = pr
+        out[name + "_config"] = _jsonable_grid_cfg(cfg)
+        out[name + "_slip"] = json.dumps(None if slip is None else {str(a): w for a, w in slip.items()})
+        out[name + "_present"] = present
+        out[name + "_tp"] = tp
+    out["numpy_version"] = np.__version__
+    np.savez_compressed(os.path.join(OUT, "tprobs_cases.npz"), **out)
+    print("transition_probs:", len(cases), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = load_reference()
     import sys
+    if "tprobs" in sys.argv[1:]:
+        transition_probs_cases(R)
+        return
     if "engine_big" in sys.argv[1:]:
         # a 1M-step subsample of BASELINE config 2 (SURVEY 8(d): reference under the shim on a subsample of the population):
         # 4096 envs x 256 steps of the unmodified reference under the engine's streams, limit 200 so that truncation occurs
@@ -518,6 +555,8 @@ def main():
     labyrinth_cases(R)
     # -- the reference driven by the engine's own Philox streams (direct device-vs-reference vectors) ---------------------
     engine_cases(R)
+    # -- GridWorld.transition_probs export ----------------------------------------------------------
+    transition_probs_cases(R)
 
 
 if __name__ == "__main__":

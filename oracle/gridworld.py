@@ -15,8 +15,8 @@ Two layers:
                        itself checked against `GridWorldPort`.
 
 Parity status: PINNED -- against golden vectors generated from the reference in the build container
-(tests/golden/gridworld_*.npz, made by oracle/gen_golden.py) and against the live reference when
-/root/reference is present (tests/test_oracle_vs_reference.py).
+(tests/golden/gridworld_*.npz and engine_*.npz, made by oracle/gen_golden.py from the unmodified reference;
+tests/test_oracle_gridworld.py, tests/test_oracle_engine_golden.py).
 
 Nothing in the product package may import this module.
 """

@@ -118,11 +118,17 @@ struct Mt19937 {
     __device__ __forceinline__ double std_exp() { return -log(1.0 - u()); }
 };
 
+// Rejection loops are capped: with finite parameters a loop accepts within a handful of trips (2^16 trips are out of
+// reach by hundreds of orders of magnitude), but a NaN shape handed in through the C ABI would never be accepted and
+// must not spin the GPU forever.  The capped exit returns NaN, which is also what numpy returns for NaN parameters.
+constexpr int kMtMaxTrips = 1 << 16;
+
 __device__ double mt_std_gamma(Mt19937& r, double shape) {  // legacy_standard_gamma
     if (shape == 1.0) return r.std_exp();
     if (shape == 0.0) return 0.0;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
     if (shape < 1.0) {
-        for (;;) {
+        for (int trip = 0; trip < kMtMaxTrips; ++trip) {
             const double u = r.u();
             const double v = r.std_exp();
             if (u <= 1.0 - shape) {
@@ -134,10 +140,11 @@ __device__ double mt_std_gamma(Mt19937& r, double shape) {  // legacy_standard_g
                 if (x <= v + y) return x;
             }
         }
+        return nan;
     }
     const double b = shape - 1.0 / 3.0;
     const double c = 1.0 / sqrt(9.0 * b);
-    for (;;) {
+    for (int trip = 0; trip < kMtMaxTrips; ++trip) {
         double x, v;
         do {
             x = r.n01();
@@ -148,11 +155,13 @@ __device__ double mt_std_gamma(Mt19937& r, double shape) {  // legacy_standard_g
         if (u < 1.0 - 0.0331 * (x * x) * (x * x)) return b * v;
         if (log(u) < 0.5 * x * x + b * (1.0 - v + log(v))) return b * v;
     }
+    return nan;
 }
 
 __device__ double mt_beta(Mt19937& r, double a, double b) {  // legacy_beta
     if (a <= 1.0 && b <= 1.0) {
-        for (;;) {  // Johnk
+        for (int trip = 0; trip <= kMtMaxTrips; ++trip) {  // Johnk
+            if (trip == kMtMaxTrips) return __longlong_as_double(0x7ff8000000000000ll);
             const double u = r.u(), v = r.u();
             const double x = pow(u, 1.0 / a), y = pow(v, 1.0 / b);
             const double xy = x + y;

@@ -100,6 +100,7 @@ class GridSpec:
         if S > 65535:
             raise ValueError("rl_envs_forge_b200 supports at most 65535 cells per grid (16-bit cell index in the table)")
         self.n_cells = S
+        self._construction_specials = dict(self.special_transitions)
         self._compile()
         self._construction_tables = (self.nxt.copy(), self.count.copy(), self.prob_row.copy())
 
@@ -232,6 +233,38 @@ class GridSpec:
                          bool(self.done[row, k]), float(self.prob_row[row, k])) for k in range(int(self.count[row]))]
         return out
 
+    def transition_probs(self, slip_distribution):
+        """The reference's `transition_probs` attribute (default_transition_probs :401-430 over calculate_next_state
+        :432-465): {((r, c), Action): {next_state: probability}} for every cell that is neither terminal nor wall.  A
+        second, differently normalised model than `mdp` -- the intended move gets p_success, then EVERY action a' (the
+        intended one included) adds (1 - p_success) * slip_distribution[a'] -- that `step` never reads; exported because
+        tabular code written against the reference may.  Uses the construction-time special transitions only."""
+        rows, cols = self.rows, self.cols
+        walls = {w for w in self.walls}
+        special = {(tuple(k[0]), int(k[1])): tuple(v[0]) for k, v in self._construction_specials.items()}
+        move = {0: (-1, 0), 1: (0, 1), 2: (1, 0), 3: (0, -1)}
+
+        def destination(cell, a):
+            if (cell, a) in special:
+                return special[(cell, a)]
+            to = (min(max(cell[0] + move[a][0], 0), rows - 1), min(max(cell[1] + move[a][1], 0), cols - 1))
+            return cell if (to in walls or to == cell) else to
+
+        slip = [(int(a), float(w)) for a, w in slip_distribution.items()]   # the reference iterates the dict in its order
+        out = {}
+        for r in range(rows):
+            for c in range(cols):
+                cell = (r, c)
+                if cell in self.terminal_states or cell in walls:
+                    continue
+                for a in Action:
+                    acc = {destination(cell, int(a)): 0 + self.p_success}
+                    for sa, w in slip:
+                        to = destination(cell, sa)
+                        acc[to] = acc.get(to, 0) + (1 - self.p_success) * w
+                    out[(cell, a)] = acc
+        return out
+
     def probability_matrix(self):
         """create_probability_matrix (:276-300) from the construction-time tables."""
         nxt, count, prob = self._construction_tables
@@ -308,6 +341,11 @@ class _GridStateLayout:
     @pos.setter
     def pos(self, value):
         v = self._torch.as_tensor(value, device=self.device).to(self._torch.int32)
+        # the kernels index the outcome table with cell * 4 + action unchecked: a cell from another grid (a snapshot of a
+        # different layout, a bad tensor) must be refused here, on this cold path, not fault on the device
+        top = getattr(self, "_max_cell", None)
+        if top is not None and v.numel() and (bool((v < 0).any()) or bool((v > top).any())):
+            raise ValueError(f"cell indices must lie in 0..{top} (rows * cols cells plus the off-grid pseudo-cell)")
         if self._packed:
             self._pl.copy_((self._pl & -65536) | (v & 0xFFFF))
         else:
@@ -415,6 +453,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         self.action_space = spaces.Batched(self.single_action_space, num_envs)
         self.observation_space = spaces.Batched(self.single_observation_space, num_envs)
         n, dev = self.num_envs, self.device
+        self._max_cell = self.spec.n_cells      # `pos` / set_state accept 0 .. n_cells (the last one = off-grid pseudo-cell)
         self._alloc_grid_state()
         # the four per-step outputs live back to back in ONE allocation (16-byte aligned sections), so the host-buffer
         # path brings them back with a single device->host copy
@@ -432,6 +471,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         self._final_obs = None
         self._fast_args = None   # cached pointer arguments of the lean step() path
         self._P = None
+        self._transition_probs = None
         self.rng = rng
         self._rng_state = self._rng_inc = None
         if rng == "pcg64":
@@ -491,6 +531,13 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         if self._P is None:
             self._P = self.spec.probability_matrix()
         return self._P
+
+    @property
+    def transition_probs(self):
+        """The reference's `transition_probs` dict (grid_world.py:82, :401-430), built at construction like there."""
+        if self._transition_probs is None:
+            self._transition_probs = self.spec.transition_probs(self.slip_distribution)
+        return self._transition_probs
 
     # -- reference-style attributes -----------------------------------------------------------------------------------
     @property
@@ -803,6 +850,7 @@ class VecGridWorldLayouts(_GridStateLayout, VecEnv):
             if li.shape[0] != n or (li < 0).any() or (li >= self.n_layouts).any():
                 raise ValueError(f"layout_index must hold {n} values in 0..{self.n_layouts - 1}")
             self._layout_index = torch.from_numpy(li.astype(np.int32)).to(dev)
+        self._max_cell = rows * cols            # `pos` / set_state accept 0 .. rows * cols (the last one = pseudo-cell)
         self._alloc_grid_state()
         self._obs = torch.zeros((n, 2), dtype=torch.int32, device=dev)
         self._reward = torch.zeros(n, dtype=torch.float32, device=dev)

@@ -74,6 +74,10 @@ class Arm:
             vals.append(float(v))
         vals += [0.0] * (2 - len(vals))
         p0, p1 = vals
+        if not (np.isfinite(p0) and np.isfinite(p1)):
+            # numpy's samplers return NaN for NaN parameters; on the device a NaN shape would never be accepted by a
+            # rejection loop -- refuse it here, loudly
+            raise ValueError(f"parameters of a {d} arm must be finite, got {p0!r}, {p1!r}")
         # numpy legacy argument checks (RandomState.normal/exponential/gamma/beta/logistic/weibull/lognormal)
         if d in ("normal", "logistic") and p1 < 0:
             raise ValueError("scale < 0")
@@ -162,9 +166,11 @@ class VecKArmedBandit(VecEnv):
         for i, a in enumerate(self.arms):
             tab[i]["family"], tab[i]["p0"], tab[i]["p1"] = a.packed()
         raw = torch.from_numpy(tab.view(np.uint8).copy())
-        stage = self._pinned("h_arms64", tuple(raw.shape), torch.uint8)
+        stage, slot = self._pinned_ring("h_arms64", tuple(raw.shape), torch.uint8)   # see _arm_table
         stage.copy_(raw)
-        return self._device_scratch("arms64", tuple(raw.shape), torch.uint8).copy_(stage, non_blocking=True)
+        dev = self._device_scratch("arms64", tuple(raw.shape), torch.uint8).copy_(stage, non_blocking=True)
+        self._mark_staged(slot)
+        return dev
 
     @property
     def reward64(self):
@@ -250,11 +256,14 @@ class VecKArmedBandit(VecEnv):
                 tab[j, i, 1], tab[j, i, 2] = p0, p1
         for a, s in zip(self.arms, saved):
             a.current_params = s
-        stage = self._pinned("h_arms", (K, self.k, 4), torch.float32)
+        # the table changes every step when an arm has param_functions, and nothing makes the host wait for the upload:
+        # rotate pinned buffers behind events so that step i+1 cannot overwrite what step i's DMA is still reading
+        stage, slot = self._pinned_ring("h_arms", (K, self.k, 4), torch.float32)
         stage.copy_(torch.from_numpy(tab))
         if self._arm_dev is None or tuple(self._arm_dev.shape) != (K, self.k, 4):
             self._arm_dev = torch.empty((K, self.k, 4), dtype=torch.float32, device=self.device)
         self._arm_dev.copy_(stage, non_blocking=True)
+        self._mark_staged(slot)
         self._arm_key = None if dynamic else key
         return self._arm_dev
 

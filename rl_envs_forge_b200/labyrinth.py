@@ -132,7 +132,10 @@ class VecLabyrinth(VecEnv):
         wall cell or the target cell, like the reference.  A dict from get_state() restores a snapshot instead."""
         torch = self._torch
         if isinstance(player_position, dict):
-            self.pos.copy_(player_position["pos"])
+            snap = torch.as_tensor(player_position["pos"], device=self.device)
+            if snap.numel() and (bool((snap < 0).any()) or bool((snap >= self.rows * self.cols).any())):
+                raise ValueError(f"player cells must lie in 0..{self.rows * self.cols - 1}")   # unchecked on the device
+            self.pos.copy_(snap)
             self.ep_len.copy_(player_position["ep_len"])
             self.ep_ret.copy_(player_position["ep_ret"])
             self._t = int(player_position.get("t", self._t))

@@ -164,6 +164,30 @@ class VecEnv:
             self._host[name] = t
         return t
 
+    def _pinned_ring(self, name, shape, dtype, depth=4):
+        """Pinned staging buffer for a host->device copy that nothing waits for on the host (a table re-uploaded every
+        step).  `depth` buffers rotate, each guarded by a CUDA event recorded after ITS copy was enqueued (`mark_staged`):
+        a buffer is rewritten only once the DMA that read it has completed, however far the host runs ahead of the stream.
+        Returns (tensor, slot); call `_mark_staged(slot)` right after enqueuing the copy."""
+        key = "ring_" + name
+        ring = self._host.get(key)
+        if ring is None or ring["shape"] != tuple(shape) or ring["dtype"] != dtype:
+            ring = {"shape": tuple(shape), "dtype": dtype, "next": 0,
+                    "slots": [[self._torch.empty(shape, dtype=dtype, pin_memory=True), None] for _ in range(depth)]}
+            self._host[key] = ring
+        i = ring["next"]
+        ring["next"] = (i + 1) % len(ring["slots"])
+        buf, ev = ring["slots"][i]
+        if ev is not None:
+            ev.synchronize()          # host blocks only if the copy issued `depth` uploads ago is still in flight
+        return buf, (key, i)
+
+    def _mark_staged(self, slot):
+        key, i = slot
+        ev = self._torch.cuda.Event()
+        ev.record(self._torch.cuda.current_stream(self.device))
+        self._host[key]["slots"][i][1] = ev
+
     def _host_in(self, name, array, dtype, shape):
         """Host array -> pinned CPU tensor of `dtype`/`shape`.  A pinned torch tensor of the right dtype is used as is (the
         device reads the caller's buffer); anything else is copied into a pinned staging buffer first."""

@@ -127,3 +127,34 @@ def test_empty_rewards_dict_uses_reference_defaults():
     """rewards={} is accepted (test_grid_world.py:211); `rewards or defaults` then restores the default dict (:83-88)."""
     spec = GridSpec(rewards={})
     assert spec.reward[0 * 4 + 0, 0] == -1 and spec.reward[0 * 4 + 1, 0] == -0.1
+
+
+def test_transition_probs_export_matches_reference():
+    """`transition_probs` (grid_world.py:82, :401-430 -- the second, differently normalised model next to `mdp`) against the
+    dicts the unmodified reference built for 13 configurations (tests/golden/tprobs_cases.npz, `gen_golden tprobs`):
+    same keys, same destinations, bit-equal probabilities."""
+    import json
+    import os
+    from tests._golden import GOLDEN
+    g = load(os.path.join(GOLDEN, "tprobs_cases.npz"))
+    names = json.loads(str(g["names"]))
+    assert len(names) >= 13
+    for name in names:
+        kw = _spec_kwargs({"config": g[name + "_config"]})
+        p = kw.get("p_success", 1.0)
+        slip = json.loads(str(g[name + "_slip"]))
+        slip = ({Action(int(a)): w for a, w in slip.items()} if slip is not None
+                else {a: (1.0 - p) / (len(Action) - 1) for a in Action})
+        spec = GridSpec(**kw)
+        tp = spec.transition_probs(slip)
+        S = spec.n_cells
+        present = np.zeros(S * 4, bool)
+        dense = np.zeros((S * 4, S))
+        for (st, a), outs in tp.items():
+            assert isinstance(a, Action) and isinstance(st, tuple)
+            row = (st[0] * spec.cols + st[1]) * 4 + int(a)
+            present[row] = True
+            for to, pr in outs.items():
+                dense[row, to[0] * spec.cols + to[1]] = pr
+        assert np.array_equal(present, g[name + "_present"]), name
+        assert np.array_equal(dense, g[name + "_tp"]), name
