@@ -57,6 +57,36 @@ def _traffic(kernel):
         return None
 
 
+def _json_profile(name):
+    try:
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def _issue_roofline(label, steps_per_s_per_gpu, pipe, algorithmic_ops, ops_note):
+    """Roofline object of an ISSUE-bound kernel (steps/s x ops / measured issue peak).  Denominator: the
+    measured instruction-issue peak of the GPU (profiles/issue_peaks.json, tools/issue_peak.cu: 8 independent FFMA chains per
+    thread -- 114 of the nominal 128 thread-instructions per SM per clock; IMAD and LOP3 chains issue at about half of
+    that).  `frac_issue` counts every EXECUTED instruction (ncu smsp__thread_inst_executed, profiles/kernel_instr.json),
+    `frac_algorithmic` only the arithmetic the reference's formulas need."""
+    peaks = _json_profile("issue_peaks.json")
+    instr = _json_profile("kernel_instr.json").get(label, {})
+    peak = peaks.get("ffma_per_s")
+    pipe_peak = peaks.get({"fp32": "ffma_per_s", "int32": "imad_per_s"}[pipe])
+    executed = instr.get("thread_instr_per_env_step")
+    out = {"bound": f"{pipe}_issue", "algorithmic_ops_per_step": algorithmic_ops, "algorithmic_ops_note": ops_note,
+           "achieved": algorithmic_ops * steps_per_s_per_gpu, "unit": "thread-ops/s per GPU",
+           "peak": peak, "peak_source": "measured issue peak, profiles/issue_peaks.json (FFMA chains)" if peak else None,
+           "pipe_peak": pipe_peak, "executed_thread_instr_per_step": executed,
+           "active_lanes_per_warp_instr": instr.get("active_lanes_per_warp_instr"),
+           "frac_algorithmic": algorithmic_ops * steps_per_s_per_gpu / peak if peak else None,
+           "frac_algorithmic_of_pipe": algorithmic_ops * steps_per_s_per_gpu / pipe_peak if pipe_peak else None,
+           "frac_issue": executed * steps_per_s_per_gpu / peak if (peak and executed) else None}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
 def _reference_gridworld():
     """(GridWorld, Action, root) of the UNMODIFIED reference -- /root/reference in the build container, the git-ignored copy
@@ -598,7 +628,11 @@ def run_ours(args):
         details["gridworld_step_python_loop"] = {"env_steps_per_s": n / sec, "envs": n, "us_per_call": sec * 1e6,
                                                  "note": "same, driven by one Python step() call per launch (host-bound)"}
         sec = ev_time(lambda: sets[0].rollout(Kr), 10)
-        details["gridworld_rollout_K64_random_policy"] = {"env_steps_per_s": n * Kr / sec, "envs": n}
+        details["gridworld_rollout_K64_random_policy"] = {
+            "env_steps_per_s": n * Kr / sec, "envs": n,
+            "roofline": _issue_roofline("gridworld_rollout", n * Kr / sec, "int32", 55,
+                                        "SURVEY 8(d): 2 draws = half a Philox4x32-10 call (~20 wide multiplies + 40 logic + 18 "
+                                        "adds per 4 outputs) + ~15 ops of table walk / auto-reset")}
         del sets[1:]
         # stream-exact mode (every env owns numpy's PCG64 generator: 42 B + 48 B of generator state per env-step) and a batch
         # that mixes eight layouts (one env per thread, tables staged back to back in shared memory)
@@ -682,10 +716,17 @@ def run_ours(args):
         acts64 = torch.empty((Kr, big), device="cuda").uniform_(-3, 3)
         rew = flg = None
         sec = ev_time(lambda: cp.rollout(Kr, acts64, return_rewards=True), 5)
-        details["cartpole_rollout_K64_ext_actions_emit"] = {"env_steps_per_s": big * Kr / sec, "envs": big,
-                                                            "GBps": (9 + 48 / Kr) * big * Kr / sec / 1e9}
+        cp_note = ("SURVEY 8(d): 26 add/mul (cart_pole.py:117-131) + 4 divides + sin + cos + 7 compares; the executed count "
+                   "adds sincosf range reduction, IEEE division sequences, flag packing, auto-reset")
+        details["cartpole_rollout_K64_ext_actions_emit"] = {
+            "env_steps_per_s": big * Kr / sec, "envs": big, "GBps": (9 + 48 / Kr) * big * Kr / sec / 1e9,
+            "hbm_frac": (9 + 48 / Kr) * big * Kr / sec / 1e9 / peak,
+            "roofline": _issue_roofline("cartpole_rollout_ext", big * Kr / sec, "fp32", 39, cp_note)}
         sec = ev_time(lambda: cp.rollout(Kr), 5)
-        details["cartpole_rollout_K64_random_policy"] = {"env_steps_per_s": big * Kr / sec, "envs": big}
+        details["cartpole_rollout_K64_random_policy"] = {
+            "env_steps_per_s": big * Kr / sec, "envs": big,
+            "roofline": _issue_roofline("cartpole_rollout_policy", big * Kr / sec, "fp32", 39 + 20,
+                                        cp_note + "; + a quarter of a Philox call (~20 ops) for the policy draw")}
         del cp, acts64
         pd = VecPendulumDisk(big, seed=seed, env_offset=rank * big)
         sec = ev_time(lambda: pd.step(a_cp), 50)
@@ -693,14 +734,24 @@ def run_ours(args):
                                          "roofline_frac": 50 * big / sec / 1e9 / peak, "moved_GBps": 42 * big / sec / 1e9,
                                          "note": "canonical 50 B/env-step; aliased observation: 42 B/env-step move"}
         sec = ev_time(lambda: pd.rollout(Kr), 5)
-        details["pendulum_disk_rollout_K64_random_policy"] = {"env_steps_per_s": big * Kr / sec, "envs": big}
+        details["pendulum_disk_rollout_K64_random_policy"] = {
+            "env_steps_per_s": big * Kr / sec, "envs": big,
+            "roofline": _issue_roofline("pendulum_rollout_policy", big * Kr / sec, "fp32", 22 + 20,
+                                        "SURVEY 8(d): 15 add/mul with constants folded (pendulum_disk.py:115-123) + sin + 6 "
+                                        "compares; + a quarter of a Philox call (~20 ops) for the policy draw")}
         del pd, a_cp
         nb = 1 << 24
         bd = VecKArmedBandit(nb, k=10, arm_params={i: dict(p) for i, p in BANDIT_ARMS.items()}, seed=seed,
                              env_offset=rank * nb)
         a_b = torch.randint(0, 10, (nb,), dtype=torch.int32, device="cuda")
         sec = ev_time(lambda: bd.step(a_b), 20)
-        details["bandit_step_10arm_mixed"] = {"env_steps_per_s": nb / sec, "envs": nb, "GBps": 12 * nb / sec / 1e9}
+        details["bandit_step_10arm_mixed"] = {
+            "env_steps_per_s": nb / sec, "envs": nb, "GBps": 12 * nb / sec / 1e9, "hbm_frac": 12 * nb / sec / 1e9 / peak,
+            "roofline": _issue_roofline("bandit_sorted", nb / sec, "fp32", 160,
+                                        "estimate for the config-3 arm mix under uniform actions (SURVEY 8(d) gives no single "
+                                        "figure): 1.7 Philox calls on average (78 ops each: normal / lognormal / logistic / "
+                                        "uniform / exponential / weibull need 1, gamma(9) ~2.2, beta(2,5) ~4.4) + ~25 ops of "
+                                        "ln / sqrt / sincos / pow per sample")}
         del bd, a_b
         # ---- ACML envs and Labyrinth stepping
         ng = 1 << 24        # 30 B of buffers per env: well past the 126 MB L2
@@ -713,14 +764,20 @@ def run_ours(args):
         gm = VecGamblersProblem(1 << 22, goal_amount=100, win_probability=0.4, start_capital=10, seed=seed,
                                 env_offset=rank * (1 << 22))
         sec = ev_time(lambda: gm.rollout(Kr), 10)
-        details["gambler_rollout_K64_random_policy"] = {"env_steps_per_s": (1 << 22) * Kr / sec, "envs": 1 << 22}
+        details["gambler_rollout_K64_random_policy"] = {
+            "env_steps_per_s": (1 << 22) * Kr / sec, "envs": 1 << 22,
+            "roofline": _issue_roofline("gambler_rollout", (1 << 22) * Kr / sec, "int32", 50,
+                                        "half a Philox call (bet + coin: ~40 ops) + ~10 ops of capital update / reset")}
         del gm
         ng = 1 << 22
         cr = VecJacksCarRental(ng, seed=seed, env_offset=rank * ng)
         a_c = torch.randint(0, 11, (ng,), dtype=torch.int32, device="cuda")
         sec = ev_time(lambda: cr.step(a_c), 20)
         details["car_rental_step"] = {"env_steps_per_s": ng / sec, "envs": ng, "GBps": 54 * ng / sec / 1e9,
-                                      "note": "four FP64 legacy-numpy Poisson draws per env-step: issue-bound"}
+                                      "note": "four FP64 legacy-numpy Poisson draws per env-step: issue-bound",
+                                      "roofline": _issue_roofline("carrental_step", ng / sec, "int32", 8 * 78 + 16 * 6,
+                                                                  "~16 Philox doubles per env-step (8 calls x 78 ops) + one FP64 "
+                                                                  "multiply-compare per double and the int32 bookkeeping")}
         sec = ev_time(lambda: cr.rollout(16), 5)
         details["car_rental_rollout_K16_random_policy"] = {"env_steps_per_s": ng * 16 / sec, "envs": ng}
         del cr, a_c
