@@ -755,6 +755,75 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             info["final_observation"] = fobs
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
 
+    # -- host-buffer step without the host wait: two env sets in flight keep PCIe busy in both directions ----------------
+    def step_async(self, actions):
+        """Enqueue one host-buffer step and return at once; `wait()` hands out the results.
+
+        The call a host-side actor loop makes when it drives TWO (or more) env sets: while the host consumes the results of
+        set A and picks A's next actions, the step of set B is crossing PCIe -- its actions host->device, its results
+        device->host -- so the link never idles between steps (a plain `step(host buffers)` leaves it idle for the host's
+        share of every step).  Each env set owns a private stream; the transports are those of step(): "zerocopy" (one
+        kernel whose action loads and output stores go straight to pinned host memory) or "staged" (copy engine in, kernel,
+        copy engine out).  Same kernels, same results as step().  Plain Philox stepping only (no injected draws, no
+        final_obs, not strict); actions: pinned CPU tensor of the wire dtype (used in place) or any host array (copied)."""
+        torch = self._torch
+        if self.rng != "philox" or self.strict or self._clock is not None:
+            raise ValueError("step_async() covers the plain Philox step (rng='philox', strict=False, no device clock)")
+        st = self.__dict__.get("_async_state")
+        if st is None:
+            st = self._async_state = {"stream": torch.cuda.Stream(device=self.device), "event": torch.cuda.Event(),
+                                      "pending": False}
+        if st["pending"]:
+            raise RuntimeError("step_async() called again before wait()")
+        n, w8 = self.num_envs, self._w8
+        act_dtype = torch.uint8 if w8 else torch.int32
+        if torch.is_tensor(actions):
+            if actions.is_cuda:
+                raise ValueError("step_async() takes HOST actions; CUDA tensors go through step()")
+            a = actions.reshape(-1)
+            if a.dtype != act_dtype:
+                a = a.clamp(-1, 255).to(torch.uint8) if w8 else a.to(torch.int32)
+        else:
+            a = np.asarray(actions).reshape(-1)
+            a = (np.where((a < 0) | (a > 255), 255, a).astype(np.uint8) if w8 and a.dtype != np.uint8
+                 else a.astype(np.uint8 if w8 else np.int32, copy=False))
+        h_act = self._host_in("action", a, act_dtype, (n,))
+        h_out = self._pinned("o_out", (self._out_bytes,), torch.uint8)
+        o_rew, o_term, o_trunc = self._out_sections
+        mode = self.host_transport if self.host_transport != "pipelined" else "staged"
+        stream = st["stream"]
+        stream.wait_stream(torch.cuda.current_stream(self.device))   # whatever was enqueued on this env before (reset, ...)
+        fn = self._lib.ef_gridworld_step_u8 if w8 else self._lib.ef_gridworld_step
+        with torch.cuda.stream(stream):
+            if mode == "zerocopy":
+                p_act, base = h_act.data_ptr(), h_out.data_ptr()
+            else:
+                p_act = _lib.ptr(self._to_device("action", h_act, act_dtype, (n,)))
+                base = self._out.data_ptr()
+            self._call(fn, self._desc, *self._state_ptrs(), _lib.ptr(self.ep_ret), p_act, None, self._seed, self._t,
+                       self.env_offset, base, base + o_rew, base + o_term, base + o_trunc, None, _lib.ptr(self._stats_raw),
+                       _lib.ptr(self.err), None, n, int(self.autoreset))
+            if mode != "zerocopy":
+                h_out.copy_(self._out, non_blocking=True)
+            st["event"].record(stream)
+        st["pending"] = True
+        self._t += 1
+
+    def wait(self):
+        """Results of the step enqueued by step_async(): (obs, reward, terminated, truncated, info) as numpy views of the
+        pinned result block (valid until this env's next host-buffer step)."""
+        st = self.__dict__.get("_async_state")
+        if st is None or not st["pending"]:
+            raise RuntimeError("wait() without a step_async() in flight")
+        st["event"].synchronize()
+        st["pending"] = False
+        n = self.num_envs
+        o_rew, o_term, o_trunc = self._out_sections
+        buf = self._host["o_out"].numpy()
+        obs_np = np.uint8 if self._w8 else np.int32
+        return (buf[:self._obs_bytes].view(obs_np).reshape(n, 2), buf[o_rew:o_rew + 4 * n].view(np.float32),
+                buf[o_term:o_term + n].view(np.bool_), buf[o_trunc:o_trunc + n].view(np.bool_), {})
+
     def rollout(self, K, actions=None, *, return_rewards=False, return_obs=False):
         """K fused steps in one kernel (state in registers, auto-reset on).  actions: CUDA int32 [K,N] or None for the
         in-kernel uniform random policy.  Returns None, (rewards fp32 [K,N], flags uint8 [K,N]) if return_rewards, or

@@ -156,6 +156,41 @@ def test_compact_host_buffer_path_equals_device_path(transport):
     assert int(a.err.cpu().numpy()[0]) == int(b.err.cpu().numpy()[0]) >= 12
 
 
+@pytest.mark.parametrize("wire,transport", [("compact", "zerocopy"), ("compact", "staged"), ("canonical", "staged"),
+                                            ("canonical", "zerocopy")])
+def test_step_async_two_sets_in_flight_equal_plain_steps(wire, transport):
+    """step_async() / wait(): two env sets stepped alternately with both steps in flight give, set by set, exactly what
+    plain step() calls with CUDA actions give (same kernels; only the host wait moved)."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    cfg = _vec_kwargs(_config2(0.8))
+    n = 20_003
+    adt = np.uint8 if wire == "compact" else np.int32
+    sets = [VecGridWorld(n, seed=9, wire=wire, env_offset=k * n, **cfg) for k in range(2)]
+    refs = [VecGridWorld(n, seed=9, wire=wire, env_offset=k * n, **cfg) for k in range(2)]
+    for e in sets:
+        e.host_transport = transport
+    rng = np.random.default_rng(1)
+    acts = [[torch.from_numpy(rng.integers(0, 4, n).astype(adt)).pin_memory() for _ in range(12)] for _ in range(2)]
+    with pytest.raises(RuntimeError):
+        sets[0].wait()
+    sets[0].step_async(acts[0][0])
+    with pytest.raises(RuntimeError):
+        sets[0].step_async(acts[0][0])
+    for i in range(24):
+        k, t = i % 2, i // 2
+        if i + 1 < 24:
+            sets[(i + 1) % 2].step_async(acts[(i + 1) % 2][(i + 1) // 2])      # the other set's step is now in flight too
+        got = sets[k].wait()
+        want = refs[k].step(acts[k][t].cuda())
+        assert got[0].dtype == adt and got[0].shape == (n, 2)
+        assert np.array_equal(got[0], want[0].cpu().numpy()) and np.array_equal(got[1], want[1].cpu().numpy())
+        assert np.array_equal(got[2], want[2].cpu().numpy()) and np.array_equal(got[3], want[3].cpu().numpy())
+    for e, r in zip(sets, refs):
+        assert torch.equal(e.pos, r.pos) and torch.equal(e.ep_ret, r.ep_ret)
+        assert torch.equal(e.stats.cpu(), r.stats.cpu())
+
+
 def test_compact_unaligned_buffers_through_the_c_abi():
     """Action / observation pointers that miss the 4- / 8-byte alignment of the vector kernel take the one-env-per-thread
     kernel; results equal the aligned call."""
