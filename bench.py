@@ -618,7 +618,7 @@ def run_ours(args):
                 dist.all_reduce(e2e_steps)
             windows.append(float(e2e_steps.item()) / float(e2e_s.item()))
         assert obs.dtype == adt and obs.shape == (n, 2)
-        transport = envs[0].host_transport
+        transport = os.environ.get("ENVFORGE_ASYNC_TRANSPORT", getattr(envs[0], "async_transport", "staged"))
         del envs
         return windows, transport
 

@@ -762,9 +762,9 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         The call a host-side actor loop makes when it drives TWO (or more) env sets: while the host consumes the results of
         set A and picks A's next actions, the step of set B is crossing PCIe -- its actions host->device, its results
         device->host -- so the link never idles between steps (a plain `step(host buffers)` leaves it idle for the host's
-        share of every step).  Each env set owns a private stream; the transports are those of step(): "zerocopy" (one
-        kernel whose action loads and output stores go straight to pinned host memory) or "staged" (copy engine in, kernel,
-        copy engine out).  Same kernels, same results as step().  Plain Philox stepping only (no injected draws, no
+        share of every step).  Each env set owns a private stream; transport "staged" (copy engine in, kernel, copy
+        engine out -- the default here, see below) or "zerocopy" (one kernel whose action loads and output stores go
+        straight to pinned host memory), chosen with `env.async_transport`.  Same kernels, same results as step().  Plain Philox stepping only (no injected draws, no
         final_obs, not strict); actions: pinned CPU tensor of the wire dtype (used in place) or any host array (copied)."""
         torch = self._torch
         if self.rng != "philox" or self.strict or self._clock is not None:
@@ -790,7 +790,13 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         h_act = self._host_in("action", a, act_dtype, (n,))
         h_out = self._pinned("o_out", (self._out_bytes,), torch.uint8)
         o_rew, o_term, o_trunc = self._out_sections
-        mode = self.host_transport if self.host_transport != "pipelined" else "staged"
+        # With several env sets in flight the copy engines win for BOTH wire formats: the H2D of one set, the kernel of
+        # another and the D2H of a third overlap, and the DMA engines keep PCIe at ~54 GB/s device->host, which the kernel's
+        # own zero-copy stores do not (measured at 2^20 envs, 2 sets in flight: compact 6.7e9 vs 5.5e9 env-steps/s, int32
+        # 3.9e9 vs 1.8e9; profiles/r02l_e2e_probe.txt).  ENVFORGE_ASYNC_TRANSPORT=zerocopy switches for A/B timing.
+        mode = os.environ.get("ENVFORGE_ASYNC_TRANSPORT", self.__dict__.get("async_transport", "staged"))
+        if mode not in ("staged", "zerocopy"):
+            raise ValueError("async transport must be 'staged' or 'zerocopy'")
         stream = st["stream"]
         stream.wait_stream(torch.cuda.current_stream(self.device))   # whatever was enqueued on this env before (reset, ...)
         fn = self._lib.ef_gridworld_step_u8 if w8 else self._lib.ef_gridworld_step

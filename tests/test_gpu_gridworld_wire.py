@@ -169,7 +169,7 @@ def test_step_async_two_sets_in_flight_equal_plain_steps(wire, transport):
     sets = [VecGridWorld(n, seed=9, wire=wire, env_offset=k * n, **cfg) for k in range(2)]
     refs = [VecGridWorld(n, seed=9, wire=wire, env_offset=k * n, **cfg) for k in range(2)]
     for e in sets:
-        e.host_transport = transport
+        e.async_transport = transport
     rng = np.random.default_rng(1)
     acts = [[torch.from_numpy(rng.integers(0, 4, n).astype(adt)).pin_memory() for _ in range(12)] for _ in range(2)]
     with pytest.raises(RuntimeError):
