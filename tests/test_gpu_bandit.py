@@ -37,8 +37,10 @@ def test_family_parity_vs_legacy_numpy_algorithms(fam, args):
         flips += int((~ok).sum())
         assert bool(done.all()) and not bool(trunc.any()) and int(obs.abs().sum()) == 0
     print(f"{fam}{args}: {flips} accept/reject flips in {3 * n} samples")
-    limit = 0 if fam in ("normal", "uniform", "exponential", "logistic", "weibull", "lognormal") else 3 * n * 2e-5
-    assert flips <= limit
+    # Rejection samplers (gamma, beta) may in principle flip an accept/reject decision that falls inside the fp32 rounding
+    # of its comparison; for these pinned seeds the count is 0 in all 12 cases (786432 samples each, measured on B200,
+    # profiles/r02m_flips.log), so 0 is what is asserted -- a changed sampler has to re-earn it.
+    assert flips == 0
     assert env.timestep == 3
 
 
@@ -76,7 +78,7 @@ def test_config3_mixed_arms_with_shift_16M():
             ref[m], _ = OB.engine_sample_vec(seed, sub[m], t, fam, vals[0], vals[1] if len(vals) > 1 else 0.0)
         flips += int((~_close(r, ref)).sum())
     print(f"config3: {flips} flips in {K * len(sub)} checked samples")
-    assert flips <= K * len(sub) * 2e-5
+    assert flips == 0      # observed on B200 for this seed (786432 checked samples); see the note in the family test
     assert env.arms[0].current_params["mean"] == pytest.approx(5 + 0.1 * K)
     st = env.episode_stats()
     assert st["episodes"] == K * n and st["length_sum"] == K * n

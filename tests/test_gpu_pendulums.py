@@ -15,8 +15,10 @@ from tests._golden import golden_files, load
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-5, 1e-6
-# accelerations are differences of terms ~100x larger than the result (divided by J = 1.91e-4 for the disk): absolute floor
-ACC_ATOL = 2e-4
+# accelerations are differences of terms ~100x larger than the result (divided by J = 1.91e-4 for the disk, |acc| up to
+# 220): absolute floor on top of the 1e-5 relative band.  Observed on B200: CartPole never leaves the relative band,
+# PendulumDisk exceeds it by at most 1.33e-5 (profiles/r02m_flips.log).
+ACC_ATOL = 2e-5
 
 
 def _within(dev, ref, angle_col=None):
@@ -111,7 +113,7 @@ def test_per_step_parity_reseeded_4M_envs(kind, n):
         assert not (bad & ~near).any()
         flips += int(bad.sum())
     print(f"{kind}: threshold-band flag/reward flips over 6 steps x {n} envs: {flips}")
-    assert flips <= n * 6 * 1e-5
+    assert flips <= 8      # 2.5e7 checked env-steps; observed 1 (CartPole) / 0 (PendulumDisk), all inside the threshold band
 
 
 @pytest.mark.parametrize("kind", ["cartpole", "pendulumdisk"])
