@@ -630,20 +630,28 @@ def run_ours(args):
     windows2, tr_c2 = time_e2e_two_sets("compact", args.e2e_windows, 2)
     windows2_32, tr_i2 = time_e2e_two_sets("canonical", max(1, args.e2e_windows // 3), 4)
     win_e2e = (win_e2e[0], time.perf_counter())
-    line["e2e"] = {"value": float(np.median(windows2)), "unit": UNIT, "h2d_bytes_per_step": 1 * n, "d2h_bytes_per_step": 8 * n,
-                   "steps": k_e2e, "windows": windows2, "best_window": max(windows2),
-                   "reported": "median window", "transport": tr_c2, "env_sets_in_flight": 2,
-                   "api": "two VecGridWorld(wire='compact') env sets driven alternately: set.step_async(pinned host uint8[N]); "
-                          "other.wait() -> numpy (obs uint8[N,2], reward f32, terminated, truncated); every step's actions "
-                          "and results cross PCIe inside the timed region",
-                   "sequential_step": {"value": float(np.median(windows)), "best_window": max(windows), "windows": windows,
-                                       "transport": tr_c,
-                                       "api": "one env set, VecGridWorld(wire='compact').step(pinned host uint8[N]) -> numpy; "
-                                              "the link idles while the host handles each result"},
-                   "canonical_int32": {"value": float(np.median(windows2_32)), "best_window": max(windows2_32),
-                                       "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 14 * n, "transport": tr_i2,
-                                       "env_sets_in_flight": 2,
-                                       "sequential_step": {"value": float(np.median(windows32)), "transport": tr_i},
+    two = {"value": float(np.median(windows2)), "best_window": max(windows2), "windows": windows2, "transport": tr_c2,
+           "env_sets_in_flight": 2,
+           "api": "two VecGridWorld(wire='compact') env sets driven alternately: set.step_async(pinned host uint8[N]); "
+                  "other.wait() -> numpy (obs uint8[N,2], reward f32, terminated, truncated)"}
+    seq = {"value": float(np.median(windows)), "best_window": max(windows), "windows": windows, "transport": tr_c,
+           "env_sets_in_flight": 1,
+           "api": "one env set, VecGridWorld(wire='compact').step(pinned host uint8[N]) -> numpy; the link idles while the "
+                  "host handles each result"}
+    # both are the public host-buffer call, every step's actions and results crossing PCIe inside the timed region; the
+    # reported value is the faster loop ON THIS BOX (one GPU: two sets in flight; eight ranks sharing one VM's host memory
+    # path: the sequential loop, which puts less pressure on it) and the other one is listed next to it
+    best, other = (two, seq) if two["value"] >= seq["value"] else (seq, two)
+    c_two, c_seq = float(np.median(windows2_32)), float(np.median(windows32))
+    line["e2e"] = {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 1 * n, "d2h_bytes_per_step": 8 * n,
+                   "steps": k_e2e, "windows": best["windows"], "best_window": best["best_window"],
+                   "reported": "median window of the faster of the two host loops", "transport": best["transport"],
+                   "env_sets_in_flight": best["env_sets_in_flight"], "api": best["api"],
+                   "two_sets_in_flight": {k: two[k] for k in ("value", "best_window", "transport")},
+                   "sequential_step": {k: seq[k] for k in ("value", "best_window", "transport")},
+                   "canonical_int32": {"value": max(c_two, c_seq), "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 14 * n,
+                                       "two_sets_in_flight": {"value": c_two, "transport": tr_i2},
+                                       "sequential_step": {"value": c_seq, "transport": tr_i},
                                        "api": "the same with VecGridWorld() and pinned host int32[N] -> numpy (obs int32[N,2], ...)"}}
 
     # ---- detail sections (not the headline): fused rollouts and the other env families at their BASELINE configs
