@@ -487,6 +487,8 @@ def run_ours(args):
     # 2^23-env population, the same seed and step count whatever the number of ranks -> the all-reduced INTEGER statistics
     # must be identical in the N = 1 / 2 / 4 / 8 lines (instances are independent, grid_world.py:495-528)
     n_inv = (1 << 23) // world
+    if world > 1:
+        dist.barrier()          # ranks enter the exchange together (the peer kernel gives up on a rank that is seconds late)
     inv_env = VecGridWorld(n_inv, seed=seed + 7, special_transitions=spec, env_offset=rank * n_inv, **CONFIG2)
     inv_env.rollout(64)
     inv_red = StatsReducer([inv_env], transport=args.stats_transport)
@@ -885,6 +887,9 @@ def run_ours(args):
                            lambda: VecCartPole(n5, seed=seed, env_offset=rank * n5))):
             e5 = make()
             r5 = StatsReducer([e5], transport=args.stats_transport)
+            if world > 1:
+                dist.barrier()  # the detail sections before this one leave the ranks seconds apart
+                torch.cuda.synchronize()
 
             def roll5():
                 e5.rollout(Kr)

@@ -472,7 +472,7 @@ int ef_stats_fold(const double* const* raw_sets, int32_t n_sets, double* out, vo
  *                            bit-identical on every rank (same order of additions).  n_sets == 0 (raw_sets ignored): the
  *                            vector was folded earlier by ef_stats_fold and out_local is the INPUT; this is how the
  *                            exchange runs on a side stream while the stepping stream goes on.  Collective: every rank must launch it
- *                            the same number of times.  A peer that does not show up within ~2 s makes the kernel give up
+ *                            the same number of times.  A peer that does not show up within ~10 s makes the kernel give up
  *                            and set status[0] (device uint32, nullable) to 1 instead of hanging the GPU.
  * ------------------------------------------------------------------------------------------------------------ */
 #define EF_PEER_HANDLE_BYTES 64

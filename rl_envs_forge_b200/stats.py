@@ -154,7 +154,7 @@ class StatsReducer:
         return self.total
 
     def check(self):
-        """Raise if a peer never showed up in an exchange (the kernel gives up after ~2 s instead of hanging the GPU)."""
+        """Raise if a peer never showed up in an exchange (the kernel gives up after ~10 s instead of hanging the GPU)."""
         if int(self._status.item()) != 0:
             raise _lib.EnvForgeError("statistics exchange timed out waiting for a peer rank")
 
