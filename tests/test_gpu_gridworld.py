@@ -215,6 +215,37 @@ def test_sharding_invariance_env_offset():
     assert float(tot[2]) == pytest.approx(float(whole.stats[2]), rel=1e-12)
 
 
+def test_config5_full_size_64M_envs_sharding_invariance_and_conservation():
+    """BASELINE configs[4] at its full size on one GPU: 2^26 GridWorld envs, fused 64-step rollout, stepped once as ONE
+    batch and once as eight shards of 2^23 envs (what eight ranks own) -- identical state and identical integer statistics.
+    Size-independent properties on top: env-steps executed + rejected = N * K, the finished episodes' lengths plus the
+    counters of the episodes still running add up to the executed env-steps, and no counter reaches the limit."""
+    import torch
+    from rl_envs_forge_b200 import StatsReducer, VecGridWorld, shard_range
+    n, K, seed = 1 << 26, 64, 5
+    cfg = _vec_kwargs(_config2(0.8))
+    whole = VecGridWorld(n, seed=seed, **cfg)
+    whole.rollout(K)
+    ws = whole.stats.cpu()
+    rejected = int(whole.err[0].item()) & 0xFFFFFFFF
+    assert int(ws[4]) + rejected == n * K and rejected > 0
+    lens = whole.ep_len
+    assert int(ws[1]) + int(lens.sum(dtype=torch.int64)) == int(ws[4])          # every executed step belongs to one episode
+    assert int(lens.max()) < cfg["episode_length_limit"]
+    pos_w, ret_w = whole.pos.clone(), whole.ep_ret.clone()
+    del whole, lens
+    shards, chunks = [], []
+    for r in range(8):
+        lo, hi = shard_range(n, r, 8)
+        e = VecGridWorld(hi - lo, seed=seed, env_offset=lo, **cfg)
+        e.rollout(K)
+        assert torch.equal(e.pos, pos_w[lo:hi]) and torch.equal(e.ep_ret, ret_w[lo:hi])
+        shards.append(e)
+    tot = StatsReducer(shards).reduce().cpu()                                   # one fold kernel over the eight env sets
+    assert int(tot[0]) == int(ws[0]) and int(tot[1]) == int(ws[1]) and int(tot[4]) == int(ws[4])
+    assert float(tot[2]) == pytest.approx(float(ws[2]), rel=1e-12)
+
+
 def test_unaligned_views_take_scalar_path():
     """State tensors that are not 16-byte aligned (views offset by one element) must still be correct."""
     import torch
