@@ -704,6 +704,23 @@ def run_ours(args):
                     "steps of one set stay ordered, steps of different sets overlap"}
         del g_par
         sets[0].disable_device_clock()
+        # persistent step server: ONE env set, K steps without a launch per step, the actions coming from a policy kernel of
+        # its own (the built-in stand-in: action = f(previous observation, k)) that runs next to the server and talks to it
+        # through per-chunk sequence words.  To be read against gridworld_step_l2_resident, which is the floor of any
+        # launch-per-step scheme BEFORE its policy kernel is added.
+        srv = VecGridWorld(n, seed=seed + 3, special_transitions=spec, env_offset=rank * n, **CONFIG2)
+        srv.serve_with_demo_policy(64)
+        torch.cuda.synchronize()
+        Ks = 4000
+        t_s = time.perf_counter()
+        srv.serve_with_demo_policy(Ks)
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t_s) / Ks
+        details["gridworld_step_server_with_policy_kernel"] = {
+            "env_steps_per_s": n / sec, "envs": n, "us_per_step": sec * 1e6, "steps": Ks,
+            "note": "ef_gridworld_serve + ef_policy_demo_serve resident together on two streams; every step's actions are "
+                    "computed by the policy kernel from the previous step's observations; host wall clock over 4000 steps"}
+        del srv
         sec = ev_time(lambda: sets[0].step(acts[0]), 200)
         details["gridworld_step_python_loop"] = {"env_steps_per_s": n / sec, "envs": n, "us_per_call": sec * 1e6,
                                                  "note": "same, driven by one Python step() call per launch (host-bound)"}

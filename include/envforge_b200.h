@@ -448,6 +448,34 @@ int ef_labyrinth_reset(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_
                        const uint8_t* mask, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Persistent step server: K GridWorld.step calls (grid_world.py:495-528, with reset :530-551 as auto-reset) of ONE env
+ * set WITHOUT a kernel launch per step, for a policy that lives on the device in a kernel of its own.  The server kernel
+ * stays resident for all K steps, keeps the (packed) state of its envs in registers and exchanges one CHUNK of
+ * ef_gridworld_serve_chunk_envs(n) consecutive envs per CTA with the action producer through two sequence words per chunk:
+ *     producer:  (k > 0: wait obs_seq[c] >= k)   read the outputs of step k-1   write action[chunk c]   act_seq[c] = k + 1
+ *     server  :  wait act_seq[c] >= k + 1         read action[chunk c]            step, write the outputs  obs_seq[c] = k + 1
+ * with release stores / acquire loads at gpu scope (`st.release.gpu` / `ld.acquire.gpu`, or __threadfence() + volatile
+ * accesses) and L2-coherent reads of whatever the other kernel wrote (`ld.global.cg` / __ldcg): both kernels run at the
+ * same time, on different streams, and must be resident together -- the server occupies one CTA of 512 threads and at
+ * most 96 registers per chunk, at most one chunk per SM.  Results are bit-identical to K ef_gridworld_step calls with the
+ * same actions.  Packed state layout only (`pos` holds cell | counter << 16, see ef_gridworld_step), n a multiple of 4,
+ * table small enough for shared memory.  act_seq / obs_seq: [ceil(n / chunk_envs)] uint32, zeroed by the caller before
+ * both kernels are launched.  The producer kernel must already be LOADED when the server starts (launched once before, or
+ * cudaFuncGetAttributes on it): CUDA loads kernels lazily and a first launch may synchronise the context, i.e. wait for
+ * the server that is waiting for it.  A wait that is not satisfied within ~5 s gives up, sets status[0] = 1 (nullable) and ends
+ * the kernel after writing the state back; `clock` / `t0` advance by the steps actually taken.
+ * ef_policy_demo_serve is a stand-in producer (tests, bench): action = (row * 3 + col + k) & 3 of the observation the env
+ * returned for step k - 1 (the content of `obs` at launch for k = 0).
+ * ------------------------------------------------------------------------------------------------------------ */
+int ef_gridworld_serve_chunk_envs(int64_t n);   /* envs per chunk for a batch of n (<= 0: the batch does not fit one CTA per SM) */
+int ef_gridworld_serve(const ef_grid_desc* grid, int32_t* pos, float* ep_ret, const int32_t* action, uint64_t seed,
+                       uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, uint8_t* terminated,
+                       uint8_t* truncated, double* stats, uint32_t* err, uint64_t* clock, uint32_t* act_seq,
+                       uint32_t* obs_seq, uint32_t* status, int64_t n, void* stream);
+int ef_policy_demo_serve(const int32_t* obs, int32_t* action, const uint32_t* obs_seq, uint32_t* act_seq, int32_t K,
+                         uint32_t* status, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Episode statistics: reduce per-env running (ep_len, ep_ret) of the envs still in flight into `out[0..3]`
  * (count, sum len, sum ret, sum ret^2) -- complements `stats`, which only sees finished episodes.
  * ------------------------------------------------------------------------------------------------------------ */

@@ -296,14 +296,16 @@ constexpr int kWarpsPerCta = kThreads / 32;
 
 // CTA epilogue: fold the per-thread statistics / error accumulators into global memory with ONE barrier and at most
 // a handful of global reductions per CTA, then add this CTA's share to the device clock.
-// All threads of the CTA must call it.  `stats`, `err`, `clock` may each be null.
+// All threads of the CTA must call it.  `stats`, `err`, `clock` may each be null.  WARPS = warps per CTA (8 everywhere but in
+// the 512-thread step server).
+template <int WARPS = kWarpsPerCta>
 __device__ __forceinline__ void cta_epilogue(const EpisodeAcc& acc, const ErrorAcc& errs, double* __restrict__ stats,
                                              uint32_t* __restrict__ err, unsigned long long* clock,
                                              unsigned long long ticket, unsigned long long clock_inc) {
-    __shared__ uint32_t s_u[kWarpsPerCta][3];            // steps, episodes, rejected
-    __shared__ unsigned long long s_len[kWarpsPerCta];
-    __shared__ double s_d[kWarpsPerCta][2];              // return, return^2
-    __shared__ uint32_t s_e[kWarpsPerCta][3];            // one offender per warp: g + 1, detail, kind
+    __shared__ uint32_t s_u[WARPS][3];            // steps, episodes, rejected
+    __shared__ unsigned long long s_len[WARPS];
+    __shared__ double s_d[WARPS][2];              // return, return^2
+    __shared__ uint32_t s_e[WARPS][3];            // one offender per warp: g + 1, detail, kind
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t steps = __reduce_add_sync(0xffffffffu, acc.steps);
     const uint32_t eps = __reduce_add_sync(0xffffffffu, acc.episodes);
@@ -336,13 +338,13 @@ __device__ __forceinline__ void cta_epilogue(const EpisodeAcc& acc, const ErrorA
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t_steps = 0ull, t_eps = 0ull, t_len = 0ull;
-        uint32_t t_rej = 0u, first = kWarpsPerCta;
+        uint32_t t_rej = 0u, first = WARPS;
         double t_r = 0.0, t_r2 = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             t_steps += s_u[w][0];
             t_eps += s_u[w][1];
-            if (s_u[w][2] != 0u && first == kWarpsPerCta) first = w;
+            if (s_u[w][2] != 0u && first == WARPS) first = w;
             t_rej += s_u[w][2];
             t_len += s_len[w];
             t_r += s_d[w][0];

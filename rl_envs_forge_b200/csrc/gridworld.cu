@@ -61,6 +61,11 @@ struct GridArgs {
     int32_t K;
     uint8_t* flags;
     unsigned long long* clock;
+    // step server only (ef_gridworld_serve)
+    uint32_t* act_seq;     // [chunks] written by the action producer: k + 1 once chunk c's actions of step k are in place
+    uint32_t* obs_seq;     // [chunks] written by the server: k + 1 once chunk c's outputs of step k are in place
+    uint32_t* status;      // set to 1 if a wait gave up
+    int32_t chunk_quads;   // quads (of four envs) per chunk = per CTA
 };
 
 // Timeline hooks of the step kernels: compiled to nothing in the product build.  `python -m rl_envs_forge_b200._build
@@ -1085,6 +1090,153 @@ __global__ void __launch_bounds__(kThreads) gridworld_reset_layouts_kernel(int32
     }
 }
 
+// ---- persistent step server ---------------------------------------------------------------------------------------------
+// K steps of ONE env set without a launch per step, for a policy that lives on the device in a kernel of its own.  The
+// server is resident for all K steps, keeps the packed state of its envs in registers and exchanges one chunk of envs per
+// CTA with the action producer through two sequence words per chunk:
+//     producer: (k > 0: wait obs_seq[c] >= k)  read obs of step k-1  ->  write actions of step k  ->  act_seq[c] = k + 1
+//     server  : wait act_seq[c] >= k + 1       read actions          ->  step, write outputs      ->  obs_seq[c] = k + 1
+// (release stores / acquire loads at gpu scope; everything another kernel wrote while this one runs is read through L2).
+// Same Philox words and table walk as K step() calls: results are bit-identical (tests/test_gpu_gridworld_serve.py).
+// Both kernels must be resident together: the server runs ONE CTA of kServeThreads per chunk with at most one chunk per
+// SM, which leaves more than half of every SM to the producer.  A wait that is not satisfied within ~5 s gives up, sets
+// `status` and ends the kernel instead of hanging the GPU.
+constexpr int kServeThreads = 512;
+constexpr int kServeQ = 4;   // quads per thread
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Thread 0 spins until *seq >= want (or gives up); returns false for the whole CTA after a give-up.
+__device__ __forceinline__ bool serve_wait(const uint32_t* seq, uint32_t want, uint32_t* status, int* s_ok) {
+    if (threadIdx.x == 0) {
+        unsigned long long t0 = 0ull;
+        uint32_t polls = 0u;
+        int ok = 1;
+        while (ld_acquire_gpu_u32(seq) < want) {
+            if ((++polls & 1023u) == 0u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                if (t0 == 0ull) t0 = now;
+                else if (now - t0 > 5000000000ull) {
+                    ok = 0;
+                    if (status) atomicExch(status, 1u);
+                    break;
+                }
+            }
+        }
+        *s_ok = ok;
+    }
+    __syncthreads();
+    return *s_ok != 0;
+}
+
+// 96 registers x 512 threads = 48 K of the SM's 64 K registers: the producer's CTA (256 threads, ~40 registers) fits next to it.
+template <int SLOTS>
+__global__ void __maxnreg__(96) gridworld_serve_kernel(const GridArgs a) {
+    const uint2* __restrict__ tab = stage_table<true>(a);
+    __shared__ int s_ok;
+    EpisodeAcc acc;
+    ErrorAcc errs;
+    const uint32_t c = blockIdx.x;
+    const int64_t q_begin = static_cast<int64_t>(c) * a.chunk_quads;
+    const int64_t quads = a.n >> 2;
+    const int32_t count = static_cast<int32_t>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(a.chunk_quads), quads - q_begin)));
+    const uint64_t t0 = a.t + clock_steps(clock_fetch(a.clock));
+    // state of this thread's quads: registers for all K steps
+    uint32_t w[kServeQ][4];
+    float ret[kServeQ][4];
+#pragma unroll
+    for (int j = 0; j < kServeQ; ++j) {
+        const int32_t local = j * kServeThreads + static_cast<int32_t>(threadIdx.x);
+        if (local < count) {
+            const int64_t base = (q_begin + local) * 4;
+            const uint4 p4 = *reinterpret_cast<const uint4*>(a.pos + base);
+            const float4 r4 = *reinterpret_cast<const float4*>(a.ep_ret + base);
+            w[j][0] = p4.x; w[j][1] = p4.y; w[j][2] = p4.z; w[j][3] = p4.w;
+            ret[j][0] = r4.x; ret[j][1] = r4.y; ret[j][2] = r4.z; ret[j][3] = r4.w;
+        }
+    }
+    int k = 0;
+    for (; k < a.K; ++k) {
+        if (!serve_wait(a.act_seq + c, static_cast<uint32_t>(k) + 1u, a.status, &s_ok)) break;
+        const uint64_t t = t0 + static_cast<uint64_t>(k);
+#pragma unroll
+        for (int j = 0; j < kServeQ; ++j) {
+            const int32_t local = j * kServeThreads + static_cast<int32_t>(threadIdx.x);
+            if (local < count) {
+                const int64_t base = (q_begin + local) * 4;
+                QuadIn in;
+                in.p4 = make_int4(static_cast<int32_t>(w[j][0]), static_cast<int32_t>(w[j][1]), static_cast<int32_t>(w[j][2]),
+                                  static_cast<int32_t>(w[j][3]));
+                in.r4 = make_float4(ret[j][0], ret[j][1], ret[j][2], ret[j][3]);
+                in.a4 = __ldcg(reinterpret_cast<const int4*>(a.action + base));   // written by the producer while we run: L2
+                PackedQuad q;
+                step_quad_packed<true, SLOTS, true, false>(a, tab, base, static_cast<uint32_t>(a.env_offset + base), t, in, false,
+                                                           acc, errs, q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    w[j][e] = q.w[e];
+                    ret[j][e] = q.ret[e];
+                }
+                const int32_t p[4] = {static_cast<int32_t>(q.w[0] & 0xffffu), static_cast<int32_t>(q.w[1] & 0xffffu),
+                                      static_cast<int32_t>(q.w[2] & 0xffffu), static_cast<int32_t>(q.w[3] & 0xffffu)};
+                store_obs4<false>(a, a.obs, base, p);
+                *reinterpret_cast<float4*>(a.reward + base) = make_float4(q.rew[0], q.rew[1], q.rew[2], q.rew[3]);
+                *reinterpret_cast<uint32_t*>(a.terminated + base) = q.term;
+                *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
+            }
+        }
+        __threadfence();    // my outputs are visible device-wide before the sequence word says so
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu_u32(a.obs_seq + c, static_cast<uint32_t>(k) + 1u);
+    }
+    // state back to memory, so that step() / rollout() continue where the server stopped
+#pragma unroll
+    for (int j = 0; j < kServeQ; ++j) {
+        const int32_t local = j * kServeThreads + static_cast<int32_t>(threadIdx.x);
+        if (local < count) {
+            const int64_t base = (q_begin + local) * 4;
+            *reinterpret_cast<uint4*>(a.pos + base) = make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
+            *reinterpret_cast<float4*>(a.ep_ret + base) = make_float4(ret[j][0], ret[j][1], ret[j][2], ret[j][3]);
+        }
+    }
+    cta_epilogue<kServeThreads / 32>(acc, errs, a.stats, a.err, a.clock, 0ull, static_cast<unsigned long long>(k));
+}
+
+// A stand-in for the user's policy kernel (tests, bench): the action of env i at step k is a fixed function of the
+// observation the env returned for step k - 1 (the observation buffer's content at launch for k = 0),
+//     action = (row * 3 + col + k) & 3,
+// computed chunk by chunk against the server's sequence words.  256 threads per chunk, resident next to the server.
+__global__ void __launch_bounds__(kThreads) policy_demo_serve_kernel(const int32_t* obs, int32_t* action, const uint32_t* obs_seq,
+                                                                     uint32_t* act_seq, int32_t chunk_quads, int32_t K,
+                                                                     uint32_t* status, int64_t n) {
+    __shared__ int s_ok;
+    const uint32_t c = blockIdx.x;
+    const int64_t q_begin = static_cast<int64_t>(c) * chunk_quads;
+    const int64_t quads = n >> 2;
+    const int32_t count = static_cast<int32_t>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(chunk_quads), quads - q_begin)));
+    for (int k = 0; k < K; ++k) {
+        if (k > 0 && !serve_wait(obs_seq + c, static_cast<uint32_t>(k), status, &s_ok)) break;
+        for (int32_t local = threadIdx.x; local < count; local += kThreads) {
+            const int64_t base = (q_begin + local) * 4;
+            const int4 o0 = __ldcg(reinterpret_cast<const int4*>(obs + 2 * base));       // (row, col) of envs 0, 1
+            const int4 o1 = __ldcg(reinterpret_cast<const int4*>(obs + 2 * base) + 1);   // envs 2, 3
+            *reinterpret_cast<int4*>(action + base) = make_int4((o0.x * 3 + o0.y + k) & 3, (o0.z * 3 + o0.w + k) & 3,
+                                                                (o1.x * 3 + o1.y + k) & 3, (o1.z * 3 + o1.w + k) & 3);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu_u32(act_seq + c, static_cast<uint32_t>(k) + 1u);
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------------
 constexpr size_t kMaxSmemTable = 96 * 1024;
 
@@ -1455,3 +1607,73 @@ extern "C" int ef_debug_set_trace(unsigned long long* buf) {
     return cuda_status(cudaMemcpyToSymbol(ef::g_trace_buf, &buf, sizeof(buf)));
 }
 #endif
+
+extern "C" int ef_gridworld_serve_chunk_envs(int64_t n) {
+    // one chunk per SM at most; whole warps of quads (128 envs), at most kServeQ quads per server thread
+    if (n <= 0) return 0;
+    const int64_t quads = (n + 3) / 4;
+    int64_t per = (quads + sm_count() - 1) / sm_count();
+    per = (per + 31) / 32 * 32;
+    const int64_t cap = static_cast<int64_t>(kServeThreads) * kServeQ;
+    if (per > cap) return -1;   // the batch is too large for one resident CTA per SM
+    return static_cast<int>(per * 4);
+}
+
+extern "C" int ef_gridworld_serve(const ef_grid_desc* grid, int32_t* pos, float* ep_ret, const int32_t* action, uint64_t seed,
+                                  uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward,
+                                  uint8_t* terminated, uint8_t* truncated, double* stats, uint32_t* err, uint64_t* clock,
+                                  uint32_t* act_seq, uint32_t* obs_seq, uint32_t* status, int64_t n, void* stream) {
+    GridArgs a{};
+    if (int s = fill_args(grid, a)) return s;
+    if (n <= 0 || K < 0 || !pos || !ep_ret || !action || !obs || !reward || !terminated || !truncated || !act_seq || !obs_seq)
+        return EF_ERR_INVALID_ARGUMENT;
+    if (!packed_ok(a, 1)) return EF_ERR_INVALID_ARGUMENT;                      // packed state word only
+    if ((n & 3) != 0) return EF_ERR_UNSUPPORTED;                                // whole quads
+    if (!aligned(pos, 16) || !aligned(ep_ret, 16) || !aligned(action, 16) || !aligned(obs, 16) || !aligned(reward, 16) ||
+        !aligned(terminated, 4) || !aligned(truncated, 4))
+        return EF_ERR_INVALID_ARGUMENT;
+    if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
+    const size_t table_bytes = static_cast<size_t>(a.table_len) * sizeof(uint2);
+    if (table_bytes > kMaxSmemTable) return EF_ERR_UNSUPPORTED;
+    const int chunk_envs = ef_gridworld_serve_chunk_envs(n);
+    if (chunk_envs <= 0) return EF_ERR_UNSUPPORTED;
+    if (K == 0) return EF_OK;
+    a.pos = pos; a.ep_ret = ep_ret; a.action = action; a.seed = seed; a.t = t0; a.env_offset = env_offset; a.K = K;
+    a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated;
+    a.stats = stats; a.err = err; a.n = n; a.autoreset = 1;
+    a.clock = reinterpret_cast<unsigned long long*>(clock);
+    a.act_seq = act_seq; a.obs_seq = obs_seq; a.status = status; a.chunk_quads = chunk_envs / 4;
+    a.rk = philox_round_keys(seed);
+    const int grid_s = static_cast<int>(((n >> 2) + a.chunk_quads - 1) / a.chunk_quads);
+    const cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {   // CUDA loads kernels lazily, and the FIRST launch of a kernel may synchronise the context: a producer kernel launched
+        // for the first time while the server is already spinning would then wait for the server, which waits for it.  The
+        // stand-in producer is loaded here, before the server starts; a user's own producer must have been loaded (launched
+        // once, or cudaFuncGetAttributes) before ef_gridworld_serve is called.
+        cudaFuncAttributes fa;
+        const cudaError_t e = cudaFuncGetAttributes(&fa, policy_demo_serve_kernel);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    auto go = [&](auto kernel) -> int {
+        if (table_bytes > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(table_bytes));
+            if (e != cudaSuccess) return cuda_status(e);
+        }
+        kernel<<<grid_s, kServeThreads, table_bytes, st>>>(a);
+        return cuda_status(cudaGetLastError());
+    };
+    return grid->n_slots == 1 ? go(gridworld_serve_kernel<1>) : go(gridworld_serve_kernel<4>);
+}
+
+extern "C" int ef_policy_demo_serve(const int32_t* obs, int32_t* action, const uint32_t* obs_seq, uint32_t* act_seq, int32_t K,
+                                    uint32_t* status, int64_t n, void* stream) {
+    if (n <= 0 || K < 0 || !obs || !action || !obs_seq || !act_seq || (n & 3) != 0) return EF_ERR_INVALID_ARGUMENT;
+    const int chunk_envs = ef_gridworld_serve_chunk_envs(n);
+    if (chunk_envs <= 0) return EF_ERR_UNSUPPORTED;
+    if (K == 0) return EF_OK;
+    const int chunk_quads = chunk_envs / 4;
+    const int grid_s = static_cast<int>(((n >> 2) + chunk_quads - 1) / chunk_quads);
+    policy_demo_serve_kernel<<<grid_s, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(obs, action, obs_seq, act_seq, chunk_quads, K,
+                                                                                         status, n);
+    return cuda_status(cudaGetLastError());
+}

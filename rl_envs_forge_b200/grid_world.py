@@ -15,6 +15,7 @@ from enum import IntEnum
 import numpy as np
 
 from . import _lib, spaces
+from ._lib import EnvForgeError
 from .vec_env import VecEnv, resolve_seed
 
 
@@ -754,6 +755,76 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         if return_final_obs:
             info["final_observation"] = fobs
         return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool), info
+
+    # -- persistent step server: K steps without a launch per step, actions from a policy kernel of its own ---------------
+    def serve_begin(self, K):
+        """Start the step server for K steps on a private stream and return what the action producer needs:
+
+            {"action": int32 [N] CUDA tensor to write, "obs" / "reward" / "terminated" / "truncated": the output tensors to
+             read, "act_seq" / "obs_seq": uint32 [chunks] sequence words, "chunk_envs": envs per chunk, "stream": the
+             server's stream, "status": int32 [1] (1 after a give-up)}
+
+        Protocol per chunk c and step k (see include/envforge_b200.h, ef_gridworld_serve): the producer waits for
+        obs_seq[c] >= k (k > 0), writes action[chunk c] and releases act_seq[c] = k + 1; the server steps the chunk and
+        releases obs_seq[c] = k + 1.  The producer must run CONCURRENTLY (its own stream, resident next to the server).
+        `serve_end()` waits for the server and returns the last outputs.  Same results as K step() calls."""
+        torch = self._torch
+        if self.rng != "philox" or self.strict or self._w8 or not self._packed or self._clock is not None:
+            raise ValueError("the step server covers the plain Philox step in the packed state layout (canonical wire)")
+        if self.__dict__.get("_serve") is not None:
+            raise RuntimeError("serve_begin() called again before serve_end()")
+        n = self.num_envs
+        chunk = int(self._lib.ef_gridworld_serve_chunk_envs(n))
+        if chunk <= 0 or n % 4:
+            raise ValueError("the step server needs num_envs to be a multiple of 4 and at most 2048 envs per SM")
+        chunks = -(-n // chunk)
+        st = {"K": int(K), "stream": torch.cuda.Stream(device=self.device),
+              "action": torch.zeros(n, dtype=torch.int32, device=self.device),
+              "act_seq": torch.zeros(chunks, dtype=torch.int32, device=self.device),
+              "obs_seq": torch.zeros(chunks, dtype=torch.int32, device=self.device),
+              "status": torch.zeros(1, dtype=torch.int32, device=self.device), "chunk_envs": chunk,
+              "obs": self._obs, "reward": self._reward, "terminated": self._term, "truncated": self._trunc}
+        cur = torch.cuda.current_stream(self.device)
+        st["stream"].wait_stream(cur)          # the zeroed sequence words, resets, earlier steps
+        with torch.cuda.stream(st["stream"]):
+            self._call(self._lib.ef_gridworld_serve, self._desc, self._pl.data_ptr(), _lib.ptr(self.ep_ret),
+                       _lib.ptr(st["action"]), self._seed, self._t, self.env_offset, int(K), _lib.ptr(self._obs),
+                       _lib.ptr(self._reward), _lib.ptr(self._term), _lib.ptr(self._trunc), _lib.ptr(self._stats_raw),
+                       _lib.ptr(self.err), None, _lib.ptr(st["act_seq"]), _lib.ptr(st["obs_seq"]), _lib.ptr(st["status"]), n)
+        self._serve = st
+        return st
+
+    def serve_end(self):
+        """Wait for the step server started by serve_begin(); returns (obs, reward, terminated, truncated) of the last step."""
+        torch = self._torch
+        st = self.__dict__.get("_serve")
+        if st is None:
+            raise RuntimeError("serve_end() without serve_begin()")
+        st["stream"].synchronize()
+        self._serve = None
+        if int(st["status"].item()) != 0:
+            taken = int(st["obs_seq"].min().item())
+            self._t += taken
+            raise EnvForgeError(f"the step server gave up waiting for actions after {taken} step(s): is the producer running "
+                                "concurrently on another stream?")
+        self._t += st["K"]
+        torch.cuda.current_stream(self.device).wait_stream(st["stream"])
+        return self._obs, self._reward, self._term.view(torch.bool), self._trunc.view(torch.bool)
+
+    def serve_with_demo_policy(self, K):
+        """K served steps driven by the built-in stand-in policy kernel (`ef_policy_demo_serve`: action = (row * 3 + col +
+        k) & 3 of the previous observation) on a second stream -- the smallest complete example of the protocol."""
+        torch = self._torch
+        st = self.serve_begin(K)
+        producer = self.__dict__.setdefault("_serve_producer_stream", torch.cuda.Stream(device=self.device))
+        producer.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(producer), torch.cuda.device(self.device):
+            _lib.check(self._lib.ef_policy_demo_serve(_lib.ptr(self._obs), _lib.ptr(st["action"]), _lib.ptr(st["obs_seq"]),
+                                                      _lib.ptr(st["act_seq"]), int(K), _lib.ptr(st["status"]), self.num_envs,
+                                                      producer.cuda_stream))
+        out = self.serve_end()
+        producer.synchronize()
+        return out
 
     # -- host-buffer step without the host wait: two env sets in flight keep PCIe busy in both directions ----------------
     def step_async(self, actions):
