@@ -720,6 +720,29 @@ def run_ours(args):
             "env_steps_per_s": n / sec, "envs": n, "us_per_step": sec * 1e6, "steps": Ks,
             "note": "ef_gridworld_serve + ef_policy_demo_serve resident together on two streams; every step's actions are "
                     "computed by the policy kernel from the previous step's observations; host wall clock over 4000 steps"}
+        # the same policy with one launch per step: [policy kernel -> step kernel] x 56 in a CUDA graph, replayed
+        from rl_envs_forge_b200 import _lib as ef_lib2
+        act_pg = torch.zeros(n, dtype=torch.int32, device="cuda")
+        g_pol = torch.cuda.CUDAGraph()
+        srv.enable_device_clock()
+        lib2 = ef_lib2.load()
+
+        def policy_then_step(k):
+            ef_lib2.check(lib2.ef_policy_demo_step(srv._obs.data_ptr(), act_pg.data_ptr(), k, n,
+                                                   torch.cuda.current_stream().cuda_stream))
+            srv.step(act_pg)
+        policy_then_step(0)
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(g_pol, stream=stream):
+                for k in range(56):
+                    policy_then_step(k)
+        sec = ev_time(g_pol.replay, 40) / 56
+        details["gridworld_step_and_policy_kernel_per_step_graph"] = {
+            "env_steps_per_s": n / sec, "envs": n, "us_per_step": sec * 1e6,
+            "note": "the same stand-in policy as an ordinary kernel: [policy kernel, step kernel] x 56 captured in a CUDA graph "
+                    "and replayed (two launches per step) -- what the step server replaces"}
+        srv.disable_device_clock()
+        del g_pol
         del srv
         sec = ev_time(lambda: sets[0].step(acts[0]), 200)
         details["gridworld_step_python_loop"] = {"env_steps_per_s": n / sec, "envs": n, "us_per_call": sec * 1e6,

@@ -456,8 +456,9 @@ int ef_labyrinth_reset(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_
  *     server  :  wait act_seq[c] >= k + 1         read action[chunk c]            step, write the outputs  obs_seq[c] = k + 1
  * with release stores / acquire loads at gpu scope (`st.release.gpu` / `ld.acquire.gpu`, or __threadfence() + volatile
  * accesses) and L2-coherent reads of whatever the other kernel wrote (`ld.global.cg` / __ldcg): both kernels run at the
- * same time, on different streams, and must be resident together -- the server occupies one CTA of 512 threads and at
- * most 96 registers per chunk, at most one chunk per SM.  Results are bit-identical to K ef_gridworld_step calls with the
+ * same time, on different streams, and must be resident together -- the server occupies one CTA of 256 threads and at
+ * most 96 registers per chunk, at most EF_SERVE_CHUNKS_PER_SM chunks per SM (every chunk is a dependency chain of its
+ * own, and the chains of an SM hide each other's latencies).  Results are bit-identical to K ef_gridworld_step calls with the
  * same actions.  Packed state layout only (`pos` holds cell | counter << 16, see ef_gridworld_step), n a multiple of 4,
  * table small enough for shared memory.  act_seq / obs_seq: [ceil(n / chunk_envs)] uint32, zeroed by the caller before
  * both kernels are launched.  The producer kernel must already be LOADED when the server starts (launched once before, or
@@ -467,6 +468,9 @@ int ef_labyrinth_reset(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_
  * ef_policy_demo_serve is a stand-in producer (tests, bench): action = (row * 3 + col + k) & 3 of the observation the env
  * returned for step k - 1 (the content of `obs` at launch for k = 0).
  * ------------------------------------------------------------------------------------------------------------ */
+#ifndef EF_SERVE_CHUNKS_PER_SM
+#define EF_SERVE_CHUNKS_PER_SM 2
+#endif
 int ef_gridworld_serve_chunk_envs(int64_t n);   /* envs per chunk for a batch of n (<= 0: the batch does not fit one CTA per SM) */
 int ef_gridworld_serve(const ef_grid_desc* grid, int32_t* pos, float* ep_ret, const int32_t* action, uint64_t seed,
                        uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, uint8_t* terminated,
@@ -474,6 +478,8 @@ int ef_gridworld_serve(const ef_grid_desc* grid, int32_t* pos, float* ep_ret, co
                        uint32_t* obs_seq, uint32_t* status, int64_t n, void* stream);
 int ef_policy_demo_serve(const int32_t* obs, int32_t* action, const uint32_t* obs_seq, uint32_t* act_seq, int32_t K,
                          uint32_t* status, int64_t n, void* stream);
+/* The same stand-in policy as an ordinary kernel, one launch per step (the baseline the server is measured against). */
+int ef_policy_demo_step(const int32_t* obs, int32_t* action, int32_t k, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Episode statistics: reduce per-env running (ep_len, ep_ret) of the envs still in flight into `out[0..3]`

@@ -103,6 +103,7 @@ SIGNATURES = {
     "ef_gridworld_serve": (C.c_int, [C.POINTER(GridDesc), _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                      _P, _I64, _P]),
     "ef_policy_demo_serve": (C.c_int, [_P, _P, _P, _P, _I32, _P, _I64, _P]),
+    "ef_policy_demo_step": (C.c_int, [_P, _P, _I32, _I64, _P]),
     "ef_cartpole_step": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _P, _P, _P, _P, _P, _P,
                                    _P, _P, _P, _I64, _I32, _P]),
     "ef_cartpole_rollout": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P,

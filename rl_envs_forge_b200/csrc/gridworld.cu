@@ -1098,11 +1098,22 @@ __global__ void __launch_bounds__(kThreads) gridworld_reset_layouts_kernel(int32
 //     server  : wait act_seq[c] >= k + 1       read actions          ->  step, write outputs      ->  obs_seq[c] = k + 1
 // (release stores / acquire loads at gpu scope; everything another kernel wrote while this one runs is read through L2).
 // Same Philox words and table walk as K step() calls: results are bit-identical (tests/test_gpu_gridworld_serve.py).
-// Both kernels must be resident together: the server runs ONE CTA of kServeThreads per chunk with at most one chunk per
-// SM, which leaves more than half of every SM to the producer.  A wait that is not satisfied within ~5 s gives up, sets
+// Both kernels must be resident together: the server runs one CTA of kServeThreads (256) per chunk and at most
+// EF_SERVE_CHUNKS_PER_SM (2) chunks per SM -- 48 K of every SM's 64 K registers -- which leaves room for the producer.
+// Publishing a chunk is `bar.sync` + one release store by thread 0 (cumulative: the CTA's stores are ordered before it).  A wait that is not satisfied within ~5 s gives up, sets
 // `status` and ends the kernel instead of hanging the GPU.
-constexpr int kServeThreads = 512;
-constexpr int kServeQ = 4;   // quads per thread
+#ifndef EF_SERVE_THREADS
+#define EF_SERVE_THREADS 256
+#endif
+#ifndef EF_SERVE_THREADFENCE
+#define EF_SERVE_THREADFENCE 0     // 1: every thread fences before the publishing barrier (measured slower: 11.5 vs 10.3 us per step)
+#endif
+#ifndef EF_SERVE_NANOSLEEP
+#define EF_SERVE_NANOSLEEP 100       // back-off between two polls of a sequence word (ns); 0 = spin
+#endif
+constexpr int kServeThreads = EF_SERVE_THREADS;   // CTAs of this size, EF_SERVE_CHUNKS_PER_SM of them per SM: every chunk is its
+constexpr int kServeQ = 4;           // own dependency chain (wait, step, publish); the chains of one SM hide each other's latencies
+constexpr int kServeProducerThreads = 128;
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
     uint32_t v;
@@ -1120,6 +1131,7 @@ __device__ __forceinline__ bool serve_wait(const uint32_t* seq, uint32_t want, u
         uint32_t polls = 0u;
         int ok = 1;
         while (ld_acquire_gpu_u32(seq) < want) {
+            if (EF_SERVE_NANOSLEEP) __nanosleep(EF_SERVE_NANOSLEEP);
             if ((++polls & 1023u) == 0u) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
@@ -1137,7 +1149,7 @@ __device__ __forceinline__ bool serve_wait(const uint32_t* seq, uint32_t want, u
     return *s_ok != 0;
 }
 
-// 96 registers x 512 threads = 48 K of the SM's 64 K registers: the producer's CTA (256 threads, ~40 registers) fits next to it.
+// 96 registers x 256 threads x 2 CTAs = 48 K of the SM's 64 K registers: the producer's CTAs (128 threads, ~40 registers) fit.
 template <int SLOTS>
 __global__ void __maxnreg__(96) gridworld_serve_kernel(const GridArgs a) {
     const uint2* __restrict__ tab = stage_table<true>(a);
@@ -1193,8 +1205,10 @@ __global__ void __maxnreg__(96) gridworld_serve_kernel(const GridArgs a) {
                 *reinterpret_cast<uint32_t*>(a.truncated + base) = q.trunc;
             }
         }
-        __threadfence();    // my outputs are visible device-wide before the sequence word says so
-        __syncthreads();
+#if EF_SERVE_THREADFENCE
+        __threadfence();   // every thread drains its own stores (in parallel) instead of thread 0's release waiting for all
+#endif
+        __syncthreads();   // every thread's stores precede the barrier; thread 0's release store is cumulative over them
         if (threadIdx.x == 0) st_release_gpu_u32(a.obs_seq + c, static_cast<uint32_t>(k) + 1u);
     }
     // state back to memory, so that step() / rollout() continue where the server stopped
@@ -1213,8 +1227,8 @@ __global__ void __maxnreg__(96) gridworld_serve_kernel(const GridArgs a) {
 // A stand-in for the user's policy kernel (tests, bench): the action of env i at step k is a fixed function of the
 // observation the env returned for step k - 1 (the observation buffer's content at launch for k = 0),
 //     action = (row * 3 + col + k) & 3,
-// computed chunk by chunk against the server's sequence words.  256 threads per chunk, resident next to the server.
-__global__ void __launch_bounds__(kThreads) policy_demo_serve_kernel(const int32_t* obs, int32_t* action, const uint32_t* obs_seq,
+// computed chunk by chunk against the server's sequence words.  128 threads per chunk, resident next to the server.
+__global__ void __launch_bounds__(kServeProducerThreads) policy_demo_serve_kernel(const int32_t* obs, int32_t* action, const uint32_t* obs_seq,
                                                                      uint32_t* act_seq, int32_t chunk_quads, int32_t K,
                                                                      uint32_t* status, int64_t n) {
     __shared__ int s_ok;
@@ -1224,16 +1238,29 @@ __global__ void __launch_bounds__(kThreads) policy_demo_serve_kernel(const int32
     const int32_t count = static_cast<int32_t>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(chunk_quads), quads - q_begin)));
     for (int k = 0; k < K; ++k) {
         if (k > 0 && !serve_wait(obs_seq + c, static_cast<uint32_t>(k), status, &s_ok)) break;
-        for (int32_t local = threadIdx.x; local < count; local += kThreads) {
+        for (int32_t local = threadIdx.x; local < count; local += kServeProducerThreads) {
             const int64_t base = (q_begin + local) * 4;
             const int4 o0 = __ldcg(reinterpret_cast<const int4*>(obs + 2 * base));       // (row, col) of envs 0, 1
             const int4 o1 = __ldcg(reinterpret_cast<const int4*>(obs + 2 * base) + 1);   // envs 2, 3
             *reinterpret_cast<int4*>(action + base) = make_int4((o0.x * 3 + o0.y + k) & 3, (o0.z * 3 + o0.w + k) & 3,
                                                                 (o1.x * 3 + o1.y + k) & 3, (o1.z * 3 + o1.w + k) & 3);
         }
+#if EF_SERVE_THREADFENCE
         __threadfence();
+#endif
         __syncthreads();
         if (threadIdx.x == 0) st_release_gpu_u32(act_seq + c, static_cast<uint32_t>(k) + 1u);
+    }
+}
+
+// The stand-in policy as an ordinary kernel (one launch per step): what the step server is measured against.
+__global__ void __launch_bounds__(kThreads) policy_demo_step_kernel(const int32_t* __restrict__ obs, int32_t* __restrict__ action,
+                                                                    int32_t k, int64_t quads) {
+    for (int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < quads;
+         v += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int4 o0 = reinterpret_cast<const int4*>(obs)[2 * v], o1 = reinterpret_cast<const int4*>(obs)[2 * v + 1];
+        reinterpret_cast<int4*>(action)[v] = make_int4((o0.x * 3 + o0.y + k) & 3, (o0.z * 3 + o0.w + k) & 3,
+                                                       (o1.x * 3 + o1.y + k) & 3, (o1.z * 3 + o1.w + k) & 3);
     }
 }
 
@@ -1609,10 +1636,11 @@ extern "C" int ef_debug_set_trace(unsigned long long* buf) {
 #endif
 
 extern "C" int ef_gridworld_serve_chunk_envs(int64_t n) {
-    // one chunk per SM at most; whole warps of quads (128 envs), at most kServeQ quads per server thread
+    // at most EF_SERVE_CHUNKS_PER_SM chunks per SM; whole warps of quads (128 envs), at most kServeQ quads per server thread
     if (n <= 0) return 0;
     const int64_t quads = (n + 3) / 4;
-    int64_t per = (quads + sm_count() - 1) / sm_count();
+    const int64_t slots = static_cast<int64_t>(sm_count()) * EF_SERVE_CHUNKS_PER_SM;
+    int64_t per = (quads + slots - 1) / slots;
     per = (per + 31) / 32 * 32;
     const int64_t cap = static_cast<int64_t>(kServeThreads) * kServeQ;
     if (per > cap) return -1;   // the batch is too large for one resident CTA per SM
@@ -1673,7 +1701,13 @@ extern "C" int ef_policy_demo_serve(const int32_t* obs, int32_t* action, const u
     if (K == 0) return EF_OK;
     const int chunk_quads = chunk_envs / 4;
     const int grid_s = static_cast<int>(((n >> 2) + chunk_quads - 1) / chunk_quads);
-    policy_demo_serve_kernel<<<grid_s, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(obs, action, obs_seq, act_seq, chunk_quads, K,
+    policy_demo_serve_kernel<<<grid_s, kServeProducerThreads, 0, static_cast<cudaStream_t>(stream)>>>(obs, action, obs_seq, act_seq, chunk_quads, K,
                                                                                          status, n);
+    return cuda_status(cudaGetLastError());
+}
+
+extern "C" int ef_policy_demo_step(const int32_t* obs, int32_t* action, int32_t k, int64_t n, void* stream) {
+    if (n <= 0 || !obs || !action || (n & 3) != 0 || !aligned(obs, 16) || !aligned(action, 16)) return EF_ERR_INVALID_ARGUMENT;
+    policy_demo_step_kernel<<<grid_for(n >> 2, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(obs, action, k, n >> 2);
     return cuda_status(cudaGetLastError());
 }

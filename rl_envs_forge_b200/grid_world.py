@@ -776,7 +776,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         n = self.num_envs
         chunk = int(self._lib.ef_gridworld_serve_chunk_envs(n))
         if chunk <= 0 or n % 4:
-            raise ValueError("the step server needs num_envs to be a multiple of 4 and at most 2048 envs per SM")
+            raise ValueError("the step server needs num_envs to be a multiple of 4 and at most 8192 envs per SM")
         chunks = -(-n // chunk)
         st = {"K": int(K), "stream": torch.cuda.Stream(device=self.device),
               "action": torch.zeros(n, dtype=torch.int32, device=self.device),
@@ -803,7 +803,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
         st["stream"].synchronize()
         self._serve = None
         if int(st["status"].item()) != 0:
-            taken = int(st["obs_seq"].min().item())
+            taken = int(st["obs_seq"].min().item())   # complete steps of the whole set; chunks that went further are mid-way
             self._t += taken
             raise EnvForgeError(f"the step server gave up waiting for actions after {taken} step(s): is the producer running "
                                 "concurrently on another stream?")
