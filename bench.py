@@ -381,39 +381,39 @@ def run_ours(args):
     torch.cuda.synchronize()
     # The K launches of a timed window = (K // G) replays of the "round" graph + ONE replay of the "tail" graph (K % G
     # launches).  Warm-up replays exactly these graphs, so no first-replay (instantiation upload) cost can land in a window.
+    # Episode statistics: one fold kernel per window on the stepping stream -- captured as the LAST node of the window's
+    # last graph, so that the window is graph replays only; for N > 1 the cross-GPU sum of the folded vector (the engine's
+    # only collective) runs on a side stream, overlapped with the window's launches: a window starts the exchange of the
+    # vector folded at the end of the previous window and waits for it (stream-side) at its own end.
+    red = StatsReducer(sets, transport=args.stats_transport)
+    red.fold()
+    red.exchange_async()        # pre-warm the exchange path (NCCL communicator / peer mailboxes) before anything is timed
+    red.wait()
+    torch.cuda.synchronize()
     stream = torch.cuda.Stream()
     graphs = {}
     with torch.cuda.stream(stream):
         for name, count in (("round", G if K >= G else 0), ("tail", K % G)):
-            if count == 0:
+            if count == 0 and name == "round":
                 continue
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
                 for i in range(count):
                     direct(i)
+                if name == "tail":
+                    red.fold()           # ef_stats_fold: one kernel node behind the window's last step
             graphs[name] = g
     torch.cuda.synchronize()
 
     def launch_window():
         for _ in range(K // G):
             graphs["round"].replay()
-        if K % G:
-            graphs["tail"].replay()
-
-    # Episode statistics: one fold kernel per window on the stepping stream; for N > 1 the cross-GPU sum of the folded
-    # vector (the engine's only collective) runs on a side stream, overlapped with the window's launches: a window starts
-    # the exchange of the vector folded at the end of the previous window and waits for it (stream-side) at its own end.
-    red = StatsReducer(sets, transport=args.stats_transport)
-    red.fold()
-    red.exchange_async()        # pre-warm the exchange path (NCCL communicator / peer mailboxes) before anything is timed
-    red.wait()
-    torch.cuda.synchronize()
+        graphs["tail"].replay()          # the K % G remaining launches (possibly none) + the statistics fold
 
     def window_body():
         if world > 1:
             red.exchange_async()
         launch_window()
-        red.fold()
         if world > 1:
             red.wait()
 
@@ -522,7 +522,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": n * world, "env_sets": R, "action_buffers": A,
                    "l2": f"inputs larger than L2: {R} rotating env sets x {(34 if sets[0]._packed else 42) * n / 1e6:.0f} MB",
-                   "launch": "CUDA graph replay of VecGridWorld.step (device step clock); warm-up replays the same graphs",
+                   "launch": "CUDA graph replay of VecGridWorld.step (device step clock), the statistics fold kernel as the graph's last node; warm-up replays the same graphs",
                    "actions": "resident in HBM", "rejected_env_steps": err_count, "parallelism": f"env-sharded x{world}",
                    "timed": f"{n_windows} windows of exactly {K} launches, median window reported",
                    "preroll_us": args.preroll_us,

@@ -329,6 +329,14 @@ typedef struct ef_arm64 {
 int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_t seed,
                    uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
                    uint32_t* err, int64_t n, void* stream);
+/* The same step with the default arms' per-env means LOOKED UP instead of re-derived: `means` is the fp32 [n,k] table
+ * ef_bandit_default_means fills for the same (k, seed, env_offset, n) -- row i belongs to env i of THIS call -- or NULL
+ * (then this is ef_bandit_step).  Bit-identical rewards either way; with two default arms in ten the table saves a
+ * Philox call + Box-Muller on a fifth of the steps (40 B of HBM per env for k = 10).  Reference: the means are drawn
+ * once per instance in _create_default_arms (k_armed_bandit.py:160-165) and kept in the Arm objects. */
+int ef_bandit_step_means(const ef_arm* arms, int32_t k, const int32_t* action, const float* means, uint64_t seed,
+                         uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
+                         uint32_t* err, int64_t n, void* stream);
 /* STREAM-EXACT KArmedBandit.step: every bandit owns the generator the reference builds for it -- numpy's legacy
  * RandomState(seed_i), MT19937 (k_armed_bandit.py:145, :215) -- and Arm.sample (:66-122) runs numpy's legacy float64
  * algorithms on it, so the reward stream of env i is that of KArmedBandit(seed=seed_i) without injected draws.

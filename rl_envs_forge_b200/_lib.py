@@ -119,6 +119,7 @@ SIGNATURES = {
                                            _P, _P, _P, _I64, _P]),
     "ef_pendulum_disk_reset": (C.c_int, [C.POINTER(PendulumParams), _P, _P, _P, _U64, _U64, _U64, _P, _I64, _P]),
     "ef_bandit_step": (C.c_int, [_P, _I32, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
+    "ef_bandit_step_means": (C.c_int, [_P, _I32, _P, _P, _U64, _U64, _U64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_step_mt19937": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _P, _U64, _P, _P, _P, _P, _P, _I64, _P]),
     "ef_bandit_default_means": (C.c_int, [_I32, _U64, _U64, _P, _I64, _P]),
     "ef_episode_stat_reduce": (C.c_int, [_P, _P, _P, _I64, _P]),

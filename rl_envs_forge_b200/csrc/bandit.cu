@@ -20,6 +20,7 @@ struct BanditArgs {
     const ef_arm* arms;  // [K, k]
     int32_t k;
     const int32_t* action;  // [K, n] or null
+    const float* means;     // [n, k] default-arm means (ef_bandit_default_means) or null: re-derived in-kernel
     uint64_t seed, t0, env_offset;
     int32_t K;
     int32_t* obs;
@@ -228,7 +229,11 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
             arm.p1 = __int_as_float(raw.z);
             arm.reserved = 0;
             Primitives pr(a.seed, g, t);
-            const float r = sample_arm(arm, pr, a.seed, g, static_cast<uint32_t>(act));
+            float r;
+            if (a.means != nullptr && static_cast<uint32_t>(arm.family) >= 8u)   // EF_ARM_DEFAULT_NORMAL, mean looked up
+                r = (__ldg(a.means + i * a.k + act) + arm.p0) + arm.p1 * pr.n();
+            else
+                r = sample_arm(arm, pr, a.seed, g, static_cast<uint32_t>(act));
             if (a.reward) a.reward[o] = r;
             acc.steps += 1u;
             acc.finish(1, r);  // every bandit step is a finished one-step episode (done is always True, :198)
@@ -244,15 +249,37 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
 // this kernel takes a tile of kTile consecutive envs, bins them by sampler code path in shared memory (warp-aggregated
 // counting sort), evaluates them in sorted order -- the 32 lanes of a warp then run the same sampler -- and writes the
 // rewards back through shared memory so global stores stay coalesced.  Results are bit-identical to the plain kernel.
-constexpr int kItemsPerThread = 8;
-constexpr int kTile = kThreads * kItemsPerThread;  // 2048 envs per tile; local index fits 12 bits
+//
+// Second pass of round 2 (profiles/r02z_bandit_ab.txt):
+//  * every bin starts on a 32-slot boundary of the sorted array (the gaps hold a sentinel), so a warp never holds two
+//    samplers; with the bins packed back to back each of the ~12 bin boundaries of a tile cost an extra warp pass;
+//  * tiles of 4096 envs (16 per thread; key / rank / action of an env wait in the reward staging array instead of in
+//    registers), which halves the share of partially filled warps again;
+//  * the 32-env groups of the sorted array are handed to the warps of the CTA dynamically (one shared counter): a
+//    group of beta(2,5) draws costs 2.5 x a group of uniform draws;
+//  * a default arm's per-env mean comes from the [n,k] table of ef_bandit_default_means when the caller passes it
+//    (ef_bandit_step_means) instead of being re-derived with a second Philox call + Box-Muller on every step.
+#ifndef EF_BANDIT_ITEMS
+#define EF_BANDIT_ITEMS 16
+#endif
+constexpr int kItemsPerThread = EF_BANDIT_ITEMS;
+constexpr int kTile = kThreads * kItemsPerThread;  // 4096 envs per tile; local index and rank fit 12 bits
+static_assert(kItemsPerThread % 8 == 0 && kTile <= 4096, "local index / rank are packed in 12 bits");
 constexpr int kBins = 16;
+constexpr int kSortedSlots = kTile + 32 * (kBins - 1);  // every bin padded to a multiple of 32
 #ifndef EF_BANDIT_CTAS
 #define EF_BANDIT_CTAS 4
 #endif
-constexpr int kSortedCtasPerSm = EF_BANDIT_CTAS;  // 64 registers x 256 threads: four resident CTAs per SM (measured: 4.98e10 vs 4.88e10 steps/s with three)
+#ifndef EF_BANDIT_DYNAMIC
+#define EF_BANDIT_DYNAMIC 1
+#endif
+#ifndef EF_BANDIT_ALIGN
+#define EF_BANDIT_ALIGN 32u   // A/B switch: 1u packs the bins back to back like the first version
+#endif
+constexpr int kSortedCtasPerSm = EF_BANDIT_CTAS;  // 64 registers x 256 threads: four resident CTAs per SM
 constexpr uint32_t kBinSkip = 15u;                 // out-of-range env or rejected action: not evaluated
-constexpr int32_t kSortedMaxArms = 1 << 20;        // action is packed next to the 12-bit local index
+constexpr int32_t kSortedMaxArms = 1 << 16;        // the action waits in 16 bits next to rank and bin
+constexpr uint32_t kEmptySlot = 0xffffffffu;
 
 __device__ __forceinline__ ef_arm load_arm(const ef_arm* __restrict__ arms, int64_t index) {
     const int4 raw = __ldg(reinterpret_cast<const int4*>(arms) + index);
@@ -277,8 +304,10 @@ __device__ __forceinline__ uint32_t arm_bin(const ef_arm& arm) {
 
 __global__ void __launch_bounds__(kThreads, kSortedCtasPerSm) bandit_step_sorted_kernel(const BanditArgs a) {
     __shared__ uint32_t s_cnt[kBins], s_base[kBins];
-    __shared__ uint32_t s_sorted[kTile];   // action << 12 | local index, ordered by bin
-    __shared__ float s_rew[kTile];
+    __shared__ uint32_t s_next;
+    __shared__ uint32_t s_sorted[kSortedSlots];   // action << 12 | local index, ordered by bin, bins 32-aligned
+    __shared__ float s_rew[kTile];                // phase 1: action << 16 | rank << 4 | bin;  afterwards: rewards
+    uint32_t* const s_tmp = reinterpret_cast<uint32_t*>(s_rew);
     EpisodeAcc acc;
     ErrorAcc errs;
     const uint32_t lane = threadIdx.x & 31u;
@@ -290,78 +319,103 @@ __global__ void __launch_bounds__(kThreads, kSortedCtasPerSm) bandit_step_sorted
         const uint64_t t = a.t0 + static_cast<uint64_t>(j);
         const ef_arm* __restrict__ arms = a.arms + static_cast<int64_t>(j) * a.k;
         if (threadIdx.x < kBins) s_cnt[threadIdx.x] = 0u;
+        if (threadIdx.x == 0) s_next = kThreads / 32;   // groups 0..7 are the warps' first ones
         __syncthreads();
-        // phase 1: actions in (coalesced; all eight loads of a thread issued before any is used), observations out,
+        // phase 1: actions in (coalesced; eight loads of a thread issued before any is used), observations out,
         // bin + rank of every env of the tile
-        uint32_t key_rank[kItemsPerThread];
-        int32_t acts[kItemsPerThread];
 #pragma unroll
-        for (int it = 0; it < kItemsPerThread; ++it) {
-            const int64_t i = base_i + static_cast<uint32_t>(it) * kThreads + threadIdx.x;
-            acts[it] = 0;
-            if (i < a.n) {
-                const int64_t o = static_cast<int64_t>(j) * a.n + i;
-                acts[it] = a.action ? __ldg(a.action + o)
-                                    : static_cast<int32_t>(__umulhi(group_word1(a.seed, static_cast<uint32_t>(a.env_offset + i), t,
-                                                                                kStreamPolicy), static_cast<uint32_t>(a.k)));
-            }
-        }
+        for (int half = 0; half < kItemsPerThread; half += 8) {
+            int32_t acts[8];
 #pragma unroll
-        for (int it = 0; it < kItemsPerThread; ++it) {
-            const uint32_t l = static_cast<uint32_t>(it) * kThreads + threadIdx.x;
-            const int64_t i = base_i + l;
-            uint32_t key = kBinSkip;
-            const int32_t act = acts[it];
-            if (i < a.n) {
-                const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
-                const int64_t o = static_cast<int64_t>(j) * a.n + i;
-                if (a.obs) a.obs[o] = act;  // observation = action (k_armed_bandit.py:200)
-                if (static_cast<uint32_t>(act) >= static_cast<uint32_t>(a.k)) {
-                    errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
-                    s_rew[l] = 0.0f;
-                } else {
-                    key = arm_bin(load_arm(arms, act));
+            for (int it = 0; it < 8; ++it) {
+                const int64_t i = base_i + static_cast<uint32_t>(half + it) * kThreads + threadIdx.x;
+                acts[it] = 0;
+                if (i < a.n) {
+                    const int64_t o = static_cast<int64_t>(j) * a.n + i;
+                    acts[it] = a.action ? __ldg(a.action + o)
+                                        : static_cast<int32_t>(__umulhi(group_word1(a.seed, static_cast<uint32_t>(a.env_offset + i), t,
+                                                                                    kStreamPolicy), static_cast<uint32_t>(a.k)));
                 }
             }
-            // warp-aggregated counting: lanes with the same bin elect a leader that reserves their slots at once
-            const uint32_t peers = __match_any_sync(0xffffffffu, key);
-            const uint32_t leader = static_cast<uint32_t>(__ffs(peers) - 1);
-            uint32_t first = 0u;
-            if (lane == leader && key != kBinSkip) first = atomicAdd(&s_cnt[key], static_cast<uint32_t>(__popc(peers)));
-            first = __shfl_sync(0xffffffffu, first, leader);
-            key_rank[it] = key | ((first + static_cast<uint32_t>(__popc(peers & ((1u << lane) - 1u)))) << 4);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const uint32_t l = static_cast<uint32_t>(half + it) * kThreads + threadIdx.x;
+                const int64_t i = base_i + l;
+                uint32_t key = kBinSkip;
+                const int32_t act = acts[it];
+                if (i < a.n) {
+                    const uint32_t g = static_cast<uint32_t>(a.env_offset + i);
+                    const int64_t o = static_cast<int64_t>(j) * a.n + i;
+                    if (a.obs) a.obs[o] = act;  // observation = action (k_armed_bandit.py:200)
+                    if (static_cast<uint32_t>(act) >= static_cast<uint32_t>(a.k)) {
+                        errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
+                    } else {
+                        key = arm_bin(load_arm(arms, act));
+                    }
+                }
+                // warp-aggregated counting: lanes with the same bin elect a leader that reserves their slots at once
+                const uint32_t peers = __match_any_sync(0xffffffffu, key);
+                const uint32_t leader = static_cast<uint32_t>(__ffs(peers) - 1);
+                uint32_t first = 0u;
+                if (lane == leader && key != kBinSkip) first = atomicAdd(&s_cnt[key], static_cast<uint32_t>(__popc(peers)));
+                first = __shfl_sync(0xffffffffu, first, leader);
+                const uint32_t rank = first + static_cast<uint32_t>(__popc(peers & ((1u << lane) - 1u)));
+                s_tmp[l] = (static_cast<uint32_t>(act) << 16) | ((rank & 0xfffu) << 4) | key;
+            }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {  // exclusive prefix over the bins (one warp)
+        if (threadIdx.x < 32) {  // exclusive prefix over the padded bin sizes (one warp), sentinels into the gaps
             const uint32_t c = lane < kBins ? s_cnt[lane] : 0u;
-            uint32_t incl = c;
+            const uint32_t cp = (lane < kBinSkip) ? ((c + (EF_BANDIT_ALIGN - 1u)) & ~(EF_BANDIT_ALIGN - 1u)) : 0u;
+            uint32_t incl = cp;
 #pragma unroll
             for (int o = 1; o < kBins; o <<= 1) {
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= static_cast<uint32_t>(o)) incl += v;
             }
-            if (lane < kBins) s_base[lane] = incl - c;
+            if (lane < kBins) s_base[lane] = incl - cp;   // s_base[kBinSkip] = all padded bins together
+            if (lane < kBinSkip)
+                for (uint32_t q = incl - cp + c; q < incl; ++q) s_sorted[q] = kEmptySlot;
         }
         __syncthreads();
-        const uint32_t total = s_base[kBinSkip];  // envs to evaluate = everything in the bins below the skip bin
+        const uint32_t total = s_base[kBinSkip];  // slots to visit = everything in the bins below the skip bin
 #pragma unroll
         for (int it = 0; it < kItemsPerThread; ++it) {
-            const uint32_t key = key_rank[it] & 15u;
+            const uint32_t l = static_cast<uint32_t>(it) * kThreads + threadIdx.x;
+            const uint32_t w = s_tmp[l];
+            const uint32_t key = w & 15u;
             if (key != kBinSkip)
-                s_sorted[s_base[key] + (key_rank[it] >> 4)] =
-                    (static_cast<uint32_t>(acts[it]) << 12) | (static_cast<uint32_t>(it) * kThreads + threadIdx.x);
+                s_sorted[s_base[key] + ((w >> 4) & 0xfffu)] = ((w >> 16) << 12) | l;
+            else
+                s_rew[l] = 0.0f;   // rejected action (or past the end of the batch): reward 0, not evaluated
         }
         __syncthreads();
-        // phase 2: evaluate in sorted order -- consecutive lanes run the same sampler
+        // phase 2: evaluate in sorted order -- the 32 lanes of a warp run the same sampler
+#if EF_BANDIT_DYNAMIC
+        for (uint32_t grp = threadIdx.x >> 5; grp * 32u < total;) {
+            const uint32_t rec = s_sorted[grp * 32u + lane];
+#else
         for (uint32_t p = threadIdx.x; p < total; p += kThreads) {
             const uint32_t rec = s_sorted[p];
-            const uint32_t l = rec & 0xfffu, act = rec >> 12;
-            const uint32_t g = static_cast<uint32_t>(a.env_offset + base_i + l);
-            LazyPrimitives pr(a.rk, g, t);
-            const float r = sample_arm(load_arm(arms, act), pr, a.seed, g, act);
-            s_rew[l] = r;
-            acc.steps += 1u;
-            acc.finish(1, r);  // every bandit step is a finished one-step episode (done is always True, :198)
+#endif
+            if (rec != kEmptySlot) {
+                const uint32_t l = rec & 0xfffu, act = rec >> 12;
+                const uint32_t g = static_cast<uint32_t>(a.env_offset + base_i + l);
+                LazyPrimitives pr(a.rk, g, t);
+                const ef_arm arm = load_arm(arms, act);
+                float r;
+                if (a.means != nullptr && static_cast<uint32_t>(arm.family) >= 8u)   // EF_ARM_DEFAULT_NORMAL, mean looked up
+                    r = (__ldg(a.means + (base_i + l) * a.k + act) + arm.p0) + arm.p1 * pr.n();
+                else
+                    r = sample_arm(arm, pr, a.seed, g, act);
+                s_rew[l] = r;
+                acc.steps += 1u;
+                acc.finish(1, r);  // every bandit step is a finished one-step episode (done is always True, :198)
+            }
+#if EF_BANDIT_DYNAMIC
+            if (lane == 0) grp = atomicAdd(&s_next, 1u);
+            grp = __shfl_sync(0xffffffffu, grp, 0);
+#endif
         }
         __syncthreads();
         // phase 3: rewards out (coalesced)
@@ -392,14 +446,14 @@ __global__ void __launch_bounds__(kThreads) bandit_means_kernel(int32_t k, uint6
 
 using namespace ef;
 
-extern "C" int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_t seed, uint64_t t0,
-                              uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
-                              uint32_t* err, int64_t n, void* stream) {
-    if (!arms || k <= 0 || K < 0 || n < 0 || !aligned(arms, 16)) return EF_ERR_INVALID_ARGUMENT;
+extern "C" int ef_bandit_step_means(const ef_arm* arms, int32_t k, const int32_t* action, const float* means, uint64_t seed,
+                                    uint64_t t0, uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
+                                    uint32_t* err, int64_t n, void* stream) {
+    if (!arms || k <= 0 || K < 0 || n < 0 || !aligned(arms, 16) || !aligned(means, 4)) return EF_ERR_INVALID_ARGUMENT;
     if (env_offset + static_cast<uint64_t>(n) > (1ull << 32)) return EF_ERR_INVALID_ARGUMENT;
     if (n == 0 || K == 0) return EF_OK;
     BanditArgs a{};
-    a.arms = arms; a.k = k; a.action = action; a.seed = seed; a.t0 = t0; a.env_offset = env_offset; a.K = K;
+    a.arms = arms; a.k = k; a.action = action; a.means = means; a.seed = seed; a.t0 = t0; a.env_offset = env_offset; a.K = K;
     a.obs = obs; a.reward = reward; a.stats = stats; a.err = err; a.n = n;
     a.rk = philox_round_keys(seed);
     const bool unsorted = getenv("ENVFORGE_BANDIT_UNSORTED") != nullptr;  // A/B + parity switch: the plain kernel
@@ -411,6 +465,12 @@ extern "C" int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* acti
         bandit_step_kernel<<<grid_for(n, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     }
     return cuda_status(cudaGetLastError());
+}
+
+extern "C" int ef_bandit_step(const ef_arm* arms, int32_t k, const int32_t* action, uint64_t seed, uint64_t t0,
+                              uint64_t env_offset, int32_t K, int32_t* obs, float* reward, double* stats,
+                              uint32_t* err, int64_t n, void* stream) {
+    return ef_bandit_step_means(arms, k, action, nullptr, seed, t0, env_offset, K, obs, reward, stats, err, n, stream);
 }
 
 extern "C" int ef_bandit_default_means(int32_t k, uint64_t seed, uint64_t env_offset, float* means, int64_t n,

@@ -83,6 +83,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                  : "memory");
 }
 
+// L2 prefetch hints.  A prefetch into L2 never breaks coherence (L2 is the point of coherence: a line that a still-running
+// producer writes afterwards is simply updated there), so they may be issued AHEAD of griddepcontrol.wait.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gmem_src, uint32_t bytes) {   // 16-byte aligned, multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_line(const void* gmem_src) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem_src));
+}
+
 // The same in two steps, for several copies completing on one barrier: arm it with the total, then issue the copies.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");

@@ -20,6 +20,12 @@
 
 #include "ef_common.cuh"
 
+#ifndef EF_STEP_L2_PREFETCH
+#define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
+#endif
+#ifndef EF_STEP_SPECULATE
+#define EF_STEP_SPECULATE 1     // 1: the first pass's outcome draws are computed ahead of griddepcontrol.wait (see the step kernel); 0: A/B
+#endif
 #ifndef EF_STEP_LEAN
 #define EF_STEP_LEAN 1       // packed-word arithmetic of step_quad_packed (0: the generic step_quad_compute; same results)
 #endif
@@ -504,7 +510,7 @@ __device__ __noinline__ uint4 packed_slow_env(const uint2* __restrict__ tab, uin
 template <bool SMEM, int SLOTS, bool FAST, bool W8>
 __device__ __forceinline__ void step_quad_packed(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
                                                  uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
-                                                 ErrorAcc& errs, PackedQuad& q) {
+                                                 ErrorAcc& errs, PackedQuad& q, const uint4* spec = nullptr) {
     int32_t act[4] = {in.a4.x, in.a4.y, in.a4.z, in.a4.w};
     q.w[0] = static_cast<uint32_t>(in.p4.x); q.w[1] = static_cast<uint32_t>(in.p4.y);
     q.w[2] = static_cast<uint32_t>(in.p4.z); q.w[3] = static_cast<uint32_t>(in.p4.w);
@@ -516,7 +522,14 @@ __device__ __forceinline__ void step_quad_packed(const GridArgs& a, const uint2*
         for (int j = 0; j < 4; ++j) act[j] = static_cast<int32_t>(wp[j] >> 30);
     }
     uint32_t r[4] = {0u, 0u, 0u, 0u};
-    if constexpr (SLOTS == 4) group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, r);
+    if constexpr (SLOTS == 4) {
+        if (spec != nullptr) {   // the quad's outcome draws of step t were computed ahead of griddepcontrol.wait
+            const uint4 d = *spec;
+            r[0] = d.x; r[1] = d.y; r[2] = d.z; r[3] = d.w;
+        } else {
+            group_words4_rk(a.rk, a.seed, g0, t, kStreamTransition, r);
+        }
+    }
     // thresholds at or beyond idx_cap are 2^32 (unreachable): clipped to 2^32 - 1 here, the index cap does the rest
     const uint32_t thr0 = a.thr0 > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(a.thr0);
     const uint32_t thr1 = a.thr1 > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(a.thr1);
@@ -620,10 +633,10 @@ __device__ __forceinline__ void store_quad_packed(const GridArgs& a, int64_t bas
 template <bool SMEM, int SLOTS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
 __device__ __forceinline__ void step_quad(const GridArgs& a, const uint2* __restrict__ tab, int64_t base, uint32_t g0,
                                           uint64_t t, const QuadIn& in, bool philox_act, EpisodeAcc& acc,
-                                          ErrorAcc& errs) {
+                                          ErrorAcc& errs, const uint4* spec = nullptr) {
     if constexpr (EF_STEP_LEAN && PACKED && !HET) {
         PackedQuad q;
-        step_quad_packed<SMEM, SLOTS, FAST, W8>(a, tab, base, g0, t, in, philox_act, acc, errs, q);
+        step_quad_packed<SMEM, SLOTS, FAST, W8>(a, tab, base, g0, t, in, philox_act, acc, errs, q, spec);
         store_quad_packed<FAST, W8>(a, base, q);
     } else {
         Quad q;
@@ -697,6 +710,9 @@ __device__ __forceinline__ void step_tail(const GridArgs& a, const uint2* __rest
 #ifndef EF_STEP_GRID_PER_SM
 #define EF_STEP_GRID_PER_SM EF_STEP_MINBLOCKS  // grid cap in CTAs per SM
 #endif
+#ifndef EF_STEP_PASSES
+#define EF_STEP_PASSES 1     // load/compute passes of EF_STEP_Q quads a thread may make in the one-wave ("small") geometry
+#endif
 #ifndef EF_STEP_Q
 #define EF_STEP_Q 4          // quads (of four envs) whose loads a thread keeps in flight at once
 #endif
@@ -713,15 +729,65 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     EF_TRACE_POINT(0);   // kernel entry
     const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
     pdl_launch_dependents();
-    pdl_wait();                                            // previous launch complete, its writes visible
-    EF_TRACE_POINT(1);   // released by the previous launch
-    EpisodeAcc acc;
-    ErrorAcc errs;
     const bool philox_act = FAST ? false : a.action == nullptr;
     const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
     const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
     const int64_t q_begin = static_cast<int64_t>(blockIdx.x) * per_cta;
     const int64_t q_end = min(q_begin + per_cta, quads);
+#if EF_STEP_L2_PREFETCH
+    // This CTA is resident up to a few microseconds before the previous launch releases it: ask L2 for the chunk's input
+    // lines now (a hint -- whatever the previous launch still writes to them lands in the same L2 lines), so that the
+    // loads below find them there instead of queueing in DRAM behind every other CTA's at the moment of release.
+    if (q_begin < q_end) {
+        const uint32_t bytes = static_cast<uint32_t>(q_end - q_begin) * 16u;   // 4 B per env of a quad
+        const int64_t e0 = q_begin * 4;
+#if EF_STEP_L2_PREFETCH == 1
+        if (threadIdx.x == 0) l2_prefetch_bulk(a.pos + e0, bytes);
+        if (threadIdx.x == 32) l2_prefetch_bulk(a.ep_ret + e0, bytes);
+        if (!PACKED && threadIdx.x == 64) l2_prefetch_bulk(a.ep_len + e0, bytes);
+        if (!W8 && !philox_act && threadIdx.x == 96) l2_prefetch_bulk(a.action + e0, bytes);
+#else
+        for (uint32_t off = threadIdx.x * 128u; off < bytes; off += kThreads * 128u) {
+            l2_prefetch_line(reinterpret_cast<const char*>(a.pos + e0) + off);
+            l2_prefetch_line(reinterpret_cast<const char*>(a.ep_ret + e0) + off);
+            if (!PACKED) l2_prefetch_line(reinterpret_cast<const char*>(a.ep_len + e0) + off);
+            if (!W8 && !philox_act) l2_prefetch_line(reinterpret_cast<const char*>(a.action + e0) + off);
+        }
+#endif
+        if (W8 && !philox_act)
+            for (uint32_t off = threadIdx.x * 128u; off < bytes / 4u; off += kThreads * 128u)
+                l2_prefetch_line(reinterpret_cast<const char*>(a.action) + e0 + off);
+    }
+#endif
+#if EF_STEP_SPECULATE
+    // Outcome draws ahead of the wait.  A draw depends on (seed, env, step index t) only, and t is known now unless the
+    // launch this one waits for is a step of the SAME env set (then the device clock still shows its t): compute the
+    // first pass's Philox words for the t seen now, park them in shared memory, and use them after the wait iff the
+    // clock then gives the same t -- otherwise they are recomputed, as without this.  Same bits either way.
+    constexpr bool kSpec = SMEM && SLOTS == 4 && PACKED && !HET && EF_STEP_LEAN != 0;
+    __shared__ uint4 s_draw[kSpec ? Q * kThreads : 1];
+    uint64_t t_spec = ~0ull;
+    if constexpr (kSpec) {
+        if (q_begin < q_end) {
+            t_spec = a.t + clock_steps(clock_fetch(a.clock));
+            const uint32_t left0 = static_cast<uint32_t>(min(q_end - q_begin, static_cast<int64_t>(Q) * kThreads));
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
+                if (local < left0) {
+                    uint32_t r[4];
+                    group_words4_rk(a.rk, a.seed, static_cast<uint32_t>(a.env_offset + (q_begin + local) * 4), t_spec,
+                                    kStreamTransition, r);
+                    s_draw[local] = make_uint4(r[0], r[1], r[2], r[3]);
+                }
+            }
+        }
+    }
+#endif
+    pdl_wait();                                            // previous launch complete, its writes visible
+    EF_TRACE_POINT(1);   // released by the previous launch
+    EpisodeAcc acc;
+    ErrorAcc errs;
     QuadIn in[Q];
     auto issue_loads = [&](int64_t chunk) {
         // 32-bit bookkeeping inside the chunk (a CTA's share is far below 2^31 quads); 64-bit only for the addresses
@@ -744,10 +810,15 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left)
+            if (local < left) {
+                const uint4* spec = nullptr;
+#if EF_STEP_SPECULATE
+                if constexpr (kSpec) spec = (chunk == q_begin && t == t_spec) ? &s_draw[local] : nullptr;
+#endif
                 step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
                                                           static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
-                                                          philox_act, acc, errs);
+                                                          philox_act, acc, errs, spec);
+            }
             if (j == 0) EF_TRACE_POINT(4);   // first quad stepped (its loads had to land)
         }
     }
@@ -1334,7 +1405,7 @@ static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* 
     // Small batches (one pass fits the resident grid): EF_STEP_Q quads per thread, all loads in flight, persistent grid.
     // Large batches: fewer quads per thread, more resident warps, CTAs scheduled dynamically over many passes.
     const int64_t quads = (n + 3) / 4;
-    const bool small = quads <= static_cast<int64_t>(sm_count()) * EF_STEP_GRID_PER_SM * kThreads * EF_STEP_Q;
+    const bool small = quads <= static_cast<int64_t>(sm_count()) * EF_STEP_GRID_PER_SM * kThreads * EF_STEP_Q * EF_STEP_PASSES;
     // One-pass grid: spread the quads over ALL resident CTA slots (at least a warp's worth each) rather than filling
     // CTAs to Q * 256 quads -- 2^20 envs would otherwise make 256 full CTAs, leaving 40 of the 148 SMs with one CTA and
     // 108 with two, and the launch lasts as long as the doubly loaded SMs.

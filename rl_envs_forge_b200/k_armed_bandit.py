@@ -106,7 +106,10 @@ class VecKArmedBandit(VecEnv):
     MT19937_MAX_ENVS = 1 << 18
 
     def __init__(self, num_envs=1, k=10, arm_params=None, seed=None, *, device=None, env_offset=0, strict=False,
-                 rng="philox"):
+                 rng="philox", mean_table=True):
+        """mean_table: keep the default arms' per-env means (`np_random.randn(k)` of one reference instance, :160-165) in an
+        fp32 [N,k] device table (4 k bytes per env) that step()/rollout() look up; False re-derives a mean from its Philox
+        stream whenever a default arm is pulled -- same bits, no table, one more Philox call on those steps."""
         if rng not in ("philox", "mt19937"):
             raise ValueError("rng must be 'philox' or 'mt19937'")
         self.rng = rng
@@ -139,6 +142,8 @@ class VecKArmedBandit(VecEnv):
         self._arm_dev = None
         self._arm_key = None
         self.arms = None
+        self.mean_table = bool(mean_table)
+        self._means_dev, self._means_key = None, None
         self._init_arms()
         if rng == "mt19937":
             self._reward64 = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -230,6 +235,21 @@ class VecKArmedBandit(VecEnv):
         self._call(self._lib.ef_bandit_default_means, self.k, self._seed, self.env_offset, _lib.ptr(out), self.num_envs)
         return out
 
+    def _means_ptr(self):
+        """Device pointer of the cached default-mean table for ef_bandit_step_means, or None (no default arm in play, or
+        mean_table=False).  Filled by ef_bandit_default_means -- the very values the kernel would re-derive -- and rebuilt
+        when reset() re-keys the generator."""
+        if not self.mean_table or not any(a.per_env_mean for a in self.arms):
+            return None
+        key = (self._seed, self.env_offset, self.k)
+        if self._means_key != key:
+            if self._means_dev is None:
+                self._means_dev = self._torch.empty((self.num_envs, self.k), dtype=self._torch.float32, device=self.device)
+            self._call(self._lib.ef_bandit_default_means, self.k, self._seed, self.env_offset, _lib.ptr(self._means_dev),
+                       self.num_envs)
+            self._means_key = key
+        return _lib.ptr(self._means_dev)
+
     @property
     def state(self):
         return self.timestep, [arm.current_params for arm in self.arms]
@@ -306,8 +326,9 @@ class VecKArmedBandit(VecEnv):
                     _lib.ptr(self.err), n, self.host_chunks, self._stream()))
             obs, rew = h_obs, h_rew
         else:
-            self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, p_act, self._seed, self._steps_since_reset,
-                       self.env_offset, 1, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self._stats_raw), _lib.ptr(self.err), n)
+            self._call(self._lib.ef_bandit_step_means, _lib.ptr(arms), self.k, p_act, self._means_ptr(), self._seed,
+                       self._steps_since_reset, self.env_offset, 1, _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self._stats_raw),
+                       _lib.ptr(self.err), n)
         self._advance(1)
         if self.strict:
             try:
@@ -345,7 +366,7 @@ class VecKArmedBandit(VecEnv):
         arms = self._arm_table(K)
         obs = torch.empty((K, n), dtype=torch.int32, device=self.device)
         rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
-        self._call(self._lib.ef_bandit_step, _lib.ptr(arms), self.k, _lib.ptr(actions), self._seed,
+        self._call(self._lib.ef_bandit_step_means, _lib.ptr(arms), self.k, _lib.ptr(actions), self._means_ptr(), self._seed,
                    self._steps_since_reset, self.env_offset, int(K), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(self._stats_raw),
                    _lib.ptr(self.err), n)
         self._advance(K)

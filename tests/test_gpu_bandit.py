@@ -180,7 +180,7 @@ def test_family_sorted_kernel_is_bit_identical_to_plain_kernel(monkeypatch):
     arms[9] = dict(distribution="beta", a=0.5, b=0.7)
     arms[10] = dict(distribution="gamma", shape=1.0, scale=2.0)
     arms[11] = dict(distribution="beta", a=0.5, b=3.0)
-    for n in (1, 31, 2047, 2049, 100_003):
+    for n in (1, 31, 2047, 2049, 4095, 4097, 100_003):         # around the 4096-env tile of the sorted kernel
         outs = []
         for unsorted in (False, True):
             if unsorted:
@@ -198,3 +198,36 @@ def test_family_sorted_kernel_is_bit_identical_to_plain_kernel(monkeypatch):
         for x, y in zip(*outs):
             assert torch.equal(x, y)
         assert int(outs[0][6][0]) == (n + 96) // 97
+
+
+def test_default_mean_table_is_bit_identical_to_rederived_means(monkeypatch):
+    """ef_bandit_step_means: a default arm's per-env mean looked up in the [n,k] table of ef_bandit_default_means must give
+    the bits of the in-kernel re-derivation (mean_table=False), in the sorted AND the plain kernel, for step, K-step
+    rollouts with given / in-kernel random actions, a non-zero env_offset, ragged n, and after reset(seed)."""
+    import torch
+    from rl_envs_forge_b200 import VecKArmedBandit
+    arms = {i: dict(p) for i, p in BANDIT_ARMS.items()}      # arms 8 and 9 stay default normals (per-env means)
+    arms[0]["param_functions"] = [{"function": lambda t: 0.1 * t, "target_param": "mean"}]
+    for n, off in ((1, 0), (4097, 0), (100_003, 12_345)):
+        outs = []
+        for table, unsorted in ((True, False), (False, False), (True, True)):
+            if unsorted:
+                monkeypatch.setenv("ENVFORGE_BANDIT_UNSORTED", "1")
+            else:
+                monkeypatch.delenv("ENVFORGE_BANDIT_UNSORTED", raising=False)
+            env = VecKArmedBandit(n, k=10, arm_params=arms, seed=5, env_offset=off, mean_table=table)
+            assert (env._means_ptr() is not None) == table
+            act = torch.from_numpy(np.random.default_rng(n).integers(0, 10, n).astype(np.int32)).cuda()
+            act[::3] = 8 + (torch.arange(0, n, 3, device="cuda") % 2).to(torch.int32)       # plenty of default-arm pulls
+            _, r1, *_ = env.step(act)
+            r1 = r1.clone()
+            _, r2 = env.rollout(3)
+            a3 = torch.from_numpy(np.random.default_rng(n + 1).integers(0, 10, (2, n)).astype(np.int32)).cuda()
+            _, r3 = env.rollout(2, a3)
+            env.reset(seed=6)                                 # re-keys the generator: the table must follow
+            _, r4, *_ = env.step(act)
+            outs.append([r1, r2.clone(), r3.clone(), r4.clone(), env.default_means.clone(), env.stats[:2].clone(), env.stats[4].clone()])
+        for other in outs[1:]:
+            for x, y in zip(outs[0], other):
+                assert torch.equal(x, y)
+        assert not torch.equal(outs[0][0], outs[0][3])        # the new seed did change the rewards

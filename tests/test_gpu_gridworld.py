@@ -478,6 +478,49 @@ def test_cuda_graph_replay_with_device_clock_equals_eager_steps():
     assert torch.equal(graphed.pos, eager.pos)
 
 
+def test_draws_computed_ahead_of_the_wait_match_in_every_launch_order():
+    """The step kernel computes its first pass's Philox draws BEFORE griddepcontrol.wait for the step index the device clock
+    shows at that moment and keeps them only if the clock shows the same index after the wait (gridworld.cu, "Outcome draws
+    ahead of the wait").  Both outcomes must give the reference bits: a graph that chains steps of ONE env set (the
+    clock moves under the early read: draws recomputed) and a graph that alternates TWO env sets (each set's clock is
+    quiescent while the other steps: early draws kept), against eager steps with host-side step counting."""
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    n, per_graph, replays = 1 << 18, 6, 5
+    cfg = _vec_kwargs(_config2(0.8))
+    acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda") for _ in range(per_graph)]
+    eager = [VecGridWorld(n, seed=41 + i, env_offset=i * n, **cfg) for i in range(2)]
+    graphed = [VecGridWorld(n, seed=41 + i, env_offset=i * n, **cfg) for i in range(2)]
+    for e in eager + graphed:
+        e.step(acts[0])
+    for e in graphed:
+        e.enable_device_clock()
+    stream = torch.cuda.Stream()
+    chain, alternate = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(chain, stream=stream):
+            for a in acts:
+                graphed[0].step(a)
+        with torch.cuda.graph(alternate, stream=stream):
+            for j, a in enumerate(acts):
+                graphed[j % 2].step(a)
+    torch.cuda.synchronize()
+    for _ in range(replays):
+        chain.replay()
+        for a in acts:
+            eager[0].step(a)
+        alternate.replay()
+        for j, a in enumerate(acts):
+            eager[j % 2].step(a)
+    torch.cuda.synchronize()
+    for gset, eset in zip(graphed, eager):
+        assert gset.step_count == eset.step_count
+        assert torch.equal(gset.pos, eset.pos) and torch.equal(gset.ep_len, eset.ep_len) and torch.equal(gset.ep_ret, eset.ep_ret)
+        assert torch.equal(gset._reward, eset._reward) and torch.equal(gset._obs, eset._obs)
+        sg, se = gset.episode_stats(), eset.episode_stats()
+        assert sg["episodes"] == se["episodes"] > 0 and sg["length_sum"] == se["length_sum"] and sg["env_steps"] == se["env_steps"]
+
+
 def test_empty_batch_is_a_noop_through_the_c_abi():
     """n = 0 (empty input): every entry point returns EF_OK without touching memory."""
     import torch

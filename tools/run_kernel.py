@@ -20,6 +20,7 @@ ap.add_argument("--n", type=int, default=1 << 22)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--K", type=int, default=64)
 ap.add_argument("--sets", type=int, default=4)
+ap.add_argument("--no-mean-table", action="store_true", help="bandit: re-derive default-arm means in the kernel")
 a = ap.parse_args()
 
 n, K = a.n, a.K
@@ -58,7 +59,7 @@ for s in range(a.sets):
                 2: dict(distribution="exponential", scale=0.2), 3: dict(distribution="gamma", shape=9, scale=0.55),
                 4: dict(distribution="logistic", loc=5, scale=0.3), 5: dict(distribution="lognormal", mean=1.6, sigma=0.3),
                 6: dict(distribution="weibull", a=2), 7: dict(distribution="beta", a=2, b=5)}
-        e = VecKArmedBandit(n, k=10, arm_params=arms, seed=1, env_offset=s * n)
+        e = VecKArmedBandit(n, k=10, arm_params=arms, seed=1, env_offset=s * n, mean_table=not a.no_mean_table)
         act = torch.randint(0, 10, (n,), dtype=torch.int32, device="cuda")
         ext = None
     envs.append(e)
