@@ -23,9 +23,26 @@
 #ifndef EF_STEP_L2_PREFETCH
 #define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
 #endif
-#ifndef EF_STEP_SPECULATE
-#define EF_STEP_SPECULATE 1     // 1: the first pass's outcome draws are computed ahead of griddepcontrol.wait (see the step kernel); 0: A/B
+// Work of the step kernel AHEAD of griddepcontrol.wait and the clock reads around it (A/B on B200, us per 2^20-env launch in a
+// CUDA-graph chain, one env set stepped repeatedly / eight sets in rotation = the headline; profiles/r02a*_chain_probe.txt):
+//   nothing ahead of the wait, every thread reads the clock                      7.03 / 8.94   (round-2 start)
+//   + bulk L2 prefetch of the CTA's inputs                                       7.02 / 7.88
+//   + early draws of 4 quads, every thread reading the clock ahead of the wait   7.91 / 7.33   (75 k reads of a word under atomic fire)
+//   + thread 0 reads it, the CTA takes it from shared memory                     7.03 / 7.34
+//   + the same for the read after the wait (one barrier, inside the load latency) 7.05 / 7.24
+//   early draws of 3 / 2 / 1 / 0 quads per thread                                7.02 / 7.23, 6.75 / 7.23, 6.73 / 7.21, 6.98 / 7.57
+// (computing ALL draws right after issuing the loads instead -- "hoisting" -- was slower than the interleaving the compiler
+// does by itself: 7.4 / 7.5.)
+#ifndef EF_STEP_PRE_QUADS
+#define EF_STEP_PRE_QUADS 1     // quads per thread whose outcome draws are computed AHEAD of griddepcontrol.wait (0..EF_STEP_Q)
 #endif
+#ifndef EF_STEP_PRE_CLOCK
+#define EF_STEP_PRE_CLOCK 1     // 1: thread 0 reads the clock word for the early draws, the CTA takes it from shared memory; 0: every thread
+#endif
+#ifndef EF_STEP_POST_CLOCK
+#define EF_STEP_POST_CLOCK 1    // 1: after the wait, thread 0 reads the clock word and the CTA takes it from shared memory behind a barrier
+#endif
+#define EF_STEP_SPECULATE (EF_STEP_PRE_QUADS > 0)
 #ifndef EF_STEP_LEAN
 #define EF_STEP_LEAN 1       // packed-word arithmetic of step_quad_packed (0: the generic step_quad_compute; same results)
 #endif
@@ -78,6 +95,7 @@ struct GridArgs {
 // -DEF_TRACE=1 --tag=_trace` builds a tools-only variant (tools/step_trace.py) in which thread 0 of every CTA stores
 // %globaltimer / clock64 at the marked points; the results of a step are the same either way.
 #ifdef EF_TRACE
+__device__ unsigned long long g_spec_count[2] = {0ull, 0ull};   // quads whose early draws were kept / recomputed
 __device__ unsigned long long* g_trace_buf = nullptr;   // [8 sets][4 steps][1024 CTAs][16 points][2]
 #define EF_TRACE_DECL unsigned long long tr_[32] = {0ull};
 #define EF_TRACE_POINT(i)                                                   \
@@ -727,6 +745,10 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     bool table_pending;
     EF_TRACE_DECL
     EF_TRACE_POINT(0);   // kernel entry
+#if EF_STEP_PRE_CLOCK == 1
+    __shared__ unsigned long long s_clk0;   // the clock word as thread 0 sees it on entry (published by the barrier of stage_table_begin)
+    if (SMEM && threadIdx.x == 0) s_clk0 = clock_fetch(a.clock);
+#endif
     const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
     pdl_launch_dependents();
     const bool philox_act = FAST ? false : a.action == nullptr;
@@ -761,18 +783,27 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #endif
 #if EF_STEP_SPECULATE
     // Outcome draws ahead of the wait.  A draw depends on (seed, env, step index t) only, and t is known now unless the
-    // launch this one waits for is a step of the SAME env set (then the device clock still shows its t): compute the
-    // first pass's Philox words for the t seen now, park them in shared memory, and use them after the wait iff the
-    // clock then gives the same t -- otherwise they are recomputed, as without this.  Same bits either way.
+    // launch this one waits for is a step of the SAME env set (then the device clock is still moving): compute the
+    // first pass's Philox words for the t PREDICTED from the clock word seen now, park them in shared memory, and use
+    // them after the wait iff the clock then gives that very t -- otherwise they are recomputed, as without this.
+    // Same bits either way.
     constexpr bool kSpec = SMEM && SLOTS == 4 && PACKED && !HET && EF_STEP_LEAN != 0;
-    __shared__ uint4 s_draw[kSpec ? Q * kThreads : 1];
+    constexpr int kPre = EF_STEP_PRE_QUADS < Q ? EF_STEP_PRE_QUADS : Q;
+    __shared__ uint4 s_draw[kSpec ? kPre * kThreads : 1];
     uint64_t t_spec = ~0ull;
     if constexpr (kSpec) {
         if (q_begin < q_end) {
-            t_spec = a.t + clock_steps(clock_fetch(a.clock));
+            // a counter caught between two whole steps = a step of this very env set is retiring CTA by CTA right now
+            // (that is why this CTA got its slot): the index after the wait will be the next one
+#if EF_STEP_PRE_CLOCK == 1
+            const unsigned long long c0 = s_clk0;
+#else
+            const unsigned long long c0 = clock_fetch(a.clock);
+#endif
+            t_spec = a.t + clock_steps(c0) + ((c0 & ((1ull << kClockShift) - 1ull)) != 0ull ? 1ull : 0ull);
             const uint32_t left0 = static_cast<uint32_t>(min(q_end - q_begin, static_cast<int64_t>(Q) * kThreads));
 #pragma unroll
-            for (int j = 0; j < Q; ++j) {
+            for (int j = 0; j < kPre; ++j) {
                 const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
                 if (local < left0) {
                     uint32_t r[4];
@@ -784,6 +815,7 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
         }
     }
 #endif
+    EF_TRACE_POINT(12);  // prefetch issued, early draws parked
     pdl_wait();                                            // previous launch complete, its writes visible
     EF_TRACE_POINT(1);   // released by the previous launch
     EpisodeAcc acc;
@@ -798,8 +830,19 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
             if (local < left) in[j] = load_quad<PACKED, FAST, HET, W8>(a, (chunk + local) * 4, philox_act);
         }
     };
+#if EF_STEP_POST_CLOCK == 1
+    // ONE thread of the CTA reads the clock word (2368 warps asking L2 for the same sector queue up behind each other:
+    // about 0.7 us at the median, and the word is under atomic fire in a same-set chain), ahead of the input loads; the
+    // CTA picks it up behind a barrier that falls into the loads' latency.
+    __shared__ unsigned long long s_clk1;
+    if (threadIdx.x == 0) s_clk1 = clock_fetch(a.clock);
+    if (q_begin < q_end) issue_loads(q_begin);
+    __syncthreads();
+    const unsigned long long clk = s_clk1;
+#else
     const unsigned long long clk = clock_fetch(a.clock);   // in flight ahead of the input loads, consumed by Philox
     if (q_begin < q_end) issue_loads(q_begin);
+#endif
     const uint64_t t = a.t + clock_steps(clk);
     EF_TRACE_POINT(2);
     for (int64_t chunk = q_begin; chunk < q_end; chunk += static_cast<int64_t>(Q) * kThreads) {
@@ -813,7 +856,11 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
             if (local < left) {
                 const uint4* spec = nullptr;
 #if EF_STEP_SPECULATE
-                if constexpr (kSpec) spec = (chunk == q_begin && t == t_spec) ? &s_draw[local] : nullptr;
+                if constexpr (kSpec)
+                    spec = (chunk == q_begin && j < kPre && t == t_spec) ? &s_draw[local] : nullptr;
+#if defined(EF_TRACE) && defined(EF_SPEC_COUNT)   // (75 k same-address atomics per launch: counts only, never with timings)
+                if constexpr (kSpec) atomicAdd(&g_spec_count[spec != nullptr ? 0 : 1], 1ull);
+#endif
 #endif
                 step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
                                                           static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
@@ -1179,6 +1226,9 @@ __global__ void __launch_bounds__(kThreads) gridworld_reset_layouts_kernel(int32
 #ifndef EF_SERVE_THREADFENCE
 #define EF_SERVE_THREADFENCE 0     // 1: every thread fences before the publishing barrier (measured slower: 11.5 vs 10.3 us per step)
 #endif
+#ifndef EF_SERVE_PREDRAW
+#define EF_SERVE_PREDRAW 1         // the step's Philox draws are computed while the CTA waits for the step's actions
+#endif
 #ifndef EF_SERVE_NANOSLEEP
 #define EF_SERVE_NANOSLEEP 100       // back-off between two polls of a sequence word (ns); 0 = spin
 #endif
@@ -1246,10 +1296,25 @@ __global__ void __maxnreg__(96) gridworld_serve_kernel(const GridArgs a) {
             ret[j][0] = r4.x; ret[j][1] = r4.y; ret[j][2] = r4.z; ret[j][3] = r4.w;
         }
     }
+    // The outcome draws of step k depend on (seed, env, t0 + k) only: every thread computes those of its quads BEFORE the
+    // wait for the step's actions and parks them in shared memory -- a third of a step's instructions off the
+    // actions -> observations critical path (EF_SERVE_PREDRAW=0: computed after the wait, as step() does; same bits).
+    __shared__ uint4 s_draw[(EF_SERVE_PREDRAW && SLOTS == 4) ? kServeQ * kServeThreads : 1];
     int k = 0;
     for (; k < a.K; ++k) {
-        if (!serve_wait(a.act_seq + c, static_cast<uint32_t>(k) + 1u, a.status, &s_ok)) break;
         const uint64_t t = t0 + static_cast<uint64_t>(k);
+        if constexpr (EF_SERVE_PREDRAW && SLOTS == 4) {
+#pragma unroll
+            for (int j = 0; j < kServeQ; ++j) {
+                const int32_t local = j * kServeThreads + static_cast<int32_t>(threadIdx.x);
+                if (local < count) {
+                    uint32_t r[4];
+                    group_words4_rk(a.rk, a.seed, static_cast<uint32_t>(a.env_offset + (q_begin + local) * 4), t, kStreamTransition, r);
+                    s_draw[local] = make_uint4(r[0], r[1], r[2], r[3]);
+                }
+            }
+        }
+        if (!serve_wait(a.act_seq + c, static_cast<uint32_t>(k) + 1u, a.status, &s_ok)) break;
 #pragma unroll
         for (int j = 0; j < kServeQ; ++j) {
             const int32_t local = j * kServeThreads + static_cast<int32_t>(threadIdx.x);
@@ -1262,7 +1327,8 @@ __global__ void __maxnreg__(96) gridworld_serve_kernel(const GridArgs a) {
                 in.a4 = __ldcg(reinterpret_cast<const int4*>(a.action + base));   // written by the producer while we run: L2
                 PackedQuad q;
                 step_quad_packed<true, SLOTS, true, false>(a, tab, base, static_cast<uint32_t>(a.env_offset + base), t, in, false,
-                                                           acc, errs, q);
+                                                           acc, errs, q,
+                                                           (EF_SERVE_PREDRAW && SLOTS == 4) ? &s_draw[local] : nullptr);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     w[j][e] = q.w[e];
@@ -1703,6 +1769,13 @@ extern "C" int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos
 // tools-only build: where the step kernels store their timeline (device buffer of 8 * 4 * 1024 * 32 uint64, or NULL)
 extern "C" int ef_debug_set_trace(unsigned long long* buf) {
     return cuda_status(cudaMemcpyToSymbol(ef::g_trace_buf, &buf, sizeof(buf)));
+}
+// tools-only build: {quads stepped with the draws computed ahead of the wait, quads whose draws were recomputed}; reset on read
+extern "C" int ef_debug_spec_counters(unsigned long long* out) {
+    const unsigned long long zero[2] = {0ull, 0ull};
+    cudaError_t e = cudaMemcpyFromSymbol(out, ef::g_spec_count, sizeof(zero));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(ef::g_spec_count, zero, sizeof(zero));
+    return cuda_status(e);
 }
 #endif
 

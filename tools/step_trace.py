@@ -21,8 +21,9 @@ from rl_envs_forge_b200 import Action, VecGridWorld, _lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--rounds", type=int, default=6)
+ap.add_argument("--sets", type=int, default=8, help="env sets in rotation (1 = one set stepped repeatedly: L2-resident chain)")
 a = ap.parse_args()
-n, R, A = a.n, 8, 7
+n, R, A = a.n, a.sets, 7
 lib = _lib.load()
 lib.ef_debug_set_trace.argtypes = [C.c_void_p]
 buf = torch.zeros(8 * 4 * 1024 * 32, dtype=torch.int64, device="cuda")
@@ -62,7 +63,7 @@ for s in range(8):
         if used.any():
             launches.append((rec[used, 1, 0].min(), s, k, rec[used]))
 launches.sort(key=lambda x: x[0])
-names = {0: "entry", 1: "released", 2: "loads issued", 13: "pre-epilogue", 14: "done"}
+names = {0: "entry", 1: "released", 2: "loads issued", 12: "pre-wait work done", 13: "pre-epilogue", 14: "done"}
 prev_rel = launches[-6][0] if len(launches) > 5 else None
 for rel0, s, k, rec in launches[-5:]:
     ncta = rec.shape[0]
