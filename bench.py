@@ -671,6 +671,22 @@ def run_ours(args):
             return s.elapsed_time(e) * 1e-3 / reps
 
         Kr = 64
+        # the headline's chain in a LONG window: the 56-launch "round" graph (every env set x action buffer pairing, cold L2)
+        # replayed back to back -- the steady-state pace, against which a 20-launch window carries its fixed costs (graph
+        # launch, a first kernel with nothing ahead of it to hide its prologue, the statistics fold, the last kernel's drain)
+        g_long = graphs.get("round")
+        if g_long is None:
+            g_long = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(stream):
+                with torch.cuda.graph(g_long, stream=stream):
+                    for i in range(G):
+                        direct(i)
+        longs = sorted(ev_time(g_long.replay, 36) / G for _ in range(5))
+        details["gridworld_step_headline_chain_long_window"] = {
+            "env_steps_per_s": n / longs[2], "envs": n, "us_per_launch": longs[2] * 1e6, "launches_per_window": 36 * G,
+            "windows_us_per_launch": [x * 1e6 for x in longs], "GBps": GRID_BYTES_PER_STEP * n / longs[2] / 1e9,
+            "roofline_frac": GRID_BYTES_PER_STEP * n / longs[2] / 1e9 / peak,
+            "note": "median of 5 windows of 36 replays of the 56-launch graph; same launches, env sets and cold L2 as the headline"}
         # the same step kernel when the batch is L2-resident (one env set stepped repeatedly: the usual RL loop)
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.stream(stream):
