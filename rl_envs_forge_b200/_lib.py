@@ -18,6 +18,7 @@ EF_STATS_MAX_SETS = 32
 EF_PEER_HANDLE_BYTES = 64
 EF_ABI_VERSION = 2
 EF_WIRE_U8 = 0x1
+EF_STEP_COLD_INPUTS = 0x2
 EF_CLOCK_SHIFT = 20
 
 EF_GRID_DONE = 0x1

@@ -23,26 +23,29 @@
 #ifndef EF_STEP_L2_PREFETCH
 #define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
 #endif
-// Work of the step kernel AHEAD of griddepcontrol.wait and the clock reads around it (A/B on B200, us per 2^20-env launch in a
-// CUDA-graph chain, one env set stepped repeatedly / eight sets in rotation = the headline; profiles/r02a*_chain_probe.txt):
-//   nothing ahead of the wait, every thread reads the clock                      7.03 / 8.94   (round-2 start)
-//   + bulk L2 prefetch of the CTA's inputs                                       7.02 / 7.88
-//   + early draws of 4 quads, every thread reading the clock ahead of the wait   7.91 / 7.33   (75 k reads of a word under atomic fire)
-//   + thread 0 reads it, the CTA takes it from shared memory                     7.03 / 7.34
-//   + the same for the read after the wait (one barrier, inside the load latency) 7.05 / 7.24
-//   early draws of 3 / 2 / 1 / 0 quads per thread                                7.02 / 7.23, 6.75 / 7.23, 6.73 / 7.21, 6.98 / 7.57
-// (computing ALL draws right after issuing the loads instead -- "hoisting" -- was slower than the interleaving the compiler
-// does by itself: 7.4 / 7.5.)
-#ifndef EF_STEP_PRE_QUADS
-#define EF_STEP_PRE_QUADS 1     // quads per thread whose outcome draws are computed AHEAD of griddepcontrol.wait (0..EF_STEP_Q)
-#endif
-#ifndef EF_STEP_PRE_CLOCK
-#define EF_STEP_PRE_CLOCK 1     // 1: thread 0 reads the clock word for the early draws, the CTA takes it from shared memory; 0: every thread
+// Work of the step kernel AHEAD of griddepcontrol.wait, and who reads the device clock.  A/B on B200, us per 2^20-env launch in a
+// CUDA-graph chain: one env set stepped repeatedly / eight sets in rotation (the headline: cold L2) / one set with a short
+// policy kernel ahead of every step (tools/chain_probe.py, tools/policy_loop_probe.py; profiles/r02a*_chain_probe.txt,
+// r02at..r02bb_*.txt):
+//   nothing ahead of the wait, every thread reads the clock after it                 7.03 / 8.94 / 9.57   (start of the round's second half)
+//   + bulk L2 prefetch of the CTA's inputs                                           7.02 / 7.88 /  --
+//   + ONE thread per CTA reads the clock after the wait (barrier inside the loads)   6.92 / 7.57 / 9.53
+//   + the clock word's line prefetched into L2 ahead of the wait                     6.85 / 6.98 / 9.65   <- args.wire & EF_STEP_COLD_INPUTS
+//   + the clock word LOADED (and discarded) by thread 0 ahead of the wait instead    6.74 / 7.25 / 9.38   <- default
+//   + Philox draws of the first 1 / 2 / 4 quads ahead of the wait (validated after)  6.73 / 7.21 / 9.76, 6.75 / 7.23 / --, 7.03 / 7.34 / --
+// The early draws were withdrawn: their gain in the chains was the early clock read they came with, and with a short
+// kernel ahead a step CTA gets its slot only 0.4 us before the release, so everything ahead of the wait is on the
+// critical path there.  Not adopted either: two launches co-resident (grid 148 x 2 passes, 4 CTAs/SM x Q = 2: 8.5-9.2 us),
+// all draws right after issuing the loads (7.4 / 7.5), griddepcontrol.launch_dependents earlier or later (no effect).
+#ifndef EF_STEP_L2_PREFETCH
+#define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
 #endif
 #ifndef EF_STEP_POST_CLOCK
-#define EF_STEP_POST_CLOCK 1    // 1: after the wait, thread 0 reads the clock word and the CTA takes it from shared memory behind a barrier
+#define EF_STEP_POST_CLOCK 1    // 1: after the wait, thread 0 reads the clock word and the CTA takes it from shared memory behind a barrier; 0: every thread (A/B)
 #endif
-#define EF_STEP_SPECULATE (EF_STEP_PRE_QUADS > 0)
+#ifndef EF_STEP_PRE_CLOCK
+#define EF_STEP_PRE_CLOCK 1     // 1: ahead of the wait thread 0 warms the clock word (load, or line prefetch under EF_STEP_COLD_INPUTS); 0: not (A/B)
+#endif
 #ifndef EF_STEP_LEAN
 #define EF_STEP_LEAN 1       // packed-word arithmetic of step_quad_packed (0: the generic step_quad_compute; same results)
 #endif
@@ -79,6 +82,7 @@ struct GridArgs {
     const int32_t* start_cells;
     int32_t n_layouts, layout_len;
     int64_t quads_per_cta;  // vector step kernel: contiguous quads per CTA
+    int32_t cold;           // vector step kernel: EF_STEP_COLD_INPUTS hint (see the kernel's prologue)
     PhiloxKeys rk;          // vector step kernel: round keys of `seed`
     // rollout only
     int32_t K;
@@ -95,7 +99,6 @@ struct GridArgs {
 // -DEF_TRACE=1 --tag=_trace` builds a tools-only variant (tools/step_trace.py) in which thread 0 of every CTA stores
 // %globaltimer / clock64 at the marked points; the results of a step are the same either way.
 #ifdef EF_TRACE
-__device__ unsigned long long g_spec_count[2] = {0ull, 0ull};   // quads whose early draws were kept / recomputed
 __device__ unsigned long long* g_trace_buf = nullptr;   // [8 sets][4 steps][1024 CTAs][16 points][2]
 #define EF_TRACE_DECL unsigned long long tr_[32] = {0ull};
 #define EF_TRACE_POINT(i)                                                   \
@@ -745,12 +748,6 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
     bool table_pending;
     EF_TRACE_DECL
     EF_TRACE_POINT(0);   // kernel entry
-#if EF_STEP_PRE_CLOCK == 1
-    __shared__ unsigned long long s_clk0;   // the clock word as thread 0 sees it on entry (published by the barrier of stage_table_begin)
-    if (SMEM && threadIdx.x == 0) s_clk0 = clock_fetch(a.clock);
-#endif
-    const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
-    pdl_launch_dependents();
     const bool philox_act = FAST ? false : a.action == nullptr;
     const int64_t quads = a.n >> 2;  // full quads; the (n & 3)-env tail goes through the generic code below
     const int64_t per_cta = a.quads_per_cta;  // ceil(quads / gridDim.x), divided on the host
@@ -781,41 +778,23 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
                 l2_prefetch_line(reinterpret_cast<const char*>(a.action) + e0 + off);
     }
 #endif
-#if EF_STEP_SPECULATE
-    // Outcome draws ahead of the wait.  A draw depends on (seed, env, step index t) only, and t is known now unless the
-    // launch this one waits for is a step of the SAME env set (then the device clock is still moving): compute the
-    // first pass's Philox words for the t PREDICTED from the clock word seen now, park them in shared memory, and use
-    // them after the wait iff the clock then gives that very t -- otherwise they are recomputed, as without this.
-    // Same bits either way.
-    constexpr bool kSpec = SMEM && SLOTS == 4 && PACKED && !HET && EF_STEP_LEAN != 0;
-    constexpr int kPre = EF_STEP_PRE_QUADS < Q ? EF_STEP_PRE_QUADS : Q;
-    __shared__ uint4 s_draw[kSpec ? kPre * kThreads : 1];
-    uint64_t t_spec = ~0ull;
-    if constexpr (kSpec) {
-        if (q_begin < q_end) {
-            // a counter caught between two whole steps = a step of this very env set is retiring CTA by CTA right now
-            // (that is why this CTA got its slot): the index after the wait will be the next one
-#if EF_STEP_PRE_CLOCK == 1
-            const unsigned long long c0 = s_clk0;
-#else
-            const unsigned long long c0 = clock_fetch(a.clock);
-#endif
-            t_spec = a.t + clock_steps(c0) + ((c0 & ((1ull << kClockShift) - 1ull)) != 0ull ? 1ull : 0ull);
-            const uint32_t left0 = static_cast<uint32_t>(min(q_end - q_begin, static_cast<int64_t>(Q) * kThreads));
-#pragma unroll
-            for (int j = 0; j < kPre; ++j) {
-                const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-                if (local < left0) {
-                    uint32_t r[4];
-                    group_words4_rk(a.rk, a.seed, static_cast<uint32_t>(a.env_offset + (q_begin + local) * 4), t_spec,
-                                    kStreamTransition, r);
-                    s_draw[local] = make_uint4(r[0], r[1], r[2], r[3]);
-                }
-            }
+#if EF_STEP_PRE_CLOCK
+    // The clock word is read right after the wait and everything waits for it.  Warm it now: with the env set's data in L2
+    // (the usual loop) a load whose result is dropped -- measured 0.1-0.3 us per launch better than a prefetch hint there;
+    // under EF_STEP_COLD_INPUTS (other env sets' traffic has pushed this set's lines out of L2 since its last step) a line
+    // prefetch, because the load would hold its warp at the wait until DRAM answers.
+    if (threadIdx.x == 0 && a.clock != nullptr) {
+        if (a.cold) {
+            l2_prefetch_line(a.clock);
+        } else {
+            unsigned long long sink;
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sink) : "l"(a.clock) : "memory");
         }
     }
 #endif
-    EF_TRACE_POINT(12);  // prefetch issued, early draws parked
+    const uint2* __restrict__ tab = stage_table_begin<SMEM>(a, &table_bar, table_pending);  // independent of the previous launch
+    pdl_launch_dependents();
+    EF_TRACE_POINT(12);  // prefetches issued, table copy under way
     pdl_wait();                                            // previous launch complete, its writes visible
     EF_TRACE_POINT(1);   // released by the previous launch
     EpisodeAcc acc;
@@ -853,19 +832,10 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #pragma unroll
         for (int j = 0; j < Q; ++j) {
             const uint32_t local = static_cast<uint32_t>(j) * kThreads + threadIdx.x;
-            if (local < left) {
-                const uint4* spec = nullptr;
-#if EF_STEP_SPECULATE
-                if constexpr (kSpec)
-                    spec = (chunk == q_begin && j < kPre && t == t_spec) ? &s_draw[local] : nullptr;
-#if defined(EF_TRACE) && defined(EF_SPEC_COUNT)   // (75 k same-address atomics per launch: counts only, never with timings)
-                if constexpr (kSpec) atomicAdd(&g_spec_count[spec != nullptr ? 0 : 1], 1ull);
-#endif
-#endif
+            if (local < left)
                 step_quad<SMEM, SLOTS, PACKED, FAST, HET, W8>(a, tab, (chunk + local) * 4,
                                                           static_cast<uint32_t>(a.env_offset + (chunk + local) * 4), t, in[j],
-                                                          philox_act, acc, errs, spec);
-            }
+                                                          philox_act, acc, errs);
             if (j == 0) EF_TRACE_POINT(4);   // first quad stepped (its loads had to land)
         }
     }
@@ -1448,8 +1418,10 @@ template <bool W8>
 static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* ep_len, float* ep_ret, const void* action,
                                const uint32_t* draw, uint64_t seed, uint64_t t, uint64_t env_offset, void* obs,
                                float* reward, uint8_t* terminated, uint8_t* truncated, void* final_obs, double* stats,
-                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream) {
+                               uint32_t* err, uint64_t* clock, int64_t n, int32_t autoreset, void* stream,
+                               int32_t hints = 0) {
     GridArgs a{};
+    a.cold = (hints & EF_STEP_COLD_INPUTS) ? 1 : 0;
     if (int s = fill_args(grid, a)) return s;
     if (n < 0 || !pos || !ep_ret) return EF_ERR_INVALID_ARGUMENT;
     if (W8 && (grid->rows > 256 || grid->cols > 256)) return EF_ERR_UNSUPPORTED;  // (row, col) must fit a byte each
@@ -1528,10 +1500,10 @@ extern "C" int ef_gridworld_step_v(const ef_gridworld_step_args* x) {
     if (x->wire & EF_WIRE_U8)  // action / obs / final_obs point at bytes (see ef_gridworld_step_u8)
         return gridworld_step_impl<true>(x->grid, x->pos, x->ep_len, x->ep_ret, x->action, x->draw, x->seed, x->t, x->env_offset,
                                          x->obs, x->reward, x->terminated, x->truncated, x->final_obs, x->stats, x->err,
-                                         x->clock, x->n, x->autoreset, x->stream);
+                                         x->clock, x->n, x->autoreset, x->stream, x->wire);
     return gridworld_step_impl<false>(x->grid, x->pos, x->ep_len, x->ep_ret, static_cast<const int32_t*>(x->action), x->draw,
                                       x->seed, x->t, x->env_offset, x->obs, x->reward, x->terminated, x->truncated,
-                                      x->final_obs, x->stats, x->err, x->clock, x->n, x->autoreset, x->stream);
+                                      x->final_obs, x->stats, x->err, x->clock, x->n, x->autoreset, x->stream, x->wire);
 }
 
 extern "C" int ef_gridworld_step_layouts(const ef_grid_desc* grid, int32_t n_layouts, const int32_t* layout_index,
@@ -1769,13 +1741,6 @@ extern "C" int ef_gridworld_reset(int32_t start_cell, int32_t cols, int32_t* pos
 // tools-only build: where the step kernels store their timeline (device buffer of 8 * 4 * 1024 * 32 uint64, or NULL)
 extern "C" int ef_debug_set_trace(unsigned long long* buf) {
     return cuda_status(cudaMemcpyToSymbol(ef::g_trace_buf, &buf, sizeof(buf)));
-}
-// tools-only build: {quads stepped with the draws computed ahead of the wait, quads whose draws were recomputed}; reset on read
-extern "C" int ef_debug_spec_counters(unsigned long long* out) {
-    const unsigned long long zero[2] = {0ull, 0ull};
-    cudaError_t e = cudaMemcpyFromSymbol(out, ef::g_spec_count, sizeof(zero));
-    if (e == cudaSuccess) e = cudaMemcpyToSymbol(ef::g_spec_count, zero, sizeof(zero));
-    return cuda_status(e);
 }
 #endif
 

@@ -399,9 +399,13 @@ class VecGridWorld(_GridStateLayout, VecEnv):
     def __init__(self, num_envs=1, rows=5, cols=5, start_state=(0, 0), terminal_states=_DEFAULT_TERMINALS, walls=None,
                  special_transitions=None, rewards=None, seed=None, slip_distribution=None, p_success=1.0,
                  episode_length_limit=None, *, device=None, env_offset=0, autoreset=True, strict=False, rng="philox",
-                 state_layout="auto", wire="canonical"):
+                 state_layout="auto", wire="canonical", cold_inputs=None):
         """`wire="compact"`: step() takes uint8 actions and returns uint8 (row, col) observations (rows, cols <= 256)
         through `ef_gridworld_step_u8` -- 9 instead of 18 bytes per env-step between host and device, same trajectories.
+
+        `cold_inputs`: the EF_STEP_COLD_INPUTS hint of the step kernel (a latency hint, results do not depend on it):
+        True / False, or None = decided per call from the env sets alive on the device (True once they exceed its L2
+        together, i.e. when a set's arrays have been evicted by the others by the time it is stepped again).
 
         `rng="philox"` (default): counter-based draws keyed by (seed, global env index, step).
         `rng="pcg64"`: every env owns the generator the reference would build for it,
@@ -413,6 +417,9 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             raise ValueError("wire must be 'canonical' or 'compact'")
         self._w8 = wire == "compact"
         self.wire = wire
+        if cold_inputs not in (None, True, False):
+            raise ValueError("cold_inputs must be None, True or False")
+        self.cold_inputs = cold_inputs
         can_pack = self._can_pack(autoreset, episode_length_limit)
         if state_layout == "packed" and not can_pack:
             raise ValueError("state_layout='packed' needs autoreset=True and 0 < episode_length_limit <= 65535")
@@ -628,7 +635,6 @@ class VecGridWorld(_GridStateLayout, VecEnv):
                 x.terminated, x.truncated = self._term.data_ptr(), self._trunc.data_ptr()
                 x.stats, x.err = self._stats_raw.data_ptr(), self.err.data_ptr()
                 x.n = self.num_envs
-                x.wire = _lib.EF_WIRE_U8 if self._w8 else 0
                 fixed = self._fast_args = (x, _lib.C.byref(x), self._lib.ef_gridworld_step_v, self.device.index,
                                            (self._obs, self._reward, self._term.view(torch.bool),
                                             self._trunc.view(torch.bool)), self.ep_ret, state_t)
@@ -639,6 +645,8 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             x.clock = None if clock is None else clock.data_ptr()
             x.seed = self._seed
             x.autoreset = int(self._autoreset)
+            cold = self._cold_inputs() if self.cold_inputs is None else self.cold_inputs
+            x.wire = (_lib.EF_WIRE_U8 if self._w8 else 0) | (_lib.EF_STEP_COLD_INPUTS if cold else 0)
             if torch.cuda.current_device() == dev_index:
                 x.stream = torch.cuda.current_stream().cuda_stream
                 status = fn(ref)

@@ -54,6 +54,38 @@ def all_reduce_stats(stats, group=None):
     return stats
 
 
+class _Residency:
+    """Which env sets are alive on which device, and how many bytes a step of each touches: the basis of the
+    EF_STEP_COLD_INPUTS hint (include/envforge_b200.h).  When the live env sets of a device together exceed its L2, a set's
+    arrays have most likely been evicted by the others' traffic by the time it is stepped again."""
+
+    def __init__(self):
+        import weakref
+        self._sets = weakref.WeakSet()
+        self.generation = 0      # bumped whenever the population changes; envs cache their verdict against it
+        self._l2 = {}
+
+    def add(self, env):
+        self._sets.add(env)
+        self.generation += 1
+
+    def bump(self, *_):
+        self.generation += 1
+
+    def l2_bytes(self, torch, device):
+        idx = device.index
+        if idx not in self._l2:
+            self._l2[idx] = int(getattr(torch.cuda.get_device_properties(device), "L2_cache_size", 0)) or (126 << 20)
+        return self._l2[idx]
+
+    def cold(self, env):
+        total = sum(e._step_bytes for e in self._sets if e.device == env.device)
+        return total > self.l2_bytes(env._torch, env.device)
+
+
+RESIDENCY = _Residency()
+
+
 class VecEnv:
     """Base class: owns the SoA buffers shared by all env families (episode counters, stats, error word)."""
 
@@ -104,6 +136,21 @@ class VecEnv:
         self.host_stage_actions = False   # pipelined: True = copy-engine H2D of the actions instead of zero-copy reads
         self._pipe_handle = None
         self._clock = None  # optional device-resident step clock (CUDA-graph capture), see enable_device_clock()
+        # bytes one step of this env set touches (state, action, outputs: the canonical 42 B per env is close enough for
+        # every family) -- see _Residency
+        self._step_bytes = 42 * self.num_envs
+        self._cold_cache = (-1, False)
+        import weakref
+        RESIDENCY.add(self)
+        weakref.finalize(self, RESIDENCY.bump)
+
+    def _cold_inputs(self):
+        """True when the live env sets on this device together exceed its L2 (cached per population change)."""
+        gen, verdict = self._cold_cache
+        if gen != RESIDENCY.generation:
+            verdict = RESIDENCY.cold(self)
+            self._cold_cache = (RESIDENCY.generation, verdict)
+        return verdict
 
     # -- device clock ---------------------------------------------------------------------------------------------
     def enable_device_clock(self):

@@ -478,19 +478,20 @@ def test_cuda_graph_replay_with_device_clock_equals_eager_steps():
     assert torch.equal(graphed.pos, eager.pos)
 
 
-def test_draws_computed_ahead_of_the_wait_match_in_every_launch_order():
-    """The step kernel computes its first pass's Philox draws BEFORE griddepcontrol.wait for the step index the device clock
-    shows at that moment and keeps them only if the clock shows the same index after the wait (gridworld.cu, "Outcome draws
-    ahead of the wait").  Both outcomes must give the reference bits: a graph that chains steps of ONE env set (the
-    clock moves under the early read: draws recomputed) and a graph that alternates TWO env sets (each set's clock is
-    quiescent while the other steps: early draws kept), against eager steps with host-side step counting."""
+@pytest.mark.parametrize("cold", [False, True])
+def test_work_ahead_of_the_wait_changes_no_result_in_any_launch_order(cold):
+    """The step kernel prefetches its inputs and warms the device clock word BEFORE griddepcontrol.wait (a load, or under the
+    EF_STEP_COLD_INPUTS hint a line prefetch) and reads the clock through one thread per CTA after it.  None of that may
+    change a bit: a graph that chains steps of ONE env set (the clock word is under atomic fire while the next launch
+    looks at it) and a graph that alternates TWO env sets, with and without the hint, against eager steps with host-side
+    step counting."""
     import torch
     from rl_envs_forge_b200 import VecGridWorld
     n, per_graph, replays = 1 << 18, 6, 5
     cfg = _vec_kwargs(_config2(0.8))
     acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda") for _ in range(per_graph)]
     eager = [VecGridWorld(n, seed=41 + i, env_offset=i * n, **cfg) for i in range(2)]
-    graphed = [VecGridWorld(n, seed=41 + i, env_offset=i * n, **cfg) for i in range(2)]
+    graphed = [VecGridWorld(n, seed=41 + i, env_offset=i * n, cold_inputs=cold, **cfg) for i in range(2)]
     for e in eager + graphed:
         e.step(acts[0])
     for e in graphed:
@@ -519,6 +520,36 @@ def test_draws_computed_ahead_of_the_wait_match_in_every_launch_order():
         assert torch.equal(gset._reward, eset._reward) and torch.equal(gset._obs, eset._obs)
         sg, se = gset.episode_stats(), eset.episode_stats()
         assert sg["episodes"] == se["episodes"] > 0 and sg["length_sum"] == se["length_sum"] and sg["env_steps"] == se["env_steps"]
+
+
+def test_cold_inputs_hint_follows_the_live_env_sets():
+    """cold_inputs=None: the hint is on once the env sets alive on the device exceed its L2 together (vec_env._Residency),
+    and off again when they are gone; an explicit True / False wins; a bad value is refused."""
+    import gc
+    import torch
+    from rl_envs_forge_b200 import VecGridWorld
+    from rl_envs_forge_b200.vec_env import RESIDENCY
+    gc.collect()
+    cfg = _vec_kwargs(_config2(0.8))
+    small = VecGridWorld(1024, **cfg)
+    l2 = RESIDENCY.l2_bytes(torch, small.device)
+    before = small._cold_inputs()
+    big = [VecGridWorld(l2 // 42 // 2 + 1024, env_offset=(i + 1) << 24, **cfg) for i in range(2)]   # 2 x (L2 / 2 + a bit)
+    assert small._cold_inputs() and big[0]._cold_inputs()
+    act = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    small.step(act)
+    assert small._fast_args[0].wire & 0x2
+    del big
+    gc.collect()
+    assert small._cold_inputs() == before
+    if not before:
+        small.step(act)
+        assert not (small._fast_args[0].wire & 0x2)
+    small.cold_inputs = True
+    small.step(act)
+    assert small._fast_args[0].wire & 0x2
+    with pytest.raises(ValueError):
+        VecGridWorld(8, cold_inputs="yes", **cfg)
 
 
 def test_empty_batch_is_a_noop_through_the_c_abi():

@@ -22,7 +22,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--rounds", type=int, default=6)
 ap.add_argument("--sets", type=int, default=8, help="env sets in rotation (1 = one set stepped repeatedly: L2-resident chain)")
+ap.add_argument("--policy", action="store_true", help="one env set, the stand-in policy kernel ahead of every step launch")
 a = ap.parse_args()
+if a.policy:
+    a.sets = 1
 n, R, A = a.n, a.sets, 7
 lib = _lib.load()
 lib.ef_debug_set_trace.argtypes = [C.c_void_p]
@@ -39,10 +42,21 @@ for i in range(G):
 torch.cuda.synchronize()
 stream = torch.cuda.Stream()
 g = torch.cuda.CUDAGraph()
+act_p = torch.zeros(n, dtype=torch.int32, device="cuda")
+
+
+def one(i):
+    if a.policy:
+        _lib.check(lib.ef_policy_demo_step(sets[0]._obs.data_ptr(), act_p.data_ptr(), i, n, torch.cuda.current_stream().cuda_stream))
+        sets[0].step(act_p)
+    else:
+        sets[i % R].step(acts[i % A])
+
+
 with torch.cuda.stream(stream):
     with torch.cuda.graph(g, stream=stream):
         for i in range(G):
-            sets[i % R].step(acts[i % A])
+            one(i)
 torch.cuda.synchronize()
 for _ in range(a.rounds):
     g.replay()
