@@ -30,6 +30,25 @@
 //   nothing ahead of the wait, every thread reads the clock after it                 7.03 / 8.94 / 9.57   (start of the round's second half)
 //   + bulk L2 prefetch of the CTA's inputs                                           7.02 / 7.88 /  --
 //   + ONE thread per CTA reads the clock after the wait (barrier inside the loads)   6.92 / 7.57 / 9.53
+//   + the clock word's line prefetched into L2 ahead of the wait                     6.99 / 7.02 / 9.70   <- COLD instantiation (EF_STEP_COLD_INPUTS)
+//   + the clock word LOADED (and discarded) by thread 0 ahead of the wait instead    6.76 / 7.30 / 9.58   <- default instantiation
+//   + Philox draws of the first 1 / 2 / 4 quads ahead of the wait (validated after)  6.73 / 7.21 / 9.76, 6.75 / 7.23 / --, 7.03 / 7.34 / --
+// The early draws were withdrawn: their gain in the chains was the early clock read they came with, and with a short
+// kernel ahead a step CTA gets its slot only 0.4 us before the release, so everything ahead of the wait is on the
+// critical path there.  Load vs prefetch of the clock word is a template parameter, not a branch: with both in the
+// instruction stream neither chain got its better number (6.82 / 7.32 whichever way the branch went).  Not adopted either:
+// two launches co-resident (grid 148 x 2 passes, 4 CTAs/SM x Q = 2: 8.5-9.2 us), all draws right after issuing the
+// loads (7.4 / 7.5), griddepcontrol.launch_dependents earlier or later (no effect).
+#ifndef EF_STEP_L2_PREFETCH
+#define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
+#endif
+// Work of the step kernel AHEAD of griddepcontrol.wait, and who reads the device clock.  A/B on B200, us per 2^20-env launch in a
+// CUDA-graph chain: one env set stepped repeatedly / eight sets in rotation (the headline: cold L2) / one set with a short
+// policy kernel ahead of every step (tools/chain_probe.py, tools/policy_loop_probe.py; profiles/r02a*_chain_probe.txt,
+// r02at..r02bb_*.txt):
+//   nothing ahead of the wait, every thread reads the clock after it                 7.03 / 8.94 / 9.57   (start of the round's second half)
+//   + bulk L2 prefetch of the CTA's inputs                                           7.02 / 7.88 /  --
+//   + ONE thread per CTA reads the clock after the wait (barrier inside the loads)   6.92 / 7.57 / 9.53
 //   + the clock word's line prefetched into L2 ahead of the wait                     6.85 / 6.98 / 9.65   <- args.wire & EF_STEP_COLD_INPUTS
 //   + the clock word LOADED (and discarded) by thread 0 ahead of the wait instead    6.74 / 7.25 / 9.38   <- default
 //   + Philox draws of the first 1 / 2 / 4 quads ahead of the wait (validated after)  6.73 / 7.21 / 9.76, 6.75 / 7.23 / --, 7.03 / 7.34 / --
@@ -742,7 +761,7 @@ __device__ __forceinline__ void step_tail(const GridArgs& a, const uint2* __rest
 // quads per CTA (grid = a few CTAs per SM, all resident), and a thread first ISSUES the 128-bit loads of all its quads
 // (up to EF_STEP_Q per pass), then steps them one after the other: a launch is one round of DRAM latency with every
 // load in flight at once, instead of a grid-stride loop that pays the latency once per iteration.
-template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false, bool W8 = false>
+template <bool SMEM, int SLOTS, int Q, int MINBLOCKS, bool PACKED, bool FAST, bool HET = false, bool W8 = false, bool COLD = false>
 __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(const GridArgs a) {
     __shared__ uint64_t table_bar;
     bool table_pending;
@@ -780,11 +799,12 @@ __global__ void __launch_bounds__(kThreads, MINBLOCKS) gridworld_step_kernel(con
 #endif
 #if EF_STEP_PRE_CLOCK
     // The clock word is read right after the wait and everything waits for it.  Warm it now: with the env set's data in L2
-    // (the usual loop) a load whose result is dropped -- measured 0.1-0.3 us per launch better than a prefetch hint there;
-    // under EF_STEP_COLD_INPUTS (other env sets' traffic has pushed this set's lines out of L2 since its last step) a line
-    // prefetch, because the load would hold its warp at the wait until DRAM answers.
+    // (the usual loop) a load whose result is dropped -- measured 0.2 us per launch better than a prefetch hint there;
+    // in the COLD instantiation (EF_STEP_COLD_INPUTS: other env sets' traffic has pushed this set's lines out of L2 since
+    // its last step) a line prefetch, 0.3 us better there.  Compile-time, not a branch: the mere presence of the load in
+    // the instruction stream costs the cold chain those 0.3 us (profiles/r02bd_cold_hint_matrix.txt, r02be_*).
     if (threadIdx.x == 0 && a.clock != nullptr) {
-        if (a.cold) {
+        if constexpr (COLD) {
             l2_prefetch_line(a.clock);
         } else {
             unsigned long long sink;
@@ -1457,6 +1477,9 @@ static int gridworld_step_impl(const ef_grid_desc* grid, int32_t* pos, int32_t* 
     const bool packed = ep_len == nullptr;
     const bool fast = action && obs && reward && terminated && truncated && !final_obs && autoreset != 0;
 #define EF_LAUNCH_VEC(SM, SL, PK, FS)                                                                                    \
+    if (small && FS && a.cold) /* the hinted instantiation exists for the one-wave kernel of the common call shape */    \
+        return launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS, false, W8, FS>, a, SM, grid_v, \
+                      st);                                                                                               \
     return small ? launch(gridworld_step_kernel<SM, SL, EF_STEP_Q, EF_STEP_MINBLOCKS, PK, FS, false, W8>, a, SM, grid_v, \
                           st)                                                                                            \
                  : launch(gridworld_step_kernel<SM, SL, EF_STEP_BIG_Q, EF_STEP_BIG_MINBLOCKS, PK, FS, false, W8>, a, SM, \

@@ -16,12 +16,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1 << 20)
 ap.add_argument("--sets", type=int, nargs="+", default=[1, 8])
 ap.add_argument("--replays", type=int, default=300)
+ap.add_argument("--cold", default="auto", choices=["auto", "0", "1"], help="EF_STEP_COLD_INPUTS hint: automatic, off, on")
 a = ap.parse_args()
+COLD = None if a.cold == "auto" else a.cold == "1"
 n, A = a.n, 7
 spec = {(SPECIAL[0], Action(SPECIAL[1])): (SPECIAL[2], SPECIAL[3])}
 acts = [torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda") for _ in range(A)]
 for R in a.sets:
-    sets = [VecGridWorld(n, seed=1, special_transitions=spec, env_offset=r * n, **CONFIG2) for r in range(R)]
+    sets = [VecGridWorld(n, seed=1, special_transitions=spec, env_offset=r * n, cold_inputs=COLD, **CONFIG2) for r in range(R)]
     G = R * A
     for i in range(G):
         sets[i % R].step(acts[i % A])
@@ -44,7 +46,7 @@ for R in a.sets:
     torch.cuda.synchronize()
     us = s.elapsed_time(t) * 1e3 / (a.replays * G)
     st = sum(e.episode_stats()["env_steps"] for e in sets)
-    print(f"{R} set(s) x {n} envs: {us:.2f} us/launch  {n / us * 1e6:.3e} env-steps/s  (env_steps {st})")
+    print(f"cold={a.cold} {R} set(s) x {n} envs: {us:.2f} us/launch  {n / us * 1e6:.3e} env-steps/s  (env_steps {st})")
     lib = _lib.load()
     if hasattr(lib, "ef_debug_spec_counters"):      # -DEF_TRACE=1 build: how often the early draws were kept
         import ctypes as C

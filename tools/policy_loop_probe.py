@@ -11,9 +11,10 @@ import torch  # noqa: E402
 from bench import CONFIG2, SPECIAL  # noqa: E402
 from rl_envs_forge_b200 import Action, VecGridWorld, _lib  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+n = 1 << 20
+COLD = {"auto": None, "0": False, "1": True}[sys.argv[1] if len(sys.argv) > 1 else "auto"]
 spec = {(SPECIAL[0], Action(SPECIAL[1])): (SPECIAL[2], SPECIAL[3])}
-env = VecGridWorld(n, seed=1, special_transitions=spec, **CONFIG2)
+env = VecGridWorld(n, seed=1, special_transitions=spec, cold_inputs=COLD, **CONFIG2)
 lib = _lib.load()
 act = torch.zeros(n, dtype=torch.int32, device="cuda")
 
@@ -43,4 +44,4 @@ for _ in range(3):
     e.record()
     torch.cuda.synchronize()
     best = min(best, s.elapsed_time(e) * 1e3 / 5600)
-print(f"policy kernel + step, n={n}: {best:.2f} us/step  {n / best * 1e6:.3e} env-steps/s")
+print(f"cold={COLD} policy kernel + step, n={n}: {best:.2f} us/step  {n / best * 1e6:.3e} env-steps/s")
