@@ -270,6 +270,9 @@ constexpr int kSortedSlots = kTile + 32 * (kBins - 1);  // every bin padded to a
 #ifndef EF_BANDIT_CTAS
 #define EF_BANDIT_CTAS 4
 #endif
+#ifndef EF_BANDIT_PREFETCH_MEANS
+#define EF_BANDIT_PREFETCH_MEANS 0   // 1 / 2: L1 / L2 prefetch of a default arm's mean while the tile is being binned (A/B)
+#endif
 #ifndef EF_BANDIT_DYNAMIC
 #define EF_BANDIT_DYNAMIC 1
 #endif
@@ -351,6 +354,16 @@ __global__ void __launch_bounds__(kThreads, kSortedCtasPerSm) bandit_step_sorted
                         errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
                     } else {
                         key = arm_bin(load_arm(arms, act));
+#if EF_BANDIT_PREFETCH_MEANS
+                        // a default arm's mean is a 4-byte gather from the [n,k] table: ask for its line now, a sort ahead of its use
+                        if (key == static_cast<uint32_t>(EF_ARM_DEFAULT_NORMAL) && a.means != nullptr) {
+#if EF_BANDIT_PREFETCH_MEANS == 1
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.means + i * a.k + act));
+#else
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.means + i * a.k + act));
+#endif
+                        }
+#endif
                     }
                 }
                 // warp-aggregated counting: lanes with the same bin elect a leader that reserves their slots at once
