@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(kThreads) bandit_step_kernel(const BanditArgs 
 //  * the 32-env groups of the sorted array are handed to the warps of the CTA dynamically (one shared counter): a
 //    group of beta(2,5) draws costs 2.5 x a group of uniform draws;
 //  * a default arm's per-env mean comes from the [n,k] table of ef_bandit_default_means when the caller passes it
-//    (ef_bandit_step_means) instead of being re-derived with a second Philox call + Box-Muller on every step.
+//    (ef_bandit_step_means) instead of being re-derived with a second Philox call + Box-Muller on every step.  (An L1 or
+//    L2 prefetch of the mean's line while the tile is binned was measured SLOWER: 5.13e10 vs 5.48e10 bandit-steps/s,
+//    profiles/r02bh_bandit_mean_prefetch_ab.txt.)
 #ifndef EF_BANDIT_ITEMS
 #define EF_BANDIT_ITEMS 16
 #endif
@@ -269,9 +271,6 @@ constexpr int kBins = 16;
 constexpr int kSortedSlots = kTile + 32 * (kBins - 1);  // every bin padded to a multiple of 32
 #ifndef EF_BANDIT_CTAS
 #define EF_BANDIT_CTAS 4
-#endif
-#ifndef EF_BANDIT_PREFETCH_MEANS
-#define EF_BANDIT_PREFETCH_MEANS 0   // 1 / 2: L1 / L2 prefetch of a default arm's mean while the tile is being binned (A/B)
 #endif
 #ifndef EF_BANDIT_DYNAMIC
 #define EF_BANDIT_DYNAMIC 1
@@ -354,16 +353,6 @@ __global__ void __launch_bounds__(kThreads, kSortedCtasPerSm) bandit_step_sorted
                         errs.record(g, static_cast<uint32_t>(act), EF_STEP_BAD_ACTION);
                     } else {
                         key = arm_bin(load_arm(arms, act));
-#if EF_BANDIT_PREFETCH_MEANS
-                        // a default arm's mean is a 4-byte gather from the [n,k] table: ask for its line now, a sort ahead of its use
-                        if (key == static_cast<uint32_t>(EF_ARM_DEFAULT_NORMAL) && a.means != nullptr) {
-#if EF_BANDIT_PREFETCH_MEANS == 1
-                            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.means + i * a.k + act));
-#else
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.means + i * a.k + act));
-#endif
-                        }
-#endif
                     }
                 }
                 // warp-aggregated counting: lanes with the same bin elect a leader that reserves their slots at once
