@@ -475,7 +475,9 @@ int ef_labyrinth_reset(const ef_labyrinth_desc* maze, int32_t* pos, int32_t* ep_
  * most 96 registers per chunk, at most EF_SERVE_CHUNKS_PER_SM chunks per SM (every chunk is a dependency chain of its
  * own, and the chains of an SM hide each other's latencies).  Results are bit-identical to K ef_gridworld_step calls with the
  * same actions.  Packed state layout only (`pos` holds cell | counter << 16, see ef_gridworld_step), n a multiple of 4,
- * table small enough for shared memory.  act_seq / obs_seq: [ceil(n / chunk_envs)] uint32, zeroed by the caller before
+ * table small enough for shared memory AND for all chunks' CTAs to be resident at once next to the kernel's own 17 KB of
+ * shared memory (else EF_ERR_UNSUPPORTED: a chunk waiting for an SM slot would wait for CTAs that wait for their actions).
+ * While a CTA waits for a step's actions it computes the step's Philox draws.  act_seq / obs_seq: [ceil(n / chunk_envs)] uint32, zeroed by the caller before
  * both kernels are launched.  The producer kernel must already be LOADED when the server starts (launched once before, or
  * cudaFuncGetAttributes on it): CUDA loads kernels lazily and a first launch may synchronise the context, i.e. wait for
  * the server that is waiting for it.  A wait that is not satisfied within ~5 s gives up, sets status[0] = 1 (nullable) and ends

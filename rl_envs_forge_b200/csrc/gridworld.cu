@@ -1819,6 +1819,12 @@ extern "C" int ef_gridworld_serve(const ef_grid_desc* grid, int32_t* pos, float*
             const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(table_bytes));
             if (e != cudaSuccess) return cuda_status(e);
         }
+        // every chunk's CTA must be resident for all K steps (a chunk that waits for a slot would wait for CTAs that wait for
+        // their actions): refuse a table too large to fit the grid next to the kernel's own shared memory
+        int per_sm = 0;
+        const cudaError_t eo = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kServeThreads, table_bytes);
+        if (eo != cudaSuccess) return cuda_status(eo);
+        if (static_cast<int64_t>(per_sm) * sm_count() < grid_s) return EF_ERR_UNSUPPORTED;
         kernel<<<grid_s, kServeThreads, table_bytes, st>>>(a);
         return cuda_status(cudaGetLastError());
     };

@@ -67,3 +67,27 @@ def test_server_gives_up_without_a_producer():
         env.serve_end()
     assert torch.equal(env.pos, before) and env.step_count == 0
     env.step(torch.zeros(4096, dtype=torch.int32, device="cuda"))      # still usable
+
+
+@pytest.mark.timeout(120)
+def test_largest_shared_memory_table_is_served_or_refused_never_hung():
+    """A 24x32 grid with slip has the largest table the kernels stage in shared memory (96 KB).  The server keeps 17 KB of
+    its own next to it and needs EVERY chunk's CTA resident at once: it must either serve that grid (bit-identical to plain
+    steps) or refuse it with EF_ERR_UNSUPPORTED before launching -- never start a grid that cannot be co-resident."""
+    from rl_envs_forge_b200 import VecGridWorld
+    from rl_envs_forge_b200._lib import EnvForgeError
+    n, K = 1 << 16, 12
+    cfg = dict(rows=24, cols=32, start_state=(0, 0), terminal_states={(23, 31): 1.0}, p_success=0.7,
+               episode_length_limit=50)
+    served = VecGridWorld(n, seed=5, **cfg)
+    plain = VecGridWorld(n, seed=5, **cfg)
+    try:
+        obs_s, rew_s, term_s, trunc_s = served.serve_with_demo_policy(K)
+    except EnvForgeError as e:
+        assert "unsupported" in str(e).lower()
+        return
+    obs = plain.reset()[0]
+    for k in range(K):
+        obs, rew, term, trunc, _ = plain.step(_demo_policy(obs, k))
+    assert torch.equal(obs_s, obs) and torch.equal(rew_s, rew) and torch.equal(term_s, term) and torch.equal(trunc_s, trunc)
+    assert torch.equal(served.pos, plain.pos) and torch.equal(served.ep_ret, plain.ep_ret)
