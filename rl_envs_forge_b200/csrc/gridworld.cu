@@ -20,9 +20,6 @@
 
 #include "ef_common.cuh"
 
-#ifndef EF_STEP_L2_PREFETCH
-#define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
-#endif
 // Work of the step kernel AHEAD of griddepcontrol.wait, and who reads the device clock.  A/B on B200, us per 2^20-env launch in a
 // CUDA-graph chain: one env set stepped repeatedly / eight sets in rotation (the headline: cold L2) / one set with a short
 // policy kernel ahead of every step (tools/chain_probe.py, tools/policy_loop_probe.py; profiles/r02a*_chain_probe.txt,
@@ -39,23 +36,6 @@
 // instruction stream neither chain got its better number (6.82 / 7.32 whichever way the branch went).  Not adopted either:
 // two launches co-resident (grid 148 x 2 passes, 4 CTAs/SM x Q = 2: 8.5-9.2 us), all draws right after issuing the
 // loads (7.4 / 7.5), griddepcontrol.launch_dependents earlier or later (no effect).
-#ifndef EF_STEP_L2_PREFETCH
-#define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
-#endif
-// Work of the step kernel AHEAD of griddepcontrol.wait, and who reads the device clock.  A/B on B200, us per 2^20-env launch in a
-// CUDA-graph chain: one env set stepped repeatedly / eight sets in rotation (the headline: cold L2) / one set with a short
-// policy kernel ahead of every step (tools/chain_probe.py, tools/policy_loop_probe.py; profiles/r02a*_chain_probe.txt,
-// r02at..r02bb_*.txt):
-//   nothing ahead of the wait, every thread reads the clock after it                 7.03 / 8.94 / 9.57   (start of the round's second half)
-//   + bulk L2 prefetch of the CTA's inputs                                           7.02 / 7.88 /  --
-//   + ONE thread per CTA reads the clock after the wait (barrier inside the loads)   6.92 / 7.57 / 9.53
-//   + the clock word's line prefetched into L2 ahead of the wait                     6.85 / 6.98 / 9.65   <- args.wire & EF_STEP_COLD_INPUTS
-//   + the clock word LOADED (and discarded) by thread 0 ahead of the wait instead    6.74 / 7.25 / 9.38   <- default
-//   + Philox draws of the first 1 / 2 / 4 quads ahead of the wait (validated after)  6.73 / 7.21 / 9.76, 6.75 / 7.23 / --, 7.03 / 7.34 / --
-// The early draws were withdrawn: their gain in the chains was the early clock read they came with, and with a short
-// kernel ahead a step CTA gets its slot only 0.4 us before the release, so everything ahead of the wait is on the
-// critical path there.  Not adopted either: two launches co-resident (grid 148 x 2 passes, 4 CTAs/SM x Q = 2: 8.5-9.2 us),
-// all draws right after issuing the loads (7.4 / 7.5), griddepcontrol.launch_dependents earlier or later (no effect).
 #ifndef EF_STEP_L2_PREFETCH
 #define EF_STEP_L2_PREFETCH 1   // 1: bulk L2 prefetch of the CTA's input chunk ahead of griddepcontrol.wait; 2: per-line prefetch; 0: none (A/B)
 #endif

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from bench import CONFIG2, SPECIAL  # noqa: E402
-from rl_envs_forge_b200 import Action, VecGridWorld, _lib  # noqa: E402
+from rl_envs_forge_b200 import Action, VecGridWorld  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=1 << 20)
@@ -47,10 +47,4 @@ for R in a.sets:
     us = s.elapsed_time(t) * 1e3 / (a.replays * G)
     st = sum(e.episode_stats()["env_steps"] for e in sets)
     print(f"cold={a.cold} {R} set(s) x {n} envs: {us:.2f} us/launch  {n / us * 1e6:.3e} env-steps/s  (env_steps {st})")
-    lib = _lib.load()
-    if hasattr(lib, "ef_debug_spec_counters"):      # -DEF_TRACE=1 build: how often the early draws were kept
-        import ctypes as C
-        out = (C.c_ulonglong * 2)()
-        lib.ef_debug_spec_counters(out)
-        print(f"    early draws kept for {out[0]} quads, recomputed for {out[1]} ({100.0 * out[0] / max(1, out[0] + out[1]):.1f} % kept)")
     del sets, g
