@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib, spaces
 from ._lib import EnvForgeError
-from .vec_env import VecEnv, resolve_seed
+from .vec_env import RESIDENCY, VecEnv, resolve_seed
 
 
 class Action(IntEnum):  # grid_world.py:11-15
@@ -635,6 +635,7 @@ class VecGridWorld(_GridStateLayout, VecEnv):
                 x.terminated, x.truncated = self._term.data_ptr(), self._trunc.data_ptr()
                 x.stats, x.err = self._stats_raw.data_ptr(), self.err.data_ptr()
                 x.n = self.num_envs
+                self._wire_cold = None      # x.wire not set yet
                 fixed = self._fast_args = (x, _lib.C.byref(x), self._lib.ef_gridworld_step_v, self.device.index,
                                            (self._obs, self._reward, self._term.view(torch.bool),
                                             self._trunc.view(torch.bool)), self.ep_ret, state_t)
@@ -645,8 +646,13 @@ class VecGridWorld(_GridStateLayout, VecEnv):
             x.clock = None if clock is None else clock.data_ptr()
             x.seed = self._seed
             x.autoreset = int(self._autoreset)
-            cold = self._cold_inputs() if self.cold_inputs is None else self.cold_inputs
-            x.wire = (_lib.EF_WIRE_U8 if self._w8 else 0) | (_lib.EF_STEP_COLD_INPUTS if cold else 0)
+            cold = self.cold_inputs
+            if cold is None:         # the automatic rule, re-evaluated only when the population of env sets changed
+                cc = self._cold_cache
+                cold = cc[1] if cc[0] == RESIDENCY.generation else self._cold_inputs()
+            if cold is not self._wire_cold:
+                x.wire = (_lib.EF_WIRE_U8 if self._w8 else 0) | (_lib.EF_STEP_COLD_INPUTS if cold else 0)
+                self._wire_cold = cold
             if torch.cuda.current_device() == dev_index:
                 x.stream = torch.cuda.current_stream().cuda_stream
                 status = fn(ref)
