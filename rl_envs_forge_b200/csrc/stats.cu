@@ -41,7 +41,16 @@ __device__ __forceinline__ void fold_to_shared(const FoldArgs& f, double (&s_par
     const int rep = threadIdx.x >> 3, field = threadIdx.x & 7;
     static_assert(EF_STATS_REPLICAS * EF_STATS_LEN == kThreads, "one thread per (replica, field)");
     double acc = 0.0;
-    for (int s = 0; s < f.n_sets; ++s) acc += f.raw[s][rep * EF_STATS_STRIDE + field];
+    // eight env sets' loads in flight at a time (their lines are as cold as the sets: one DRAM round trip per batch instead
+    // of one per set); the additions keep their order, so the sum keeps its bits
+    for (int s0 = 0; s0 < f.n_sets; s0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (s0 + u < f.n_sets) ? f.raw[s0 + u][rep * EF_STATS_STRIDE + field] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (s0 + u < f.n_sets) acc += v[u];
+    }
     s_part[rep][field] = acc;
     __syncthreads();
     if (threadIdx.x < EF_STATS_LEN) {
